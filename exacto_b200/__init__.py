@@ -1,0 +1,22 @@
+"""exacto_b200 -- B200 (sm_100a) implementation of exacto's ciphertext-multiplication hot path.
+
+Host mirror of the reference's public surface for that path (same names, argument meaning
+and error behaviour) over the C ABI of ``libexacto_b200.so`` (include/exacto_b200.h):
+
+    ring/      CoeffPoly, NttPoly, RnsPoly, RnsBasis, make_plan
+    params/    BfvParamsBuilder, BfvParams, DbfvParams, compact_bfv, compact_dbfv, u64_dbfv
+    bfv/       BfvCiphertext, RelinKey, bfv_mul_and_relin, bfv_add, bfv_sub, bfv_neg
+    dbfv/      DbfvCiphertext, dbfv_mul, dbfv_add, dbfv_sub, dbfv_neg
+    bootstrap/ dbfv_mul_then_bootstrap, dbfv_mul_chain_then_bootstrap (orchestration only)
+
+There is no CPU fallback: every operation needs the CUDA library and a GPU.
+"""
+from .error import ExactoError
+from .params import (BfvParams, BfvParamsBuilder, DbfvParams, RnsBasis, cfg3_prime_dbfv, compact_bfv,
+                     compact_dbfv, compute_gadget_digits, set_default_device, small_bfv, u64_dbfv)
+from .ring import CoeffPoly, NttPoly, Plan, RnsPoly, make_plan
+from .bfv import BfvCiphertext, RelinKey, bfv_add, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_neg, bfv_sub
+from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
+from .bootstrap import BootstrapKey, dbfv_bootstrap, dbfv_mul_chain_then_bootstrap, dbfv_mul_then_bootstrap
+
+__all__ = [n for n in dir() if not n.startswith("_")]

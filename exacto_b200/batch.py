@@ -1,0 +1,94 @@
+"""Device-resident batched entry points (throughput path).
+
+Ciphertext batches live in HBM as ``torch.int64`` CUDA tensors holding the u64 residues
+bit-for-bit (torch is plumbing: memory + streams); the work is done by the C ABI
+(``exb_dbfv_mul``, ``exb_bfv_mul_and_relin``, ``exb_ntt_*``) on the current torch stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native
+from .bfv import RelinKey
+from .error import InvalidParam
+from .params import BfvParams, DbfvParams
+
+
+def to_device(arr: np.ndarray, device=None) -> torch.Tensor:
+    """numpy uint64 -> CUDA int64 tensor with the same bits."""
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.uint64).view(np.int64))
+    return t.to(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def _check(t: torch.Tensor, shape_tail, what: str):
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise InvalidParam(f"{what}: need a contiguous CUDA int64 tensor")
+    if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise InvalidParam(f"{what}: trailing shape {tuple(t.shape)} != (..., {shape_tail})")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def ntt_forward(params: BfvParams, index: int, polys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NttPoly::from_coeff_poly (ring/ntt.rs:42-55) over [..., n]."""
+    n = params.ring_degree
+    _check(polys, (n,), "ntt_forward")
+    out = torch.empty_like(polys) if out is None else out
+    ctx = params.context(polys.device.index)
+    _native.check(_native.lib().exb_ntt_forward(ctx.handle, index, polys.data_ptr(), out.data_ptr(),
+                                                polys.numel() // n, _stream(polys)))
+    return out
+
+
+def ntt_inverse(params: BfvParams, index: int, polys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NttPoly::to_coeff_poly (ring/ntt.rs:58-67) over [..., n]."""
+    n = params.ring_degree
+    _check(polys, (n,), "ntt_inverse")
+    out = torch.empty_like(polys) if out is None else out
+    ctx = params.context(polys.device.index)
+    _native.check(_native.lib().exb_ntt_inverse(ctx.handle, index, polys.data_ptr(), out.data_ptr(),
+                                                polys.numel() // n, _stream(polys)))
+    return out
+
+
+def bfv_mul_and_relin(params: BfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: RelinKey,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bfv/eval.rs:73-82 over [B, 2, n]."""
+    n = params.ring_degree
+    _check(ct1, (2, n), "ct1"); _check(ct2, (2, n), "ct2")
+    if ct1.shape != ct2.shape:
+        raise InvalidParam("ct1/ct2 shape mismatch")
+    out = torch.empty_like(ct1) if out is None else out
+    ctx = params.context(ct1.device.index)
+    _native.check(_native.lib().exb_bfv_mul_and_relin(ctx.handle, ct1.data_ptr(), ct2.data_ptr(), rlk.native(ctx),
+                                                      out.data_ptr(), ct1.numel() // (2 * n), _stream(ct1)))
+    return out
+
+
+def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: RelinKey,
+             out: Optional[torch.Tensor] = None, *, all_products: bool = False, limb_mask: int = 0) -> torch.Tensor:
+    """dbfv/eval.rs:82-149 over [B, d, 2, n].  ``limb_mask`` selects output limbs (multi-GPU k-sharding)."""
+    n, d = params.bfv_params.ring_degree, params.num_digits
+    _check(ct1, (d, 2, n), "ct1"); _check(ct2, (d, 2, n), "ct2")
+    if ct1.shape != ct2.shape:
+        raise InvalidParam("ct1/ct2 shape mismatch")
+    out = torch.empty_like(ct1) if out is None else out
+    ctx = params.bfv_params.context(ct1.device.index)
+    flags = _native.EXB_DBFV_ALL_PRODUCTS if all_products else 0
+    _native.check(_native.lib().exb_dbfv_mul(ctx.handle, params.base, d, params.plain_modulus, ct1.data_ptr(),
+                                             ct2.data_ptr(), rlk.native(ctx), out.data_ptr(),
+                                             ct1.numel() // (d * 2 * n), flags, limb_mask, _stream(ct1)))
+    return out
+
+
+def launch_count() -> int:
+    return int(_native.lib().exb_launch_count())

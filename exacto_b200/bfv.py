@@ -1,0 +1,136 @@
+"""bfv/: BfvCiphertext, RelinKey and the evaluation functions of bfv/eval.rs that sit
+on the ciphertext-multiplication hot path, with the reference's signatures and error
+behaviour; the arithmetic runs in libexacto_b200.so on the GPU.
+
+    bfv_mul_and_relin(ct1, ct2, rlk)   bfv/eval.rs:73-82
+    bfv_add / bfv_sub / bfv_neg        bfv/eval.rs:14-62
+    relinearize passthrough rules      bfv/keyswitch.rs:59-70
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .error import ExactoError, InvalidParam
+from .params import BfvParams
+from .ring import NttPoly, Plan, RnsPoly, _ptr, _u64
+
+
+class BfvCiphertext:
+    """bfv/mod.rs:19-24: ``c`` is a list of RnsPoly (2, or 3 before relinearisation)."""
+
+    def __init__(self, c: List[RnsPoly], params: BfvParams):
+        self.c = c
+        self.params = params
+
+    def degree(self) -> int:
+        return len(self.c) - 1
+
+    # -- array views used by the batched entry points --------------------------------
+    @staticmethod
+    def from_array(arr, params: BfvParams) -> "BfvCiphertext":
+        """arr: [k][n] NTT-domain residues mod q_0 (single ciphertext prime)."""
+        arr = _u64(arr)
+        plan = Plan(params, 0)
+        q = plan.modulus()
+        return BfvCiphertext([RnsPoly([NttPoly(arr[i].copy(), q, plan)], params.ring_degree)
+                              for i in range(arr.shape[0])], params)
+
+    def to_array(self) -> np.ndarray:
+        return np.stack([ci.components[0].evals for ci in self.c])
+
+
+class RelinKey:
+    """bfv/keygen.rs:39-45: ``keys[g] = (rlk0_g, rlk1_g)`` in the NTT domain.  The device copy
+    (Montgomery form) is created on first use and cached per device."""
+
+    def __init__(self, keys, params: BfvParams):
+        if isinstance(keys, np.ndarray):
+            self.array = _u64(keys)                                    # [G][2][n]
+        else:
+            self.array = np.stack([np.stack([k0.components[0].evals, k1.components[0].evals])
+                                   for (k0, k1) in keys]) if len(keys) else np.zeros((0, 2, params.ring_degree), np.uint64)
+        self.params = params
+        self._native = {}
+
+    @property
+    def keys(self):
+        plan = Plan(self.params, 0)
+        q, n = plan.modulus(), self.params.ring_degree
+        return [(RnsPoly([NttPoly(self.array[g, 0], q, plan)], n), RnsPoly([NttPoly(self.array[g, 1], q, plan)], n))
+                for g in range(self.array.shape[0])]
+
+    def native(self, ctx) -> ctypes.c_void_p:
+        key = id(ctx)
+        if key not in self._native:
+            h = ctypes.c_void_p()
+            _native.check(_native.lib().exb_relin_key_load(ctx.handle, _ptr(self.array), self.array.shape[0],
+                                                           ctypes.byref(h)))
+            self._native[key] = (h, ctx)
+        return self._native[key][0]
+
+    def __del__(self):
+        try:
+            for h, _ctx in self._native.values():
+                _native.lib().exb_relin_key_destroy(h)
+        except Exception:
+            pass
+
+
+def _zip_op(ct1: BfvCiphertext, ct2: BfvCiphertext, op: str, lone_rhs) -> BfvCiphertext:
+    c = []
+    for i in range(max(len(ct1.c), len(ct2.c))):
+        a = ct1.c[i] if i < len(ct1.c) else None
+        b = ct2.c[i] if i < len(ct2.c) else None
+        if a is not None and b is not None:
+            c.append(getattr(a, op)(b))
+        elif a is not None:
+            c.append(a)
+        else:
+            c.append(lone_rhs(b))
+    return BfvCiphertext(c, ct1.params)
+
+
+def bfv_add(ct1: BfvCiphertext, ct2: BfvCiphertext) -> BfvCiphertext:
+    """bfv/eval.rs:14-31 (ragged lengths allowed)."""
+    return _zip_op(ct1, ct2, "add", lambda b: b)
+
+
+def bfv_sub(ct1: BfvCiphertext, ct2: BfvCiphertext) -> BfvCiphertext:
+    """bfv/eval.rs:34-51."""
+    return _zip_op(ct1, ct2, "sub", lambda b: b.neg())
+
+
+def bfv_neg(ct: BfvCiphertext) -> BfvCiphertext:
+    """bfv/eval.rs:54-60."""
+    return BfvCiphertext([ci.neg() for ci in ct.c], ct.params)
+
+
+def _check_degree1(ct1: BfvCiphertext, ct2: BfvCiphertext):
+    if len(ct1.c) != 2 or len(ct2.c) != 2:                              # bfv/eval.rs:93-97
+        raise InvalidParam("multiplication requires degree-1 ciphertexts")
+
+
+def bfv_mul_and_relin(ct1: BfvCiphertext, ct2: BfvCiphertext, rlk: RelinKey) -> BfvCiphertext:
+    """bfv/eval.rs:73-82.  Borrows the inputs, returns a fresh ciphertext sharing ct1.params."""
+    _check_degree1(ct1, ct2)
+    params = ct1.params
+    out = bfv_mul_and_relin_batch(params, ct1.to_array()[None], ct2.to_array()[None], rlk)
+    return BfvCiphertext.from_array(out[0], params)
+
+
+def bfv_mul_and_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray, rlk: RelinKey,
+                            device: Optional[int] = None) -> np.ndarray:
+    """Batched host-buffer form: ct [B][2][n] -> [B][2][n] (exb_bfv_mul_and_relin_host)."""
+    ct1, ct2 = _u64(ct1), _u64(ct2)
+    n = params.ring_degree
+    if ct1.shape != ct2.shape or ct1.shape[1:] != (2, n):
+        raise InvalidParam("multiplication requires degree-1 ciphertexts")
+    ctx = params.context(device)
+    out = np.empty_like(ct1)
+    _native.check(_native.lib().exb_bfv_mul_and_relin_host(ctx.handle, _ptr(ct1), _ptr(ct2), rlk.native(ctx),
+                                                           _ptr(out), ct1.shape[0]))
+    return out

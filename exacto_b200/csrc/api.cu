@@ -1,0 +1,492 @@
+// api.cu -- C ABI (include/exacto_b200.h): context construction (host-side
+// precomputation of plans and HPS constants), device memory plumbing, and the
+// batched hot-path entry points that sequence the kernels of kernels.cu.
+//
+// The host-side restatements of the reference (params, plans, dispatch, dBFV plan)
+// live in host_setup.cpp; this file adds the CUDA side: uploads, workspaces, streams
+// and the launch sequence, incl. reduction::reduce (dbfv/reduction.rs:15-60).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/exacto_b200.h"
+#include "kernels.cuh"
+
+using namespace exb;
+
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define EXB_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(EXB_CUDA_ERROR, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+static const int kSlots = 3;
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    u64 *ext = nullptr, *r01 = nullptr, *excess = nullptr;
+    void *digits = nullptr;
+    size_t ext_b = 0, r01_b = 0, excess_b = 0, digits_b = 0;
+    u64 *in1 = nullptr, *in2 = nullptr, *out = nullptr;   // staging for the *_host entry points
+    size_t in_b = 0, out_b = 0;
+};
+
+struct StageEvents {
+    cudaEvent_t ev[5];
+    bool has_reduce;
+};
+
+struct exb_context : HostSetup {
+    int device = 0;
+    bool profiling = false;
+    std::vector<StageEvents> events;
+    std::vector<Tw *> d_tables;       // owned device twiddle tables
+    Workspace ws[kSlots];
+};
+
+struct exb_relin_key {
+    exb_context *ctx = nullptr;
+    u64 *d_mont = nullptr;            // [num_keys][2][n], Montgomery form
+    u32 num_keys = 0;
+};
+
+static int grow(void **p, size_t *have, size_t want) {
+    if (*have >= want) return EXB_OK;
+    if (*p) EXB_CUDA(cudaFree(*p));
+    *p = nullptr; *have = 0;
+    EXB_CUDA(cudaMalloc(p, want));
+    *have = want;
+    return EXB_OK;
+}
+
+extern "C" const char *exb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *exb_version(void) { return "exacto_b200 0.1 (sm_100a)"; }
+extern "C" unsigned long long exb_launch_count(void) { return exb::g_launch_count; }
+
+extern "C" void exb_context_destroy(exb_context *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (StageEvents &se : c->events) for (auto &e : se.ev) cudaEventDestroy(e);
+    for (Tw *t : c->d_tables) cudaFree(t);
+    for (Workspace &w : c->ws) {
+        cudaFree(w.ext); cudaFree(w.r01); cudaFree(w.excess); cudaFree(w.digits);
+        cudaFree(w.in1); cudaFree(w.in2); cudaFree(w.out);
+        if (w.stream) cudaStreamDestroy(w.stream);
+    }
+    delete c;
+}
+
+extern "C" int exb_context_create(const exb_bfv_params *p, int device, exb_context **out) {
+    if (!p || !out) return fail(EXB_INVALID_PARAM, "null argument");
+    *out = nullptr;
+    exb_context *c = new exb_context();
+    c->device = device;
+    std::string err;
+    int rc = host_setup_build(p, c, &err);
+    if (rc != EXB_OK) { delete c; return fail(rc, err); }
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) {
+        delete c;
+        return fail(EXB_CUDA_ERROR, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    }
+    const u32 n = c->n;
+    for (int b = 0; b < kMaxBases; b++) {
+        if (!c->has_plan[b]) continue;
+        Tw *df = nullptr, *di = nullptr;
+        if (cudaMalloc(&df, sizeof(Tw) * n) != cudaSuccess || cudaMalloc(&di, sizeof(Tw) * n) != cudaSuccess ||
+            cudaMemcpy(df, c->twf[b].data(), sizeof(Tw) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(di, c->twi[b].data(), sizeof(Tw) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+            std::string m = std::string("twiddle upload: ") + cudaGetErrorString(cudaGetLastError());
+            cudaFree(df); cudaFree(di);
+            exb_context_destroy(c);
+            return fail(EXB_CUDA_ERROR, m);
+        }
+        c->d_tables.push_back(df); c->d_tables.push_back(di);
+        c->P.twf[b] = df; c->P.twi[b] = di;
+    }
+    for (Workspace &w : c->ws)
+        if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            exb_context_destroy(c);
+            return fail(EXB_CUDA_ERROR, "cudaStreamCreate failed");
+        }
+    *out = c;
+    return EXB_OK;
+}
+
+extern "C" int exb_profile_enable(exb_context *c, int on) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    c->profiling = on != 0;
+    return EXB_OK;
+}
+
+extern "C" int exb_profile_read(exb_context *c, double *ms, unsigned long long *launches) {
+    if (!c || !ms || !launches) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    for (StageEvents &se : c->events) {
+        EXB_CUDA(cudaEventSynchronize(se.ev[4]));
+        for (int k = 0; k < 4; k++) {
+            float t = 0.f;
+            EXB_CUDA(cudaEventElapsedTime(&t, se.ev[k], se.ev[k + 1]));
+            if (k < 3 || se.has_reduce) { ms[k] += t; launches[k] += 1; }
+        }
+        for (auto &e : se.ev) cudaEventDestroy(e);
+    }
+    c->events.clear();
+    return EXB_OK;
+}
+
+extern "C" int exb_context_gadget(const exb_context *c, uint64_t *base, uint32_t *digits) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    if (base) *base = c->gadget_base;
+    if (digits) *digits = c->gadget_digits;
+    return EXB_OK;
+}
+
+extern "C" int exb_context_psi(const exb_context *c, uint32_t idx, uint64_t *psi) {
+    if (!c || !psi) return fail(EXB_INVALID_PARAM, "null argument");
+    if (idx >= c->psi.size()) return fail(EXB_INVALID_PARAM, "modulus index out of range");
+    *psi = c->psi[idx];
+    return EXB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// plumbing
+// ---------------------------------------------------------------------------------
+extern "C" int exb_device_alloc(exb_context *c, size_t bytes, void **p) {
+    if (!c || !p) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaMalloc(p, bytes ? bytes : 8));
+    return EXB_OK;
+}
+extern "C" int exb_device_free(exb_context *c, void *p) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaFree(p));
+    return EXB_OK;
+}
+extern "C" int exb_copy_to_device(exb_context *c, void *dst, const void *src, size_t bytes, void *stream) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return EXB_OK;
+}
+extern "C" int exb_copy_to_host(exb_context *c, void *dst, const void *src, size_t bytes, void *stream) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return EXB_OK;
+}
+extern "C" int exb_synchronize(exb_context *c, void *stream) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return EXB_OK;
+}
+
+static int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(EXB_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(e));
+    return EXB_OK;
+}
+
+static int check_base(const exb_context *c, u32 idx) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    const u32 A = (u32)c->aux_moduli.size();
+    if (idx != 0 && (A > (u32)kMaxAux || idx > A))
+        return fail(EXB_MODULUS_MISMATCH, "modulus index " + std::to_string(idx) + " has no device plan");
+    return EXB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// ring ops
+// ---------------------------------------------------------------------------------
+extern "C" int exb_ntt_forward(exb_context *c, uint32_t idx, const uint64_t *in, uint64_t *out, size_t count,
+                               void *stream) {
+    int rc = check_base(c, idx);
+    if (rc) return rc;
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_ntt_fwd(c->P, (int)idx, in, out, count, (cudaStream_t)stream);
+    return check_launch("ntt_fwd");
+}
+extern "C" int exb_ntt_inverse(exb_context *c, uint32_t idx, const uint64_t *in, uint64_t *out, size_t count,
+                               void *stream) {
+    int rc = check_base(c, idx);
+    if (rc) return rc;
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_ntt_inv(c->P, (int)idx, in, out, count, (cudaStream_t)stream);
+    return check_launch("ntt_inv");
+}
+
+static int ntt_host(exb_context *c, u32 idx, const u64 *in, u64 *out, size_t count, bool fwd) {
+    int rc = check_base(c, idx);
+    if (rc) return rc;
+    if (count == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    Workspace &w = c->ws[0];
+    const size_t bytes = count * c->n * sizeof(u64);
+    rc = grow((void **)&w.in1, &w.in_b, bytes);
+    if (rc) return rc;
+    EXB_CUDA(cudaMemcpyAsync(w.in1, in, bytes, cudaMemcpyHostToDevice, w.stream));
+    if (fwd) launch_ntt_fwd(c->P, (int)idx, w.in1, w.in1, count, w.stream);
+    else launch_ntt_inv(c->P, (int)idx, w.in1, w.in1, count, w.stream);
+    rc = check_launch("ntt_host");
+    if (rc) return rc;
+    EXB_CUDA(cudaMemcpyAsync(out, w.in1, bytes, cudaMemcpyDeviceToHost, w.stream));
+    EXB_CUDA(cudaStreamSynchronize(w.stream));
+    return EXB_OK;
+}
+extern "C" int exb_ntt_forward_host(exb_context *c, uint32_t idx, const uint64_t *in, uint64_t *out, size_t count) {
+    return ntt_host(c, idx, in, out, count, true);
+}
+extern "C" int exb_ntt_inverse_host(exb_context *c, uint32_t idx, const uint64_t *in, uint64_t *out, size_t count) {
+    return ntt_host(c, idx, in, out, count, false);
+}
+
+static int poly_op(exb_context *c, u32 idx, PolyOp op, const u64 *a, const u64 *b, u64 scalar, u64 *out,
+                   size_t words, void *stream) {
+    int rc = check_base(c, idx);
+    if (rc) return rc;
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_poly_op(c->P.mod[idx], op, a, b, scalar, out, words, (cudaStream_t)stream);
+    return check_launch("poly_op");
+}
+extern "C" int exb_poly_add(exb_context *c, uint32_t i, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t w, void *s) {
+    return poly_op(c, i, OP_ADD, a, b, 0, o, w, s);
+}
+extern "C" int exb_poly_sub(exb_context *c, uint32_t i, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t w, void *s) {
+    return poly_op(c, i, OP_SUB, a, b, 0, o, w, s);
+}
+extern "C" int exb_poly_neg(exb_context *c, uint32_t i, const uint64_t *a, uint64_t *o, size_t w, void *s) {
+    return poly_op(c, i, OP_NEG, a, nullptr, 0, o, w, s);
+}
+extern "C" int exb_poly_mul(exb_context *c, uint32_t i, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t w, void *s) {
+    return poly_op(c, i, OP_MUL, a, b, 0, o, w, s);
+}
+extern "C" int exb_poly_scalar_mul(exb_context *c, uint32_t i, const uint64_t *a, uint64_t scalar, uint64_t *o, size_t w, void *s) {
+    int rc = check_base(c, i);
+    if (rc) return rc;
+    return poly_op(c, i, OP_SCALAR_MUL, a, nullptr, scalar % c->P.mod[i].m, o, w, s);   // ring/ntt.rs:133
+}
+extern "C" int exb_bfv_add(exb_context *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t batch, void *s) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    return poly_op(c, 0, OP_ADD, a, b, 0, o, batch * 2 * (size_t)c->n, s);
+}
+
+// ---------------------------------------------------------------------------------
+// relinearisation key
+// ---------------------------------------------------------------------------------
+extern "C" void exb_relin_key_destroy(exb_relin_key *k) {
+    if (!k) return;
+    if (k->ctx) cudaSetDevice(k->ctx->device);
+    cudaFree(k->d_mont);
+    delete k;
+}
+
+static int relin_key_make(exb_context *c, const u64 *src, bool src_is_host, u32 num_keys, cudaStream_t stream,
+                          exb_relin_key **out) {
+    if (!c || !out || (!src && num_keys)) return fail(EXB_INVALID_PARAM, "null argument");
+    int rc = check_base(c, 0);
+    if (rc) return rc;
+    EXB_CUDA(cudaSetDevice(c->device));
+    exb_relin_key *k = new exb_relin_key();
+    k->ctx = c; k->num_keys = num_keys;
+    const size_t words = (size_t)num_keys * 2 * c->n;
+    if (cudaMalloc(&k->d_mont, words ? words * 8 : 8) != cudaSuccess) { delete k; return fail(EXB_CUDA_ERROR, "cudaMalloc relin key"); }
+    if (words) {
+        cudaError_t e = cudaMemcpyAsync(k->d_mont, src, words * 8, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) { exb_relin_key_destroy(k); return fail(EXB_CUDA_ERROR, cudaGetErrorString(e)); }
+        launch_poly_op(c->P.mod[0], OP_TO_MONT, k->d_mont, nullptr, 0, k->d_mont, words, stream);
+        rc = check_launch("relin key to Montgomery");
+        if (rc) { exb_relin_key_destroy(k); return rc; }
+        e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { exb_relin_key_destroy(k); return fail(EXB_CUDA_ERROR, cudaGetErrorString(e)); }
+    }
+    *out = k;
+    return EXB_OK;
+}
+extern "C" int exb_relin_key_load(exb_context *c, const uint64_t *rlk_host, uint32_t num_keys, exb_relin_key **out) {
+    return relin_key_make(c, rlk_host, true, num_keys, c ? c->ws[0].stream : nullptr, out);
+}
+extern "C" int exb_relin_key_load_device(exb_context *c, const uint64_t *rlk_dev, uint32_t num_keys, void *stream,
+                                         exb_relin_key **out) {
+    return relin_key_make(c, rlk_dev, false, num_keys, (cudaStream_t)stream, out);
+}
+
+// ---------------------------------------------------------------------------------
+// dBFV plan: which products / limbs are needed (dbfv/eval.rs:109-114, reduction.rs:28-52)
+// ---------------------------------------------------------------------------------
+extern "C" int exb_dbfv_small_reps(uint64_t base, uint32_t d, uint64_t pm, int64_t *reps) {
+    std::string err;
+    int rc = host_small_reps(base, d, pm, reps, &err);
+    return rc ? fail(rc, err) : EXB_OK;
+}
+
+static int build_plan(u32 d, u64 base, u64 pm, u32 flags, u32 limb_mask, HostPlan *hp) {
+    std::string err;
+    int rc = host_build_plan(d, base, pm, flags, limb_mask, hp, &err);
+    return rc ? fail(rc, err) : EXB_OK;
+}
+
+static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G, size_t *ext_b, size_t *r01_b,
+                                size_t *dig_b, size_t *exc_b) {
+    const size_t n = c->n, A = c->aux_moduli.size(), d = hp.M.d;
+    *ext_b = 2 * d * 2 * (1 + A) * n * 8;
+    *r01_b = (size_t)hp.M.num_products * 2 * n * 8;
+    *dig_b = (size_t)hp.M.num_products * (G ? G : 1) * n * (c->digits32 ? 4 : 2);
+    *exc_b = (size_t)(hp.M.num_limbs - hp.num_low) * 2 * n * 8;
+    return *ext_b + *r01_b + *dig_b + *exc_b;
+}
+
+// Run the pipeline for `pairs` pairs whose inputs/outputs are on the device.
+static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1,
+                     const u64 *ct2, u64 *out, size_t pairs, cudaStream_t stream) {
+    DeviceParams P = c->P;
+    const u32 G = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;   // keyswitch.rs:86-89
+    P.gadget_digits = G;
+    size_t eb, rb, db, xb;
+    ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
+    int rc;
+    if ((rc = grow((void **)&w.ext, &w.ext_b, eb * pairs))) return rc;
+    if ((rc = grow((void **)&w.r01, &w.r01_b, rb * pairs))) return rc;
+    if ((rc = grow(&w.digits, &w.digits_b, db * pairs))) return rc;
+    if (xb && (rc = grow((void **)&w.excess, &w.excess_b, xb * pairs))) return rc;
+    StageEvents se;
+    se.has_reduce = false;
+    const bool prof = c->profiling;
+    if (prof) {
+        for (auto &e : se.ev) EXB_CUDA(cudaEventCreate(&e));
+        EXB_CUDA(cudaEventRecord(se.ev[0], stream));
+    }
+    launch_lift(P, hp.M, ct1, ct2, w.ext, pairs, stream);
+    if (prof) EXB_CUDA(cudaEventRecord(se.ev[1], stream));
+    launch_tensor(P, hp.M, ct1, w.ext, w.r01, w.digits, c->digits32, pairs, stream);
+    if (prof) EXB_CUDA(cudaEventRecord(se.ev[2], stream));
+    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);
+    if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
+    // reduction::reduce for non-zero small representatives (dbfv/reduction.rs:34-52)
+    const u32 d = hp.M.d;
+    const size_t n = c->n, nx = hp.M.num_limbs - hp.num_low;
+    const u64 q = c->ct_moduli[0];
+    for (u32 j = d; j + 1 < 2 * d; j++) {
+        if (hp.excess_index[j] < 0) continue;
+        for (u32 i = 0; i < d; i++) {
+            const int64_t rep = hp.reps[(size_t)(j - d) * d + i];
+            if (rep == 0) continue;
+            bool computed = false;
+            for (u32 l = 0; l < hp.M.num_limbs; l++) if (hp.M.limb_k[l] == i) computed = true;
+            if (!computed) continue;
+            const u64 mag = rep < 0 ? (u64)(-(rep + 1)) + 1 : (u64)rep;
+            launch_reduce_mac(P, out + (size_t)i * 2 * n, w.excess + (size_t)hp.excess_index[j] * 2 * n, mag % q,
+                              rep < 0, (size_t)d * 2 * n, nx * 2 * n, pairs, stream);
+            se.has_reduce = true;
+        }
+    }
+    if (prof) {
+        EXB_CUDA(cudaEventRecord(se.ev[4], stream));
+        c->events.push_back(se);
+    }
+    return check_launch("ct-mul pipeline");
+}
+
+static int mul_precheck(exb_context *c, const exb_relin_key *rlk) {
+    if (!c || !rlk) return fail(EXB_INVALID_PARAM, "null argument");
+    if (rlk->ctx != c) return fail(EXB_INVALID_PARAM, "relinearisation key belongs to another context");
+    if (c->mul_status != EXB_OK) return fail(c->mul_status, c->mul_error);
+    return EXB_OK;
+}
+
+static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G) {
+    size_t eb, rb, db, xb;
+    const size_t per = ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
+    size_t chunk = ((size_t)4 << 30) / (per ? per : 1);
+    return chunk ? chunk : 1;
+}
+
+extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                            const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                            uint32_t flags, uint32_t limb_mask, void *stream) {
+    int rc = mul_precheck(c, rlk);
+    if (rc) return rc;
+    if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
+    HostPlan hp;
+    if ((rc = build_plan(d, base, pm, flags, limb_mask, &hp))) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    const size_t stride = (size_t)d * 2 * c->n;
+    const size_t chunk = device_chunk_pairs(c, hp, c->gadget_digits);
+    for (size_t off = 0; off < batch; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        rc = run_pairs(c, c->ws[0], hp, rlk, ct1 + off * stride, ct2 + off * stride, out + off * stride, cnt,
+                       (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return EXB_OK;
+}
+
+extern "C" int exb_bfv_mul_and_relin(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
+                                     const exb_relin_key *rlk, uint64_t *out, size_t batch, void *stream) {
+    // one product per pair: the d = 1 case of the same pipeline (base is irrelevant)
+    return exb_dbfv_mul(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0, 0, stream);
+}
+
+// Host-buffer entry: chunks pipelined over kSlots streams (H2D, kernels, D2H overlap).
+extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                                 const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                                 uint32_t flags) {
+    int rc = mul_precheck(c, rlk);
+    if (rc) return rc;
+    if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
+    HostPlan hp;
+    if ((rc = build_plan(d, base, pm, flags, 0, &hp))) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    const size_t stride = (size_t)d * 2 * c->n;
+    size_t chunk = 2048 / (hp.M.num_products ? hp.M.num_products : 1);
+    if (chunk < 1) chunk = 1;
+    if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
+    size_t ci = 0;
+    for (size_t off = 0; off < batch; off += chunk, ci++) {
+        Workspace &w = c->ws[ci % kSlots];
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        const size_t bytes = cnt * stride * 8;
+        if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
+        // in2 and out share the growth bookkeeping of out_b
+        if (w.out_b < chunk * stride * 8) {
+            if (w.in2) EXB_CUDA(cudaFree(w.in2));
+            if (w.out) EXB_CUDA(cudaFree(w.out));
+            w.in2 = w.out = nullptr; w.out_b = 0;
+            EXB_CUDA(cudaMalloc((void **)&w.in2, chunk * stride * 8));
+            EXB_CUDA(cudaMalloc((void **)&w.out, chunk * stride * 8));
+            w.out_b = chunk * stride * 8;
+        }
+        EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+        EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+        if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream))) return rc;
+        EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
+    return EXB_OK;
+}
+
+extern "C" int exb_bfv_mul_and_relin_host(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
+                                          const exb_relin_key *rlk, uint64_t *out, size_t batch) {
+    return exb_dbfv_mul_host(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0);
+}

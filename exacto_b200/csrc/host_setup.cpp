@@ -1,0 +1,356 @@
+// host_setup.cpp -- see host_setup.hpp.  Pure C++ (unsigned __int128), no CUDA.
+//
+// Host restatements: BfvParamsBuilder::build params/mod.rs:81-124,
+// compute_gadget_digits params/mod.rs:126-140, RnsBasis::new ring/rns.rs:35-63,
+// make_plan ring/ntt.rs:19-29, bfv_mul_no_relin dispatch bfv/eval.rs:89-108,
+// single-aux guard bfv/eval.rs:170-178, schoolbook_overflow_risk bfv/eval.rs:457-464,
+// hps_scale setup bfv/eval.rs:275-286,342-347, SmallReps::compute_simple
+// dbfv/lattice.rs:104-122.
+#include "host_setup.hpp"
+
+#include <cstring>
+
+namespace exb {
+
+typedef unsigned __int128 u128;
+typedef __int128 i128;
+
+static int fail(std::string *err, int code, const std::string &msg) {
+    if (err) *err = msg;
+    return code;
+}
+
+static std::string u128_str(u128 v) {
+    char buf[48];
+    int pos = 47;
+    buf[pos] = 0;
+    do { buf[--pos] = (char)('0' + (int)(v % 10)); v /= 10; } while (v);
+    return std::string(buf + pos);
+}
+
+// ---- number theory -----------------------------------------------------------------
+static u64 h_mul(u64 a, u64 b, u64 m) { return (u64)((u128)a * b % m); }
+static u64 h_pow(u64 b, u64 e, u64 m) {
+    u64 r = 1 % m;
+    b %= m;
+    while (e) { if (e & 1) r = h_mul(r, b, m); b = h_mul(b, b, m); e >>= 1; }
+    return r;
+}
+static bool h_inv(u64 a, u64 m, u64 *out) {  // extended Euclid (ring/modular.rs:102-121)
+    i128 old_r = a, r = m, old_s = 1, s = 0;
+    while (r != 0) {
+        i128 qq = old_r / r, t = r;
+        r = old_r - qq * r; old_r = t;
+        t = s; s = old_s - qq * s; old_s = t;
+    }
+    if (old_r != 1) return false;
+    *out = (u64)(((old_s % (i128)m) + (i128)m) % (i128)m);
+    return true;
+}
+static bool h_is_prime(u64 m) {
+    if (m < 2) return false;
+    static const u64 b[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+    for (u64 p : b) { if (m == p) return true; if (m % p == 0) return false; }
+    u64 dd = m - 1; int s = 0;
+    while (!(dd & 1)) { dd >>= 1; s++; }
+    for (u64 a : b) {
+        u64 x = h_pow(a, dd, m);
+        if (x == 1 || x == m - 1) continue;
+        bool comp = true;
+        for (int r = 1; r < s; r++) { x = h_mul(x, x, m); if (x == m - 1) { comp = false; break; } }
+        if (comp) return false;
+    }
+    return true;
+}
+static u64 shoup_of(u64 w, u64 m) { return (u64)(((u128)w << 64) / m); }
+static u32 bitrev32(u32 x, u32 bits) {
+    u32 r = 0;
+    for (u32 i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+// minimal big integers (little-endian base 2^32) for compute_gadget_digits
+static void bn_mul(std::vector<u32> &a, u64 m) {
+    std::vector<u32> r(a.size() + 2, 0);
+    const u32 mw[2] = {(u32)m, (u32)(m >> 32)};
+    for (size_t i = 0; i < a.size(); i++)
+        for (int j = 0; j < 2; j++) {
+            u64 carry = (u64)a[i] * mw[j];
+            for (size_t k = i + j; carry; k++) {
+                const u64 t = (u64)r[k] + (carry & 0xffffffffu);
+                r[k] = (u32)t;
+                carry = (carry >> 32) + (t >> 32);
+            }
+        }
+    while (r.size() > 1 && r.back() == 0) r.pop_back();
+    a = r;
+}
+static int bn_cmp(const std::vector<u32> &a, const std::vector<u32> &b) {
+    if (a.size() != b.size()) return a.size() < b.size() ? -1 : 1;
+    for (size_t i = a.size(); i-- > 0;)
+        if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return 0;
+}
+
+// make_plan (ring/ntt.rs:19-29) + the per-modulus constants of modarith.cuh.
+// psi = x^((m-1)/2n) for the first x = 2, 3, .. with psi^n == m - 1.
+static int build_modulus(u32 n, u32 logn, u64 m, Modulus *mod, std::vector<Tw> *twf, std::vector<Tw> *twi,
+                         u64 *psi_out, std::string *err) {
+    if (!h_is_prime(m) || (m - 1) % (2ull * n) != 0)
+        return fail(err, EXB_INVALID_PARAM,
+                    "cannot create NTT plan for n=" + std::to_string(n) + ", q=" + std::to_string(m) +
+                        " (need prime q ≡ 1 mod " + std::to_string(2ull * n) + ")");
+    if (m >> 62)
+        return fail(err, EXB_NOT_IMPLEMENTED,
+                    "device path supports NTT primes below 2^62, got " + std::to_string(m));
+    const u64 e = (m - 1) / (2ull * n);
+    u64 psi = 0;
+    for (u64 x = 2; x < m; x++) {
+        const u64 c = h_pow(x, e, m);
+        if (h_pow(c, n, m) == m - 1) { psi = c; break; }
+    }
+    if (!psi) return fail(err, EXB_INVALID_PARAM, "no primitive 2n-th root of unity");
+    u64 psi_inv = 0, ninv = 0;
+    if (!h_inv(psi, m, &psi_inv) || !h_inv(n % m, m, &ninv))
+        return fail(err, EXB_INVALID_PARAM, "psi or n not invertible");
+    twf->resize(n); twi->resize(n);
+    u64 pw = 1, ipw = 1;
+    for (u32 k = 0; k < n; k++) {
+        const u32 r = bitrev32(k, logn);
+        (*twf)[r].w = pw;  (*twf)[r].s = shoup_of(pw, m);
+        (*twi)[r].w = ipw; (*twi)[r].s = shoup_of(ipw, m);
+        pw = h_mul(pw, psi, m); ipw = h_mul(ipw, psi_inv, m);
+    }
+    mod->m = m; mod->two_m = 2 * m;
+    mod->mu = (u64)(((u128)1 << 64) / m);
+    u64 inv = m;                                           // Newton: m^-1 mod 2^64
+    for (int i = 0; i < 6; i++) inv *= 2 - m * inv;
+    mod->minv_neg = (u64)0 - inv;
+    mod->r_mod = (u64)(((u128)1 << 64) % m);
+    mod->r_mod_s = shoup_of(mod->r_mod, m);
+    mod->r2_mod = h_mul(mod->r_mod, mod->r_mod, m);
+    mod->ninv = ninv; mod->ninv_s = shoup_of(ninv, m);
+    mod->ninv_w = h_mul(ninv, (*twi)[1].w, m);
+    mod->ninv_w_s = shoup_of(mod->ninv_w, m);
+    *psi_out = psi;
+    return EXB_OK;
+}
+
+static bool schoolbook_overflow_risk(u64 p, u64 q, u32 n) {   // bfv/eval.rs:457-464
+    auto sat = [](u128 a, u128 b) -> u128 {
+        if (a == 0 || b == 0) return 0;
+        if (a > (~(u128)0) / b) return ~(u128)0;
+        return a * b;
+    };
+    const u128 i128_max = (~(u128)0) >> 1;
+    const u128 mc = q / 2, mt = sat(sat((u128)n, mc), mc), ms = sat(mt, (u128)p);
+    return mt > i128_max || ms > i128_max;
+}
+
+// The dispatch of bfv_mul_no_relin (bfv/eval.rs:89-108), evaluated once per parameter set.
+static void decide_mul_support(HostSetup *c) {
+    const u32 A = (u32)c->aux_moduli.size();
+    const u64 q = c->ct_moduli[0];
+    c->mul_status = EXB_OK;
+    if (c->ct_moduli.size() > 1) {
+        c->mul_status = EXB_NOT_IMPLEMENTED;
+        c->mul_error = "multi-prime ciphertext modulus: the reference's BigInt path (bfv/eval.rs:113-147) is "
+                       "not provided by the device library";
+    } else if (A == 0) {
+        c->mul_status = EXB_NOT_IMPLEMENTED;
+        c->mul_error = schoolbook_overflow_risk(c->plain, q, c->n)
+                           ? "schoolbook BFV multiplication can overflow i128 for these parameters; use HPS "
+                             "auxiliary basis"
+                           : "schoolbook BFV multiplication (no auxiliary basis) is not provided by the device "
+                             "library; use HPS auxiliary basis";
+    } else if (A == 1 && (u128)c->aux_moduli[0] <= ((u128)c->n * q) / 2) {   // bfv/eval.rs:170-178
+        c->mul_status = EXB_INVALID_PARAM;
+        c->mul_error = "single aux prime too small for HPS centering: P=" + std::to_string(c->aux_moduli[0]) +
+                       " <= n*Q/2=" + u128_str(((u128)c->n * q) / 2);
+    } else if (A > 2) {                                                       // bfv/eval.rs:405-409
+        c->mul_status = EXB_INVALID_PARAM;
+        c->mul_error = "HPS scaling supports 1 or 2 aux primes, got " + std::to_string(A);
+    } else if (c->plain >= q) {
+        c->mul_status = EXB_NOT_IMPLEMENTED;
+        c->mul_error = "device path needs plain_modulus < ciphertext prime";
+    } else if (c->gadget_base < 2 || c->gadget_base > (1ull << 32)) {
+        c->mul_status = EXB_NOT_IMPLEMENTED;
+        c->mul_error = "device path supports gadget bases in [2, 2^32]";
+    }
+}
+
+static int fill_scale_consts(HostSetup *c, std::string *err) {
+    ScaleConsts &s = c->P.sc;
+    memset(&s, 0, sizeof s);
+    const u32 A = (u32)c->aux_moduli.size();
+    const u64 q = c->ct_moduli[0], p = c->plain;
+    s.q = q; s.half_q = q / 2; s.num_aux = A;
+    if (A == 0 || A > 2 || p >= q) return EXB_OK;      // multiplication is refused by decide_mul_support
+    u128 big_p = 1;
+    for (u32 j = 0; j < A; j++) {
+        s.pj[j] = c->aux_moduli[j];
+        s.pj_mu[j] = (u64)(((u128)1 << 64) / s.pj[j]);
+        big_p *= s.pj[j];
+    }
+    s.big_p.lo = (u64)big_p; s.big_p.hi = (u64)(big_p >> 64);
+    const u128 hp = big_p / 2;
+    s.half_big_p.lo = (u64)hp; s.half_big_p.hi = (u64)(hp >> 64);
+    s.plain = p; s.plain_s = shoup_of(p, q);
+    u64 qinv[2] = {0, 0};
+    for (u32 j = 0; j < A; j++)
+        if (!h_inv(q % s.pj[j], s.pj[j], &qinv[j]))
+            return fail(err, EXB_INVALID_PARAM, "q not invertible mod p_j");
+    if (A == 1) {
+        s.K[0] = qinv[0];
+        s.C[0] = p;
+    } else {
+        u64 p1_inv_p0, p0_inv_p1;
+        if (!h_inv(s.pj[1] % s.pj[0], s.pj[0], &p1_inv_p0) || !h_inv(s.pj[0] % s.pj[1], s.pj[1], &p0_inv_p1))
+            return fail(err, EXB_INVALID_PARAM, "aux primes not coprime");
+        s.K[0] = h_mul(qinv[0], p1_inv_p0, s.pj[0]);
+        s.K[1] = h_mul(qinv[1], p0_inv_p1, s.pj[1]);
+        s.other[0] = s.pj[1]; s.other[1] = s.pj[0];
+        s.C[0] = h_mul(p, s.pj[1] % q, q);
+        s.C[1] = h_mul(p, s.pj[0] % q, q);
+    }
+    for (u32 j = 0; j < A; j++) {
+        s.K_s[j] = shoup_of(s.K[j], s.pj[j]);
+        s.C_s[j] = shoup_of(s.C[j], q);
+    }
+    s.CP = h_mul(p, (u64)(big_p % q), q);
+    s.CP2 = (u64)(((u128)s.CP * 2) % q);
+    return EXB_OK;
+}
+
+int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
+    if (!p || !c) return fail(err, EXB_INVALID_PARAM, "null argument");
+    const u32 n = p->ring_degree;
+    if (n < 2 || (n & (n - 1)))                                           // params/mod.rs:82-84
+        return fail(err, EXB_INVALID_RING_DEGREE, "ring degree must be a power of 2, got " + std::to_string(n));
+    if (p->num_ct_moduli == 0 || !p->ct_moduli)                           // :85-87
+        return fail(err, EXB_INVALID_PARAM, "must specify at least one ciphertext modulus");
+    if (p->plain_modulus < 2)                                             // :88-90
+        return fail(err, EXB_INVALID_PARAM, "plaintext modulus must be >= 2");
+    if (n > 8192) return fail(err, EXB_NOT_IMPLEMENTED, "device path supports ring degrees up to 8192");
+    if (p->num_aux_moduli && !p->aux_moduli) return fail(err, EXB_INVALID_PARAM, "null aux_moduli");
+
+    c->n = n; c->logn = 0;
+    while ((1u << c->logn) < n) c->logn++;
+    c->ct_moduli.assign(p->ct_moduli, p->ct_moduli + p->num_ct_moduli);
+    c->aux_moduli.clear();
+    if (p->num_aux_moduli) c->aux_moduli.assign(p->aux_moduli, p->aux_moduli + p->num_aux_moduli);
+    c->plain = p->plain_modulus;
+    // gadget parameters: params/mod.rs:98-112, compute_gadget_digits :126-140
+    c->gadget_base = p->gadget_base ? p->gadget_base : (1ull << 16);
+    if (p->gadget_digits) {
+        c->gadget_digits = p->gadget_digits;
+    } else if (c->gadget_base < 2) {
+        c->gadget_digits = 1;
+    } else {
+        std::vector<u32> Q{1}, pw{1};                  // smallest k with base^k >= Q = prod q_i
+        for (u64 m : c->ct_moduli) bn_mul(Q, m);
+        u32 digits = 0;
+        while (bn_cmp(pw, Q) < 0) { bn_mul(pw, c->gadget_base); digits++; }
+        c->gadget_digits = digits ? digits : 1;
+    }
+    c->digits32 = c->gadget_base > 65536;
+
+    memset(&c->P, 0, sizeof c->P);
+    c->P.n = n; c->P.logn = c->logn;
+    const u32 A = (u32)c->aux_moduli.size();
+    c->P.num_aux = A <= (u32)kMaxAux ? A : 0;
+    c->P.gadget_digits = c->gadget_digits;
+    c->P.gadget_base = c->gadget_base;
+    c->P.gadget_log2 = 0;
+    if (c->gadget_base >= 2 && (c->gadget_base & (c->gadget_base - 1)) == 0)
+        for (u32 w = 1; w < 64; w++) if ((1ull << w) == c->gadget_base) c->P.gadget_log2 = w;
+
+    // modulus indices: 0 = q_0, 1..A = aux primes, then the remaining ciphertext primes.
+    // Device plans: q_0 always, aux primes when the HPS path can use them (A <= 2); any
+    // other modulus is validated (make_plan) but gets no device plan.
+    std::vector<u64> all;
+    all.push_back(c->ct_moduli[0]);
+    for (u64 a : c->aux_moduli) all.push_back(a);
+    for (size_t i = 1; i < c->ct_moduli.size(); i++) all.push_back(c->ct_moduli[i]);
+    c->psi.assign(all.size(), 0);
+    for (int b = 0; b < kMaxBases; b++) { c->has_plan[b] = false; c->twf[b].clear(); c->twi[b].clear(); }
+    for (size_t b = 0; b < all.size(); b++) {
+        Modulus mod; std::vector<Tw> twf, twi;
+        int rc = build_modulus(n, c->logn, all[b], &mod, &twf, &twi, &c->psi[b], err);
+        if (rc != EXB_OK) return rc;
+        if (b == 0 || (b <= A && A <= (u32)kMaxAux)) {
+            c->P.mod[b] = mod; c->has_plan[b] = true;
+            c->twf[b].swap(twf); c->twi[b].swap(twi);
+        }
+    }
+    int rc = fill_scale_consts(c, err);
+    if (rc != EXB_OK) return rc;
+    decide_mul_support(c);
+    return EXB_OK;
+}
+
+// ---- dBFV plan ------------------------------------------------------------------------
+static u128 pow_mod_u128(u128 b, u128 e, u128 m) {       // dbfv/lattice.rs:234-247
+    u128 r = 1;
+    b %= m;
+    while (e > 0) { if (e & 1) r = r * b % m; e >>= 1; if (e > 0) b = b * b % m; }
+    return r;
+}
+
+int host_small_reps(u64 base, u32 d, u64 pm, int64_t *reps, std::string *err) {
+    if (base < 2 || d < 1 || !reps) return fail(err, EXB_INVALID_PARAM, "bad small-reps arguments");
+    for (u32 j = d; j + 2 <= 2 * d; j++) {
+        u64 val;
+        if (pm == 0) { val = 1; for (u32 k = 0; k < j; k++) val *= base; }   // wrapping_pow :108-110
+        else val = (u64)pow_mod_u128(base, j, pm);
+        for (u32 i = 0; i < d; i++) { reps[(size_t)(j - d) * d + i] = (int64_t)(val % base); val /= base; }
+    }
+    return EXB_OK;
+}
+
+int host_build_plan(u32 d, u64 base, u64 pm, u32 flags, u32 limb_mask, HostPlan *hp, std::string *err) {
+    if (d < 1 || d > (u32)kMaxDigits)
+        return fail(err, EXB_NOT_IMPLEMENTED, "device path supports 1..16 dBFV digits");
+    MulPlan &M = hp->M;
+    memset(&M, 0, sizeof M);
+    M.d = d;
+    hp->num_low = 0;
+    hp->reps.assign((size_t)(d > 1 ? d - 1 : 0) * d, 0);
+    if (d > 1) {
+        int rc = host_small_reps(base, d, pm, hp->reps.data(), err);
+        if (rc) return rc;
+    }
+    const u32 all = (1u << d) - 1u;
+    const u32 mask = (limb_mask & all) ? (limb_mask & all) : all;
+    std::vector<bool> need(2 * d - 1, false);
+    for (u32 k = 0; k < d; k++) need[k] = (mask >> k) & 1u;
+    for (u32 j = d; j + 1 < 2 * d; j++) {
+        bool used = (flags & EXB_DBFV_ALL_PRODUCTS) != 0;
+        for (u32 i = 0; i < d && !used; i++)
+            if (((mask >> i) & 1u) && hp->reps[(size_t)(j - d) * d + i] != 0) used = true;
+        need[j] = used;
+    }
+    hp->excess_index.assign(2 * d - 1, -1);
+    u32 nl = 0, nx = 0;
+    for (u32 k = 0; k < 2 * d - 1; k++) {
+        if (!need[k]) continue;
+        M.limb_k[nl++] = (uint8_t)k;
+        if (k < d) hp->num_low++;
+        else hp->excess_index[k] = (int)nx++;
+    }
+    M.num_limbs = nl;
+    M.num_low = hp->num_low;
+    u32 np = 0;
+    for (u32 i = 0; i < d; i++)
+        for (u32 j = 0; j < d; j++) {
+            if (need[i + j]) {
+                M.prod_i[np] = (uint8_t)i; M.prod_j[np] = (uint8_t)j; M.prod_of[i][j] = (int16_t)np; np++;
+            } else {
+                M.prod_of[i][j] = -1;
+            }
+        }
+    M.num_products = np;
+    return EXB_OK;
+}
+
+}  // namespace exb

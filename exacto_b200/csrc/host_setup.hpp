@@ -1,0 +1,79 @@
+// host_setup.hpp -- pure host-side (no CUDA calls) construction of everything the
+// kernels need: NTT plans, HPS constants, the bfv_mul_no_relin dispatch decision
+// and the dBFV work plan.  Shared by api.cu (the product) and by the host
+// emulator under tests/host_emul (which replays the kernels on CPU threads).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/exacto_b200.h"
+#include "hps.cuh"
+#include "modarith.cuh"
+#include "ntt_core.cuh"
+
+namespace exb {
+
+constexpr int kMaxAux = 2;
+constexpr int kMaxBases = 1 + kMaxAux;
+constexpr int kMaxDigits = 16;                 // dBFV digits d
+constexpr int kMaxProducts = kMaxDigits * kMaxDigits;
+constexpr int kMaxLimbs = 2 * kMaxDigits - 1;
+
+// Everything a fused kernel needs about the parameter set (passed by value).
+struct DeviceParams {
+    u32 n, logn;
+    u32 num_aux;                 // A
+    u32 gadget_digits;           // G (number of relin keys actually used)
+    u64 gadget_base;             // B
+    u32 gadget_log2;             // w if B == 2^w, else 0
+    u32 pad_;
+    Modulus mod[kMaxBases];      // [0] = q, [1..A] = aux primes
+    const Tw *twf[kMaxBases];    // forward twiddles (psi_rev) per base
+    const Tw *twi[kMaxBases];    // inverse twiddles (psi_inv_rev) per base
+    ScaleConsts sc;
+};
+
+// Work decomposition of one dbfv_mul (bfv_mul_and_relin is d = 1).
+struct MulPlan {
+    u32 d;                                   // limbs per ciphertext
+    u32 num_products;                        // live products per pair
+    u32 num_limbs;                           // output limbs k that are computed
+    u32 num_low;                             // computed limbs with k < d (they come first)
+    uint8_t prod_i[kMaxProducts];            // product -> lhs limb i
+    uint8_t prod_j[kMaxProducts];            // product -> rhs limb j
+    uint8_t limb_k[kMaxLimbs];               // computed limb index -> k
+    uint8_t pad2_;
+    int16_t prod_of[kMaxDigits][kMaxDigits]; // (i, j) -> product index or -1
+};
+
+struct HostSetup {
+    u32 n = 0, logn = 0;
+    std::vector<u64> ct_moduli, aux_moduli;
+    std::vector<u64> psi;                    // per modulus index (0 = q_0, 1..A = aux, then q_1..)
+    u64 plain = 0, gadget_base = 0;
+    u32 gadget_digits = 0;
+    bool digits32 = false;                   // gadget digits need 32-bit storage
+    int mul_status = EXB_OK;                 // bfv_mul_no_relin dispatch result for these params
+    std::string mul_error;
+    DeviceParams P;                          // table pointers are filled by the owner
+    bool has_plan[kMaxBases] = {false, false, false};
+    std::vector<Tw> twf[kMaxBases], twi[kMaxBases];
+};
+
+// BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new (ring/rns.rs:35-63).
+int host_setup_build(const exb_bfv_params *p, HostSetup *hs, std::string *err);
+
+struct HostPlan {
+    MulPlan M;
+    u32 num_low = 0;                         // computed limbs with k < d
+    std::vector<int64_t> reps;               // [(d-1)][d] small representatives
+    std::vector<int> excess_index;           // k -> index in the excess buffer or -1
+};
+
+// SmallReps::compute_simple (dbfv/lattice.rs:104-122).
+int host_small_reps(u64 base, u32 d, u64 plain_modulus, int64_t *reps, std::string *err);
+// Work items of dbfv_mul (dbfv/eval.rs:109-114) minus products whose limb reduce discards.
+int host_build_plan(u32 d, u64 base, u64 plain_modulus, u32 flags, u32 limb_mask, HostPlan *hp,
+                    std::string *err);
+
+}  // namespace exb

@@ -1,0 +1,499 @@
+// kernels.cu -- sm_100a kernels of the ciphertext-multiplication hot path.
+//
+//   K1/K2  ntt_fwd_kernel / ntt_inv_kernel   ring/ntt.rs:42-67 (concrete-ntt fwd / inv+normalize)
+//   K3     poly_op_kernel                    ring/ntt.rs:75-139, ring/rns.rs:159-217
+//   K4     lift_kernel                       bfv/eval.rs:217-247 base_extend_centered (once per limb)
+//   K3+K5  tensor_kernel                     bfv/eval.rs:187-203 tensor + hps_scale, keyswitch.rs:11-52 digits
+//   K6+K7  relin_kernel                      bfv/keyswitch.rs:83-95 + dbfv/eval.rs:125-132 per-k sums
+//          reduce_mac_kernel                 dbfv/reduction.rs:34-52 (general rep != 0 case)
+//
+// No tensor cores: nothing here is a dense contraction; the work is 64-bit modular
+// arithmetic on the integer pipes, staged through shared memory.
+#include "kernels.cuh"
+
+// Dynamic shared memory.  tests/host_emul compiles this file with g++ and a shim
+// (EXB_HOST_EMUL) that maps CUDA's execution model onto CPU threads + barriers.
+#ifndef EXB_HOST_EMUL
+#define EXB_DYN_SMEM(name) extern __shared__ __align__(16) u64 name[]
+#endif
+
+namespace exb {
+
+unsigned long long g_launch_count = 0;
+
+// ---------------------------------------------------------------------------------
+// Shared-memory transforms.  LOGN == 12: 256 threads, radix-16 register passes on a
+// swizzled image.  LOGN == 0: any n = 2^logn, radix-2 stages on a linear image.
+// Both start and end with a block barrier; outputs are canonical.
+// ---------------------------------------------------------------------------------
+template <int LOGN>
+struct Lay {
+    static __device__ __forceinline__ u32 at(u32 e) { return e; }
+};
+template <>
+struct Lay<12> {
+    static __device__ __forceinline__ u32 at(u32 e) { return swz(e); }
+};
+
+template <int LOGN>
+__device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
+    const u64 q = mod.m, q2 = mod.two_m;
+    if constexpr (LOGN == 12) {
+        const u32 t = threadIdx.x;
+        u64 v[16];
+        __syncthreads();
+        load16<8>(v, sm, t);
+        fwd_pass16<12, 8>(v, tw, t, q, q2);
+        store16<8>(v, sm, t);
+        __syncthreads();
+        load16<4>(v, sm, t);
+        fwd_pass16<12, 4>(v, tw, t, q, q2);
+        store16<4>(v, sm, t);
+        __syncthreads();
+        load16<0>(v, sm, t);
+        fwd_pass16<12, 0>(v, tw, t, q, q2);
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = reduce4(v[k], q, q2);
+        store16<0>(v, sm, t);
+        __syncthreads();
+    } else {
+        const u32 n = 1u << logn;
+        u32 len = n;
+        for (u32 m = 1; m < n; m <<= 1) {
+            len >>= 1;
+            __syncthreads();
+            for (u32 b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+                const u32 i = b / len, j = b - i * len;
+                u64 *x = sm + 2 * i * len + j;
+                ct_bfly(x[0], x[len], tw[m + i], q, q2);
+            }
+        }
+        __syncthreads();
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) sm[e] = reduce4(sm[e], q, q2);
+        __syncthreads();
+    }
+}
+
+// Inputs in [0, 2q).
+template <int LOGN>
+__device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
+    const u64 q = mod.m, q2 = mod.two_m;
+    if constexpr (LOGN == 12) {
+        const u32 t = threadIdx.x;
+        u64 v[16];
+        __syncthreads();
+        load16<0>(v, sm, t);
+        inv_pass16<12, 0, false>(v, tw, t, mod);
+        store16<0>(v, sm, t);
+        __syncthreads();
+        load16<4>(v, sm, t);
+        inv_pass16<12, 4, false>(v, tw, t, mod);
+        store16<4>(v, sm, t);
+        __syncthreads();
+        load16<8>(v, sm, t);
+        inv_pass16<12, 8, true>(v, tw, t, mod);
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = csub(v[k], q);
+        store16<8>(v, sm, t);
+        __syncthreads();
+    } else {
+        const u32 n = 1u << logn;
+        u32 len = 1;
+        for (u32 m = n; m > 1; m >>= 1) {
+            const u32 h = m >> 1;
+            __syncthreads();
+            for (u32 b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+                const u32 i = b / len, j = b - i * len;
+                u64 *x = sm + 2 * i * len + j;
+                if (h == 1) {  // last stage: fold n^-1 (plan.normalize, ring/ntt.rs:62)
+                    const u64 s2 = x[0] + x[len], dd = x[0] - x[len] + q2;
+                    x[0] = shoup_lazy(s2, mod.ninv, mod.ninv_s, q);
+                    x[len] = shoup_lazy(dd, mod.ninv_w, mod.ninv_w_s, q);
+                } else {
+                    gs_bfly(x[0], x[len], tw[h + i], q, q2);
+                }
+            }
+            len <<= 1;
+        }
+        __syncthreads();
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) sm[e] = csub(sm[e], q);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K1 / K2: batched standalone transforms, one polynomial per CTA.
+// ---------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(256)
+ntt_fwd_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw, Modulus mod,
+               u32 logn) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = 1u << logn;
+    const u64 *src = in + (size_t)blockIdx.x * n;
+    u64 *dst = out + (size_t)blockIdx.x * n;
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = src[e];
+    fwd_sm<LOGN>(smem, tw, mod, logn);
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(256)
+ntt_inv_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw, Modulus mod,
+               u32 logn) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = 1u << logn;
+    const u64 *src = in + (size_t)blockIdx.x * n;
+    u64 *dst = out + (size_t)blockIdx.x * n;
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = src[e];
+    inv_sm<LOGN>(smem, tw, mod, logn);
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
+}
+
+// ---------------------------------------------------------------------------------
+// K3: element-wise ring ops on canonical residues.
+// ---------------------------------------------------------------------------------
+__global__ void poly_op_kernel(Modulus mod, int op, const u64 *__restrict__ a, const u64 *__restrict__ b,
+                               u64 scalar, u64 *__restrict__ out, size_t words) {
+    const u64 m = mod.m;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const u64 x = a[i];
+        u64 r;
+        switch (op) {
+            case OP_ADD: r = mod_add(x, b[i], m); break;
+            case OP_SUB: r = mod_sub(x, b[i], m); break;
+            case OP_NEG: r = mod_neg(x, m); break;
+            case OP_MUL: {
+                const u64 t = csub(mont_mul_lazy(x, b[i], m, mod.minv_neg), m);
+                r = csub(mont_mul_lazy(t, mod.r2_mod, m, mod.minv_neg), m);
+                break;
+            }
+            case OP_SCALAR_MUL: {
+                const u64 t = csub(mont_mul_lazy(x, scalar, m, mod.minv_neg), m);
+                r = csub(mont_mul_lazy(t, mod.r2_mod, m, mod.minv_neg), m);
+                break;
+            }
+            default: r = csub(mont_mul_lazy(x, mod.r2_mod, m, mod.minv_neg), m); break;  // OP_TO_MONT
+        }
+        out[i] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K4: lift.  One CTA per input polynomial: INTT_q -> centred reduce mod p_j ->
+// NTT_pj.  Right-hand-side polynomials are written in Montgomery form (x * 2^64)
+// in every base so the tensor kernel needs one REDC per product.
+// ext layout: [pair][side][limb][comp][1+A][n]; slot 0 of side 0 is unused.
+// ---------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(256)
+lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
+            const u64 *__restrict__ ct2, u64 *__restrict__ ext) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = P.n, A = P.num_aux;
+    u64 *coef = smem, *work = smem + n;
+    const u32 idx = blockIdx.x;
+    const u32 comp = idx & 1u;
+    const u32 limb = (idx >> 1) % d;
+    const u32 side = (idx / (2 * d)) & 1u;
+    const size_t pair = idx / (4 * d);
+    const u64 *src = (side ? ct2 : ct1) + ((pair * d + limb) * 2 + comp) * (size_t)n;
+    u64 *dst = ext + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)(1 + A)) * n;
+    const Modulus &mq = P.mod[0];
+
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 x = src[e];
+        coef[Lay<LOGN>::at(e)] = x;
+        if (side) dst[e] = shoup(x, mq.r_mod, mq.r_mod_s, mq.m);
+    }
+    inv_sm<LOGN>(coef, P.twi[0], mq, P.logn);
+    for (u32 j = 0; j < A; j++) {
+        const Modulus &mp = P.mod[1 + j];
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x)
+            work[Lay<LOGN>::at(e)] =
+                ext_centered(coef[Lay<LOGN>::at(e)], mq.m, P.sc.half_q, mp.m, mp.mu);
+        fwd_sm<LOGN>(work, P.twf[1 + j], mp, P.logn);
+        u64 *o = dst + (size_t)(1 + j) * n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u64 x = work[Lay<LOGN>::at(e)];
+            if (side) x = shoup(x, mp.r_mod, mp.r_mod_s, mp.m);
+            o[e] = x;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K3+K5: tensor + scale.  One CTA per (pair, product, component): point-wise
+// product in every base, INTT per base, then hps_scale per coefficient.
+// Components 0/1 leave round(p t/q) mod q (coefficient domain) in r01;
+// component 2 leaves its balanced gadget digits.
+// ---------------------------------------------------------------------------------
+template <int LOGN, typename DigT>
+__global__ void __launch_bounds__(256)
+tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+              const u64 *__restrict__ ct1, const u64 *__restrict__ ext, u64 *__restrict__ r01,
+              DigT *__restrict__ digits) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = P.n, A = P.num_aux, d = M.d, NP = M.num_products;
+    const u32 idx = blockIdx.x;
+    const u32 comp = idx % 3u;
+    const u32 prod = (idx / 3u) % NP;
+    const size_t pair = idx / (3u * NP);
+    const u32 li = M.prod_i[prod], lj = M.prod_j[prod];
+    const size_t bases = 1 + A;
+
+    for (u32 b = 0; b <= A; b++) {
+        const Modulus &mb = P.mod[b];
+        const u64 *l0, *l1;
+        if (b == 0) {
+            l0 = ct1 + ((pair * d + li) * 2) * (size_t)n;
+            l1 = l0 + n;
+        } else {
+            l0 = ext + ((((pair * 2 + 0) * d + li) * 2 + 0) * bases + b) * n;
+            l1 = l0 + bases * n;
+        }
+        const u64 *r0 = ext + ((((pair * 2 + 1) * d + lj) * 2 + 0) * bases + b) * n;
+        const u64 *r1 = r0 + bases * n;
+        u64 *buf = smem + (size_t)b * n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u64 v;
+            if (comp == 0) v = mont_mul_lazy(l0[e], r0[e], mb.m, mb.minv_neg);
+            else if (comp == 2) v = mont_mul_lazy(l1[e], r1[e], mb.m, mb.minv_neg);
+            else v = mont_mul2_lazy(l0[e], r1[e], l1[e], r0[e], mb.m, mb.minv_neg);
+            buf[Lay<LOGN>::at(e)] = v;
+        }
+        inv_sm<LOGN>(buf, P.twi[b], mb, P.logn);
+    }
+
+    const u64 *ba = smem, *b0 = smem + n, *b1 = smem + 2 * (size_t)n;
+    if (comp < 2) {
+        u64 *o = r01 + ((pair * NP + prod) * 2 + comp) * (size_t)n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            const u32 p = Lay<LOGN>::at(e);
+            o[e] = hps_scale_coeff(ba[p], b0[p], A == 2 ? b1[p] : 0, P.sc);
+        }
+    } else {
+        const u32 G = P.gadget_digits;
+        DigT *o = digits + ((pair * NP + prod) * (size_t)G) * n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            const u32 p = Lay<LOGN>::at(e);
+            const u64 c2 = hps_scale_coeff(ba[p], b0[p], A == 2 ? b1[p] : 0, P.sc);
+            i64 rem = center_i64(c2, P.sc.q, P.sc.half_q);
+            if (P.gadget_log2) {
+                for (u32 g = 0; g < G; g++) o[(size_t)g * n + e] = (DigT)gadget_digit_pow2(rem, P.gadget_log2);
+            } else {
+                for (u32 g = 0; g < G; g++)
+                    o[(size_t)g * n + e] = (DigT)gadget_digit_general(rem, (i64)P.gadget_base);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K6+K7: relinearise + per-k accumulation.  One CTA per (pair, output limb k):
+//   c0 = NTT(sum r0) + sum_g NTT(sum digits_g) * rlk0_g     (likewise c1)
+// All sums are exact mod q, so any association is bit-equal to the reference's
+// per-product relinearize followed by bfv_add (dbfv/eval.rs:125-132).
+// ---------------------------------------------------------------------------------
+template <int LOGN, typename DigT>
+__global__ void __launch_bounds__(256)
+relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+             const u64 *__restrict__ r01, const DigT *__restrict__ digits,
+             const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = P.n, d = M.d, NP = M.num_products, NL = M.num_limbs, G = P.gadget_digits;
+    const Modulus &mq = P.mod[0];
+    const u64 q = mq.m;
+    u64 *work = smem, *acc0 = smem + n, *acc1 = smem + 2 * (size_t)n;
+    const u32 limb = blockIdx.x % NL;
+    const size_t pair = blockIdx.x / NL;
+    const u32 k = M.limb_k[limb];
+    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+
+    for (u32 comp = 0; comp < 2; comp++) {
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u64 s = 0;
+            for (u32 i = i_lo; i <= i_hi; i++) {
+                const size_t pr = (size_t)M.prod_of[i][k - i];
+                s = mod_add(s, r01[((pair * NP + pr) * 2 + comp) * n + e], q);
+            }
+            work[Lay<LOGN>::at(e)] = s;
+        }
+        fwd_sm<LOGN>(work, P.twf[0], mq, P.logn);
+        u64 *acc = comp ? acc1 : acc0;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) acc[e] = work[Lay<LOGN>::at(e)];
+    }
+    for (u32 g = 0; g < G; g++) {
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            i64 s = 0;
+            for (u32 i = i_lo; i <= i_hi; i++) {
+                const size_t pr = (size_t)M.prod_of[i][k - i];
+                s += (i64)digits[((pair * NP + pr) * G + g) * n + e];
+            }
+            u64 v;
+            const u64 mag = s < 0 ? (u64)(-s) : (u64)s;
+            if (mag < q) v = (s < 0 && mag) ? q - mag : mag;
+            else { const u64 r = mag % q; v = (s < 0 && r) ? q - r : r; }
+            work[Lay<LOGN>::at(e)] = v;
+        }
+        fwd_sm<LOGN>(work, P.twf[0], mq, P.logn);
+        const u64 *k0 = rlk_mont + ((size_t)g * 2) * n, *k1 = k0 + n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            const u64 x = work[Lay<LOGN>::at(e)];
+            acc0[e] = mod_add(acc0[e], csub(mont_mul_lazy(x, k0[e], q, mq.minv_neg), q), q);
+            acc1[e] = mod_add(acc1[e], csub(mont_mul_lazy(x, k1[e], q, mq.minv_neg), q), q);
+        }
+    }
+    u64 *dst = k < d ? out + ((pair * d + k) * 2) * (size_t)n
+                     : excess + ((pair * (NL - M.num_low) + (limb - M.num_low)) * 2) * (size_t)n;
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        dst[e] = acc0[e];
+        dst[n + e] = acc1[e];
+    }
+}
+
+// out_limb += (+/-) s * excess_limb over 2n words per pair (dbfv/reduction.rs:34-52, :65-93).
+__global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const u64 *__restrict__ excess_limb,
+                                  u64 s_mont, int negative, size_t out_stride, size_t excess_stride,
+                                  u32 words, size_t pairs) {
+    const u64 m = mod.m;
+    const size_t total = pairs * words;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pair = i / words, e = i - pair * words;
+        u64 v = csub(mont_mul_lazy(excess_limb[pair * excess_stride + e], s_mont, m, mod.minv_neg), m);
+        if (negative) v = mod_neg(v, m);
+        u64 *o = out_limb + pair * out_stride + e;
+        *o = mod_add(*o, v, m);
+    }
+}
+
+#ifndef EXB_HOST_EMUL
+// ---------------------------------------------------------------------------------
+// Launchers
+// ---------------------------------------------------------------------------------
+static inline u32 block_threads(const DeviceParams &P) {
+    if (P.logn == 12) return 256;
+    u32 t = P.n / 2;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+template <typename K>
+static void set_smem(K kernel, size_t bytes) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    const size_t sm = (size_t)P.n * 8;
+    if (P.logn == 12) {
+        set_smem(ntt_fwd_kernel<12>, sm);
+        ntt_fwd_kernel<12><<<(unsigned)count, 256, sm, s>>>(in, out, P.twf[base], P.mod[base], P.logn);
+    } else {
+        set_smem(ntt_fwd_kernel<0>, sm);
+        ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.mod[base], P.logn);
+    }
+    g_launch_count++;
+}
+
+void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    const size_t sm = (size_t)P.n * 8;
+    if (P.logn == 12) {
+        set_smem(ntt_inv_kernel<12>, sm);
+        ntt_inv_kernel<12><<<(unsigned)count, 256, sm, s>>>(in, out, P.twi[base], P.mod[base], P.logn);
+    } else {
+        set_smem(ntt_inv_kernel<0>, sm);
+        ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.mod[base], P.logn);
+    }
+    g_launch_count++;
+}
+
+void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64 scalar, u64 *out,
+                    size_t words, cudaStream_t s) {
+    if (words == 0) return;
+    size_t blocks = (words + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    poly_op_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, (int)op, a, b, scalar, out, words);
+    g_launch_count++;
+}
+
+void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
+                 size_t pairs, cudaStream_t s) {
+    if (pairs == 0) return;
+    const size_t sm = (size_t)P.n * 8 * 2;
+    const unsigned grid = (unsigned)(pairs * 4 * M.d);
+    if (P.logn == 12) {
+        set_smem(lift_kernel<12>, sm);
+        lift_kernel<12><<<grid, 256, sm, s>>>(P, M.d, ct1, ct2, ext);
+    } else {
+        set_smem(lift_kernel<0>, sm);
+        lift_kernel<0><<<grid, block_threads(P), sm, s>>>(P, M.d, ct1, ct2, ext);
+    }
+    g_launch_count++;
+}
+
+template <typename DigT>
+static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
+                            DigT *digits, size_t pairs, cudaStream_t s) {
+    const size_t sm = (size_t)P.n * 8 * (1 + P.num_aux);
+    const unsigned grid = (unsigned)(pairs * M.num_products * 3);
+    if (P.logn == 12) {
+        set_smem(tensor_kernel<12, DigT>, sm);
+        tensor_kernel<12, DigT><<<grid, 256, sm, s>>>(P, M, ct1, ext, r01, digits);
+    } else {
+        set_smem(tensor_kernel<0, DigT>, sm);
+        tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits);
+    }
+    g_launch_count++;
+}
+
+void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
+                   void *digits, bool digits32, size_t pairs, cudaStream_t s) {
+    if (pairs == 0) return;
+    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ext, r01, (int32_t *)digits, pairs, s);
+    else launch_tensor_t<int16_t>(P, M, ct1, ext, r01, (int16_t *)digits, pairs, s);
+}
+
+template <typename DigT>
+static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r01, const DigT *digits,
+                           const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s) {
+    const size_t sm = (size_t)P.n * 8 * 3;
+    const unsigned grid = (unsigned)(pairs * M.num_limbs);
+    if (P.logn == 12) {
+        set_smem(relin_kernel<12, DigT>, sm);
+        relin_kernel<12, DigT><<<grid, 256, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+    } else {
+        set_smem(relin_kernel<0, DigT>, sm);
+        relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+    }
+    g_launch_count++;
+}
+
+void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits, bool digits32,
+                  const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s) {
+    if (pairs == 0) return;
+    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s);
+    else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s);
+}
+
+void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_limb, u64 abs_scalar_mod_q,
+                       bool negative, size_t out_stride, size_t excess_stride, size_t pairs, cudaStream_t s) {
+    if (pairs == 0) return;
+    const Modulus &m = P.mod[0];
+    // scalar in Montgomery form so one REDC gives x * s mod q
+    const u64 s_mont = (u64)(((unsigned __int128)abs_scalar_mod_q << 64) % m.m);
+    const u32 words = 2 * P.n;
+    size_t blocks = (pairs * words + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    reduce_mac_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, out_limb, excess_limb, s_mont, negative ? 1 : 0,
+                                                      out_stride, excess_stride, words, pairs);
+    g_launch_count++;
+}
+
+#endif  // EXB_HOST_EMUL
+
+}  // namespace exb

@@ -1,0 +1,46 @@
+// kernels.cuh -- launch-side declarations shared by kernels.cu and api.cu.
+#pragma once
+#ifndef EXB_HOST_EMUL
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "host_setup.hpp"
+
+namespace exb {
+
+enum PolyOp { OP_ADD = 0, OP_SUB = 1, OP_NEG = 2, OP_MUL = 3, OP_SCALAR_MUL = 4, OP_TO_MONT = 5 };
+
+#ifndef EXB_HOST_EMUL
+// Ring-level batched kernels (device pointers, `count` polynomials of n words).
+void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s);
+void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s);
+
+void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64 scalar, u64 *out,
+                    size_t words, cudaStream_t s);
+
+// Fused ciphertext-multiplication pipeline.
+//   ct1, ct2 : [pairs][d][2][n]  NTT domain, canonical mod q
+//   ext      : [pairs][2 sides][d][2][1+A][n]  (workspace)
+//   r01      : [pairs][products][2][n] u64      (workspace, coefficient domain)
+//   digits   : [pairs][products][G][n] int16|int32 (workspace)
+//   rlk_mont : [G][2][n] relin key in Montgomery form
+//   out      : [pairs][d][2][n];  excess: [pairs][num_limbs - d'][2][n] for k >= d
+void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
+                 size_t pairs, cudaStream_t s);
+void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
+                   void *digits, bool digits32, size_t pairs, cudaStream_t s);
+void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
+                  bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
+                  cudaStream_t s);
+// out[pairs][d][2][n] limb i += rep * excess limb (signed scalar, reduction.rs:34-52)
+void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_limb, u64 abs_scalar_mod_q,
+                       bool negative, size_t out_stride, size_t excess_stride, size_t pairs,
+                       cudaStream_t s);
+
+#endif  // EXB_HOST_EMUL
+
+// Count of kernels launched by this library (bench.py's gpu_launches).
+extern unsigned long long g_launch_count;
+
+}  // namespace exb

@@ -1,0 +1,173 @@
+/*
+ * exacto_b200.h -- C ABI of libexacto_b200.so, the B200 (sm_100a) implementation
+ * of exacto's ciphertext-multiplication hot path.
+ *
+ * The reference (RajeshRk18/exacto, pure Rust, CPU only) has no FFI layer; its
+ * boundary for this path is the `pub fn` surface cited beside each entry point
+ * below (file:line under /root/reference/src/).  A Rust maintainer binds these
+ * symbols with an `extern "C"` block (INTEGRATION.md shows it) and keeps the
+ * reference's signatures on top.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  `*_dev` pointers are CUDA device pointers
+ *     on the context's device, `*_host` pointers are host memory (pinned host
+ *     memory makes the copies asynchronous).
+ *   - Polynomials are n 64-bit words of canonical residues in [0, modulus).
+ *     Ciphertext polynomials are in the NTT (evaluation) domain like the
+ *     reference's NttPoly (ring/ntt.rs:11-15).  The evaluation order is this
+ *     library's own (natural -> bit-reversed, psi = x^((q-1)/2n) for the first
+ *     x >= 2 whose psi has order 2n); concrete-ntt's order is unpinned by the
+ *     reference.  Use exb_ntt_* to move between domains.
+ *   - BFV ciphertext batch  : [batch][2][n]        (BfvCiphertext.c, bfv/mod.rs:19-24)
+ *     dBFV ciphertext batch : [batch][d][2][n]     (DbfvCiphertext.limbs, dbfv/ciphertext.rs:10-22)
+ *     relinearisation key   : [G][2][n]            (RelinKey.keys[g] = (rlk0, rlk1), bfv/keygen.rs:39-45)
+ *   - Every function returns an exb_status (1:1 with ExactoError, error.rs:4-31);
+ *     exb_last_error() gives the message of the calling thread's last failure.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
+ *     are stream-ordered and asynchronous unless they take host pointers.
+ *   - One hot-path call may be in flight per context (it owns the workspace);
+ *     use one context per stream for concurrency.  There is no CPU fallback:
+ *     every entry point fails with EXB_NOT_IMPLEMENTED / a CUDA error rather
+ *     than computing on the host.
+ */
+#ifndef EXACTO_B200_H
+#define EXACTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum exb_status {
+    EXB_OK = 0,
+    EXB_INVALID_PARAM = 1,        /* ExactoError::InvalidParam        */
+    EXB_DIMENSION_MISMATCH = 2,   /* ExactoError::DimensionMismatch   */
+    EXB_MODULUS_MISMATCH = 3,     /* ExactoError::ModulusMismatch     */
+    EXB_INVALID_RING_DEGREE = 4,  /* ExactoError::InvalidRingDegree   */
+    EXB_DECRYPTION_ERROR = 5,     /* ExactoError::DecryptionError     */
+    EXB_DECOMPOSITION_ERROR = 6,  /* ExactoError::DecompositionError  */
+    EXB_LATTICE_ERROR = 7,        /* ExactoError::LatticeError        */
+    EXB_MISSING_KEY = 8,          /* ExactoError::MissingKey          */
+    EXB_NOT_IMPLEMENTED = 9,      /* ExactoError::NotImplemented      */
+    EXB_CUDA_ERROR = 100          /* no reference counterpart         */
+} exb_status;
+
+/* BfvParams (params/mod.rs:11-27) restricted to what the hot path reads. */
+typedef struct exb_bfv_params {
+    uint32_t ring_degree;          /* n, power of two                               */
+    uint32_t num_ct_moduli;        /* ct_basis.moduli.len()                         */
+    const uint64_t *ct_moduli;
+    uint32_t num_aux_moduli;       /* 0 = aux_basis None                            */
+    const uint64_t *aux_moduli;
+    uint64_t plain_modulus;        /* p                                             */
+    uint64_t gadget_base;          /* 0 = auto 2^16 (params/mod.rs:102-108)         */
+    uint32_t gadget_digits;        /* 0 = compute_gadget_digits (params/mod.rs:126) */
+} exb_bfv_params;
+
+typedef struct exb_context exb_context;       /* BfvParams + plans + workspace on one GPU */
+typedef struct exb_relin_key exb_relin_key;   /* device-resident RelinKey                 */
+
+/* Flags of exb_dbfv_mul*. */
+enum {
+    /* Compute all d*d products like dbfv/eval.rs:109-122 even when the output
+     * limbs they feed are discarded by reduce (dbfv/reduction.rs:28-52).  The
+     * default skips those dead products; the result is bit-identical. */
+    EXB_DBFV_ALL_PRODUCTS = 1u
+};
+
+const char *exb_last_error(void);
+const char *exb_version(void);
+
+/* ---- context: BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new
+ * (ring/rns.rs:35-63) + make_plan (ring/ntt.rs:19-29) -------------------------- */
+int exb_context_create(const exb_bfv_params *params, int device, exb_context **out);
+void exb_context_destroy(exb_context *ctx);
+/* Effective values after defaults were applied. */
+int exb_context_gadget(const exb_context *ctx, uint64_t *gadget_base, uint32_t *gadget_digits);
+/* psi of modulus `modulus_index` (0 = q, 1.. = aux primes). */
+int exb_context_psi(const exb_context *ctx, uint32_t modulus_index, uint64_t *psi);
+/* Number of kernels this library has launched in this process. */
+unsigned long long exb_launch_count(void);
+
+/* Per-kernel device timing of the ct-mul pipeline (CUDA events recorded on the launching stream
+ * between the kernels; no extra synchronisation).  stage: 0 = lift, 1 = tensor+scale, 2 = relin,
+ * 3 = reduce.  exb_profile_read synchronises the recorded events, adds their times (ms) and launch
+ * counts into the arrays (4 entries each) and clears the record. */
+int exb_profile_enable(exb_context *ctx, int on);
+int exb_profile_read(exb_context *ctx, double *stage_ms, unsigned long long *stage_launches);
+
+/* ---- device memory plumbing (so a host without a CUDA runtime binding can drive it) */
+int exb_device_alloc(exb_context *ctx, size_t bytes, void **dev_ptr);
+int exb_device_free(exb_context *ctx, void *dev_ptr);
+int exb_copy_to_device(exb_context *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int exb_copy_to_host(exb_context *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int exb_synchronize(exb_context *ctx, void *stream);
+
+/* ---- ring/: NttPoly::from_coeff_poly (ring/ntt.rs:42-55) and NttPoly::to_coeff_poly
+ * (ring/ntt.rs:58-67), batched over `count` polynomials; in == out allowed. -------- */
+int exb_ntt_forward(exb_context *ctx, uint32_t modulus_index, const uint64_t *in_dev, uint64_t *out_dev,
+                    size_t count, void *stream);
+int exb_ntt_inverse(exb_context *ctx, uint32_t modulus_index, const uint64_t *in_dev, uint64_t *out_dev,
+                    size_t count, void *stream);
+int exb_ntt_forward_host(exb_context *ctx, uint32_t modulus_index, const uint64_t *in_host,
+                         uint64_t *out_host, size_t count);
+int exb_ntt_inverse_host(exb_context *ctx, uint32_t modulus_index, const uint64_t *in_host,
+                         uint64_t *out_host, size_t count);
+
+/* Point-wise ops on `words` residues: NttPoly::add/sub/neg/mul/scalar_mul
+ * (ring/ntt.rs:75-139), RnsPoly::* (ring/rns.rs:159-217), CoeffPoly::* (ring/poly.rs:40-136). */
+int exb_poly_add(exb_context *ctx, uint32_t modulus_index, const uint64_t *a_dev, const uint64_t *b_dev,
+                 uint64_t *out_dev, size_t words, void *stream);
+int exb_poly_sub(exb_context *ctx, uint32_t modulus_index, const uint64_t *a_dev, const uint64_t *b_dev,
+                 uint64_t *out_dev, size_t words, void *stream);
+int exb_poly_neg(exb_context *ctx, uint32_t modulus_index, const uint64_t *a_dev, uint64_t *out_dev,
+                 size_t words, void *stream);
+int exb_poly_mul(exb_context *ctx, uint32_t modulus_index, const uint64_t *a_dev, const uint64_t *b_dev,
+                 uint64_t *out_dev, size_t words, void *stream);
+int exb_poly_scalar_mul(exb_context *ctx, uint32_t modulus_index, const uint64_t *a_dev, uint64_t scalar,
+                        uint64_t *out_dev, size_t words, void *stream);
+
+/* ---- RelinKey (bfv/keygen.rs:39-45).  `num_keys` entries of (rlk0, rlk1), NTT domain;
+ * relinearize uses min(gadget_digits, num_keys) of them (bfv/keyswitch.rs:86-89). ---- */
+int exb_relin_key_load(exb_context *ctx, const uint64_t *rlk_host, uint32_t num_keys, exb_relin_key **out);
+int exb_relin_key_load_device(exb_context *ctx, const uint64_t *rlk_dev, uint32_t num_keys, void *stream,
+                              exb_relin_key **out);
+void exb_relin_key_destroy(exb_relin_key *key);
+
+/* ---- bfv_mul_and_relin (bfv/eval.rs:73-82), batched over independent pairs.
+ * Dispatch and errors follow bfv_mul_no_relin (bfv/eval.rs:89-108):
+ *   single-aux P <= n*q/2      -> EXB_INVALID_PARAM  "single aux prime too small for HPS centering..."
+ *   more than 2 aux primes     -> EXB_INVALID_PARAM  "HPS scaling supports 1 or 2 aux primes..."
+ *   no aux basis, i128 overflow-> EXB_NOT_IMPLEMENTED "schoolbook BFV multiplication can overflow i128..."
+ *   no aux basis otherwise, or more than one ciphertext prime -> EXB_NOT_IMPLEMENTED (the
+ *   reference's O(n^2) schoolbook / BigInt branches are outside the device path). */
+int exb_bfv_mul_and_relin(exb_context *ctx, const uint64_t *ct1_dev, const uint64_t *ct2_dev,
+                          const exb_relin_key *rlk, uint64_t *out_dev, size_t batch, void *stream);
+int exb_bfv_mul_and_relin_host(exb_context *ctx, const uint64_t *ct1_host, const uint64_t *ct2_host,
+                               const exb_relin_key *rlk, uint64_t *out_host, size_t batch);
+/* bfv_add (bfv/eval.rs:14-31) on degree-1 ciphertexts. */
+int exb_bfv_add(exb_context *ctx, const uint64_t *a_dev, const uint64_t *b_dev, uint64_t *out_dev,
+                size_t batch, void *stream);
+
+/* ---- dbfv_mul (dbfv/eval.rs:82-149) incl. reduction::reduce (dbfv/reduction.rs:15-60),
+ * batched.  `base`, `num_digits`, `dbfv_plain_modulus` are DbfvParams (params/mod.rs:143-192;
+ * 0 = 2^64).  The limb-count and mul_depth guards (dbfv/eval.rs:90-102) read ciphertext
+ * metadata and therefore live in the host wrapper that owns it.
+ * `limb_mask`: bit k set = compute output limb k (0 = all d limbs); lets ranks of a
+ * multi-GPU job own disjoint limbs before an all-gather.  Limbs not selected are left
+ * untouched in out. */
+int exb_dbfv_mul(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
+                 const uint64_t *ct1_dev, const uint64_t *ct2_dev, const exb_relin_key *rlk,
+                 uint64_t *out_dev, size_t batch, uint32_t flags, uint32_t limb_mask, void *stream);
+int exb_dbfv_mul_host(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
+                      const uint64_t *ct1_host, const uint64_t *ct2_host, const exb_relin_key *rlk,
+                      uint64_t *out_host, size_t batch, uint32_t flags);
+/* SmallReps::compute_simple (dbfv/lattice.rs:104-122): reps[(d-1)][d]. */
+int exb_dbfv_small_reps(uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus, int64_t *reps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXACTO_B200_H */

@@ -1,0 +1,102 @@
+"""Shared helpers of the test-suite (oracle-side; never imported by the product)."""
+import ctypes
+import hashlib
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import oracle as O                      # noqa: E402
+from oracle import harness as H         # noqa: E402
+
+GOLDEN_PATH = os.path.join(ROOT, "tests", "golden", "ctmul_golden.npz")
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+CASES = make_golden.CASES
+golden_inputs = make_golden.inputs
+digest = make_golden.digest
+
+
+def golden():
+    return np.load(GOLDEN_PATH)
+
+
+def to_params(P: O.OracleParams):
+    """OracleParams -> exacto_b200.BfvParams (same numbers through the reference-style builder)."""
+    import exacto_b200 as E
+    b = (E.BfvParamsBuilder().ring_degree(P.n).plain_modulus(P.plain_modulus).ct_moduli([P.q])
+         .aux_moduli(list(P.aux)).gadget_base(P.gadget_base))
+    return b.build()
+
+
+def to_dbfv_params(P: O.OracleParams, base, d, pm):
+    import exacto_b200 as E
+    return E.DbfvParams.new(to_params(P), base, d, pm)
+
+
+class Emulator:
+    """ctypes front-end of tests/host_emul/libexb_emul.so (the product kernels on CPU threads)."""
+
+    def __init__(self):
+        import __graft_entry__ as g
+        L = ctypes.CDLL(g.build_emulator())
+        u64, u32, vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p
+        L.emu_last_error.restype = ctypes.c_char_p
+        L.emu_create.argtypes = [u32, vp, u32, vp, u32, u64, u64, u32, ctypes.POINTER(vp)]
+        L.emu_destroy.argtypes = [vp]
+        L.emu_info.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u64)]
+        L.emu_ntt.argtypes = [vp, u32, ctypes.c_int, vp, vp, ctypes.c_size_t]
+        L.emu_poly_op.argtypes = [vp, u32, ctypes.c_int, vp, vp, u64, vp, ctypes.c_size_t]
+        L.emu_dbfv_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, u32, u32]
+        self.L = L
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def create(self, n, ct_moduli, aux, plain, gadget_base=0, gadget_digits=0):
+        ct = np.array(ct_moduli, np.uint64)
+        ax = np.array(list(aux) or [0], np.uint64)
+        h = ctypes.c_void_p()
+        rc = self.L.emu_create(n, self._p(ct), len(ct_moduli), self._p(ax), len(aux), plain, gadget_base,
+                               gadget_digits, ctypes.byref(h))
+        return rc, h, self.L.emu_last_error().decode()
+
+    def from_oracle(self, P: O.OracleParams):
+        rc, h, err = self.create(P.n, [P.q], P.aux, P.plain_modulus, P.gadget_base, P.gadget_digits)
+        assert rc == 0, err
+        return h
+
+    def info(self, h):
+        gb, gd, ms, psi = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_int(), ctypes.c_uint64()
+        self.L.emu_info(h, ctypes.byref(gb), ctypes.byref(gd), ctypes.byref(ms), ctypes.byref(psi))
+        return gb.value, gd.value, ms.value, psi.value, self.L.emu_last_error().decode()
+
+    def ntt(self, h, base, forward, x):
+        x = np.ascontiguousarray(x, np.uint64)
+        out = np.zeros_like(x)
+        rc = self.L.emu_ntt(h, base, 1 if forward else 0, self._p(x), self._p(out), x.size // x.shape[-1])
+        assert rc == 0
+        return out
+
+    def poly_op(self, h, base, op, a, b=None, scalar=0):
+        a = np.ascontiguousarray(a, np.uint64)
+        bb = np.ascontiguousarray(b if b is not None else a, np.uint64)
+        out = np.zeros_like(a)
+        self.L.emu_poly_op(h, base, op, self._p(a), self._p(bb), scalar, self._p(out), a.size)
+        return out
+
+    def dbfv_mul(self, h, base, d, pm, ct1, ct2, rlk, flags=0, limb_mask=0, out=None):
+        ct1, ct2, rlk = (np.ascontiguousarray(v, np.uint64) for v in (ct1, ct2, rlk))
+        pairs = ct1.size // (d * 2 * ct1.shape[-1])
+        out = np.zeros_like(ct1) if out is None else out
+        rc = self.L.emu_dbfv_mul(h, base, d, pm, self._p(ct1), self._p(ct2), self._p(rlk), rlk.shape[0],
+                                 self._p(out), pairs, flags, limb_mask)
+        return rc, out, self.L.emu_last_error().decode()

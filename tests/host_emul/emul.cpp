@@ -1,0 +1,205 @@
+// emul.cpp -- TEST INFRASTRUCTURE: replays the product's CUDA kernels on the CPU.
+//
+// exacto_b200/csrc/kernels.cu is compiled *unchanged* by g++ under a small shim that
+// maps CUDA's execution model onto OS threads: one std::thread per CUDA thread of a
+// block, pthread barriers for __syncthreads, a heap buffer for dynamic shared
+// memory, blocks executed one after another.  This lets the CPU-only test tier check
+// the real kernel source (index math, barriers, lazy-reduction bounds, constants
+// from host_setup.cpp) bit-for-bit against the oracle before any GPU time is spent.
+// It is NOT a fallback: nothing in exacto_b200/ links or loads this library.
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+// ---- CUDA shim ---------------------------------------------------------------------
+#define EXB_HOST_EMUL 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(x) alignas(x)
+
+struct emu_dim3 { unsigned x, y, z; };
+static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+static thread_local void *emu_smem_ptr;
+static pthread_barrier_t *emu_barrier;
+static inline void __syncthreads() { pthread_barrier_wait(emu_barrier); }
+#define EXB_DYN_SMEM(name) exb::u64 *name = (exb::u64 *)emu_smem_ptr
+
+#include "../../exacto_b200/csrc/kernels.cu"
+
+using namespace exb;
+
+// Run `grid` blocks of `block` threads; body() is the kernel call.
+template <typename F>
+static void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F body) {
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, nullptr, block);
+    emu_barrier = &bar;
+    void *smem = nullptr;
+    if (posix_memalign(&smem, 128, smem_bytes ? smem_bytes : 128)) abort();
+    std::vector<std::thread> threads;
+    threads.reserve(block);
+    for (unsigned t = 0; t < block; t++)
+        threads.emplace_back([=, &bar]() {
+            threadIdx = {t, 0, 0};
+            blockDim = {block, 1, 1};
+            gridDim = {grid, 1, 1};
+            emu_smem_ptr = smem;
+            for (unsigned b = 0; b < grid; b++) {
+                blockIdx = {b, 0, 0};
+                body();
+                pthread_barrier_wait(&bar);   // blocks run back to back on the same "SM"
+            }
+        });
+    for (auto &th : threads) th.join();
+    free(smem);
+    pthread_barrier_destroy(&bar);
+}
+
+static unsigned emu_block_threads(const DeviceParams &P) {
+    if (P.logn == 12) return 256;
+    unsigned t = P.n / 2;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+}
+
+struct emu_ctx {
+    HostSetup hs;
+    std::string err;
+};
+
+static thread_local std::string g_emu_err;
+
+extern "C" {
+
+const char *emu_last_error(void) { return g_emu_err.c_str(); }
+
+int emu_create(uint32_t n, const uint64_t *ct_moduli, uint32_t num_ct, const uint64_t *aux, uint32_t num_aux,
+               uint64_t plain, uint64_t gadget_base, uint32_t gadget_digits, emu_ctx **out) {
+    exb_bfv_params p;
+    p.ring_degree = n; p.num_ct_moduli = num_ct; p.ct_moduli = ct_moduli;
+    p.num_aux_moduli = num_aux; p.aux_moduli = aux; p.plain_modulus = plain;
+    p.gadget_base = gadget_base; p.gadget_digits = gadget_digits;
+    emu_ctx *c = new emu_ctx();
+    int rc = host_setup_build(&p, &c->hs, &g_emu_err);
+    if (rc) { delete c; return rc; }
+    for (int b = 0; b < kMaxBases; b++)
+        if (c->hs.has_plan[b]) { c->hs.P.twf[b] = c->hs.twf[b].data(); c->hs.P.twi[b] = c->hs.twi[b].data(); }
+    *out = c;
+    return 0;
+}
+
+void emu_destroy(emu_ctx *c) { delete c; }
+
+int emu_info(const emu_ctx *c, uint64_t *gadget_base, uint32_t *gadget_digits, int *mul_status, uint64_t *psi0) {
+    *gadget_base = c->hs.gadget_base; *gadget_digits = c->hs.gadget_digits;
+    *mul_status = c->hs.mul_status; *psi0 = c->hs.psi[0];
+    g_emu_err = c->hs.mul_error;
+    return 0;
+}
+
+int emu_ntt(emu_ctx *c, uint32_t base, int forward, const uint64_t *in, uint64_t *out, size_t count) {
+    const DeviceParams &P = c->hs.P;
+    if (base >= (uint32_t)kMaxBases || !c->hs.has_plan[base]) { g_emu_err = "no plan"; return EXB_MODULUS_MISMATCH; }
+    const unsigned thr = emu_block_threads(P);
+    const size_t sm = (size_t)P.n * 8;
+    if (P.logn == 12) {
+        if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<12>(in, out, P.twf[base], P.mod[base], P.logn); });
+        else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<12>(in, out, P.twi[base], P.mod[base], P.logn); });
+    } else {
+        if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<0>(in, out, P.twf[base], P.mod[base], P.logn); });
+        else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<0>(in, out, P.twi[base], P.mod[base], P.logn); });
+    }
+    return 0;
+}
+
+int emu_poly_op(emu_ctx *c, uint32_t base, int op, const uint64_t *a, const uint64_t *b, uint64_t scalar,
+                uint64_t *out, size_t words) {
+    const Modulus m = c->hs.P.mod[base];
+    if (op == OP_SCALAR_MUL) scalar %= m.m;
+    emu_launch(4, 64, 0, [&]() { poly_op_kernel(m, op, a, b, scalar, out, words); });
+    return 0;
+}
+
+// Same launch sequence as run_pairs() in exacto_b200/csrc/api.cu.
+int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1, const uint64_t *ct2,
+                 const uint64_t *rlk, uint32_t num_keys, uint64_t *out, size_t pairs, uint32_t flags,
+                 uint32_t limb_mask) {
+    HostSetup &hs = c->hs;
+    if (hs.mul_status != EXB_OK) { g_emu_err = hs.mul_error; return hs.mul_status; }
+    HostPlan hp;
+    int rc = host_build_plan(d, base, pm, flags, limb_mask, &hp, &g_emu_err);
+    if (rc) return rc;
+    DeviceParams P = hs.P;
+    const uint32_t G = num_keys < hs.gadget_digits ? num_keys : hs.gadget_digits;
+    P.gadget_digits = G;
+    const size_t n = hs.n, A = hs.aux_moduli.size();
+    const MulPlan &M = hp.M;
+    const size_t nx = M.num_limbs - hp.num_low;
+    std::vector<u64> ext(pairs * 2 * d * 2 * (1 + A) * n), r01(pairs * M.num_products * 2 * n + 1);
+    std::vector<u64> excess(pairs * nx * 2 * n + 1), rlk_mont((size_t)num_keys * 2 * n + 1);
+    std::vector<int32_t> dig32;
+    std::vector<int16_t> dig16;
+    if (hs.digits32) dig32.resize(pairs * M.num_products * (G ? G : 1) * n);
+    else dig16.resize(pairs * M.num_products * (G ? G : 1) * n);
+    const Modulus mq = P.mod[0];
+    const size_t kw = (size_t)num_keys * 2 * n;
+    if (kw) emu_launch(4, 64, 0, [&]() { poly_op_kernel(mq, OP_TO_MONT, rlk, nullptr, 0, rlk_mont.data(), kw); });
+
+    const unsigned thr = emu_block_threads(P);
+    u64 *extp = ext.data(), *r01p = r01.data(), *xp = excess.data();
+    const u64 *rk = rlk_mont.data();
+    if (P.logn == 12) {
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
+        if (hs.digits32) {
+            int32_t *dg = dig32.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int32_t>(P, M, r01p, dg, rk, out, xp); });
+        } else {
+            int16_t *dg = dig16.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int16_t>(P, M, r01p, dg, rk, out, xp); });
+        }
+    } else {
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, ct1, ct2, extp); });
+        if (hs.digits32) {
+            int32_t *dg = dig32.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int32_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, xp); });
+        } else {
+            int16_t *dg = dig16.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, xp); });
+        }
+    }
+    const u64 q = hs.ct_moduli[0];
+    for (uint32_t j = d; j + 1 < 2 * d; j++) {
+        if (hp.excess_index[j] < 0) continue;
+        for (uint32_t i = 0; i < d; i++) {
+            const int64_t rep = hp.reps[(size_t)(j - d) * d + i];
+            if (rep == 0) continue;
+            bool computed = false;
+            for (uint32_t l = 0; l < M.num_limbs; l++) if (M.limb_k[l] == i) computed = true;
+            if (!computed) continue;
+            const u64 mag = rep < 0 ? (u64)(-(rep + 1)) + 1 : (u64)rep;
+            const u64 s_mont = (u64)(((unsigned __int128)(mag % q) << 64) % q);
+            u64 *ol = out + (size_t)i * 2 * n;
+            const u64 *el = xp + (size_t)hp.excess_index[j] * 2 * n;
+            emu_launch(4, 64, 0, [&]() {
+                reduce_mac_kernel(mq, ol, el, s_mont, rep < 0 ? 1 : 0, (size_t)d * 2 * n, nx * 2 * n, (u32)(2 * n), pairs);
+            });
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""CPU tier: the product's CUDA kernels (exacto_b200/csrc/kernels.cu, compiled unchanged by g++
+under tests/host_emul's CUDA shim: one OS thread per CUDA thread, pthread barriers for
+__syncthreads) against the oracle and the golden fixtures.  Checks index math, barriers,
+lazy-reduction bounds and the host-precomputed constants before any GPU time is spent."""
+import numpy as np
+import pytest
+
+from common import CASES, Emulator, H, O, digest, golden, golden_inputs
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return Emulator()
+
+
+@pytest.mark.parametrize("n,moduli", [(16, [65537]), (64, [1152921504606830593, 18014398509998081]),
+                                      (1024, [1099509805057, 562949953443841]),
+                                      (4096, [1152921504606830593, 18014398509998081, 36028797018972161])])
+def test_ntt_kernels(emu, n, moduli):
+    rc, h, err = emu.create(n, moduli[:1], moduli[1:], 2)
+    assert rc == 0, err
+    rng = np.random.default_rng(n)
+    for base, m in enumerate(moduli):
+        x = rng.integers(0, m, (2, n), dtype=np.uint64)
+        x[0, :4] = [0, 1, m - 1, m // 2]
+        y = emu.ntt(h, base, True, x)
+        assert np.array_equal(y, O.ntt_fwd(x, m))
+        assert np.array_equal(emu.ntt(h, base, False, y), x)
+    assert emu.info(h)[3] == O.find_psi(n, moduli[0])
+
+
+def test_poly_ops(emu):
+    q = 1152921504606830593
+    rc, h, err = emu.create(64, [q], [], 2)
+    assert rc == 0, err
+    rng = np.random.default_rng(8)
+    a, b = rng.integers(0, q, 64, dtype=np.uint64), rng.integers(0, q, 64, dtype=np.uint64)
+    a[:3] = [0, q - 1, 1]; b[:3] = [0, q - 1, q - 1]
+    ao, bo = a.astype(object), b.astype(object)
+    assert np.array_equal(emu.poly_op(h, 0, 0, a, b), np.array((ao + bo) % q, dtype=np.uint64))
+    assert np.array_equal(emu.poly_op(h, 0, 1, a, b), np.array((ao - bo) % q, dtype=np.uint64))
+    assert np.array_equal(emu.poly_op(h, 0, 2, a), np.array((-ao) % q, dtype=np.uint64))
+    assert np.array_equal(emu.poly_op(h, 0, 3, a, b), np.array((ao * bo) % q, dtype=np.uint64))
+    assert np.array_equal(emu.poly_op(h, 0, 4, a, scalar=2 ** 64 - 1), np.array((ao * ((2 ** 64 - 1) % q)) % q, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("name", ["toy16_a1", "n64_a2_rep", "n32_a2_base7", "compact_dbfv", "cfg3p_dbfv"])
+def test_dbfv_mul_matches_golden(emu, name):
+    P, base, d, pm, seed, full = CASES[name]
+    g = golden()
+    ct1, ct2, rlk = golden_inputs(P, d, seed)
+    h = emu.from_oracle(P)
+    rc, out, err = emu.dbfv_mul(h, base, d, pm, ct1, ct2, rlk)
+    assert rc == 0, err
+    assert digest(out) == str(g[f"{name}/dbfv_sha256"])
+    # bfv_mul_and_relin is the d = 1 case of the same pipeline
+    rc, one, err = emu.dbfv_mul(h, 2, 1, 0, ct1[:1], ct2[:1], rlk)
+    assert rc == 0, err
+    assert digest(one[0]) == str(g[f"{name}/bfv_sha256"])
+
+
+def test_flags_masks_and_batches(emu):
+    P, base, d, pm = CASES["n64_a2_rep"][:4]
+    h = emu.from_oracle(P)
+    rng = np.random.default_rng(21)
+    ct1 = rng.integers(0, P.q, (3, d, 2, P.n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (3, d, 2, P.n), dtype=np.uint64)
+    rlk = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    want = np.stack([O.dbfv_mul(P, base, d, pm, a, b, rlk) for a, b in zip(ct1, ct2)])
+    rc, got, err = emu.dbfv_mul(h, base, d, pm, ct1, ct2, rlk)
+    assert rc == 0 and np.array_equal(got, want), err
+    rc, got_all, _ = emu.dbfv_mul(h, base, d, pm, ct1, ct2, rlk, flags=1)       # EXB_DBFV_ALL_PRODUCTS
+    assert np.array_equal(got_all, want)
+    # zero small reps (p = b^d): dead products skipped vs computed give identical limbs
+    want0 = np.stack([O.dbfv_mul(P, 16, 2, 256, a, b, rlk) for a, b in zip(ct1, ct2)])
+    for flags in (0, 1):
+        rc, g0, _ = emu.dbfv_mul(h, 16, 2, 256, ct1, ct2, rlk, flags=flags)
+        assert np.array_equal(g0, want0)
+    # limb masks: each rank's limbs are exact, other limbs untouched
+    sentinel = np.full_like(ct1, 7)
+    rc, part, _ = emu.dbfv_mul(h, base, d, pm, ct1, ct2, rlk, limb_mask=0b10, out=sentinel.copy())
+    assert np.array_equal(part[:, 1], want[:, 1]) and np.array_equal(part[:, 0], sentinel[:, 0])
+    # relinearize uses min(G, rlk.keys.len()) keys (bfv/keyswitch.rs:86-89)
+    rc, short, _ = emu.dbfv_mul(h, 2, 1, 0, ct1[:1, :1], ct2[:1, :1], rlk[:2])
+    full_key = O.bfv_mul_and_relin(P, ct1[0, 0], ct2[0, 0], np.concatenate([rlk[:2], np.zeros_like(rlk[2:])]))
+    assert np.array_equal(short[0, 0], full_key)
+
+
+def test_edge_inputs(emu):
+    """All-zero, all-(q-1), half-boundary inputs: the centring / rounding branches."""
+    P = H.cfg3_prime().bfv
+    h = emu.from_oracle(P)
+    q, n = P.q, P.n
+    rlk = np.random.default_rng(4).integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    pats = [np.zeros(n, np.uint64), np.full(n, q - 1, np.uint64), np.full(n, q // 2, np.uint64),
+            np.full(n, q // 2 + 1, np.uint64)]
+    ct1 = np.stack([np.stack([O.ntt_fwd(pats[i], q), O.ntt_fwd(pats[(i + 1) % 4], q)]) for i in range(4)])
+    ct2 = np.stack([np.stack([O.ntt_fwd(pats[(i + 2) % 4], q), O.ntt_fwd(pats[(i + 3) % 4], q)]) for i in range(4)])
+    rc, got, err = emu.dbfv_mul(h, 2, 1, 0, ct1[:, None], ct2[:, None], rlk)
+    assert rc == 0, err
+    assert np.array_equal(got[:, 0], O.bfv_mul_and_relin(P, ct1, ct2, rlk, threads=4))
+
+
+def test_dispatch_errors(emu):
+    n = 4096
+    rc, h, _ = emu.create(n, [18014398509506561], [36028797018972161], 1040407, 256)
+    assert rc == 0
+    st = emu.info(h)
+    assert st[2] == 1 and "single aux prime too small for HPS centering" in st[4]
+    rc, h, _ = emu.create(n, [18014398509506561], [], 1040407, 256)
+    st = emu.info(h)
+    assert st[2] == 9 and "schoolbook BFV multiplication can overflow i128" in st[4]
+    rc, h, _ = emu.create(16, [65537, 1099509805057], [], 257, 8)
+    st = emu.info(h)
+    assert st[1] == 19 and st[2] == 9 and "multi-prime" in st[4]
+    rc, h, err = emu.create(4096, [0xFFFFFFFFFFE00001], [], 257)
+    assert rc == 1 and "cannot create NTT plan" in err
+    rc, h, err = emu.create(1000, [65537], [], 257)
+    assert rc == 4

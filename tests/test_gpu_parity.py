@@ -1,0 +1,252 @@
+"""GPU tier: parity of the CUDA path (through the C ABI of libexacto_b200.so) with the oracle,
+the golden fixtures and the reference's own known-answer tests.  Integer arithmetic: the
+bar is bit-exact.  Citations are into /root/reference/src/."""
+import numpy as np
+import pytest
+
+import exacto_b200 as E
+from common import CASES, H, O, digest, golden, golden_inputs, to_dbfv_params, to_params
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(native_lib):
+    assert torch.cuda.is_available(), "the gpu tier needs a CUDA device"
+
+
+# ---- ring/ntt.rs:170-212 + per-prime parity ------------------------------------------------------
+def test_reference_ntt_tests_n16():
+    n, q = 16, 65537
+    plan = E.make_plan(n, q)
+    a = E.CoeffPoly.from_coeffs(np.array([1, 2, 3, 4] + [0] * 12), q)
+    b = E.CoeffPoly.from_coeffs(np.array([5, 6, 7, 8] + [0] * 12), q)
+    na, nb = E.NttPoly.from_coeff_poly(a, plan), E.NttPoly.from_coeff_poly(b, plan)
+    assert na.to_coeff_poly() == a                                                   # :170-178
+    assert np.array_equal(na.mul(nb).to_coeff_poly().coeffs, O.poly_mul_naive(a.coeffs, b.coeffs, q))   # :181-195
+    assert np.array_equal(na.add(nb).to_coeff_poly().coeffs, (a.coeffs + b.coeffs) % np.uint64(q))      # :198-212
+    assert np.array_equal(na.evals, O.ntt_fwd(a.coeffs, q))
+    # X^3 * X^3 = -X^2 (ring/poly.rs:195-202) through the NTT at n=16
+    x3 = E.CoeffPoly.from_coeffs(np.eye(16, dtype=np.uint64)[3], q)
+    sq = E.NttPoly.from_coeff_poly(x3, plan)
+    assert np.array_equal(sq.mul(sq).to_coeff_poly().coeffs, np.eye(16, dtype=np.uint64)[6])
+    x15 = E.NttPoly.from_coeff_poly(E.CoeffPoly.from_coeffs(np.eye(16, dtype=np.uint64)[15], q), plan)
+    want = np.zeros(16, np.uint64); want[14] = q - 1
+    assert np.array_equal(x15.mul(x15).to_coeff_poly().coeffs, want)
+
+
+@pytest.mark.parametrize("n,q", [(1024, 1099509805057), (1024, 562949953443841), (4096, 1152921504606830593),
+                                 (4096, 18014398509998081), (4096, 36028797018972161), (4096, 576460752308273153),
+                                 (2048, 1152921504606830593), (8192, 1152921504606830593), (2, 65537)])
+def test_ntt_vs_oracle(n, q):
+    from exacto_b200 import batch
+    plan = E.make_plan(n, q)
+    rng = np.random.default_rng(n + q % 1000)
+    x = rng.integers(0, q, (5, n), dtype=np.uint64)
+    x[0, :2] = [0, q - 1]
+    x[1] = q - 1
+    x[2] = 0
+    dx = batch.to_device(x)
+    fy = batch.ntt_forward(plan.params, 0, dx)
+    assert np.array_equal(batch.to_host(fy), O.ntt_fwd(x, q))
+    assert np.array_equal(batch.to_host(batch.ntt_inverse(plan.params, 0, fy)), x)
+    assert batch.to_host(batch.ntt_forward(plan.params, 0, dx, out=dx)).tobytes() == batch.to_host(fy).tobytes()   # in place
+    g = golden()
+    key = f"ntt/{n}_{q}"
+    if key in g:
+        ramp = (np.arange(n, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(12345)) % np.uint64(q)
+        assert digest(batch.to_host(batch.ntt_forward(plan.params, 0, batch.to_device(ramp)))) == str(g[key])
+
+
+def test_ntt_linearity_full_size():
+    """Size-independent property at the bench size: NTT(a + b) = NTT(a) + NTT(b), round trip."""
+    from exacto_b200 import batch
+    P = E.u64_dbfv().bfv_params
+    for idx in range(3):
+        q = P.modulus(idx)
+        rng = np.random.default_rng(idx)
+        a = rng.integers(0, q, (512, 4096), dtype=np.uint64); b = rng.integers(0, q, (512, 4096), dtype=np.uint64)
+        s = np.array((a.astype(object) + b.astype(object)) % q, dtype=np.uint64)
+        fa, fb, fs = (batch.to_host(batch.ntt_forward(P, idx, batch.to_device(v))) for v in (a, b, s))
+        assert np.array_equal(np.array((fa.astype(object) + fb.astype(object)) % q, dtype=np.uint64), fs)
+        assert np.array_equal(batch.to_host(batch.ntt_inverse(P, idx, batch.to_device(fs))), s)
+
+
+def test_ring_types_ops():
+    q, n = 1099509805057, 1024
+    plan = E.make_plan(n, q)
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, q, n, dtype=np.uint64), rng.integers(0, q, n, dtype=np.uint64)
+    A, B = E.NttPoly(a, q, plan), E.NttPoly(b, q, plan)
+    ao, bo = a.astype(object), b.astype(object)
+    assert np.array_equal(A.add(B).evals, np.array((ao + bo) % q, dtype=np.uint64))
+    assert np.array_equal(A.sub(B).evals, np.array((ao - bo) % q, dtype=np.uint64))
+    assert np.array_equal(A.neg().evals, np.array((-ao) % q, dtype=np.uint64))
+    assert np.array_equal(A.mul(B).evals, np.array((ao * bo) % q, dtype=np.uint64))
+    assert np.array_equal(A.scalar_mul(2 ** 63 + 5).evals, np.array((ao * ((2 ** 63 + 5) % q)) % q, dtype=np.uint64))
+    with pytest.raises(E.ExactoError) as e:
+        A.add(E.NttPoly(a[:16], 65537, E.make_plan(16, 65537)))
+    assert e.value.kind == "ModulusMismatch"
+    cp = E.CoeffPoly(a, q)
+    assert cp.add(E.CoeffPoly(b, q)) == E.CoeffPoly(np.array((ao + bo) % q, dtype=np.uint64), q)
+    r = E.RnsPoly.from_coeff_poly(cp, plan.params)
+    assert r.to_coeff_poly() == cp and r.mul(r).num_components() == 1
+
+
+# ---- golden fixtures through bfv_mul_and_relin / dbfv_mul ----------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_cases(name):
+    P, base, d, pm, seed, full = CASES[name]
+    g = golden()
+    ct1, ct2, rlk_arr = golden_inputs(P, d, seed)
+    assert digest(ct1, ct2, rlk_arr) == str(g[f"{name}/in_sha256"])
+    params = to_dbfv_params(P, base, d, pm)
+    rlk = E.RelinKey(rlk_arr, params.bfv_params)
+    out = E.dbfv_mul(E.DbfvCiphertext.from_array(ct1, params), E.DbfvCiphertext.from_array(ct2, params), rlk)
+    assert (out.degree, out.mul_depth, out.num_limbs()) == (d, 1, d)               # dbfv/eval.rs:138-146
+    assert digest(out.to_array()) == str(g[f"{name}/dbfv_sha256"])
+    one = E.bfv_mul_and_relin(E.BfvCiphertext.from_array(ct1[0], params.bfv_params),
+                              E.BfvCiphertext.from_array(ct2[0], params.bfv_params), rlk)
+    assert len(one.c) == 2 and digest(one.to_array()) == str(g[f"{name}/bfv_sha256"])
+    if full:
+        assert np.array_equal(out.to_array(), g[f"{name}/dbfv_out"])
+
+
+@pytest.mark.parametrize("name,batch_n", [("compact_dbfv", 5), ("cfg3p_dbfv", 3), ("u64_dbfv", 2), ("n64_a2_rep", 7)])
+def test_batched_vs_oracle_host_and_device(name, batch_n):
+    from exacto_b200 import batch
+    P, base, d, pm, seed, _ = CASES[name]
+    rng = np.random.default_rng(seed + 7)
+    ct1 = rng.integers(0, P.q, (batch_n, d, 2, P.n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (batch_n, d, 2, P.n), dtype=np.uint64)
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    want = np.stack([O.dbfv_mul(P, base, d, pm, a, b, rlk_arr, threads=O.max_threads()) for a, b in zip(ct1, ct2)])
+    params = to_dbfv_params(P, base, d, pm)
+    rlk = E.RelinKey(rlk_arr, params.bfv_params)
+    assert np.array_equal(E.dbfv_mul_batch(params, ct1, ct2, rlk), want)                        # host buffers
+    assert np.array_equal(E.dbfv_mul_batch(params, ct1, ct2, rlk, all_products=True), want)     # reference's d^2 schedule
+    d1, d2 = batch.to_device(ct1), batch.to_device(ct2)
+    assert np.array_equal(batch.to_host(batch.dbfv_mul(params, d1, d2, rlk)), want)             # device resident
+    # k-sharded: two "ranks" own disjoint limbs
+    from exacto_b200.sharding import limb_masks
+    acc = torch.zeros_like(d1)
+    for m in limb_masks(d, 2):
+        if m:
+            batch.dbfv_mul(params, d1, d2, rlk, out=acc, limb_mask=m)
+    assert np.array_equal(batch.to_host(acc), want)
+    bw = O.bfv_mul_and_relin(P, ct1[:, 0], ct2[:, 0], rlk_arr, threads=O.max_threads())
+    assert np.array_equal(E.bfv_mul_and_relin_batch(params.bfv_params, ct1[:, 0], ct2[:, 0], rlk), bw)
+    assert np.array_equal(batch.to_host(batch.bfv_mul_and_relin(params.bfv_params, batch.to_device(ct1[:, 0]),
+                                                                 batch.to_device(ct2[:, 0]), rlk)), bw)
+
+
+def test_edge_patterns_cfg4():
+    """0, 1, floor(q/2), floor(q/2)+1, q-1 patterns (the centring / rounding / wrap branches)."""
+    P = H.u64_dbfv().bfv
+    q, n = P.q, P.n
+    rng = np.random.default_rng(77)
+    rlk_arr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    pats = [np.zeros(n, np.uint64), np.ones(n, np.uint64), np.full(n, q // 2, np.uint64),
+            np.full(n, q // 2 + 1, np.uint64), np.full(n, q - 1, np.uint64)]
+    ct1 = np.stack([np.stack([O.ntt_fwd(pats[i], q), O.ntt_fwd(pats[(i + 1) % 5], q)]) for i in range(5)])
+    ct2 = np.stack([np.stack([O.ntt_fwd(pats[(i + 2) % 5], q), O.ntt_fwd(pats[(i + 3) % 5], q)]) for i in range(5)])
+    params = to_params(P)
+    got = E.bfv_mul_and_relin_batch(params, ct1, ct2, E.RelinKey(rlk_arr, params))
+    assert np.array_equal(got, O.bfv_mul_and_relin(P, ct1, ct2, rlk_arr, threads=O.max_threads()))
+    zero = np.zeros((1, 2, n), np.uint64)
+    assert not E.bfv_mul_and_relin_batch(params, zero, ct2[:1], E.RelinKey(rlk_arr, params)).any()
+    assert E.bfv_mul_and_relin_batch(params, ct1[:0], ct2[:0], E.RelinKey(rlk_arr, params)).shape == (0, 2, n)   # empty batch
+
+
+# ---- decrypt KATs of the reference with valid keys ----------------------------------------------------------
+def test_compact_bfv_kats():
+    """bfv/eval.rs:883-900 (3 * 7 = 21) + add/sub (:845-881)."""
+    P, params = H.compact_bfv(), E.compact_bfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(P, rng); rlk = E.RelinKey(H.gen_relin_key(P, s, rng), params)
+    enc = lambda m: E.BfvCiphertext.from_array(H.encrypt_sk(P, H.encode_scalar(P, m), s, rng), params)
+    assert int(H.decrypt(P, E.bfv_mul_and_relin(enc(3), enc(7), rlk).to_array(), s)[0]) == 21
+    assert int(H.decrypt(P, E.bfv_add(enc(10), enc(20)).to_array(), s)[0]) == 30
+    assert int(H.decrypt(P, E.bfv_sub(enc(50), enc(20)).to_array(), s)[0]) == 30
+    assert int(H.decrypt(P, E.bfv_neg(enc(5)).to_array(), s)[0]) == 257 - 5
+
+
+def test_compact_dbfv_kats():
+    """dbfv/eval.rs:224-290: 3*7, (3+X)(2+X), 15*15 / 10*20 / 12*12 mod 256, add, sub."""
+    S, params = H.compact_dbfv(), E.compact_dbfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(S.bfv, rng); rlk = E.RelinKey(H.gen_relin_key(S.bfv, s, rng), params.bfv_params)
+    enc = lambda v: E.DbfvCiphertext.from_array(H.dbfv_encrypt_sk(S, v, s, rng), params)
+    dec = lambda ct: H.dbfv_decrypt(S, ct.to_array(), s)
+    assert dec(E.dbfv_mul(enc(3), enc(7), rlk)) == 21
+    for a, b in [(15, 15), (10, 20), (12, 12)]:
+        assert dec(E.dbfv_mul(enc(a), enc(b), rlk)) == a * b % 256
+    assert dec(E.dbfv_add(enc(10), enc(20))) == 30 and dec(E.dbfv_sub(enc(50), enc(20))) == 30
+    pa = np.zeros(S.bfv.n, np.uint64); pb = np.zeros(S.bfv.n, np.uint64)
+    pa[:2] = [3, 1]; pb[:2] = [2, 1]
+    prod = E.dbfv_mul(E.DbfvCiphertext.from_array(H.dbfv_encrypt_poly_sk(S, pa, s, rng), params),
+                      E.DbfvCiphertext.from_array(H.dbfv_encrypt_poly_sk(S, pb, s, rng), params), rlk)
+    assert H.dbfv_decrypt_poly(S, prod.to_array(), s)[:3].tolist() == [6, 5, 1]
+    with pytest.raises(E.ExactoError, match="chained dBFV multiplication requires ciphertext-level lattice reduction"):
+        E.dbfv_mul(prod, enc(5), rlk)                                                 # dbfv/eval.rs:292-313
+
+
+def test_u64_profile_kats():
+    """dbfv/eval.rs:345-382 (BFV 3*7, 0*5, 10*20, 100*100) and :521-564 (dBFV 3*7, 1000*2000)."""
+    S, params = H.u64_dbfv(), E.u64_dbfv()
+    rng = np.random.default_rng(101)
+    s = H.gen_secret_key(S.bfv, rng); rlk = E.RelinKey(H.gen_relin_key(S.bfv, s, rng), params.bfv_params)
+    encb = lambda m: E.BfvCiphertext.from_array(H.encrypt_sk(S.bfv, H.encode_scalar(S.bfv, m), s, rng), params.bfv_params)
+    for a, b in [(3, 7), (0, 5), (10, 20), (100, 100)]:
+        assert int(H.decrypt(S.bfv, E.bfv_mul_and_relin(encb(a), encb(b), rlk).to_array(), s)[0]) == a * b
+    enc = lambda v: E.DbfvCiphertext.from_array(H.dbfv_encrypt_sk(S, v, s, rng), params)
+    assert H.dbfv_decrypt(S, E.dbfv_mul(enc(3), enc(7), rlk).to_array(), s) == 21
+    assert H.dbfv_decrypt(S, E.dbfv_mul(enc(1000), enc(2000), rlk).to_array(), s) == 2_000_000
+    assert H.dbfv_decrypt(S, E.dbfv_mul(enc(2 ** 32 + 3), enc(2 ** 32 + 5), rlk).to_array(), s) == ((2 ** 32 + 3) * (2 ** 32 + 5)) % 2 ** 64
+
+
+def test_commutativity_full_size():
+    """Size-independent property at the bench size: the integer tensor is symmetric, so
+    dbfv_mul(a, b) == dbfv_mul(b, a) bit for bit; zero times anything is zero."""
+    from exacto_b200 import batch
+    params = E.u64_dbfv()
+    P = params.bfv_params
+    q, n, d = P.modulus(0), 4096, 8
+    rng = np.random.default_rng(5)
+    a = batch.to_device(rng.integers(0, q, (16, d, 2, n), dtype=np.uint64))
+    b = batch.to_device(rng.integers(0, q, (16, d, 2, n), dtype=np.uint64))
+    rlk = E.RelinKey(rng.integers(0, q, (8, 2, n), dtype=np.uint64), P)
+    ab, ba = batch.dbfv_mul(params, a, b, rlk), batch.dbfv_mul(params, b, a, rlk)
+    assert torch.equal(ab, ba) and ab.abs().sum().item() != 0
+    assert not batch.dbfv_mul(params, torch.zeros_like(a), b, rlk).any()
+    assert torch.equal(batch.dbfv_mul(params, a, b, rlk, all_products=True), ab)
+
+
+# ---- error pins through the native context (dbfv/eval.rs:385-453) ---------------------------------------------
+def test_native_error_pins():
+    n = 4096
+    z = np.zeros((1, 2, n), np.uint64)
+    p1 = (E.BfvParamsBuilder().ring_degree(n).plain_modulus(1040407).ct_moduli([18014398509506561])
+          .aux_moduli([36028797018972161]).gadget_base(256).build())
+    with pytest.raises(E.ExactoError, match="single aux prime too small") as e:
+        E.bfv_mul_and_relin_batch(p1, z, z, E.RelinKey(np.zeros((p1.gadget_digits, 2, n), np.uint64), p1))
+    assert e.value.kind == "InvalidParam"
+    p0 = (E.BfvParamsBuilder().ring_degree(n).plain_modulus(1040407).ct_moduli([18014398509506561])
+          .gadget_base(256).build())
+    with pytest.raises(E.ExactoError, match="schoolbook BFV multiplication can overflow i128") as e:
+        E.bfv_mul_and_relin_batch(p0, z, z, E.RelinKey(np.zeros((p0.gadget_digits, 2, n), np.uint64), p0))
+    assert e.value.kind == "NotImplemented"
+    small = E.small_bfv()     # BASELINE config 3 as literally written: no aux basis -> the reference errors too
+    with pytest.raises(E.ExactoError, match="schoolbook BFV multiplication can overflow i128"):
+        E.bfv_mul_and_relin_batch(small, z, z, E.RelinKey(np.zeros((small.gadget_digits, 2, n), np.uint64), small))
+    p3 = (E.BfvParamsBuilder().ring_degree(n).plain_modulus(257).ct_moduli([1152921504606830593])
+          .aux_moduli([18014398509998081, 36028797018972161, 576460752308273153]).build())
+    with pytest.raises(E.ExactoError, match="HPS scaling supports 1 or 2 aux primes, got 3"):
+        E.bfv_mul_and_relin_batch(p3, z, z, E.RelinKey(np.zeros((p3.gadget_digits, 2, n), np.uint64), p3))
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()

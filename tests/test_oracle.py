@@ -1,0 +1,169 @@
+"""CPU tier: pins the oracle against every known-answer test the reference holds for the
+ciphertext-multiplication path, against the independent definition oracle and against
+the committed golden fixtures.  Citations are into /root/reference/src/."""
+import numpy as np
+import pytest
+
+from common import CASES, H, O, digest, golden, golden_inputs
+from oracle import definition as D
+
+
+# ---- ring/modular.rs tests :127-202 (m = 65537) -----------------------------------------
+def test_modular_ops_match_u128():
+    m = 65537
+    rng = np.random.default_rng(1)
+    for a, b in rng.integers(0, m, (200, 2)):
+        a, b = int(a), int(b)
+        assert O.mod_mul(a, b, m) == a * b % m
+        assert O.mod_add(a, b, m) == (a + b) % m
+        assert O.mod_sub(a, b, m) == (a - b) % m
+        assert O.mod_neg(a, m) == (-a) % m
+    assert O.mod_pow(3, 65536, m) == 1
+    assert O.mod_inv(3, m) * 3 % m == 1
+    assert O.mod_inv(0, m) is None
+
+
+# ---- ring/poly.rs:195-202: X^3 * X^3 = -X^2 in Z_17[X]/(X^4+1) ----------------------------
+def test_negacyclic_wrap_sign():
+    a = np.array([0, 0, 0, 1], np.uint64)
+    assert O.poly_mul_naive(a, a, 17).tolist() == [0, 0, 16, 0]
+
+
+# ---- ring/ntt.rs:170-212 (n = 16, q = 65537) -------------------------------------------------
+def test_ntt_roundtrip_and_mul_vs_schoolbook():
+    n, q = 16, 65537
+    rng = np.random.default_rng(2)
+    a, b = rng.integers(0, q, n, dtype=np.uint64), rng.integers(0, q, n, dtype=np.uint64)
+    fa, fb = O.ntt_fwd(a, q), O.ntt_fwd(b, q)
+    assert np.array_equal(O.ntt_inv(fa, q), a)
+    prod = np.array((fa.astype(object) * fb.astype(object)) % q, dtype=np.uint64)
+    assert np.array_equal(O.ntt_inv(prod, q), O.poly_mul_naive(a, b, q))
+    s = np.array((fa.astype(object) + fb.astype(object)) % q, dtype=np.uint64)
+    assert np.array_equal(O.ntt_inv(s, q), (a + b) % np.uint64(q))
+
+
+@pytest.mark.parametrize("n,q", [(1024, 1099509805057), (4096, 1152921504606830593), (4096, 36028797018972161)])
+def test_ntt_is_negacyclic_convolution(n, q):
+    rng = np.random.default_rng(3)
+    a = np.zeros(n, np.uint64); b = np.zeros(n, np.uint64)
+    idx = rng.choice(n, 6, replace=False)
+    a[idx] = rng.integers(1, q, 6, dtype=np.uint64); b[idx[::-1]] = rng.integers(1, q, 6, dtype=np.uint64)
+    a[n - 1] = q - 1; b[n - 1] = 2                       # forces the X^n = -1 wrap
+    fa, fb = O.ntt_fwd(a, q), O.ntt_fwd(b, q)
+    prod = np.array((fa.astype(object) * fb.astype(object)) % q, dtype=np.uint64)
+    assert np.array_equal(O.ntt_inv(prod, q), O.poly_mul_naive(a, b, q))
+
+
+# ---- bfv/keyswitch.rs:109-152 gadget KATs ---------------------------------------------------------
+def test_gadget_kats():
+    assert O.gadget_decompose([42], 65537, 16, 2).ravel().tolist() == [65531, 3]
+    q, base, G = 65537, 16, 4
+    coeffs = np.array([12345, 54321, 100, 0], np.uint64)
+    dg = O.gadget_decompose(coeffs, q, base, G)
+    for pos in range(4):
+        assert sum(int(dg[g, pos]) * base ** g for g in range(G)) % q == int(coeffs[pos])
+    assert O.gadget_decompose([q - 1], q, 16, 4)[0, 0] == q - 1
+    for c in [0, 1, 7, 8, 9, q // 2, q // 2 + 1, q - 9, q - 8]:
+        assert O.gadget_decompose([c], q, 16, 4).ravel().tolist() == D.gadget_decompose(c, q, 16, 4)
+
+
+# ---- oracle (literal HPS schedule) == definition oracle (round(p t / q)) ----------------------------
+@pytest.mark.parametrize("name", ["toy16_a1", "n64_a2_rep", "n32_a2_base7"])
+def test_literal_oracle_equals_definition(name):
+    P, base, d, pm, seed, _ = CASES[name]
+    ct1, ct2, rlk = golden_inputs(P, d, seed + 100)
+    out = O.dbfv_mul(P, base, d, pm, ct1, ct2, rlk)
+    want = D.dbfv_mul_coeff(O.ntt_inv(ct1, P.q), O.ntt_inv(ct2, P.q), O.ntt_inv(rlk, P.q), P.q, P.plain_modulus,
+                            P.gadget_base, P.gadget_digits, base, d, pm)
+    assert np.array_equal(O.ntt_inv(out, P.q), np.array(want, dtype=np.uint64))
+
+
+def test_small_reps_zero_for_all_configs():
+    """SURVEY finding 3: p = b^d in every preset, so every small representative is zero."""
+    for base, d, pm in [(16, 2, 256), (256, 2, 65536), (256, 8, 0)]:
+        assert not O.small_reps(base, d, pm).any()
+        assert np.array_equal(O.small_reps(base, d, pm), np.array(D.small_reps(base, d, pm), dtype=np.int64))
+    assert O.small_reps(16, 2, 250).tolist() == [[6, 0]]
+
+
+# ---- golden fixtures ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_golden(name):
+    P, base, d, pm, seed, full = CASES[name]
+    g = golden()
+    ct1, ct2, rlk = golden_inputs(P, d, seed)
+    assert digest(ct1, ct2, rlk) == str(g[f"{name}/in_sha256"]), "seeded inputs drifted"
+    out = O.dbfv_mul(P, base, d, pm, ct1, ct2, rlk, threads=O.max_threads())
+    assert digest(out) == str(g[f"{name}/dbfv_sha256"])
+    assert digest(O.bfv_mul_and_relin(P, ct1[0], ct2[0], rlk)) == str(g[f"{name}/bfv_sha256"])
+    if full:
+        assert np.array_equal(out, g[f"{name}/dbfv_out"])
+
+
+# ---- decrypt KATs with valid keys (bfv/eval.rs:883-900, dbfv/eval.rs:224-290,345-382,521-564) --------------
+def test_compact_bfv_mul_decrypts():
+    P = H.compact_bfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(P, rng); rlk = H.gen_relin_key(P, s, rng)
+    for a, b in [(3, 7), (0, 5), (10, 20)]:
+        c1 = H.encrypt_sk(P, H.encode_scalar(P, a), s, rng); c2 = H.encrypt_sk(P, H.encode_scalar(P, b), s, rng)
+        assert int(H.decrypt(P, O.bfv_mul_and_relin(P, c1, c2, rlk), s)[0]) == a * b % P.plain_modulus
+        assert int(H.decrypt(P, O.bfv_mul_no_relin(P, c1, c2), s)[0]) == a * b % P.plain_modulus
+        assert int(H.decrypt(P, O.bfv_add(P, c1, c2), s)[0]) == (a + b) % P.plain_modulus
+
+
+def test_compact_dbfv_mul_decrypts():
+    S = H.compact_dbfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(S.bfv, rng); rlk = H.gen_relin_key(S.bfv, s, rng)
+    for a, b in [(3, 7), (15, 15), (10, 20), (12, 12)]:
+        ca, cb = H.dbfv_encrypt_sk(S, a, s, rng), H.dbfv_encrypt_sk(S, b, s, rng)
+        out = O.dbfv_mul(S.bfv, S.base, S.d, S.plain_modulus, ca, cb, rlk)
+        assert H.dbfv_decrypt(S, out, s) == a * b % 256
+    # (3 + X)(2 + X) = 6 + 5X + X^2   (dbfv/eval.rs:243-268)
+    pa = np.zeros(S.bfv.n, np.uint64); pb = np.zeros(S.bfv.n, np.uint64)
+    pa[:2] = [3, 1]; pb[:2] = [2, 1]
+    out = O.dbfv_mul(S.bfv, S.base, S.d, S.plain_modulus, H.dbfv_encrypt_poly_sk(S, pa, s, rng),
+                     H.dbfv_encrypt_poly_sk(S, pb, s, rng), rlk)
+    assert H.dbfv_decrypt_poly(S, out, s)[:3].tolist() == [6, 5, 1]
+
+
+def test_u64_profile_decrypts():
+    S = H.u64_dbfv()
+    rng = np.random.default_rng(101)
+    s = H.gen_secret_key(S.bfv, rng); rlk = H.gen_relin_key(S.bfv, s, rng)
+    for a, b in [(3, 7), (100, 100)]:                                  # dbfv/eval.rs:345-382
+        c1 = H.encrypt_sk(S.bfv, H.encode_scalar(S.bfv, a), s, rng); c2 = H.encrypt_sk(S.bfv, H.encode_scalar(S.bfv, b), s, rng)
+        assert int(H.decrypt(S.bfv, O.bfv_mul_and_relin(S.bfv, c1, c2, rlk), s)[0]) == a * b
+    for v in [0, 255, 256, 2 ** 64 - 1]:                               # dbfv/eval.rs:315-327
+        assert H.dbfv_decrypt(S, H.dbfv_encrypt_sk(S, v, s, rng), s) == v
+    ca, cb = H.dbfv_encrypt_sk(S, 1000, s, rng), H.dbfv_encrypt_sk(S, 2000, s, rng)   # dbfv/eval.rs:548-564
+    out = O.dbfv_mul(S.bfv, S.base, S.d, S.plain_modulus, ca, cb, rlk, threads=O.max_threads())
+    assert H.dbfv_decrypt(S, out, s) == 2_000_000
+
+
+# ---- error pins (dbfv/eval.rs:385-453) ------------------------------------------------------------------------
+def test_error_pins():
+    n = 4096
+    z = np.zeros((2, n), np.uint64)
+    P1 = O.OracleParams(n=n, q=18014398509506561, aux=(36028797018972161,), plain_modulus=1040407, gadget_base=256)
+    with pytest.raises(O.OracleError, match="single aux prime too small"):
+        O.bfv_mul_and_relin(P1, z, z, np.zeros((P1.gadget_digits, 2, n), np.uint64))
+    P0 = O.OracleParams(n=n, q=18014398509506561, aux=(), plain_modulus=1040407, gadget_base=256)
+    with pytest.raises(O.OracleError, match="schoolbook BFV multiplication can overflow i128") as ei:
+        O.bfv_mul_and_relin(P0, z, z, np.zeros((P0.gadget_digits, 2, n), np.uint64))
+    assert ei.value.kind == "NotImplemented"
+    P3 = O.OracleParams(n=16, q=1099509805057, aux=(562949953443841, 18014398509998081 - 8192 * 0 + 0, 36028797018972161)[:1] * 3,
+                        plain_modulus=257)
+    with pytest.raises(O.OracleError, match="HPS scaling supports 1 or 2 aux primes"):
+        O.bfv_mul_and_relin(P3, np.zeros((2, 16), np.uint64), np.zeros((2, 16), np.uint64),
+                            np.zeros((P3.gadget_digits, 2, 16), np.uint64))
+
+
+def test_schoolbook_branch_small_params():
+    """bfv/eval.rs:416-454 on parameters where i128 does not overflow (n=16, q=65537)."""
+    P = O.OracleParams(n=16, q=65537, aux=(), plain_modulus=17, gadget_base=16)
+    rng = np.random.default_rng(5)
+    ct1, ct2 = rng.integers(0, P.q, (2, 16), dtype=np.uint64), rng.integers(0, P.q, (2, 16), dtype=np.uint64)
+    got = O.ntt_inv(O.bfv_mul_no_relin(P, O.ntt_fwd(ct1, P.q), O.ntt_fwd(ct2, P.q)), P.q)
+    assert np.array_equal(got, np.array(D.bfv_mul_no_relin_coeff(ct1, ct2, P.q, 17), dtype=np.uint64))
