@@ -132,6 +132,18 @@ static int build_modulus(u32 n, u32 logn, u64 m, Modulus *mod, std::vector<Tw> *
     mod->ninv = ninv; mod->ninv_s = shoup_of(ninv, m);
     mod->ninv_w = h_mul(ninv, (*twi)[1].w, m);
     mod->ninv_w_s = shoup_of(mod->ninv_w, m);
+    mod->neg_m = (u64)0 - m;
+    mod->four_m = 4 * m;
+    mod->hi_four_m = (u32)(mod->four_m >> 32);
+    u32 bits = 0;
+    while (bits < 64 && (m >> bits)) bits++;
+    mod->rhi = 0; mod->rsh = 0; mod->lazy = 0;
+    if (bits >= 37 && bits <= 60) {                        // approximate-butterfly fast paths
+        const u32 sh = bits - 1;                           // 2^(32+sh)/m in [2^31, 2^32)
+        mod->rhi = (u32)(((u128)1 << (32 + sh)) / m);
+        mod->rsh = sh - 32;
+        mod->lazy = bits <= 55 ? 2 : 1;
+    }
     *psi_out = psi;
     return EXB_OK;
 }
@@ -280,6 +292,7 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
         if (rc != EXB_OK) return rc;
         if (b == 0 || (b <= A && A <= (u32)kMaxAux)) {
             c->P.mod[b] = mod; c->has_plan[b] = true;
+            for (u32 k = 0; k < 16 && k < n; k++) { c->P.headf[b].t[k] = twf[k]; c->P.headi[b].t[k] = twi[k]; }
             c->twf[b].swap(twf); c->twi[b].swap(twi);
         }
     }

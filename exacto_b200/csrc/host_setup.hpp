@@ -30,6 +30,8 @@ struct DeviceParams {
     Modulus mod[kMaxBases];      // [0] = q, [1..A] = aux primes
     const Tw *twf[kMaxBases];    // forward twiddles (psi_rev) per base
     const Tw *twi[kMaxBases];    // inverse twiddles (psi_inv_rev) per base
+    TwHead headf[kMaxBases];     // twf[0..15] / twi[0..15] by value (constant-bank operands)
+    TwHead headi[kMaxBases];
     ScaleConsts sc;
 };
 

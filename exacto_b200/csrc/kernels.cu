@@ -11,6 +11,9 @@
 // arithmetic on the integer pipes, staged through shared memory.
 #include "kernels.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 // Dynamic shared memory.  tests/host_emul compiles this file with g++ and a shim
 // (EXB_HOST_EMUL) that maps CUDA's execution model onto CPU threads + barriers.
 #ifndef EXB_HOST_EMUL
@@ -20,6 +23,17 @@
 namespace exb {
 
 unsigned long long g_launch_count = 0;
+
+// Streaming 64-bit load that does not allocate in L1 (keeps L1 for the twiddle tables).
+__device__ __forceinline__ u64 ld_stream(const u64 *p) {
+#ifndef EXB_HOST_EMUL
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 
 // ---------------------------------------------------------------------------------
 // Shared-memory transforms.  LOGN == 12: 256 threads, radix-16 register passes on a
@@ -35,27 +49,56 @@ struct Lay<12> {
     static __device__ __forceinline__ u32 at(u32 e) { return swz(e); }
 };
 
+template <int LAZY>
+__device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod) {
+    const LazyC c = make_lazyc(mod);
+    const u32 t = threadIdx.x;
+    u64 v[16];
+    __syncthreads();
+    load16<8>(v, sm, t);
+    fwd_pass16<12, 8, LAZY>(v, tw, t, c);
+    store16<8>(v, sm, t);
+    __syncthreads();
+    load16<4>(v, sm, t);
+    fwd_pass16<12, 4, LAZY>(v, tw, t, c);
+    store16<4>(v, sm, t);
+    __syncthreads();
+    load16<0>(v, sm, t);
+    fwd_pass16<12, 0, LAZY>(v, tw, t, c);
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
+    store16<0>(v, sm, t);
+    __syncthreads();
+}
+
+// Inputs < 4q (LAZY >= 1) or < 2q (LAZY == 0).
+template <int LAZY>
+__device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod) {
+    const LazyC c = make_lazyc(mod);
+    const u32 t = threadIdx.x;
+    u64 v[16];
+    __syncthreads();
+    load16<0>(v, sm, t);
+    inv_pass16<12, 0, false, LAZY>(v, tw, t, mod, c);
+    store16<0>(v, sm, t);
+    __syncthreads();
+    load16<4>(v, sm, t);
+    inv_pass16<12, 4, false, LAZY>(v, tw, t, mod, c);
+    store16<4>(v, sm, t);
+    __syncthreads();
+    load16<8>(v, sm, t);
+    inv_pass16<12, 8, true, LAZY>(v, tw, t, mod, c);
+    store16<8>(v, sm, t);
+    __syncthreads();
+}
+
 template <int LOGN>
 __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        const u32 t = threadIdx.x;
-        u64 v[16];
-        __syncthreads();
-        load16<8>(v, sm, t);
-        fwd_pass16<12, 8>(v, tw, t, q, q2);
-        store16<8>(v, sm, t);
-        __syncthreads();
-        load16<4>(v, sm, t);
-        fwd_pass16<12, 4>(v, tw, t, q, q2);
-        store16<4>(v, sm, t);
-        __syncthreads();
-        load16<0>(v, sm, t);
-        fwd_pass16<12, 0>(v, tw, t, q, q2);
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = reduce4(v[k], q, q2);
-        store16<0>(v, sm, t);
-        __syncthreads();
+        if (mod.lazy == 2) fwd_sm12<2>(sm, tw, mod);
+        else if (mod.lazy == 1) fwd_sm12<1>(sm, tw, mod);
+        else fwd_sm12<0>(sm, tw, mod);
     } else {
         const u32 n = 1u << logn;
         u32 len = n;
@@ -79,23 +122,9 @@ template <int LOGN>
 __device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        const u32 t = threadIdx.x;
-        u64 v[16];
-        __syncthreads();
-        load16<0>(v, sm, t);
-        inv_pass16<12, 0, false>(v, tw, t, mod);
-        store16<0>(v, sm, t);
-        __syncthreads();
-        load16<4>(v, sm, t);
-        inv_pass16<12, 4, false>(v, tw, t, mod);
-        store16<4>(v, sm, t);
-        __syncthreads();
-        load16<8>(v, sm, t);
-        inv_pass16<12, 8, true>(v, tw, t, mod);
-#pragma unroll
-        for (int k = 0; k < 16; k++) v[k] = csub(v[k], q);
-        store16<8>(v, sm, t);
-        __syncthreads();
+        if (mod.lazy == 2) inv_sm12<2>(sm, tw, mod);
+        else if (mod.lazy == 1) inv_sm12<1>(sm, tw, mod);
+        else inv_sm12<0>(sm, tw, mod);
     } else {
         const u32 n = 1u << logn;
         u32 len = 1;
@@ -132,7 +161,7 @@ ntt_fwd_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__re
     const u32 n = 1u << logn;
     const u64 *src = in + (size_t)blockIdx.x * n;
     u64 *dst = out + (size_t)blockIdx.x * n;
-    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = src[e];
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = ld_stream(src + e);
     fwd_sm<LOGN>(smem, tw, mod, logn);
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
 }
@@ -145,9 +174,136 @@ ntt_inv_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__re
     const u32 n = 1u << logn;
     const u64 *src = in + (size_t)blockIdx.x * n;
     u64 *dst = out + (size_t)blockIdx.x * n;
-    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = src[e];
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = ld_stream(src + e);
     inv_sm<LOGN>(smem, tw, mod, logn);
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
+}
+
+// ---------------------------------------------------------------------------------
+// K1 / K2 fast path (n = 4096): persistent CTAs, one polynomial in flight per CTA plus
+// the next one being prefetched into the other shared-memory buffer with cp.async
+// (L2 -> smem, no registers, no L1 allocation, so L1 keeps the twiddle tables).
+// First-pass twiddles come from the kernel-parameter constant bank (TwHead).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+#ifndef EXB_HOST_EMUL
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#else
+    memcpy(smem_dst, gsrc, 16);
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef EXB_HOST_EMUL
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef EXB_HOST_EMUL
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+// 16-byte chunk c of a polynomial (elements 2c, 2c+1) lives at chunk swz16(c) of the image.
+__device__ __forceinline__ u32 swz16(u32 c) { return c ^ ((c >> 3) & 7u); }
+
+__device__ __forceinline__ void prefetch_poly(u64 *buf, const u64 *src) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 c = i * 256 + threadIdx.x;
+        cp_async16(buf + 2 * swz16(c), src + 2 * c);
+    }
+}
+
+__device__ __forceinline__ void store_poly(u64 *dst, const u64 *buf) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 c = i * 256 + threadIdx.x;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(buf + 2 * swz16(c));
+        *reinterpret_cast<ulonglong2 *>(dst + 2 * c) = v;
+    }
+}
+
+// DBG (lab only, selected by env EXB_NTT_DBG): 1 = copy only, 2 = all twiddles from the constant
+// bank (wrong results, isolates twiddle-load cost), 3 = skip the per-thread-twiddle pass.
+struct TwHeadWrap {
+    const TwHead &h;
+    __device__ __forceinline__ const Tw &operator[](u32 i) const { return h.t[i & 15u]; }
+};
+
+template <bool FWD, int LAZY, int DBG = 0>
+__global__ void __launch_bounds__(256, 2)
+ntt12_persist_kernel(const u64 *in, u64 *out, const Tw *__restrict__ tw, const __grid_constant__ TwHead head,
+                     const __grid_constant__ Modulus mod, u32 count) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const LazyC c = make_lazyc(mod);
+    const u32 t = threadIdx.x;
+    u32 poly = blockIdx.x;
+    if (poly >= count) return;
+    u32 cur = 0;
+    prefetch_poly(smem, in + (size_t)poly * n);
+    cp_async_commit();
+    for (; poly < count; poly += gridDim.x) {
+        u64 *buf = smem + cur * n;
+        const u32 next = poly + gridDim.x;
+        if (next < count) prefetch_poly(smem + (cur ^ 1) * n, in + (size_t)next * n);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        u64 v[16];
+        if (DBG == 1) {
+        } else if (DBG == 2 && FWD) {
+            const TwHeadWrap hw{head};
+            load16<8>(v, buf, t);
+            fwd_pass16<12, 8, LAZY>(v, head, t, c);
+            store16<8>(v, buf, t);
+            __syncthreads();
+            load16<4>(v, buf, t);
+            fwd_pass16<12, 4, LAZY>(v, hw, t, c);
+            store16<4>(v, buf, t);
+            __syncthreads();
+            load16<0>(v, buf, t);
+            fwd_pass16<12, 0, LAZY>(v, hw, t, c);
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
+            store16<0>(v, buf, t);
+        } else if (FWD) {
+            load16<8>(v, buf, t);
+            fwd_pass16<12, 8, LAZY>(v, head, t, c);
+            store16<8>(v, buf, t);
+            __syncthreads();
+            load16<4>(v, buf, t);
+            fwd_pass16<12, 4, LAZY>(v, tw, t, c);
+            store16<4>(v, buf, t);
+            __syncthreads();
+            if (DBG != 3) {
+            load16<0>(v, buf, t);
+            fwd_pass16<12, 0, LAZY>(v, tw, t, c);
+#pragma unroll
+            for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
+            store16<0>(v, buf, t);
+            }
+        } else {
+            load16<0>(v, buf, t);
+            inv_pass16<12, 0, false, LAZY>(v, tw, t, mod, c);
+            store16<0>(v, buf, t);
+            __syncthreads();
+            load16<4>(v, buf, t);
+            inv_pass16<12, 4, false, LAZY>(v, tw, t, mod, c);
+            store16<4>(v, buf, t);
+            __syncthreads();
+            load16<8>(v, buf, t);
+            inv_pass16<12, 8, true, LAZY>(v, head, t, mod, c);
+            store16<8>(v, buf, t);
+        }
+        __syncthreads();
+        store_poly(out + (size_t)poly * n, buf);
+        __syncthreads();      // buf is the prefetch target of the next iteration
+        cur ^= 1;
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------
@@ -373,6 +529,8 @@ __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const
 // ---------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------
+constexpr int kNumSMs = 148;   // B200
+
 static inline u32 block_threads(const DeviceParams &P) {
     if (P.logn == 12) return 256;
     u32 t = P.n / 2;
@@ -386,12 +544,32 @@ static void set_smem(K kernel, size_t bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+template <bool FWD, int LAZY>
+static void launch_ntt12_l(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    const size_t sm = 2 * 4096 * 8;
+    const unsigned grid = (unsigned)(count < (size_t)kNumSMs * 2 ? count : (size_t)kNumSMs * 2);
+    static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;
+    const Tw *tw = FWD ? P.twf[base] : P.twi[base];
+    const TwHead &head = FWD ? P.headf[base] : P.headi[base];
+    if (dbg == 1) { set_smem(ntt12_persist_kernel<FWD, LAZY, 1>, sm); ntt12_persist_kernel<FWD, LAZY, 1><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
+    if (dbg == 2) { set_smem(ntt12_persist_kernel<FWD, LAZY, 2>, sm); ntt12_persist_kernel<FWD, LAZY, 2><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
+    if (dbg == 3) { set_smem(ntt12_persist_kernel<FWD, LAZY, 3>, sm); ntt12_persist_kernel<FWD, LAZY, 3><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
+    set_smem(ntt12_persist_kernel<FWD, LAZY>, sm);
+    ntt12_persist_kernel<FWD, LAZY><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+}
+template <bool FWD>
+static void launch_ntt12(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    const u32 lazy = P.mod[base].lazy;
+    if (lazy == 2) launch_ntt12_l<FWD, 2>(P, base, in, out, count, s);
+    else if (lazy == 1) launch_ntt12_l<FWD, 1>(P, base, in, out, count, s);
+    else launch_ntt12_l<FWD, 0>(P, base, in, out, count, s);
+}
+
 void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
     if (count == 0) return;
     const size_t sm = (size_t)P.n * 8;
     if (P.logn == 12) {
-        set_smem(ntt_fwd_kernel<12>, sm);
-        ntt_fwd_kernel<12><<<(unsigned)count, 256, sm, s>>>(in, out, P.twf[base], P.mod[base], P.logn);
+        launch_ntt12<true>(P, base, in, out, count, s);
     } else {
         set_smem(ntt_fwd_kernel<0>, sm);
         ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.mod[base], P.logn);
@@ -403,8 +581,7 @@ void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, si
     if (count == 0) return;
     const size_t sm = (size_t)P.n * 8;
     if (P.logn == 12) {
-        set_smem(ntt_inv_kernel<12>, sm);
-        ntt_inv_kernel<12><<<(unsigned)count, 256, sm, s>>>(in, out, P.twi[base], P.mod[base], P.logn);
+        launch_ntt12<false>(P, base, in, out, count, s);
     } else {
         set_smem(ntt_inv_kernel<0>, sm);
         ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.mod[base], P.logn);

@@ -95,6 +95,84 @@ EXB_HD u64 mont_mul2_lazy(u64 a, u64 b, u64 c, u64 d, u64 m, u64 minv_neg) {
     return mont_redc_lazy(add128(mul_wide(a, b), mul_wide(c, d)), m, minv_neg);
 }
 
+// ---- Hand-scheduled Shoup multiply-accumulate for the NTT butterflies ----------------
+// Measured on B200 (tools/ubench2.cu): IMAD.LO ~1 issue cycle per warp, IMAD.WIDE ~2,
+// IMAD.HI ~2.5, a 64-bit compare + conditional subtract ~6.  So the butterfly uses an
+// *approximate* quotient  Q' = y1*s1 + hi32(y1*s0) + hi32(y0*s1)  in [Q-2, Q]
+// (1 WIDE + 2 HI instead of 4 WIDE + carries) and folds every addition into the IMAD
+// accumulate operands:  result = addend + y*w + Q' * (2^64 - m)  (mod 2^64)
+//                              = addend + T,   T = y*w mod m + e*m,  T in [0, 4m).
+// Valid for any y < 2^64 as long as addend + 4m < 2^64.
+EXB_HD u64 shoup_mad4(u64 y, u64 w, u64 s, u64 neg_m, u64 addend) {
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u64 qq, acc;\n\t"
+        ".reg .u32 y0, y1, w0, w1, s0, s1, n0, n1, q0, q1, t1, t2, lo, hi, x;\n\t"
+        "mov.b64 {y0, y1}, %1;\n\t"
+        "mov.b64 {w0, w1}, %2;\n\t"
+        "mov.b64 {s0, s1}, %3;\n\t"
+        "mov.b64 {n0, n1}, %4;\n\t"
+        "mul.wide.u32 qq, y1, s1;\n\t"           // y1*s1
+        "mul.hi.u32 t1, y1, s0;\n\t"             // hi32(y1*s0)
+        "mul.hi.u32 t2, y0, s1;\n\t"             // hi32(y0*s1)
+        "mov.b64 {q0, q1}, qq;\n\t"
+        "add.cc.u32 q0, q0, t1;\n\t"
+        "addc.u32 q1, q1, 0;\n\t"
+        "add.cc.u32 q0, q0, t2;\n\t"
+        "addc.u32 q1, q1, 0;\n\t"
+        "mad.wide.u32 acc, y0, w0, %5;\n\t"      // addend + y0*w0        (64-bit accumulate)
+        "mad.wide.u32 acc, q0, n0, acc;\n\t"     // + q0*n0
+        "mul.lo.u32 x, y0, w1;\n\t"              // cross terms, all land in the high word
+        "mad.lo.u32 x, y1, w0, x;\n\t"
+        "mad.lo.u32 x, q0, n1, x;\n\t"
+        "mad.lo.u32 x, q1, n0, x;\n\t"
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "add.u32 hi, hi, x;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(y), "l"(w), "l"(s), "l"(neg_m), "l"(addend));
+    return r;
+#else
+    const u64 y0 = (u32)y, y1 = y >> 32, s0 = (u32)s, s1 = s >> 32;
+    const u64 q = y1 * s1 + ((y1 * s0) >> 32) + ((y0 * s1) >> 32);
+    return addend + y * w + q * neg_m;
+#endif
+}
+
+// Cheap bound control: if the high word shows x > k*m, subtract k*m.  `hi_km` = (k*m) >> 32.
+// After it, x < k*m + 2^32 whenever x < 2*k*m before.  3 instructions instead of ~6.
+EXB_HD u64 csub_hi(u64 x, u64 km, u32 hi_km) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 lo, hi, k0, k1;\n\t"
+        "mov.b64 {lo, hi}, %0;\n\t"
+        "mov.b64 {k0, k1}, %1;\n\t"
+        "setp.gt.u32 p, hi, %2;\n\t"
+        "@p sub.cc.u32 lo, lo, k0;\n\t"
+        "@p subc.u32 hi, hi, k1;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "+l"(x) : "l"(km), "r"(hi_km));
+    return x;
+#else
+    return (u32)(x >> 32) > hi_km ? x - km : x;
+#endif
+}
+
+// Reduce any x < 2^64 to [0, 2m) with one 32-bit high-word Barrett estimate:
+// k = floor((x >> 32) * rhi / 2^rsh) is floor(x/m) or one less (needs m >= 2^36).
+EXB_HD u64 reduce_to_2m(u64 x, u64 neg_m, u32 rhi, u32 rsh) {
+#if defined(__CUDA_ARCH__)
+    const u32 k = __umulhi((u32)(x >> 32), rhi) >> rsh;
+#else
+    const u32 k = (u32)(((u64)(u32)(x >> 32) * rhi) >> 32) >> rsh;
+#endif
+    return x + (u64)k * neg_m;
+}
+
 // Per-modulus constants, computed on the host (context.cpp).
 struct Modulus {
     u64 m;          // the prime
@@ -108,6 +186,12 @@ struct Modulus {
     u64 ninv_s;
     u64 ninv_w;     // n^-1 * psi_inv_rev[1] mod m  (last inverse stage, folded normalise)
     u64 ninv_w_s;
+    u64 neg_m;      // 2^64 - m
+    u64 four_m;     // 4m (lazy-bound bias of the approximate butterflies)
+    u32 hi_four_m;  // (4m) >> 32
+    u32 rhi;        // floor(2^(32+sh) / m), sh = bits(m) - 1   (high-word Barrett)
+    u32 rsh;        // sh - 32
+    u32 lazy;       // 0: exact Harvey path (m < 2^62); 1: m < 2^60; 2: m < 2^55 (see ntt_core.cuh)
 };
 
 }  // namespace exb

@@ -6,8 +6,8 @@
 //             stage with m groups uses psi_rev[m + g]  (psi_rev[k] = psi^bitrev(k))
 //   inverse : Gentleman-Sande, bit-reversed in -> natural out, stage with h
 //             groups uses psi_inv_rev[h + g]; n^-1 is folded into the last stage.
-// Lazy reduction (Harvey): forward keeps values in [0, 4q), inverse in [0, 2q);
-// any prime q < 2^62 works.
+// Lazy reduction: the exact Harvey butterflies (forward [0, 4q), inverse [0, 2q)) work for
+// any prime q < 2^62; primes with head-room use cheaper approximate butterflies (LAZY 1/2).
 //
 // An n = 2^LOGN transform is done by n/16 threads; each thread keeps 16
 // coefficients in registers and runs 4 butterfly stages per pass, exchanging
@@ -51,62 +51,142 @@ EXB_HD u32 elem_index(u32 t, u32 k) {
     return (pre << (S + 4)) | (k << S) | lo;
 }
 
+// [0, 4q) -> [0, q)
+EXB_HD u64 reduce4(u64 x, u64 q, u64 q2) { return csub(csub(x, q2), q); }
+
+// ---- Lazy-bound butterfly variants ---------------------------------------------------
+// LAZY = 0 : exact Harvey butterflies above, any prime < 2^62.
+// LAZY = 1 : prime < 2^60.  Approximate Shoup quotient (T in [0,4q)), X' fused into the IMAD
+//            chain, bounds kept by a cheap high-word conditional subtract of 4q:
+//            forward values stay in [0, 8q + 2^32), inverse values in [0, 4q + 2^45).
+// LAZY = 2 : prime < 2^55 (>= 9 bits of head-room).  No conditional subtracts at all in the
+//            forward transform (values < 52q after 12 stages); the inverse lets sums double
+//            and re-centres them once with a high-word Barrett step (see inv_stage).
+struct LazyC {  // per-modulus constants kept in registers by the passes
+    u64 q, q2, neg_q, four_q;
+    u32 hi_four_q, rhi, rsh;
+};
+EXB_HD LazyC make_lazyc(const Modulus &m) {
+    LazyC c;
+    c.q = m.m; c.q2 = m.two_m; c.neg_q = m.neg_m; c.four_q = m.four_m;
+    c.hi_four_q = m.hi_four_m; c.rhi = m.rhi; c.rsh = m.rsh;
+    return c;
+}
+
+template <int LAZY>
+EXB_HD void ct_bfly_l(u64 &x, u64 &y, const Tw t, const LazyC &c) {
+    if (LAZY == 0) {
+        ct_bfly(x, y, t, c.q, c.q2);
+    } else {
+        const u64 X = LAZY == 1 ? csub_hi(x, c.four_q, c.hi_four_q) : x;
+        const u64 xn = shoup_mad4(y, t.w, t.s, c.neg_q, X);        // X + T, T in [0, 4q)
+        y = (X + X + c.four_q) - xn;                                // X - T + 4q
+        x = xn;
+    }
+}
+
+// BIAS: a multiple of q that is >= the bound of y (LAZY >= 1).
+template <int LAZY>
+EXB_HD void gs_bfly_l(u64 &x, u64 &y, const Tw t, const LazyC &c, const u64 bias) {
+    if (LAZY == 0) {
+        gs_bfly(x, y, t, c.q, c.q2);
+    } else {
+        const u64 S = x + y;
+        const u64 D = x + bias - y;
+        x = LAZY == 1 ? csub_hi(S, c.four_q, c.hi_four_q) : S;
+        y = shoup_mad4(D, t.w, t.s, c.neg_q, 0);                    // in [0, 4q)
+    }
+}
+
+// Exact canonical value of any x < 2^64 (LAZY >= 1): high-word Barrett to [0, 2q), then one csub.
+EXB_HD u64 reduce_full(u64 x, const LazyC &c) { return csub(reduce_to_2m(x, c.neg_q, c.rhi, c.rsh), c.q); }
+
 // One butterfly stage J (0..3) of a forward pass over local bits [S, S+4): global
 // stage P + J with P = LOGN-4-S.  Compile-time J keeps v[] in registers.
-template <int LOGN, int S, int J>
-EXB_HD void fwd_stage(u64 (&v)[16], const Tw *__restrict__ tw, u32 pre, u64 q, u64 q2) {
+// First 16 twiddles by value: lives in the kernel-parameter constant bank, so the pass whose
+// twiddles are the same for every thread (stages 0-3 forward, the last 4 inverse) reads them
+// as uniform operands instead of issuing loads.
+struct TwHead {
+    Tw t[16];
+    EXB_HD const Tw &operator[](u32 i) const { return t[i]; }
+};
+
+template <int LOGN, int S, int J, int LAZY, class TW>
+EXB_HD void fwd_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
     constexpr int P = LOGN - 4 - S;
     constexpr int half = 8 >> J;
 #pragma unroll
     for (int g = 0; g < (1 << J); g++) {
         const Tw w = tw[(1u << (P + J)) + (pre << J) + g];
 #pragma unroll
-        for (int u = 0; u < half; u++) ct_bfly(v[g * 2 * half + u], v[g * 2 * half + u + half], w, q, q2);
+        for (int u = 0; u < half; u++) ct_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w, c);
     }
 }
 
-template <int LOGN, int S>
-EXB_HD void fwd_pass16(u64 (&v)[16], const Tw *__restrict__ tw, u32 t, u64 q, u64 q2) {
+template <int LOGN, int S, int LAZY, class TW>
+EXB_HD void fwd_pass16(u64 (&v)[16], const TW &tw, u32 t, const LazyC &c) {
     const u32 pre = t >> S;
-    fwd_stage<LOGN, S, 0>(v, tw, pre, q, q2);
-    fwd_stage<LOGN, S, 1>(v, tw, pre, q, q2);
-    fwd_stage<LOGN, S, 2>(v, tw, pre, q, q2);
-    fwd_stage<LOGN, S, 3>(v, tw, pre, q, q2);
+    fwd_stage<LOGN, S, 0, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, 1, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, 2, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, 3, LAZY>(v, tw, pre, c);
 }
 
-// Inverse stage J of a pass over local bits [S, S+4): pairs local bit J.
-template <int LOGN, int S, int J>
-EXB_HD void inv_stage(u64 (&v)[16], const Tw *__restrict__ tw, u32 pre, u64 q, u64 q2) {
+// Final reduction of forward outputs to [0, q).
+template <int LAZY>
+EXB_HD u64 fwd_final(u64 x, const LazyC &c) { return LAZY == 0 ? reduce4(x, c.q, c.q2) : reduce_full(x, c); }
+
+// Inverse stage J of a pass over local bits [S, S+4): pairs local bit J; global stage index
+// GS = S + J (0 .. LOGN-1).  For LAZY == 2 the sum outputs double every stage; they are
+// re-centred to [0, 2q) after global stage kRecentre, so every stage's bound is 4q << r with
+// r = stages since the last re-centre (inputs of the transform must be < 4q).
+constexpr int kRecentre = 5;
+template <int LOGN, int S, int J, int LAZY, class TW>
+EXB_HD void inv_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
     constexpr int P = LOGN - 4 - S;
     constexpr int half = 1 << J;
+    constexpr int GSI = S + J;
+    constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
+    const u64 bias = LAZY == 2 ? (c.four_q << r) : (c.four_q << 1);
 #pragma unroll
     for (int g = 0; g < (8 >> J); g++) {
         const Tw w = tw[(1u << (P + 3 - J)) + (pre << (3 - J)) + g];
 #pragma unroll
-        for (int u = 0; u < half; u++) gs_bfly(v[g * 2 * half + u], v[g * 2 * half + u + half], w, q, q2);
+        for (int u = 0; u < half; u++) {
+            gs_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w, c, bias);
+            if (LAZY == 2 && GSI == kRecentre)
+                v[g * 2 * half + u] = reduce_to_2m(v[g * 2 * half + u], c.neg_q, c.rhi, c.rsh);
+        }
     }
 }
 
 // Inverse pass.  If LAST, the final stage (global h = 1) multiplies by n^-1 (x side)
 // and n^-1 * psi_inv_rev[1] (y side) instead: plan.normalize folded in.
-template <int LOGN, int S, bool LAST>
-EXB_HD void inv_pass16(u64 (&v)[16], const Tw *__restrict__ tw, u32 t, const Modulus &mod) {
-    const u64 q = mod.m, q2 = mod.two_m;
+template <int LOGN, int S, bool LAST, int LAZY, class TW>
+EXB_HD void inv_pass16(u64 (&v)[16], const TW &tw, u32 t, const Modulus &mod, const LazyC &c) {
     const u32 pre = t >> S;
-    inv_stage<LOGN, S, 0>(v, tw, pre, q, q2);
-    inv_stage<LOGN, S, 1>(v, tw, pre, q, q2);
-    inv_stage<LOGN, S, 2>(v, tw, pre, q, q2);
+    inv_stage<LOGN, S, 0, LAZY>(v, tw, pre, c);
+    inv_stage<LOGN, S, 1, LAZY>(v, tw, pre, c);
+    inv_stage<LOGN, S, 2, LAZY>(v, tw, pre, c);
     if constexpr (LAST) {
         const u64 ni = mod.ninv, nis = mod.ninv_s, nw = mod.ninv_w, nws = mod.ninv_w_s;
+        constexpr int GSI = S + 3;
+        constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
+        const u64 bias = LAZY == 0 ? c.q2 : (LAZY == 2 ? (c.four_q << r) : (c.four_q << 1));
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const u64 S2 = v[u] + v[u + 8];        // < 4q, Shoup takes any u64
-            const u64 D = v[u] - v[u + 8] + q2;
-            v[u] = shoup_lazy(S2, ni, nis, q);
-            v[u + 8] = shoup_lazy(D, nw, nws, q);
+            const u64 S2 = v[u] + v[u + 8];        // Shoup takes any u64
+            const u64 D = v[u] + bias - v[u + 8];
+            if (LAZY == 0) {
+                v[u] = csub(shoup_lazy(S2, ni, nis, c.q), c.q);
+                v[u + 8] = csub(shoup_lazy(D, nw, nws, c.q), c.q);
+            } else {                                // [0, 4q) -> [0, q)
+                v[u] = reduce4(shoup_mad4(S2, ni, nis, c.neg_q, 0), c.q, c.q2);
+                v[u + 8] = reduce4(shoup_mad4(D, nw, nws, c.neg_q, 0), c.q, c.q2);
+            }
         }
     } else {
-        inv_stage<LOGN, S, 3>(v, tw, pre, q, q2);
+        inv_stage<LOGN, S, 3, LAZY>(v, tw, pre, c);
     }
 }
 
@@ -124,8 +204,5 @@ EXB_HD void store16(const u64 (&v)[16], u64 *sm, u32 t) {
 #pragma unroll
     for (int k = 0; k < 16; k++) sm[swz(elem_index<S>(t, k))] = v[k];
 }
-
-// [0, 4q) -> [0, q)
-EXB_HD u64 reduce4(u64 x, u64 q, u64 q2) { return csub(csub(x, q2), q); }
 
 }  // namespace exb

@@ -27,6 +27,7 @@
 #define __align__(x) alignas(x)
 
 struct emu_dim3 { unsigned x, y, z; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
 static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 static thread_local void *emu_smem_ptr;
 static pthread_barrier_t *emu_barrier;
@@ -113,8 +114,14 @@ int emu_ntt(emu_ctx *c, uint32_t base, int forward, const uint64_t *in, uint64_t
     const unsigned thr = emu_block_threads(P);
     const size_t sm = (size_t)P.n * 8;
     if (P.logn == 12) {
-        if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<12>(in, out, P.twf[base], P.mod[base], P.logn); });
-        else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<12>(in, out, P.twi[base], P.mod[base], P.logn); });
+        // persistent fast path: few "CTAs" so every block loops over several polynomials
+        const unsigned grid = count < 3 ? (unsigned)count : 3u;
+        const Modulus &m = P.mod[base];
+        const u32 cnt = (u32)count;
+#define EMU_NTT12(FWD, LZ) emu_launch(grid, 256, 2 * sm, [&]() { ntt12_persist_kernel<FWD, LZ>(in, out, FWD ? P.twf[base] : P.twi[base], FWD ? P.headf[base] : P.headi[base], m, cnt); })
+        if (forward) { if (m.lazy == 2) EMU_NTT12(true, 2); else if (m.lazy == 1) EMU_NTT12(true, 1); else EMU_NTT12(true, 0); }
+        else { if (m.lazy == 2) EMU_NTT12(false, 2); else if (m.lazy == 1) EMU_NTT12(false, 1); else EMU_NTT12(false, 0); }
+#undef EMU_NTT12
     } else {
         if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<0>(in, out, P.twf[base], P.mod[base], P.logn); });
         else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<0>(in, out, P.twi[base], P.mod[base], P.logn); });
