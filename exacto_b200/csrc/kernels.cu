@@ -49,56 +49,81 @@ struct Lay<12> {
     static __device__ __forceinline__ u32 at(u32 e) { return swz(e); }
 };
 
-template <int LAZY>
-__device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod) {
-    const LazyC c = make_lazyc(mod);
-    const u32 t = threadIdx.x;
-    u64 v[16];
-    __syncthreads();
-    load16<8>(v, sm, t);
-    fwd_pass16<12, 8, LAZY>(v, tw, t, c);
-    store16<8>(v, sm, t);
-    __syncthreads();
-    load16<4>(v, sm, t);
-    fwd_pass16<12, 4, LAZY>(v, tw, t, c);
-    store16<4>(v, sm, t);
-    __syncthreads();
-    load16<0>(v, sm, t);
-    fwd_pass16<12, 0, LAZY>(v, tw, t, c);
+// n = 4096 transforms on the swizzled image by 4096 >> NB threads (NB = 3: 512 threads x 8
+// values, four 3-stage passes; NB = 4: 256 threads x 16 values, three 4-stage passes).
+// The first forward / last inverse pass takes its (thread-uniform) twiddles from `head`.
+constexpr int kNB = 3;                       // values-per-thread exponent used by the fused kernels
+constexpr int kThreads12 = 4096 >> kNB;
+
+template <int NB, int LAZY>
+__device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head,
+                                           const LazyC &c, const u32 t) {
+    u64 v[1 << NB];
+    if constexpr (NB == 4) {
+        load_vals<4, 8>(v, sm, t); fwd_pass<12, 8, 4, LAZY>(v, head, t, c); store_vals<4, 8>(v, sm, t);
+        __syncthreads();
+        load_vals<4, 4>(v, sm, t); fwd_pass<12, 4, 4, LAZY>(v, tw, t, c); store_vals<4, 4>(v, sm, t);
+        __syncthreads();
+        load_vals<4, 0>(v, sm, t); fwd_pass<12, 0, 4, LAZY>(v, tw, t, c);
+    } else {
+        load_vals<3, 9>(v, sm, t); fwd_pass<12, 9, 3, LAZY>(v, head, t, c); store_vals<3, 9>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 6>(v, sm, t); fwd_pass<12, 6, 3, LAZY>(v, tw, t, c); store_vals<3, 6>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 3>(v, sm, t); fwd_pass<12, 3, 3, LAZY>(v, tw, t, c); store_vals<3, 3>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 0>(v, sm, t); fwd_pass<12, 0, 3, LAZY>(v, tw, t, c);
+    }
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
-    store16<0>(v, sm, t);
-    __syncthreads();
+    for (int k = 0; k < (1 << NB); k++) v[k] = fwd_final<LAZY>(v[k], c);
+    store_vals<NB, 0>(v, sm, t);
 }
 
-// Inputs < 4q (LAZY >= 1) or < 2q (LAZY == 0).
+// Inputs < 4q (LAZY >= 1) or < 2q (LAZY == 0); outputs canonical.
+template <int NB, int LAZY>
+__device__ __forceinline__ void inv_body12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head,
+                                           const Modulus &mod, const LazyC &c, const u32 t) {
+    u64 v[1 << NB];
+    if constexpr (NB == 4) {
+        load_vals<4, 0>(v, sm, t); inv_pass<12, 0, 4, false, LAZY>(v, tw, t, mod, c); store_vals<4, 0>(v, sm, t);
+        __syncthreads();
+        load_vals<4, 4>(v, sm, t); inv_pass<12, 4, 4, false, LAZY>(v, tw, t, mod, c); store_vals<4, 4>(v, sm, t);
+        __syncthreads();
+        load_vals<4, 8>(v, sm, t); inv_pass<12, 8, 4, true, LAZY>(v, head, t, mod, c); store_vals<4, 8>(v, sm, t);
+    } else {
+        load_vals<3, 0>(v, sm, t); inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 0>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 3>(v, sm, t); inv_pass<12, 3, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 3>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 6>(v, sm, t); inv_pass<12, 6, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 6>(v, sm, t);
+        __syncthreads();
+        load_vals<3, 9>(v, sm, t); inv_pass<12, 9, 3, true, LAZY>(v, head, t, mod, c); store_vals<3, 9>(v, sm, t);
+    }
+}
+
 template <int LAZY>
-__device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod) {
+__device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
     const LazyC c = make_lazyc(mod);
-    const u32 t = threadIdx.x;
-    u64 v[16];
     __syncthreads();
-    load16<0>(v, sm, t);
-    inv_pass16<12, 0, false, LAZY>(v, tw, t, mod, c);
-    store16<0>(v, sm, t);
+    fwd_body12<kNB, LAZY>(sm, tw, head, c, threadIdx.x);
     __syncthreads();
-    load16<4>(v, sm, t);
-    inv_pass16<12, 4, false, LAZY>(v, tw, t, mod, c);
-    store16<4>(v, sm, t);
+}
+template <int LAZY>
+__device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
+    const LazyC c = make_lazyc(mod);
     __syncthreads();
-    load16<8>(v, sm, t);
-    inv_pass16<12, 8, true, LAZY>(v, tw, t, mod, c);
-    store16<8>(v, sm, t);
+    inv_body12<kNB, LAZY>(sm, tw, head, mod, c, threadIdx.x);
     __syncthreads();
 }
 
 template <int LOGN>
-__device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
+__device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
+                                       u32 logn) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        if (mod.lazy == 2) fwd_sm12<2>(sm, tw, mod);
-        else if (mod.lazy == 1) fwd_sm12<1>(sm, tw, mod);
-        else fwd_sm12<0>(sm, tw, mod);
+        if (mod.lazy == 2) fwd_sm12<2>(sm, tw, head, mod);
+        else if (mod.lazy == 1) fwd_sm12<1>(sm, tw, head, mod);
+        else fwd_sm12<0>(sm, tw, head, mod);
     } else {
         const u32 n = 1u << logn;
         u32 len = n;
@@ -119,12 +144,13 @@ __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const
 
 // Inputs in [0, 2q).
 template <int LOGN>
-__device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const Modulus &mod, u32 logn) {
+__device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
+                                       u32 logn) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        if (mod.lazy == 2) inv_sm12<2>(sm, tw, mod);
-        else if (mod.lazy == 1) inv_sm12<1>(sm, tw, mod);
-        else inv_sm12<0>(sm, tw, mod);
+        if (mod.lazy == 2) inv_sm12<2>(sm, tw, head, mod);
+        else if (mod.lazy == 1) inv_sm12<1>(sm, tw, head, mod);
+        else inv_sm12<0>(sm, tw, head, mod);
     } else {
         const u32 n = 1u << logn;
         u32 len = 1;
@@ -154,28 +180,28 @@ __device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const
 // K1 / K2: batched standalone transforms, one polynomial per CTA.
 // ---------------------------------------------------------------------------------
 template <int LOGN>
-__global__ void __launch_bounds__(256)
-ntt_fwd_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw, Modulus mod,
-               u32 logn) {
+__global__ void __launch_bounds__(512)
+ntt_fwd_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw,
+               const __grid_constant__ TwHead head, const __grid_constant__ Modulus mod, u32 logn) {
     EXB_DYN_SMEM(smem);
     const u32 n = 1u << logn;
     const u64 *src = in + (size_t)blockIdx.x * n;
     u64 *dst = out + (size_t)blockIdx.x * n;
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = ld_stream(src + e);
-    fwd_sm<LOGN>(smem, tw, mod, logn);
+    fwd_sm<LOGN>(smem, tw, head, mod, logn);
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(256)
-ntt_inv_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw, Modulus mod,
-               u32 logn) {
+__global__ void __launch_bounds__(512)
+ntt_inv_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const Tw *__restrict__ tw,
+               const __grid_constant__ TwHead head, const __grid_constant__ Modulus mod, u32 logn) {
     EXB_DYN_SMEM(smem);
     const u32 n = 1u << logn;
     const u64 *src = in + (size_t)blockIdx.x * n;
     u64 *dst = out + (size_t)blockIdx.x * n;
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) smem[Lay<LOGN>::at(e)] = ld_stream(src + e);
-    inv_sm<LOGN>(smem, tw, mod, logn);
+    inv_sm<LOGN>(smem, tw, head, mod, logn);
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = smem[Lay<LOGN>::at(e)];
 }
 
@@ -208,98 +234,54 @@ __device__ __forceinline__ void cp_async_wait() {
 // 16-byte chunk c of a polynomial (elements 2c, 2c+1) lives at chunk swz16(c) of the image.
 __device__ __forceinline__ u32 swz16(u32 c) { return c ^ ((c >> 3) & 7u); }
 
+template <int THREADS>
 __device__ __forceinline__ void prefetch_poly(u64 *buf, const u64 *src) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const u32 c = i * 256 + threadIdx.x;
+    for (int i = 0; i < 2048 / THREADS; i++) {
+        const u32 c = i * THREADS + threadIdx.x;
         cp_async16(buf + 2 * swz16(c), src + 2 * c);
     }
 }
 
+template <int THREADS>
 __device__ __forceinline__ void store_poly(u64 *dst, const u64 *buf) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const u32 c = i * 256 + threadIdx.x;
+    for (int i = 0; i < 2048 / THREADS; i++) {
+        const u32 c = i * THREADS + threadIdx.x;
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(buf + 2 * swz16(c));
         *reinterpret_cast<ulonglong2 *>(dst + 2 * c) = v;
     }
 }
 
-// DBG (lab only, selected by env EXB_NTT_DBG): 1 = copy only, 2 = all twiddles from the constant
-// bank (wrong results, isolates twiddle-load cost), 3 = skip the per-thread-twiddle pass.
-struct TwHeadWrap {
-    const TwHead &h;
-    __device__ __forceinline__ const Tw &operator[](u32 i) const { return h.t[i & 15u]; }
-};
-
-template <bool FWD, int LAZY, int DBG = 0>
-__global__ void __launch_bounds__(256, 2)
+// NB = 3: 512 threads x 8 values (<= 64 registers, 2 CTAs = 32 warps per SM);
+// NB = 4: 256 threads x 16 values.  DBG = 1 (lab, env EXB_NTT_DBG): copy only.
+template <bool FWD, int LAZY, int NB, int DBG = 0>
+__global__ void __launch_bounds__(4096 >> NB, NB == 3 ? 2 : 2)
 ntt12_persist_kernel(const u64 *in, u64 *out, const Tw *__restrict__ tw, const __grid_constant__ TwHead head,
                      const __grid_constant__ Modulus mod, u32 count) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
+    constexpr int THREADS = 4096 >> NB;
     const LazyC c = make_lazyc(mod);
     const u32 t = threadIdx.x;
     u32 poly = blockIdx.x;
     if (poly >= count) return;
     u32 cur = 0;
-    prefetch_poly(smem, in + (size_t)poly * n);
+    prefetch_poly<THREADS>(smem, in + (size_t)poly * n);
     cp_async_commit();
     for (; poly < count; poly += gridDim.x) {
         u64 *buf = smem + cur * n;
         const u32 next = poly + gridDim.x;
-        if (next < count) prefetch_poly(smem + (cur ^ 1) * n, in + (size_t)next * n);
+        if (next < count) prefetch_poly<THREADS>(smem + (cur ^ 1) * n, in + (size_t)next * n);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        u64 v[16];
-        if (DBG == 1) {
-        } else if (DBG == 2 && FWD) {
-            const TwHeadWrap hw{head};
-            load16<8>(v, buf, t);
-            fwd_pass16<12, 8, LAZY>(v, head, t, c);
-            store16<8>(v, buf, t);
-            __syncthreads();
-            load16<4>(v, buf, t);
-            fwd_pass16<12, 4, LAZY>(v, hw, t, c);
-            store16<4>(v, buf, t);
-            __syncthreads();
-            load16<0>(v, buf, t);
-            fwd_pass16<12, 0, LAZY>(v, hw, t, c);
-#pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
-            store16<0>(v, buf, t);
-        } else if (FWD) {
-            load16<8>(v, buf, t);
-            fwd_pass16<12, 8, LAZY>(v, head, t, c);
-            store16<8>(v, buf, t);
-            __syncthreads();
-            load16<4>(v, buf, t);
-            fwd_pass16<12, 4, LAZY>(v, tw, t, c);
-            store16<4>(v, buf, t);
-            __syncthreads();
-            if (DBG != 3) {
-            load16<0>(v, buf, t);
-            fwd_pass16<12, 0, LAZY>(v, tw, t, c);
-#pragma unroll
-            for (int k = 0; k < 16; k++) v[k] = fwd_final<LAZY>(v[k], c);
-            store16<0>(v, buf, t);
-            }
-        } else {
-            load16<0>(v, buf, t);
-            inv_pass16<12, 0, false, LAZY>(v, tw, t, mod, c);
-            store16<0>(v, buf, t);
-            __syncthreads();
-            load16<4>(v, buf, t);
-            inv_pass16<12, 4, false, LAZY>(v, tw, t, mod, c);
-            store16<4>(v, buf, t);
-            __syncthreads();
-            load16<8>(v, buf, t);
-            inv_pass16<12, 8, true, LAZY>(v, head, t, mod, c);
-            store16<8>(v, buf, t);
+        if (DBG != 1) {
+            if (FWD) fwd_body12<NB, LAZY>(buf, tw, head, c, t);
+            else inv_body12<NB, LAZY>(buf, tw, head, mod, c, t);
         }
         __syncthreads();
-        store_poly(out + (size_t)poly * n, buf);
+        store_poly<THREADS>(out + (size_t)poly * n, buf);
         __syncthreads();      // buf is the prefetch target of the next iteration
         cur ^= 1;
     }
@@ -343,7 +325,7 @@ __global__ void poly_op_kernel(Modulus mod, int op, const u64 *__restrict__ a, c
 // ext layout: [pair][side][limb][comp][1+A][n]; slot 0 of side 0 is unused.
 // ---------------------------------------------------------------------------------
 template <int LOGN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
 lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
             const u64 *__restrict__ ct2, u64 *__restrict__ ext) {
     EXB_DYN_SMEM(smem);
@@ -363,13 +345,13 @@ lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict
         coef[Lay<LOGN>::at(e)] = x;
         if (side) dst[e] = shoup(x, mq.r_mod, mq.r_mod_s, mq.m);
     }
-    inv_sm<LOGN>(coef, P.twi[0], mq, P.logn);
+    inv_sm<LOGN>(coef, P.twi[0], P.headi[0], mq, P.logn);
     for (u32 j = 0; j < A; j++) {
         const Modulus &mp = P.mod[1 + j];
         for (u32 e = threadIdx.x; e < n; e += blockDim.x)
             work[Lay<LOGN>::at(e)] =
                 ext_centered(coef[Lay<LOGN>::at(e)], mq.m, P.sc.half_q, mp.m, mp.mu);
-        fwd_sm<LOGN>(work, P.twf[1 + j], mp, P.logn);
+        fwd_sm<LOGN>(work, P.twf[1 + j], P.headf[1 + j], mp, P.logn);
         u64 *o = dst + (size_t)(1 + j) * n;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
             u64 x = work[Lay<LOGN>::at(e)];
@@ -386,7 +368,7 @@ lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict
 // component 2 leaves its balanced gadget digits.
 // ---------------------------------------------------------------------------------
 template <int LOGN, typename DigT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
 tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
               const u64 *__restrict__ ct1, const u64 *__restrict__ ext, u64 *__restrict__ r01,
               DigT *__restrict__ digits) {
@@ -419,7 +401,7 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
             else v = mont_mul2_lazy(l0[e], r1[e], l1[e], r0[e], mb.m, mb.minv_neg);
             buf[Lay<LOGN>::at(e)] = v;
         }
-        inv_sm<LOGN>(buf, P.twi[b], mb, P.logn);
+        inv_sm<LOGN>(buf, P.twi[b], P.headi[b], mb, P.logn);
     }
 
     const u64 *ba = smem, *b0 = smem + n, *b1 = smem + 2 * (size_t)n;
@@ -453,7 +435,7 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
 // per-product relinearize followed by bfv_add (dbfv/eval.rs:125-132).
 // ---------------------------------------------------------------------------------
 template <int LOGN, typename DigT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
 relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
              const u64 *__restrict__ r01, const DigT *__restrict__ digits,
              const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess) {
@@ -476,7 +458,7 @@ relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mul
             }
             work[Lay<LOGN>::at(e)] = s;
         }
-        fwd_sm<LOGN>(work, P.twf[0], mq, P.logn);
+        fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
         u64 *acc = comp ? acc1 : acc0;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) acc[e] = work[Lay<LOGN>::at(e)];
     }
@@ -493,7 +475,7 @@ relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mul
             else { const u64 r = mag % q; v = (s < 0 && r) ? q - r : r; }
             work[Lay<LOGN>::at(e)] = v;
         }
-        fwd_sm<LOGN>(work, P.twf[0], mq, P.logn);
+        fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
         const u64 *k0 = rlk_mont + ((size_t)g * 2) * n, *k1 = k0 + n;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
             const u64 x = work[Lay<LOGN>::at(e)];
@@ -532,7 +514,7 @@ __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const
 constexpr int kNumSMs = 148;   // B200
 
 static inline u32 block_threads(const DeviceParams &P) {
-    if (P.logn == 12) return 256;
+    if (P.logn == 12) return kThreads12;
     u32 t = P.n / 2;
     if (t < 32) t = 32;
     if (t > 256) t = 256;
@@ -544,18 +526,26 @@ static void set_smem(K kernel, size_t bytes) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-template <bool FWD, int LAZY>
-static void launch_ntt12_l(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+template <bool FWD, int LAZY, int NB>
+static void launch_ntt12_nb(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
     const size_t sm = 2 * 4096 * 8;
     const unsigned grid = (unsigned)(count < (size_t)kNumSMs * 2 ? count : (size_t)kNumSMs * 2);
     static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;
     const Tw *tw = FWD ? P.twf[base] : P.twi[base];
     const TwHead &head = FWD ? P.headf[base] : P.headi[base];
-    if (dbg == 1) { set_smem(ntt12_persist_kernel<FWD, LAZY, 1>, sm); ntt12_persist_kernel<FWD, LAZY, 1><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
-    if (dbg == 2) { set_smem(ntt12_persist_kernel<FWD, LAZY, 2>, sm); ntt12_persist_kernel<FWD, LAZY, 2><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
-    if (dbg == 3) { set_smem(ntt12_persist_kernel<FWD, LAZY, 3>, sm); ntt12_persist_kernel<FWD, LAZY, 3><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count); return; }
-    set_smem(ntt12_persist_kernel<FWD, LAZY>, sm);
-    ntt12_persist_kernel<FWD, LAZY><<<grid, 256, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+    if (dbg == 1) {
+        set_smem(ntt12_persist_kernel<FWD, LAZY, NB, 1>, sm);
+        ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+        return;
+    }
+    set_smem(ntt12_persist_kernel<FWD, LAZY, NB>, sm);
+    ntt12_persist_kernel<FWD, LAZY, NB><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+}
+template <bool FWD, int LAZY>
+static void launch_ntt12_l(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    static const int nb = getenv("EXB_NTT_NB") ? atoi(getenv("EXB_NTT_NB")) : kNB;   // lab switch
+    if (nb == 4) launch_ntt12_nb<FWD, LAZY, 4>(P, base, in, out, count, s);
+    else launch_ntt12_nb<FWD, LAZY, 3>(P, base, in, out, count, s);
 }
 template <bool FWD>
 static void launch_ntt12(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
@@ -572,7 +562,7 @@ void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, si
         launch_ntt12<true>(P, base, in, out, count, s);
     } else {
         set_smem(ntt_fwd_kernel<0>, sm);
-        ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.mod[base], P.logn);
+        ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.headf[base], P.mod[base], P.logn);
     }
     g_launch_count++;
 }
@@ -584,7 +574,7 @@ void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, si
         launch_ntt12<false>(P, base, in, out, count, s);
     } else {
         set_smem(ntt_inv_kernel<0>, sm);
-        ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.mod[base], P.logn);
+        ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.headi[base], P.mod[base], P.logn);
     }
     g_launch_count++;
 }
@@ -605,7 +595,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
     const unsigned grid = (unsigned)(pairs * 4 * M.d);
     if (P.logn == 12) {
         set_smem(lift_kernel<12>, sm);
-        lift_kernel<12><<<grid, 256, sm, s>>>(P, M.d, ct1, ct2, ext);
+        lift_kernel<12><<<grid, kThreads12, sm, s>>>(P, M.d, ct1, ct2, ext);
     } else {
         set_smem(lift_kernel<0>, sm);
         lift_kernel<0><<<grid, block_threads(P), sm, s>>>(P, M.d, ct1, ct2, ext);
@@ -620,7 +610,7 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
     if (P.logn == 12) {
         set_smem(tensor_kernel<12, DigT>, sm);
-        tensor_kernel<12, DigT><<<grid, 256, sm, s>>>(P, M, ct1, ext, r01, digits);
+        tensor_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, ct1, ext, r01, digits);
     } else {
         set_smem(tensor_kernel<0, DigT>, sm);
         tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits);
@@ -642,7 +632,7 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     const unsigned grid = (unsigned)(pairs * M.num_limbs);
     if (P.logn == 12) {
         set_smem(relin_kernel<12, DigT>, sm);
-        relin_kernel<12, DigT><<<grid, 256, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+        relin_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
     } else {
         set_smem(relin_kernel<0, DigT>, sm);
         relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);

@@ -42,13 +42,13 @@ EXB_HD void gs_bfly(u64 &x, u64 &y, const Tw t, const u64 q, const u64 q2) {
     y = shoup_lazy(D, t.w, t.s, q);
 }
 
-// Element owned by thread `t` at local index k of the pass whose 4 local bits sit
-// at bit position S of the coefficient index.
-template <int S>
+// Element owned by thread `t` at local index k of the pass whose NB local bits sit at bit
+// position S of the coefficient index (a pass = NB butterfly stages on 2^NB register values).
+template <int NB, int S>
 EXB_HD u32 elem_index(u32 t, u32 k) {
     const u32 lo = t & ((1u << S) - 1u);
     const u32 pre = t >> S;
-    return (pre << (S + 4)) | (k << S) | lo;
+    return (pre << (S + NB)) | (k << S) | lo;
 }
 
 // [0, 4q) -> [0, q)
@@ -104,17 +104,19 @@ EXB_HD u64 reduce_full(u64 x, const LazyC &c) { return csub(reduce_to_2m(x, c.ne
 // One butterfly stage J (0..3) of a forward pass over local bits [S, S+4): global
 // stage P + J with P = LOGN-4-S.  Compile-time J keeps v[] in registers.
 // First 16 twiddles by value: lives in the kernel-parameter constant bank, so the pass whose
-// twiddles are the same for every thread (stages 0-3 forward, the last 4 inverse) reads them
+// twiddles are the same for every thread (the first forward / last inverse pass) reads them
 // as uniform operands instead of issuing loads.
 struct TwHead {
     Tw t[16];
     EXB_HD const Tw &operator[](u32 i) const { return t[i]; }
 };
 
-template <int LOGN, int S, int J, int LAZY, class TW>
-EXB_HD void fwd_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
-    constexpr int P = LOGN - 4 - S;
-    constexpr int half = 8 >> J;
+// One butterfly stage J (0..NB-1) of a forward pass over local bits [S, S+NB): global stage
+// P + J with P = LOGN-NB-S.  Compile-time J keeps v[] in registers.
+template <int LOGN, int S, int NB, int J, int LAZY, class TW>
+EXB_HD void fwd_stage(u64 (&v)[1 << NB], const TW &tw, u32 pre, const LazyC &c) {
+    constexpr int P = LOGN - NB - S;
+    constexpr int half = (1 << NB) >> (J + 1);
 #pragma unroll
     for (int g = 0; g < (1 << J); g++) {
         const Tw w = tw[(1u << (P + J)) + (pre << J) + g];
@@ -123,34 +125,34 @@ EXB_HD void fwd_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
     }
 }
 
-template <int LOGN, int S, int LAZY, class TW>
-EXB_HD void fwd_pass16(u64 (&v)[16], const TW &tw, u32 t, const LazyC &c) {
+template <int LOGN, int S, int NB, int LAZY, class TW>
+EXB_HD void fwd_pass(u64 (&v)[1 << NB], const TW &tw, u32 t, const LazyC &c) {
     const u32 pre = t >> S;
-    fwd_stage<LOGN, S, 0, LAZY>(v, tw, pre, c);
-    fwd_stage<LOGN, S, 1, LAZY>(v, tw, pre, c);
-    fwd_stage<LOGN, S, 2, LAZY>(v, tw, pre, c);
-    fwd_stage<LOGN, S, 3, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, NB, 0, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, NB, 1, LAZY>(v, tw, pre, c);
+    fwd_stage<LOGN, S, NB, 2, LAZY>(v, tw, pre, c);
+    if constexpr (NB >= 4) fwd_stage<LOGN, S, NB, 3, LAZY>(v, tw, pre, c);
 }
 
 // Final reduction of forward outputs to [0, q).
 template <int LAZY>
 EXB_HD u64 fwd_final(u64 x, const LazyC &c) { return LAZY == 0 ? reduce4(x, c.q, c.q2) : reduce_full(x, c); }
 
-// Inverse stage J of a pass over local bits [S, S+4): pairs local bit J; global stage index
-// GS = S + J (0 .. LOGN-1).  For LAZY == 2 the sum outputs double every stage; they are
+// Inverse stage J of a pass over local bits [S, S+NB): pairs local bit J; global stage index
+// GSI = S + J (0 .. LOGN-1).  For LAZY == 2 the sum outputs double every stage; they are
 // re-centred to [0, 2q) after global stage kRecentre, so every stage's bound is 4q << r with
 // r = stages since the last re-centre (inputs of the transform must be < 4q).
 constexpr int kRecentre = 5;
-template <int LOGN, int S, int J, int LAZY, class TW>
-EXB_HD void inv_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
-    constexpr int P = LOGN - 4 - S;
+template <int LOGN, int S, int NB, int J, int LAZY, class TW>
+EXB_HD void inv_stage(u64 (&v)[1 << NB], const TW &tw, u32 pre, const LazyC &c) {
+    constexpr int P = LOGN - NB - S;
     constexpr int half = 1 << J;
     constexpr int GSI = S + J;
     constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
     const u64 bias = LAZY == 2 ? (c.four_q << r) : (c.four_q << 1);
 #pragma unroll
-    for (int g = 0; g < (8 >> J); g++) {
-        const Tw w = tw[(1u << (P + 3 - J)) + (pre << (3 - J)) + g];
+    for (int g = 0; g < ((1 << NB) >> (J + 1)); g++) {
+        const Tw w = tw[(1u << (P + NB - 1 - J)) + (pre << (NB - 1 - J)) + g];
 #pragma unroll
         for (int u = 0; u < half; u++) {
             gs_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w, c, bias);
@@ -160,49 +162,70 @@ EXB_HD void inv_stage(u64 (&v)[16], const TW &tw, u32 pre, const LazyC &c) {
     }
 }
 
-// Inverse pass.  If LAST, the final stage (global h = 1) multiplies by n^-1 (x side)
-// and n^-1 * psi_inv_rev[1] (y side) instead: plan.normalize folded in.
-template <int LOGN, int S, bool LAST, int LAZY, class TW>
-EXB_HD void inv_pass16(u64 (&v)[16], const TW &tw, u32 t, const Modulus &mod, const LazyC &c) {
-    const u32 pre = t >> S;
-    inv_stage<LOGN, S, 0, LAZY>(v, tw, pre, c);
-    inv_stage<LOGN, S, 1, LAZY>(v, tw, pre, c);
-    inv_stage<LOGN, S, 2, LAZY>(v, tw, pre, c);
-    if constexpr (LAST) {
-        const u64 ni = mod.ninv, nis = mod.ninv_s, nw = mod.ninv_w, nws = mod.ninv_w_s;
-        constexpr int GSI = S + 3;
-        constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
-        const u64 bias = LAZY == 0 ? c.q2 : (LAZY == 2 ? (c.four_q << r) : (c.four_q << 1));
+// Last inverse stage (global h = 1): multiplies by n^-1 (x side) and n^-1 * psi_inv_rev[1]
+// (y side) instead of the twiddle: plan.normalize (ring/ntt.rs:62) folded in.  Outputs canonical.
+template <int LOGN, int NB, int LAZY>
+EXB_HD void inv_last_stage(u64 (&v)[1 << NB], const Modulus &mod, const LazyC &c) {
+    const u64 ni = mod.ninv, nis = mod.ninv_s, nw = mod.ninv_w, nws = mod.ninv_w_s;
+    constexpr int GSI = LOGN - 1;
+    constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
+    constexpr int H = (1 << NB) / 2;
+    const u64 bias = LAZY == 0 ? c.q2 : (LAZY == 2 ? (c.four_q << r) : (c.four_q << 1));
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const u64 S2 = v[u] + v[u + 8];        // Shoup takes any u64
-            const u64 D = v[u] + bias - v[u + 8];
-            if (LAZY == 0) {
-                v[u] = csub(shoup_lazy(S2, ni, nis, c.q), c.q);
-                v[u + 8] = csub(shoup_lazy(D, nw, nws, c.q), c.q);
-            } else {                                // [0, 4q) -> [0, q)
-                v[u] = reduce4(shoup_mad4(S2, ni, nis, c.neg_q, 0), c.q, c.q2);
-                v[u + 8] = reduce4(shoup_mad4(D, nw, nws, c.neg_q, 0), c.q, c.q2);
-            }
+    for (int u = 0; u < H; u++) {
+        const u64 S2 = v[u] + v[u + H];        // Shoup takes any u64
+        const u64 D = v[u] + bias - v[u + H];
+        if (LAZY == 0) {
+            v[u] = csub(shoup_lazy(S2, ni, nis, c.q), c.q);
+            v[u + H] = csub(shoup_lazy(D, nw, nws, c.q), c.q);
+        } else {                                // [0, 4q) -> [0, q)
+            v[u] = reduce4(shoup_mad4(S2, ni, nis, c.neg_q, 0), c.q, c.q2);
+            v[u + H] = reduce4(shoup_mad4(D, nw, nws, c.neg_q, 0), c.q, c.q2);
         }
-    } else {
-        inv_stage<LOGN, S, 3, LAZY>(v, tw, pre, c);
     }
 }
 
-// ---- whole-transform helpers on a swizzled shared-memory image ------------------
-// `sm` holds n = 2^LOGN coefficients at swz(e).  These are the per-thread bodies;
-// the caller provides the barriers between passes.
-
-template <int S>
-EXB_HD void load16(u64 (&v)[16], const u64 *sm, u32 t) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = sm[swz(elem_index<S>(t, k))];
+// Inverse pass; LAST = the pass that contains global stage LOGN-1 (S + NB == LOGN).
+template <int LOGN, int S, int NB, bool LAST, int LAZY, class TW>
+EXB_HD void inv_pass(u64 (&v)[1 << NB], const TW &tw, u32 t, const Modulus &mod, const LazyC &c) {
+    const u32 pre = t >> S;
+    inv_stage<LOGN, S, NB, 0, LAZY>(v, tw, pre, c);
+    inv_stage<LOGN, S, NB, 1, LAZY>(v, tw, pre, c);
+    if constexpr (NB >= 4) inv_stage<LOGN, S, NB, 2, LAZY>(v, tw, pre, c);
+    if constexpr (LAST) inv_last_stage<LOGN, NB, LAZY>(v, mod, c);
+    else inv_stage<LOGN, S, NB, NB - 1, LAZY>(v, tw, pre, c);
 }
-template <int S>
-EXB_HD void store16(const u64 (&v)[16], u64 *sm, u32 t) {
+
+// ---- register <-> swizzled shared-memory image -----------------------------------------
+// `sm` holds n coefficients at swz(e).  The S = 0 pass owns 2^NB consecutive coefficients per
+// thread and moves them as 128-bit words (swz keeps 16-byte pairs together and conflict-free).
+template <int NB, int S>
+EXB_HD void load_vals(u64 (&v)[1 << NB], const u64 *sm, u32 t) {
+    if constexpr (S == 0) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) sm[swz(elem_index<S>(t, k))] = v[k];
+        for (int k = 0; k < (1 << NB); k += 2) {
+            const u64 *p = sm + swz(elem_index<NB, 0>(t, k));
+            v[k] = p[0];
+            v[k + 1] = p[1];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < (1 << NB); k++) v[k] = sm[swz(elem_index<NB, S>(t, k))];
+    }
+}
+template <int NB, int S>
+EXB_HD void store_vals(const u64 (&v)[1 << NB], u64 *sm, u32 t) {
+    if constexpr (S == 0) {
+#pragma unroll
+        for (int k = 0; k < (1 << NB); k += 2) {
+            u64 *p = sm + swz(elem_index<NB, 0>(t, k));
+            p[0] = v[k];
+            p[1] = v[k + 1];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < (1 << NB); k++) sm[swz(elem_index<NB, S>(t, k))] = v[k];
+    }
 }
 
 }  // namespace exb

@@ -66,7 +66,7 @@ static void emu_launch(unsigned grid, unsigned block, size_t smem_bytes, F body)
 }
 
 static unsigned emu_block_threads(const DeviceParams &P) {
-    if (P.logn == 12) return 256;
+    if (P.logn == 12) return kThreads12;
     unsigned t = P.n / 2;
     if (t < 32) t = 32;
     if (t > 256) t = 256;
@@ -114,17 +114,20 @@ int emu_ntt(emu_ctx *c, uint32_t base, int forward, const uint64_t *in, uint64_t
     const unsigned thr = emu_block_threads(P);
     const size_t sm = (size_t)P.n * 8;
     if (P.logn == 12) {
-        // persistent fast path: few "CTAs" so every block loops over several polynomials
+        // persistent fast path: few "CTAs" so every block loops over several polynomials;
+        // both register tilings (8 and 16 values per thread) are exercised: odd/even count
         const unsigned grid = count < 3 ? (unsigned)count : 3u;
         const Modulus &m = P.mod[base];
         const u32 cnt = (u32)count;
-#define EMU_NTT12(FWD, LZ) emu_launch(grid, 256, 2 * sm, [&]() { ntt12_persist_kernel<FWD, LZ>(in, out, FWD ? P.twf[base] : P.twi[base], FWD ? P.headf[base] : P.headi[base], m, cnt); })
+        const bool nb4 = (count & 1) == 0;
+#define EMU_NTT12(FWD, LZ) do { if (nb4) emu_launch(grid, 256, 2 * sm, [&]() { ntt12_persist_kernel<FWD, LZ, 4>(in, out, FWD ? P.twf[base] : P.twi[base], FWD ? P.headf[base] : P.headi[base], m, cnt); }); \
+        else emu_launch(grid, 512, 2 * sm, [&]() { ntt12_persist_kernel<FWD, LZ, 3>(in, out, FWD ? P.twf[base] : P.twi[base], FWD ? P.headf[base] : P.headi[base], m, cnt); }); } while (0)
         if (forward) { if (m.lazy == 2) EMU_NTT12(true, 2); else if (m.lazy == 1) EMU_NTT12(true, 1); else EMU_NTT12(true, 0); }
         else { if (m.lazy == 2) EMU_NTT12(false, 2); else if (m.lazy == 1) EMU_NTT12(false, 1); else EMU_NTT12(false, 0); }
 #undef EMU_NTT12
     } else {
-        if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<0>(in, out, P.twf[base], P.mod[base], P.logn); });
-        else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<0>(in, out, P.twi[base], P.mod[base], P.logn); });
+        if (forward) emu_launch((unsigned)count, thr, sm, [&]() { ntt_fwd_kernel<0>(in, out, P.twf[base], P.headf[base], P.mod[base], P.logn); });
+        else emu_launch((unsigned)count, thr, sm, [&]() { ntt_inv_kernel<0>(in, out, P.twi[base], P.headi[base], P.mod[base], P.logn); });
     }
     return 0;
 }
