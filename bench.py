@@ -92,6 +92,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """Host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle takes an explicit count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def synth(seed: int, pairs: int, q: int):
     rng = np.random.default_rng(seed)
     ct1 = rng.integers(0, q, (pairs, D, 2, N), dtype=np.uint64)
@@ -127,8 +135,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     sample = 2                                   # dbfv_muls per step (bounded sample of the workload)
     work = CpuWork()
     for _ in range(args.warmup):
@@ -276,8 +283,7 @@ def run_gpu(args):
         if not args.no_ntt:
             line["ntt"] = bench_ntt(torch, batch, P, peak, peak_src, args)
         if world == 1 and not args.no_cpu:
-            import oracle as O
-            threads = O.max_threads()
+            threads = host_threads()
             work = CpuWork()
             per = work.run(args.cpu_trials, threads) / args.cpu_trials
             per1 = work.run(2, 1) / 2
