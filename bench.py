@@ -334,8 +334,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="exacto_b200", choices=["exacto_b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=128, help="ciphertext pairs per GPU per step")
-    ap.add_argument("--e2e-pairs", type=int, default=128)
+    ap.add_argument("--pairs", type=int, default=148, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--e2e-pairs", type=int, default=148)
     ap.add_argument("--all-products", action="store_true", help="compute all 64 products like the reference")
     ap.add_argument("--ntt-count", type=int, default=16384)
     ap.add_argument("--ntt-reps", type=int, default=10)

@@ -122,6 +122,18 @@ extern "C" int exb_context_create(const exb_bfv_params *p, int device, exb_conte
         c->d_tables.push_back(df); c->d_tables.push_back(di);
         c->P.twf[b] = df; c->P.twi[b] = di;
     }
+    for (u32 i = 0; c->P.sb.enabled && i < c->P.sb.K; i++) {
+        Tw32 *df = nullptr, *di = nullptr;
+        if (cudaMalloc(&df, sizeof(Tw32) * n) != cudaSuccess || cudaMalloc(&di, sizeof(Tw32) * n) != cudaSuccess ||
+            cudaMemcpy(df, c->twf32[i].data(), sizeof(Tw32) * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(di, c->twi32[i].data(), sizeof(Tw32) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(df); cudaFree(di);
+            exb_context_destroy(c);
+            return fail(EXB_CUDA_ERROR, "small-basis twiddle upload failed");
+        }
+        c->d_tables.push_back(reinterpret_cast<Tw *>(df)); c->d_tables.push_back(reinterpret_cast<Tw *>(di));
+        c->P.sb.twf[i] = df; c->P.sb.twi[i] = di;
+    }
     for (Workspace &w : c->ws)
         if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) {
             exb_context_destroy(c);
@@ -349,6 +361,7 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
                                 size_t *dig_b, size_t *exc_b) {
     const size_t n = c->n, A = c->aux_moduli.size(), d = hp.M.d;
     *ext_b = 2 * d * 2 * (1 + A) * n * 8;
+    if (c->P.sb.enabled && c->logn == 12) *ext_b = d * 2 * n * 8 + 2 * d * 2 * (size_t)c->P.sb.K * n * 4;
     *r01_b = (size_t)hp.M.num_products * 2 * n * 8;
     *dig_b = (size_t)hp.M.num_products * (G ? G : 1) * n * (c->digits32 ? 4 : 2);
     *exc_b = (size_t)(hp.M.num_limbs - hp.num_low) * 2 * n * 8;

@@ -8,6 +8,7 @@
 // dbfv/lattice.rs:104-122.
 #include "host_setup.hpp"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace exb {
@@ -234,6 +235,91 @@ static int fill_scale_consts(HostSetup *c, std::string *err) {
     return EXB_OK;
 }
 
+// ---- internal 30-bit auxiliary basis (ntt32_core.cuh, hps32.cuh) ---------------------------
+static int build_mod32(u32 n, u32 logn, u32 p, Mod32 *m, std::vector<Tw32> *twf, std::vector<Tw32> *twi) {
+    const u64 e = (p - 1) / (2ull * n);
+    u64 psi = 0;
+    for (u64 x = 2; x < p; x++) {
+        const u64 c = h_pow(x, e, p);
+        if (h_pow(c, n, p) == (u64)p - 1) { psi = c; break; }
+    }
+    u64 psi_inv = 0, ninv = 0;
+    if (!psi || !h_inv(psi, p, &psi_inv) || !h_inv(n % p, p, &ninv)) return EXB_INVALID_PARAM;
+    auto sh = [&](u64 w) { return (u32)((w << 32) / p); };
+    twf->resize(n); twi->resize(n);
+    u64 pw = 1, ipw = 1;
+    for (u32 k = 0; k < n; k++) {
+        const u32 r = bitrev32(k, logn);
+        (*twf)[r].w = (u32)pw;  (*twf)[r].s = sh(pw);
+        (*twi)[r].w = (u32)ipw; (*twi)[r].s = sh(ipw);
+        pw = pw * psi % p; ipw = ipw * psi_inv % p;
+    }
+    memset(m, 0, sizeof *m);
+    m->p = p; m->two_p = 2 * p; m->neg_p = (u32)0 - p;
+    u32 inv = p;
+    for (int i = 0; i < 5; i++) inv *= 2 - p * inv;
+    m->pinv_neg = (u32)0 - inv;
+    m->r_mod = (u32)(((u64)1 << 32) % p); m->r_mod_s = sh(m->r_mod);
+    m->one_s = (u32)(((u64)1 << 32) / p);
+    m->ninv = (u32)ninv; m->ninv_s = sh(ninv);
+    m->ninv_w = (u32)(ninv * (*twi)[1].w % p); m->ninv_w_s = sh(m->ninv_w);
+    return EXB_OK;
+}
+
+// Enable the internal basis only when the result is provably identical to the reference's:
+//   |m| <= Mmax = n*q/2 + 2 for every input (|t| <= 2 n (q/2)^2 for the middle tensor term);
+//   the reference's centred CRT of m (bfv/eval.rs:316-321, :385-388) cannot wrap: P_ref/2 > Mmax;
+//   ours cannot either and alpha is exact: P' >= 2^8 * Mmax (fixed-point error < 2^-28).
+static void build_small_basis(HostSetup *c) {
+    SmallBasis &sb = c->P.sb;
+    memset(&sb, 0, sizeof sb);
+    const char *env = getenv("EXB_AUX_BASIS");
+    if (env && strcmp(env, "reference") == 0) return;
+    const u32 A = (u32)c->aux_moduli.size(), n = c->n;
+    if (c->logn != 12 || c->mul_status != EXB_OK || A < 1 || A > (u32)kMaxAux) return;
+    const u64 q = c->ct_moduli[0];
+    if (c->P.mod[0].lazy == 0) return;                       // needs 2^36 <= q < 2^60
+    const u128 mmax = ((u128)n * q) / 2 + 2;
+    u128 pref = 1;
+    for (u64 a : c->aux_moduli) pref *= a;
+    if (pref / 2 <= mmax) return;
+    std::vector<u32> primes;
+    u128 prod = 1;
+    const u128 need = mmax << 8;
+    for (u64 cand = (((u64)1 << 30) - 1) / (2ull * n) * (2ull * n) + 1; cand > ((u64)1 << 29) && prod < need;
+         cand -= 2ull * n) {
+        if (cand >= ((u64)1 << 30) || !h_is_prime(cand) || cand == q) continue;
+        bool clash = false;
+        for (u64 a : c->aux_moduli) clash |= (a == cand);
+        if (clash) continue;
+        primes.push_back((u32)cand);
+        prod *= cand;
+        if (primes.size() > (size_t)kMaxSmall) return;
+    }
+    if (prod < need || primes.size() > (size_t)kMaxSmall) return;
+    const u32 K = (u32)primes.size();
+    Scale32Consts &s = sb.sc;
+    s.K = K;
+    const u64 p = c->plain;
+    for (u32 i = 0; i < K; i++) {
+        if (build_mod32(n, c->logn, primes[i], &s.m[i], &c->twf32[i], &c->twi32[i]) != EXB_OK) return;
+        for (u32 k = 0; k < 16; k++) { sb.headf[i].t[k] = c->twf32[i][k]; sb.headi[i].t[k] = c->twi32[i][k]; }
+        const u64 pi = primes[i];
+        const u128 cof = prod / pi;                            // P'/p_i
+        u64 inv = 0;
+        if (!h_inv((u64)((u128)(q % pi) * (u64)(cof % pi) % pi), pi, &inv)) return;
+        s.Kp[i] = (u32)inv; s.Kp_s[i] = (u32)((inv << 32) / pi);
+        s.g[i] = (u32)(((u64)1 << 60) / pi);
+        s.C[i] = h_mul(p % q, (u64)(cof % q), q);
+        s.C_s[i] = shoup_of(s.C[i], q);
+    }
+    const u64 pp = h_mul(p % q, (u64)(prod % q), q);
+    for (u32 a = 0; a <= K; a++) s.CP[a] = (u64)((u128)pp * a % q);
+    c->small_primes.assign(primes.begin(), primes.end());
+    sb.K = K;
+    sb.enabled = 1;
+}
+
 int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
     if (!p || !c) return fail(err, EXB_INVALID_PARAM, "null argument");
     const u32 n = p->ring_degree;
@@ -299,6 +385,7 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
     int rc = fill_scale_consts(c, err);
     if (rc != EXB_OK) return rc;
     decide_mul_support(c);
+    build_small_basis(c);
     return EXB_OK;
 }
 

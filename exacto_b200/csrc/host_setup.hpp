@@ -8,6 +8,7 @@
 
 #include "../../include/exacto_b200.h"
 #include "hps.cuh"
+#include "hps32.cuh"
 #include "modarith.cuh"
 #include "ntt_core.cuh"
 
@@ -18,6 +19,16 @@ constexpr int kMaxBases = 1 + kMaxAux;
 constexpr int kMaxDigits = 16;                 // dBFV digits d
 constexpr int kMaxProducts = kMaxDigits * kMaxDigits;
 constexpr int kMaxLimbs = 2 * kMaxDigits - 1;
+
+// Internal 30-bit auxiliary basis (see ntt32_core.cuh / hps32.cuh): replaces the reference's aux
+// primes inside the lift / tensor kernels when that is provably result-identical.
+struct SmallBasis {
+    u32 enabled, K;
+    const Tw32 *twf[kMaxSmall];
+    const Tw32 *twi[kMaxSmall];
+    TwHead32 headf[kMaxSmall], headi[kMaxSmall];
+    Scale32Consts sc;
+};
 
 // Everything a fused kernel needs about the parameter set (passed by value).
 struct DeviceParams {
@@ -33,6 +44,7 @@ struct DeviceParams {
     TwHead headf[kMaxBases];     // twf[0..15] / twi[0..15] by value (constant-bank operands)
     TwHead headi[kMaxBases];
     ScaleConsts sc;
+    SmallBasis sb;
 };
 
 // Work decomposition of one dbfv_mul (bfv_mul_and_relin is d = 1).
@@ -60,6 +72,8 @@ struct HostSetup {
     DeviceParams P;                          // table pointers are filled by the owner
     bool has_plan[kMaxBases] = {false, false, false};
     std::vector<Tw> twf[kMaxBases], twi[kMaxBases];
+    std::vector<Tw32> twf32[kMaxSmall], twi32[kMaxSmall];   // internal small basis (if P.sb.enabled)
+    std::vector<u64> small_primes;
 };
 
 // BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new (ring/rns.rs:35-63).

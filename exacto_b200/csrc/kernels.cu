@@ -116,6 +116,38 @@ __device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, con
     __syncthreads();
 }
 
+// 32-bit transforms of the internal auxiliary basis (n = 4096, 512 threads x 8 values).
+__device__ __forceinline__ void fwd32_sm(u32 *sm, const Tw32 *__restrict__ tw, const TwHead32 &head, const Mod32 &m) {
+    const u32 t = threadIdx.x;
+    u32 v[8];
+    __syncthreads();
+    load_vals32<3, 9>(v, sm, t); fwd_pass32<12, 9, 3>(v, head, t, m); store_vals32<3, 9>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 6>(v, sm, t); fwd_pass32<12, 6, 3>(v, tw, t, m); store_vals32<3, 6>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 3>(v, sm, t); fwd_pass32<12, 3, 3>(v, tw, t, m); store_vals32<3, 3>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 0>(v, sm, t); fwd_pass32<12, 0, 3>(v, tw, t, m);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = csub32(csub32(v[k], m.two_p), m.p);
+    store_vals32<3, 0>(v, sm, t);
+    __syncthreads();
+}
+// Inputs in [0, 2p); outputs canonical.
+__device__ __forceinline__ void inv32_sm(u32 *sm, const Tw32 *__restrict__ tw, const TwHead32 &head, const Mod32 &m) {
+    const u32 t = threadIdx.x;
+    u32 v[8];
+    __syncthreads();
+    load_vals32<3, 0>(v, sm, t); inv_pass32<12, 0, 3, false>(v, tw, t, m); store_vals32<3, 0>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 3>(v, sm, t); inv_pass32<12, 3, 3, false>(v, tw, t, m); store_vals32<3, 3>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 6>(v, sm, t); inv_pass32<12, 6, 3, false>(v, tw, t, m); store_vals32<3, 6>(v, sm, t);
+    __syncthreads();
+    load_vals32<3, 9>(v, sm, t); inv_pass32<12, 9, 3, true>(v, head, t, m); store_vals32<3, 9>(v, sm, t);
+    __syncthreads();
+}
+
 template <int LOGN>
 __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
                                        u32 logn) {
@@ -429,6 +461,114 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
 }
 
 // ---------------------------------------------------------------------------------
+// K4' / K5': lift and tensor+scale on the internal 30-bit auxiliary basis (n = 4096 only;
+// see ntt32_core.cuh for why this is result-identical).  Layouts:
+//   ext_q : [pair][limb][comp][n] u64      right operand mod q in Montgomery form
+//   ext_s : [pair][side][limb][comp][K][n] u32   both operands mod the small primes
+//           (right operand in Montgomery form, R = 2^32)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads12, 2)
+lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
+              const u64 *__restrict__ ct2, u64 *__restrict__ ext_q, u32 *__restrict__ ext_s) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const u32 K = P.sb.K;
+    u64 *coef = smem;
+    u32 *work = reinterpret_cast<u32 *>(smem + n);
+    const u32 idx = blockIdx.x;
+    const u32 comp = idx & 1u;
+    const u32 limb = (idx >> 1) % d;
+    const u32 side = (idx / (2 * d)) & 1u;
+    const size_t pair = idx / (4 * d);
+    const u64 *src = (side ? ct2 : ct1) + ((pair * d + limb) * 2 + comp) * (size_t)n;
+    u64 *dq = ext_q + ((pair * d + limb) * 2 + comp) * (size_t)n;
+    u32 *ds = ext_s + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)K) * n;
+    const Modulus &mq = P.mod[0];
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 x = src[e];
+        coef[swz(e)] = x;
+        if (side) dq[e] = shoup(x, mq.r_mod, mq.r_mod_s, mq.m);
+    }
+    inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12);
+    for (u32 i = 0; i < K; i++) {
+        const Mod32 &m = P.sb.sc.m[i];
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x)
+            work[swz32(e)] = ext32_centered(coef[swz(e)], mq.m, P.sc.half_q, m);
+        fwd32_sm(work, P.sb.twf[i], P.sb.headf[i], m);
+        u32 *o = ds + (size_t)i * n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u32 x = work[swz32(e)];
+            if (side) x = shoup32(x, m.r_mod, m.r_mod_s, m.p);
+            o[e] = x;
+        }
+    }
+}
+
+template <typename DigT>
+__global__ void __launch_bounds__(kThreads12, 2)
+tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+                const u64 *__restrict__ ct1, const u64 *__restrict__ ext_q, const u32 *__restrict__ ext_s,
+                u64 *__restrict__ r01, DigT *__restrict__ digits) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const u32 K = P.sb.K, d = M.d, NP = M.num_products;
+    const u32 idx = blockIdx.x;
+    const u32 comp = idx % 3u;
+    const u32 prod = (idx / 3u) % NP;
+    const size_t pair = idx / (3u * NP);
+    const u32 li = M.prod_i[prod], lj = M.prod_j[prod];
+    u64 *bq = smem;
+    u32 *bs = reinterpret_cast<u32 *>(smem + n);
+    {   // base q: 64-bit Montgomery point-wise + INTT
+        const Modulus &mb = P.mod[0];
+        const u64 *l0 = ct1 + ((pair * d + li) * 2) * (size_t)n, *l1 = l0 + n;
+        const u64 *r0 = ext_q + ((pair * d + lj) * 2) * (size_t)n, *r1 = r0 + n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u64 v;
+            if (comp == 0) v = mont_mul_lazy(l0[e], r0[e], mb.m, mb.minv_neg);
+            else if (comp == 2) v = mont_mul_lazy(l1[e], r1[e], mb.m, mb.minv_neg);
+            else v = mont_mul2_lazy(l0[e], r1[e], l1[e], r0[e], mb.m, mb.minv_neg);
+            bq[swz(e)] = v;
+        }
+        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
+    }
+    for (u32 i = 0; i < K; i++) {   // small primes: 32-bit Montgomery point-wise + INTT
+        const Mod32 &m = P.sb.sc.m[i];
+        const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + li) * 2) * (size_t)K + i) * n, *l1 = l0 + (size_t)K * n;
+        const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + lj) * 2) * (size_t)K + i) * n, *r1 = r0 + (size_t)K * n;
+        u32 *buf = bs + (size_t)i * n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            u64 z;
+            if (comp == 0) z = (u64)l0[e] * r0[e];
+            else if (comp == 2) z = (u64)l1[e] * r1[e];
+            else z = (u64)l0[e] * r1[e] + (u64)l1[e] * r0[e];
+            buf[swz32(e)] = mont32_redc_lazy(z, m.p, m.pinv_neg);
+        }
+        inv32_sm(buf, P.sb.twi[i], P.sb.headi[i], m);
+    }
+    const LazyC lq = make_lazyc(P.mod[0]);
+    const u32 G = P.gadget_digits;
+    u64 *o01 = r01 + ((pair * NP + prod) * 2 + (comp < 2 ? comp : 0)) * (size_t)n;
+    DigT *od = digits + ((pair * NP + prod) * (size_t)G) * n;
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        u32 b[kMaxSmall];
+#pragma unroll
+        for (u32 i = 0; i < (u32)kMaxSmall; i++) b[i] = i < K ? bs[(size_t)i * n + swz32(e)] : 0u;
+        const u64 r = hps_scale32_coeff(bq[swz(e)], b, P.sc, P.sb.sc, lq);
+        if (comp < 2) {
+            o01[e] = r;
+        } else {
+            i64 rem = center_i64(r, P.sc.q, P.sc.half_q);
+            if (P.gadget_log2) {
+                for (u32 g = 0; g < G; g++) od[(size_t)g * n + e] = (DigT)gadget_digit_pow2(rem, P.gadget_log2);
+            } else {
+                for (u32 g = 0; g < G; g++) od[(size_t)g * n + e] = (DigT)gadget_digit_general(rem, (i64)P.gadget_base);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // K6+K7: relinearise + per-k accumulation.  One CTA per (pair, output limb k):
 //   c0 = NTT(sum r0) + sum_g NTT(sum digits_g) * rlk0_g     (likewise c1)
 // All sums are exact mod q, so any association is bit-equal to the reference's
@@ -588,9 +728,22 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
     g_launch_count++;
 }
 
+// ext points at ext_q followed by ext_s when the internal small basis is enabled.
+static inline u32 *ext_small_part(const DeviceParams &P, const MulPlan &M, u64 *ext, size_t pairs) {
+    return reinterpret_cast<u32 *>(ext + pairs * M.d * 2 * (size_t)P.n);
+}
+
 void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
                  size_t pairs, cudaStream_t s) {
     if (pairs == 0) return;
+    if (P.sb.enabled && P.logn == 12) {
+        const size_t sm32 = 4096 * 8 + 4096 * 4;
+        set_smem(lift32_kernel, sm32);
+        lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext,
+                                                                           ext_small_part(P, M, ext, pairs));
+        g_launch_count++;
+        return;
+    }
     const size_t sm = (size_t)P.n * 8 * 2;
     const unsigned grid = (unsigned)(pairs * 4 * M.d);
     if (P.logn == 12) {
@@ -608,6 +761,14 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
                             DigT *digits, size_t pairs, cudaStream_t s) {
     const size_t sm = (size_t)P.n * 8 * (1 + P.num_aux);
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
+    if (P.sb.enabled && P.logn == 12) {
+        const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
+        set_smem(tensor32_kernel<DigT>, sm32);
+        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(
+            P, M, ct1, ext, ext_small_part(P, M, const_cast<u64 *>(ext), pairs), r01, digits);
+        g_launch_count++;
+        return;
+    }
     if (P.logn == 12) {
         set_smem(tensor_kernel<12, DigT>, sm);
         tensor_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, ct1, ext, r01, digits);

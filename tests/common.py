@@ -54,6 +54,7 @@ class Emulator:
         L.emu_info.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u32), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(u64)]
         L.emu_ntt.argtypes = [vp, u32, ctypes.c_int, vp, vp, ctypes.c_size_t]
         L.emu_poly_op.argtypes = [vp, u32, ctypes.c_int, vp, vp, u64, vp, ctypes.c_size_t]
+        L.emu_small_primes.argtypes = [vp, vp]
         L.emu_dbfv_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, u32, u32]
         self.L = L
 
@@ -78,6 +79,11 @@ class Emulator:
         gb, gd, ms, psi = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_int(), ctypes.c_uint64()
         self.L.emu_info(h, ctypes.byref(gb), ctypes.byref(gd), ctypes.byref(ms), ctypes.byref(psi))
         return gb.value, gd.value, ms.value, psi.value, self.L.emu_last_error().decode()
+
+    def small_primes(self, h):
+        out = np.zeros(8, np.uint64)
+        k = self.L.emu_small_primes(h, self._p(out))
+        return [int(v) for v in out[:k]]
 
     def ntt(self, h, base, forward, x):
         x = np.ascontiguousarray(x, np.uint64)

@@ -95,6 +95,9 @@ int emu_create(uint32_t n, const uint64_t *ct_moduli, uint32_t num_ct, const uin
     if (rc) { delete c; return rc; }
     for (int b = 0; b < kMaxBases; b++)
         if (c->hs.has_plan[b]) { c->hs.P.twf[b] = c->hs.twf[b].data(); c->hs.P.twi[b] = c->hs.twi[b].data(); }
+    for (u32 i = 0; c->hs.P.sb.enabled && i < c->hs.P.sb.K; i++) {
+        c->hs.P.sb.twf[i] = c->hs.twf32[i].data(); c->hs.P.sb.twi[i] = c->hs.twi32[i].data();
+    }
     *out = c;
     return 0;
 }
@@ -106,6 +109,13 @@ int emu_info(const emu_ctx *c, uint64_t *gadget_base, uint32_t *gadget_digits, i
     *mul_status = c->hs.mul_status; *psi0 = c->hs.psi[0];
     g_emu_err = c->hs.mul_error;
     return 0;
+}
+
+// Internal small auxiliary basis chosen for this parameter set (0 = reference basis in use).
+int emu_small_primes(const emu_ctx *c, uint64_t *primes) {
+    if (!c->hs.P.sb.enabled) return 0;
+    for (size_t i = 0; i < c->hs.small_primes.size(); i++) primes[i] = c->hs.small_primes[i];
+    return (int)c->hs.small_primes.size();
 }
 
 int emu_ntt(emu_ctx *c, uint32_t base, int forward, const uint64_t *in, uint64_t *out, size_t count) {
@@ -155,7 +165,10 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     const size_t n = hs.n, A = hs.aux_moduli.size();
     const MulPlan &M = hp.M;
     const size_t nx = M.num_limbs - hp.num_low;
-    std::vector<u64> ext(pairs * 2 * d * 2 * (1 + A) * n), r01(pairs * M.num_products * 2 * n + 1);
+    const bool small = P.sb.enabled && P.logn == 12;
+    std::vector<u64> ext(small ? pairs * d * 2 * n + (pairs * 2 * d * 2 * P.sb.K * n + 1) / 2 + 2
+                               : pairs * 2 * d * 2 * (1 + A) * n),
+        r01(pairs * M.num_products * 2 * n + 1);
     std::vector<u64> excess(pairs * nx * 2 * n + 1), rlk_mont((size_t)num_keys * 2 * n + 1);
     std::vector<int32_t> dig32;
     std::vector<int16_t> dig16;
@@ -168,7 +181,20 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     const unsigned thr = emu_block_threads(P);
     u64 *extp = ext.data(), *r01p = r01.data(), *xp = excess.data();
     const u64 *rk = rlk_mont.data();
-    if (P.logn == 12) {
+    if (small) {
+        u32 *exts = reinterpret_cast<u32 *>(extp + pairs * d * 2 * n);
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 12, [&]() { lift32_kernel(P, d, ct1, ct2, extp, exts); });
+        const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
+        if (hs.digits32) {
+            int32_t *dg = dig32.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, extp, exts, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int32_t>(P, M, r01p, dg, rk, out, xp); });
+        } else {
+            int16_t *dg = dig16.data();
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, extp, exts, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int16_t>(P, M, r01p, dg, rk, out, xp); });
+        }
+    } else if (P.logn == 12) {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();

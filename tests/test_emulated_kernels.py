@@ -117,3 +117,44 @@ def test_dispatch_errors(emu):
     assert rc == 1 and "cannot create NTT plan" in err
     rc, h, err = emu.create(1000, [65537], [], 257)
     assert rc == 4
+
+
+def test_internal_small_basis_selection(emu, monkeypatch):
+    """The 30-bit internal auxiliary basis is used exactly when it is provably result-identical
+    (n = 4096 fast path, two-aux configs where the reference's centred CRT cannot wrap)."""
+    for name in ("cfg3p_dbfv", "u64_dbfv"):
+        P = CASES[name][0]
+        primes = emu.small_primes(emu.from_oracle(P))
+        assert len(primes) == 3 and all(p < 2 ** 30 and p % 8192 == 1 and O.is_prime(p) for p in primes)
+        prod = primes[0] * primes[1] * primes[2]
+        assert prod >= (P.n * P.q // 2 + 2) << 8
+    assert emu.small_primes(emu.from_oracle(CASES["compact_dbfv"][0])) == []          # n = 1024: generic path
+    monkeypatch.setenv("EXB_AUX_BASIS", "reference")
+    assert emu.small_primes(emu.from_oracle(CASES["cfg3p_dbfv"][0])) == []
+
+
+def test_reference_aux_basis_path_still_exact(emu, monkeypatch):
+    """The 64-bit reference-basis kernels (used whenever the internal basis is not allowed) stay covered."""
+    monkeypatch.setenv("EXB_AUX_BASIS", "reference")
+    P, base, d, pm, seed, _ = CASES["cfg3p_dbfv"]
+    ct1, ct2, rlk = golden_inputs(P, d, seed)
+    rc, out, err = emu.dbfv_mul(emu.from_oracle(P), base, d, pm, ct1, ct2, rlk)
+    assert rc == 0, err
+    assert digest(out) == str(golden()[f"cfg3p_dbfv/dbfv_sha256"])
+
+
+def test_small_basis_adversarial_inputs(emu):
+    """Extreme tensor magnitudes: all coefficients at +-q/2 so |m| reaches its n*q/2 bound."""
+    P = H.u64_dbfv().bfv
+    h = emu.from_oracle(P)
+    assert emu.small_primes(h)
+    q, n = P.q, P.n
+    hi, lo = np.full(n, q // 2, np.uint64), np.full(n, q // 2 + 1, np.uint64)
+    alt = np.where(np.arange(n) % 2 == 0, np.uint64(q // 2), np.uint64(q // 2 + 1))
+    pats = [hi, lo, alt]
+    rlk = np.random.default_rng(9).integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    ct1 = np.stack([np.stack([O.ntt_fwd(pats[i], q), O.ntt_fwd(pats[(i + 1) % 3], q)]) for i in range(3)])
+    ct2 = np.stack([np.stack([O.ntt_fwd(pats[(i + 2) % 3], q), O.ntt_fwd(pats[i], q)]) for i in range(3)])
+    rc, got, err = emu.dbfv_mul(h, 2, 1, 0, ct1[:, None], ct2[:, None], rlk)
+    assert rc == 0, err
+    assert np.array_equal(got[:, 0], O.bfv_mul_and_relin(P, ct1, ct2, rlk, threads=4))

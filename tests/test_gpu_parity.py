@@ -250,3 +250,18 @@ def test_native_error_pins():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_both_aux_basis_paths(monkeypatch):
+    """cfg 3' and cfg 4 through both tensor paths: the internal 30-bit auxiliary basis (default when it is
+    provably result-identical) and the reference's own aux primes (EXB_AUX_BASIS=reference)."""
+    g = golden()
+    for name in ("cfg3p_dbfv", "u64_dbfv"):
+        P, base, d, pm, seed, _ = CASES[name]
+        ct1, ct2, rlk_arr = golden_inputs(P, d, seed)
+        for mode in ("reference", "internal"):
+            monkeypatch.setenv("EXB_AUX_BASIS", mode)
+            params = to_dbfv_params(P, base, d, pm)            # fresh params -> fresh native context
+            rlk = E.RelinKey(rlk_arr, params.bfv_params)
+            out = E.dbfv_mul_batch(params, ct1[None], ct2[None], rlk)
+            assert digest(out[0]) == str(g[f"{name}/dbfv_sha256"]), (name, mode)
