@@ -461,6 +461,89 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
 }
 
 // ---------------------------------------------------------------------------------
+// 8 consecutive coefficients per thread with 128-bit accesses (n = 4096 kernels): global rows
+// are read/written as whole 64-byte (u64) / 32-byte (u32) / 16-byte (int16) pieces, and the
+// swizzled shared-memory images keep every 16-byte pair together and conflict-free.
+// ---------------------------------------------------------------------------------
+struct alignas(16) Vec16 { u32 w[4]; };
+
+__device__ __forceinline__ void ldg_u64x4(const u64 *p, u64 *v) {   // 4 consecutive u64, 16-byte aligned
+    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(p)[0], b = reinterpret_cast<const ulonglong2 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void stg_u64x4(u64 *p, const u64 *v) {
+    ulonglong2 a, b;
+    a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
+    reinterpret_cast<ulonglong2 *>(p)[0] = a; reinterpret_cast<ulonglong2 *>(p)[1] = b;
+}
+__device__ __forceinline__ void ldg_u32x8(const u32 *p, u32 *v) {   // 8 consecutive u32, 16-byte aligned
+    const Vec16 a = reinterpret_cast<const Vec16 *>(p)[0], b = reinterpret_cast<const Vec16 *>(p)[1];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = a.w[i]; v[4 + i] = b.w[i]; }
+}
+__device__ __forceinline__ void stg_u32x8(u32 *p, const u32 *v) {
+    Vec16 a, b;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a.w[i] = v[i]; b.w[i] = v[4 + i]; }
+    reinterpret_cast<Vec16 *>(p)[0] = a; reinterpret_cast<Vec16 *>(p)[1] = b;
+}
+// swizzled u64 image: elements e0 .. e0+3 (e0 % 4 == 0) are two 16-byte chunks
+__device__ __forceinline__ void lds_u64x4(const u64 *sm, u32 e0, u64 *v) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(sm + swz(e0));
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(sm + swz(e0 + 2));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void sts_u64x4(u64 *sm, u32 e0, const u64 *v) {
+    ulonglong2 a, b;
+    a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
+    *reinterpret_cast<ulonglong2 *>(sm + swz(e0)) = a;
+    *reinterpret_cast<ulonglong2 *>(sm + swz(e0 + 2)) = b;
+}
+// swizzled u32 image: elements e0 .. e0+7 (e0 % 8 == 0) are two 16-byte chunks
+__device__ __forceinline__ void lds_u32x8(const u32 *sm, u32 e0, u32 *v) {
+    const Vec16 a = *reinterpret_cast<const Vec16 *>(sm + swz32(e0)), b = *reinterpret_cast<const Vec16 *>(sm + swz32(e0 + 4));
+#pragma unroll
+    for (int i = 0; i < 4; i++) { v[i] = a.w[i]; v[4 + i] = b.w[i]; }
+}
+__device__ __forceinline__ void sts_u32x8(u32 *sm, u32 e0, const u32 *v) {
+    Vec16 a, b;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { a.w[i] = v[i]; b.w[i] = v[4 + i]; }
+    *reinterpret_cast<Vec16 *>(sm + swz32(e0)) = a;
+    *reinterpret_cast<Vec16 *>(sm + swz32(e0 + 4)) = b;
+}
+// 8 consecutive gadget digits (int16: one 16-byte piece, int32: two)
+template <typename DigT>
+__device__ __forceinline__ void ldg_dig8(const DigT *p, i64 *acc) {
+    if constexpr (sizeof(DigT) == 2) {
+        const Vec16 a = *reinterpret_cast<const Vec16 *>(p);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            acc[2 * i] += (i64)(int16_t)(a.w[i] & 0xffffu);
+            acc[2 * i + 1] += (i64)(int16_t)(a.w[i] >> 16);
+        }
+    } else {
+        const Vec16 a = reinterpret_cast<const Vec16 *>(p)[0], b = reinterpret_cast<const Vec16 *>(p)[1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { acc[i] += (i64)(int32_t)a.w[i]; acc[4 + i] += (i64)(int32_t)b.w[i]; }
+    }
+}
+template <typename DigT>
+__device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
+    if constexpr (sizeof(DigT) == 2) {
+        Vec16 a;
+#pragma unroll
+        for (int i = 0; i < 4; i++) a.w[i] = ((u32)d[2 * i] & 0xffffu) | ((u32)d[2 * i + 1] << 16);
+        *reinterpret_cast<Vec16 *>(p) = a;
+    } else {
+        Vec16 a, b;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a.w[i] = (u32)d[i]; b.w[i] = (u32)d[4 + i]; }
+        reinterpret_cast<Vec16 *>(p)[0] = a; reinterpret_cast<Vec16 *>(p)[1] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // K4' / K5': lift and tensor+scale on the internal 30-bit auxiliary basis (n = 4096 only;
 // see ntt32_core.cuh for why this is result-identical).  Layouts:
 //   ext_q : [pair][limb][comp][n] u64      right operand mod q in Montgomery form
@@ -484,23 +567,30 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restri
     u64 *dq = ext_q + ((pair * d + limb) * 2 + comp) * (size_t)n;
     u32 *ds = ext_s + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)K) * n;
     const Modulus &mq = P.mod[0];
-    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
-        const u64 x = src[e];
-        coef[swz(e)] = x;
-        if (side) dq[e] = shoup(x, mq.r_mod, mq.r_mod_s, mq.m);
+    const u32 e0 = 8 * threadIdx.x;
+    u64 x[8];
+    ldg_u64x4(src + e0, x); ldg_u64x4(src + e0 + 4, x + 4);
+    sts_u64x4(coef, e0, x); sts_u64x4(coef, e0 + 4, x + 4);
+    if (side) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = shoup(x[k], mq.r_mod, mq.r_mod_s, mq.m);
+        stg_u64x4(dq + e0, x); stg_u64x4(dq + e0 + 4, x + 4);
     }
     inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12);
+    lds_u64x4(coef, e0, x); lds_u64x4(coef, e0 + 4, x + 4);      // canonical coefficients stay in registers
     for (u32 i = 0; i < K; i++) {
         const Mod32 &m = P.sb.sc.m[i];
-        for (u32 e = threadIdx.x; e < n; e += blockDim.x)
-            work[swz32(e)] = ext32_centered(coef[swz(e)], mq.m, P.sc.half_q, m);
+        u32 y[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) y[k] = ext32_centered(x[k], mq.m, P.sc.half_q, m);
+        sts_u32x8(work, e0, y);
         fwd32_sm(work, P.sb.twf[i], P.sb.headf[i], m);
-        u32 *o = ds + (size_t)i * n;
-        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
-            u32 x = work[swz32(e)];
-            if (side) x = shoup32(x, m.r_mod, m.r_mod_s, m.p);
-            o[e] = x;
+        lds_u32x8(work, e0, y);
+        if (side) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) y[k] = shoup32(y[k], m.r_mod, m.r_mod_s, m.p);
         }
+        stg_u32x8(ds + (size_t)i * n + e0, y);
     }
 }
 
@@ -519,16 +609,26 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     const u32 li = M.prod_i[prod], lj = M.prod_j[prod];
     u64 *bq = smem;
     u32 *bs = reinterpret_cast<u32 *>(smem + n);
-    {   // base q: 64-bit Montgomery point-wise + INTT
+    const u32 e0 = 8 * threadIdx.x;
+    {   // base q: 64-bit Montgomery point-wise + INTT (two halves of 4 coefficients: register budget)
         const Modulus &mb = P.mod[0];
         const u64 *l0 = ct1 + ((pair * d + li) * 2) * (size_t)n, *l1 = l0 + n;
         const u64 *r0 = ext_q + ((pair * d + lj) * 2) * (size_t)n, *r1 = r0 + n;
-        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
-            u64 v;
-            if (comp == 0) v = mont_mul_lazy(l0[e], r0[e], mb.m, mb.minv_neg);
-            else if (comp == 2) v = mont_mul_lazy(l1[e], r1[e], mb.m, mb.minv_neg);
-            else v = mont_mul2_lazy(l0[e], r1[e], l1[e], r0[e], mb.m, mb.minv_neg);
-            bq[swz(e)] = v;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 eh = e0 + 4 * h;
+            u64 a[4], b[4], v[4];
+            if (comp == 1) {
+                u64 c[4], dd[4];
+                ldg_u64x4(l0 + eh, a); ldg_u64x4(r1 + eh, b); ldg_u64x4(l1 + eh, c); ldg_u64x4(r0 + eh, dd);
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = mont_mul2_lazy(a[k], b[k], c[k], dd[k], mb.m, mb.minv_neg);
+            } else {
+                ldg_u64x4((comp == 0 ? l0 : l1) + eh, a); ldg_u64x4((comp == 0 ? r0 : r1) + eh, b);
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = mont_mul_lazy(a[k], b[k], mb.m, mb.minv_neg);
+            }
+            sts_u64x4(bq, eh, v);
         }
         inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
     }
@@ -536,34 +636,50 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         const Mod32 &m = P.sb.sc.m[i];
         const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + li) * 2) * (size_t)K + i) * n, *l1 = l0 + (size_t)K * n;
         const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + lj) * 2) * (size_t)K + i) * n, *r1 = r0 + (size_t)K * n;
-        u32 *buf = bs + (size_t)i * n;
-        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
-            u64 z;
-            if (comp == 0) z = (u64)l0[e] * r0[e];
-            else if (comp == 2) z = (u64)l1[e] * r1[e];
-            else z = (u64)l0[e] * r1[e] + (u64)l1[e] * r0[e];
-            buf[swz32(e)] = mont32_redc_lazy(z, m.p, m.pinv_neg);
+        u32 a[8], b[8], v[8];
+        if (comp == 1) {
+            u32 c[8], dd[8];
+            ldg_u32x8(l0 + e0, a); ldg_u32x8(r1 + e0, b); ldg_u32x8(l1 + e0, c); ldg_u32x8(r0 + e0, dd);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = mont32_redc_lazy((u64)a[k] * b[k] + (u64)c[k] * dd[k], m.p, m.pinv_neg);
+        } else {
+            ldg_u32x8((comp == 0 ? l0 : l1) + e0, a); ldg_u32x8((comp == 0 ? r0 : r1) + e0, b);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = mont32_redc_lazy((u64)a[k] * b[k], m.p, m.pinv_neg);
         }
-        inv32_sm(buf, P.sb.twi[i], P.sb.headi[i], m);
+        sts_u32x8(bs + (size_t)i * n, e0, v);
+        inv32_sm(bs + (size_t)i * n, P.sb.twi[i], P.sb.headi[i], m);
     }
     const LazyC lq = make_lazyc(P.mod[0]);
     const u32 G = P.gadget_digits;
-    u64 *o01 = r01 + ((pair * NP + prod) * 2 + (comp < 2 ? comp : 0)) * (size_t)n;
-    DigT *od = digits + ((pair * NP + prod) * (size_t)G) * n;
-    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+    u64 av[8];
+    u32 bv[kMaxSmall][8];
+    lds_u64x4(bq, e0, av); lds_u64x4(bq, e0 + 4, av + 4);
+#pragma unroll
+    for (u32 i = 0; i < (u32)kMaxSmall; i++)
+        if (i < K) lds_u32x8(bs + (size_t)i * n, e0, bv[i]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
         u32 b[kMaxSmall];
 #pragma unroll
-        for (u32 i = 0; i < (u32)kMaxSmall; i++) b[i] = i < K ? bs[(size_t)i * n + swz32(e)] : 0u;
-        const u64 r = hps_scale32_coeff(bq[swz(e)], b, P.sc, P.sb.sc, lq);
-        if (comp < 2) {
-            o01[e] = r;
-        } else {
-            i64 rem = center_i64(r, P.sc.q, P.sc.half_q);
-            if (P.gadget_log2) {
-                for (u32 g = 0; g < G; g++) od[(size_t)g * n + e] = (DigT)gadget_digit_pow2(rem, P.gadget_log2);
-            } else {
-                for (u32 g = 0; g < G; g++) od[(size_t)g * n + e] = (DigT)gadget_digit_general(rem, (i64)P.gadget_base);
-            }
+        for (u32 i = 0; i < (u32)kMaxSmall; i++) b[i] = i < K ? bv[i][k] : 0u;
+        av[k] = hps_scale32_coeff(av[k], b, P.sc, P.sb.sc, lq);
+    }
+    if (comp < 2) {
+        u64 *o01 = r01 + ((pair * NP + prod) * 2 + comp) * (size_t)n;
+        stg_u64x4(o01 + e0, av); stg_u64x4(o01 + e0 + 4, av + 4);
+    } else {
+        DigT *od = digits + ((pair * NP + prod) * (size_t)G) * n;
+        i64 rem[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) rem[k] = center_i64(av[k], P.sc.q, P.sc.half_q);
+        for (u32 g = 0; g < G; g++) {
+            i64 dg[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                dg[k] = P.gadget_log2 ? gadget_digit_pow2(rem[k], P.gadget_log2)
+                                      : gadget_digit_general(rem[k], (i64)P.gadget_base);
+            stg_dig8<DigT>(od + (size_t)g * n + e0, dg);
         }
     }
 }
@@ -629,6 +745,81 @@ relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mul
         dst[e] = acc0[e];
         dst[n + e] = acc1[e];
     }
+}
+
+// n = 4096 specialisation of relin_kernel: 8 consecutive coefficients per thread, 128-bit accesses.
+template <typename DigT>
+__global__ void __launch_bounds__(kThreads12, 2)
+relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+               const u64 *__restrict__ r01, const DigT *__restrict__ digits,
+               const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const u32 d = M.d, NP = M.num_products, NL = M.num_limbs, G = P.gadget_digits;
+    const Modulus &mq = P.mod[0];
+    const u64 q = mq.m;
+    u64 *work = smem, *acc0 = smem + n, *acc1 = smem + 2 * (size_t)n;
+    const u32 limb = blockIdx.x % NL;
+    const size_t pair = blockIdx.x / NL;
+    const u32 k = M.limb_k[limb];
+    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+    const u32 e0 = 8 * threadIdx.x;
+
+    for (u32 comp = 0; comp < 2; comp++) {
+        u64 sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (u32 i = i_lo; i <= i_hi; i++) {
+            const size_t pr = (size_t)M.prod_of[i][k - i];
+            const u64 *src = r01 + ((pair * NP + pr) * 2 + comp) * n + e0;
+            u64 v[8];
+            ldg_u64x4(src, v); ldg_u64x4(src + 4, v + 4);
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
+        }
+        sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+        fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+        u64 *acc = comp ? acc1 : acc0;
+        lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+        sts_u64x4(acc, e0, sum); sts_u64x4(acc, e0 + 4, sum + 4);
+    }
+    for (u32 g = 0; g < G; g++) {
+        i64 ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (u32 i = i_lo; i <= i_hi; i++) {
+            const size_t pr = (size_t)M.prod_of[i][k - i];
+            ldg_dig8<DigT>(digits + ((pair * NP + pr) * G + g) * n + e0, ds);
+        }
+        u64 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u64 mag = ds[j] < 0 ? (u64)(-ds[j]) : (u64)ds[j];
+            const u64 r = mag < q ? mag : mag % q;
+            v[j] = (ds[j] < 0 && r) ? q - r : r;
+        }
+        sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
+        fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+        const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            u64 x[4], kk[4], a[4];
+            lds_u64x4(work, e0 + 4 * h, x);
+            ldg_u64x4(k0 + 4 * h, kk);
+            lds_u64x4(acc0, e0 + 4 * h, a);
+#pragma unroll
+            for (int j = 0; j < 4; j++) a[j] = mod_add(a[j], csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q), q);
+            sts_u64x4(acc0, e0 + 4 * h, a);
+            ldg_u64x4(k1 + 4 * h, kk);
+            lds_u64x4(acc1, e0 + 4 * h, a);
+#pragma unroll
+            for (int j = 0; j < 4; j++) a[j] = mod_add(a[j], csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q), q);
+            sts_u64x4(acc1, e0 + 4 * h, a);
+        }
+    }
+    u64 *dst = k < d ? out + ((pair * d + k) * 2) * (size_t)n
+                     : excess + ((pair * (NL - M.num_low) + (limb - M.num_low)) * 2) * (size_t)n;
+    u64 v[8];
+    lds_u64x4(acc0, e0, v); lds_u64x4(acc0, e0 + 4, v + 4);
+    stg_u64x4(dst + e0, v); stg_u64x4(dst + e0 + 4, v + 4);
+    lds_u64x4(acc1, e0, v); lds_u64x4(acc1, e0 + 4, v + 4);
+    stg_u64x4(dst + n + e0, v); stg_u64x4(dst + n + e0 + 4, v + 4);
 }
 
 // out_limb += (+/-) s * excess_limb over 2n words per pair (dbfv/reduction.rs:34-52, :65-93).
@@ -792,8 +983,8 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     const size_t sm = (size_t)P.n * 8 * 3;
     const unsigned grid = (unsigned)(pairs * M.num_limbs);
     if (P.logn == 12) {
-        set_smem(relin_kernel<12, DigT>, sm);
-        relin_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+        set_smem(relin12_kernel<DigT>, sm);
+        relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
     } else {
         set_smem(relin_kernel<0, DigT>, sm);
         relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);

@@ -188,22 +188,22 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, extp, exts, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int32_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp); });
         } else {
             int16_t *dg = dig16.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, extp, exts, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int16_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp); });
         }
     } else if (P.logn == 12) {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int32_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp); });
         } else {
             int16_t *dg = dig16.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<12, int16_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp); });
         }
     } else {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, ct1, ct2, extp); });
