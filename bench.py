@@ -60,7 +60,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -171,6 +171,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     params = E.u64_dbfv()
     P = params.bfv_params
@@ -249,9 +250,13 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         n_products = 64 if args.all_products else 36
-        # algorithmic bytes of the tensor+scale kernel per pair:
-        # unique inputs (both operands, every base) + its outputs (r0, r1 u64; G digit planes int16)
-        tensor_bytes = 2 * D * 2 * (1 + A) * N * 8 + n_products * (2 * N * 8 + G * N * 2)
+        # algorithmic bytes of the tensor+scale kernel per pair: unique inputs
+        # (both operands in every base it reads) + its outputs (r0, r1 u64; G digit planes int16)
+        if os.environ.get("EXB_AUX_BASIS") == "reference":
+            in_bytes = 2 * D * 2 * (1 + A) * N * 8                      # q + two 64-bit aux bases
+        else:
+            in_bytes = 2 * D * 2 * N * 8 + 2 * D * 2 * 3 * N * 4        # q (u64) + three 30-bit internal primes (u32)
+        tensor_bytes = in_bytes + n_products * (2 * N * 8 + G * N * 2)
         t_ms = stage_ms[1] / max(stage_n[1], 1)
         achieved = tensor_bytes * pairs / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         stages = {nm: {"ms_per_launch": stage_ms[i] / max(stage_n[i], 1), "launches": int(stage_n[i])}
@@ -272,7 +277,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": e2e_pairs * ct_bytes, "pairs_per_step": e2e_pairs, "result_checksum": checksum},
             "gpu_launches": int(launches),
             "bfv_mul_and_relin_equiv_per_s": value * 64,
-            "roofline": {"kernel": "tensor_kernel (pointwise tensor + 9 INTT + hps_scale + gadget digits)",
+            "roofline": {"kernel": "tensor32_kernel (per product and component: point-wise tensor in q + 3 internal 30-bit primes, 4 INTT, hps_scale, gadget digits)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
                          "peak_source": peak_src, "share_of_step": stage_ms[1] / total_stage,

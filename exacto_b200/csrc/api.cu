@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -472,7 +473,10 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     const size_t stride = (size_t)d * 2 * c->n;
-    size_t chunk = 2048 / (hp.M.num_products ? hp.M.num_products : 1);
+    // chunk size: enough CTAs to fill the GPU a few times, small enough that H2D / kernels / D2H of
+    // consecutive chunks overlap on the three streams (EXB_HOST_CHUNK_PRODUCTS overrides, lab only)
+    static const size_t chunk_products = getenv("EXB_HOST_CHUNK_PRODUCTS") ? (size_t)atol(getenv("EXB_HOST_CHUNK_PRODUCTS")) : 512;
+    size_t chunk = chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
     if (chunk < 1) chunk = 1;
     if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
     size_t ci = 0;
