@@ -90,5 +90,49 @@ def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: Reli
     return out
 
 
+def _poly_binary(name: str, params: BfvParams, index: int, a: torch.Tensor, b: Optional[torch.Tensor],
+                 out: Optional[torch.Tensor], scalar: int = 0) -> torch.Tensor:
+    _check(a, (params.ring_degree,), name)
+    out = torch.empty_like(a) if out is None else out
+    ctx = params.context(a.device.index)
+    L = _native.lib()
+    if name == "exb_poly_neg":
+        rc = L.exb_poly_neg(ctx.handle, index, a.data_ptr(), out.data_ptr(), a.numel(), _stream(a))
+    elif name == "exb_poly_scalar_mul":
+        rc = L.exb_poly_scalar_mul(ctx.handle, index, a.data_ptr(), scalar % (1 << 64), out.data_ptr(), a.numel(), _stream(a))
+    else:
+        _check(b, (params.ring_degree,), name)
+        if a.shape != b.shape:
+            raise InvalidParam("operand shape mismatch")
+        rc = getattr(L, name)(ctx.handle, index, a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream(a))
+    _native.check(rc)
+    return out
+
+
+def poly_add(params, index, a, b, out=None):
+    """NttPoly::add (ring/ntt.rs:75-89) over [..., n]."""
+    return _poly_binary("exb_poly_add", params, index, a, b, out)
+
+
+def poly_sub(params, index, a, b, out=None):
+    """NttPoly::sub (ring/ntt.rs:92-105)."""
+    return _poly_binary("exb_poly_sub", params, index, a, b, out)
+
+
+def poly_neg(params, index, a, out=None):
+    """NttPoly::neg (ring/ntt.rs:108-113)."""
+    return _poly_binary("exb_poly_neg", params, index, a, None, out)
+
+
+def poly_mul(params, index, a, b, out=None):
+    """NttPoly::mul (ring/ntt.rs:119-129)."""
+    return _poly_binary("exb_poly_mul", params, index, a, b, out)
+
+
+def poly_scalar_mul(params, index, a, scalar: int, out=None):
+    """NttPoly::scalar_mul (ring/ntt.rs:132-139)."""
+    return _poly_binary("exb_poly_scalar_mul", params, index, a, None, out, scalar)
+
+
 def launch_count() -> int:
     return int(_native.lib().exb_launch_count())

@@ -134,3 +134,42 @@ def bfv_mul_and_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray,
     _native.check(_native.lib().exb_bfv_mul_and_relin_host(ctx.handle, _ptr(ct1), _ptr(ct2), rlk.native(ctx),
                                                            _ptr(out), ct1.shape[0]))
     return out
+
+
+# ---- plaintext operations used by the polynomial evaluator (bootstrap/digit_extract.rs) -------------
+def scale_plaintext(plaintext, params: BfvParams) -> RnsPoly:
+    """bfv/encrypt.rs:181-229 for a single ciphertext prime: NTT(Delta * m mod q), Delta = floor(q / p)."""
+    from .ring import CoeffPoly
+    q = params.ct_basis.moduli[0]
+    delta = q // params.plain_modulus
+    coeffs = np.array([(int(m) % q) * delta % q for m in plaintext.coeffs], dtype=np.uint64)
+    return RnsPoly.from_coeff_poly(CoeffPoly(coeffs, q), params)
+
+
+def trivial_encrypt(m: int, params: BfvParams) -> BfvCiphertext:
+    """bootstrap/digit_extract.rs:161-177: ct = (Delta * m, 0), zero noise."""
+    from .ring import CoeffPoly
+    pt = np.zeros(params.ring_degree, np.uint64)
+    pt[0] = m % params.plain_modulus
+    return BfvCiphertext([scale_plaintext(CoeffPoly(pt, params.plain_modulus), params), RnsPoly.zero(params)], params)
+
+
+def bfv_plain_mul(ct: BfvCiphertext, plaintext) -> BfvCiphertext:
+    """bfv/eval.rs:468-486: every component times NTT(plaintext) (no Delta scaling)."""
+    pt = RnsPoly.from_coeff_poly(plaintext, ct.params)
+    return BfvCiphertext([ci.mul(pt) for ci in ct.c], ct.params)
+
+
+def bfv_plain_add(ct: BfvCiphertext, plaintext) -> BfvCiphertext:
+    """bfv/eval.rs:489-504: c0 += Delta * m."""
+    c = list(ct.c)
+    c[0] = c[0].add(scale_plaintext(plaintext, ct.params))
+    return BfvCiphertext(c, ct.params)
+
+
+def bfv_scalar_mul(ct: BfvCiphertext, scalar: int) -> BfvCiphertext:
+    """bootstrap/digit_extract.rs:192-197: multiply by the constant plaintext `scalar mod p`."""
+    from .ring import CoeffPoly
+    pt = np.zeros(ct.params.ring_degree, np.uint64)
+    pt[0] = scalar % ct.params.plain_modulus
+    return bfv_plain_mul(ct, CoeffPoly(pt, ct.params.plain_modulus))

@@ -11,7 +11,11 @@ from __future__ import annotations
 
 from typing import Callable, Optional, Sequence
 
-from .bfv import RelinKey
+import math
+
+import numpy as np
+
+from .bfv import (BfvCiphertext, RelinKey, bfv_add, bfv_mul_and_relin, bfv_scalar_mul, trivial_encrypt)
 from .dbfv import DbfvCiphertext, dbfv_mul
 from .error import InvalidParam, NotImplementedErr
 from .params import BfvParams
@@ -58,3 +62,83 @@ def dbfv_mul_chain_then_bootstrap(cts: Sequence[DbfvCiphertext], rlk: RelinKey, 
         rhs = ct if _same_bfv(acc.params.bfv_params, ct.params.bfv_params) else dbfv_bootstrap(ct, bsk)   # :276-283
         acc = dbfv_mul_then_bootstrap(acc, rhs, bsk.boot_rlk if use_boot_rlk else rlk, bsk)
     return acc
+
+
+# ---- Paterson-Stockmeyer polynomial evaluation ---------------------------------
+def _ps_plan(num_coeffs: int):
+    d = max(num_coeffs - 1, 0)
+    k = max(int(math.ceil(math.sqrt(d + 1.0))), 2)                      # digit_extract.rs:112
+    return d, k, (d + k) // k
+
+
+def eval_poly_homomorphic(ct_x: BfvCiphertext, poly_coeffs, rlk: RelinKey) -> BfvCiphertext:
+    """bootstrap/digit_extract.rs:100-157: f(x) on an encrypted x with baby steps x^1..x^k (multiplication
+    tree :119-125) and a giant-step Horner recursion (:151-154); every product is bfv_mul_and_relin."""
+    params = ct_x.params
+    coeffs = [int(c) for c in poly_coeffs]
+    d, k, num_groups = _ps_plan(len(coeffs))
+    if d == 0:
+        return trivial_encrypt(coeffs[0], params)
+    baby = [trivial_encrypt(1, params), ct_x]
+    for i in range(2, k + 1):
+        half = i // 2
+        baby.append(bfv_mul_and_relin(baby[half], baby[i - half], rlk))
+    groups = []
+    for i in range(num_groups):
+        g = trivial_encrypt(0, params)
+        for j in range(k):
+            idx = i * k + j
+            if idx >= len(coeffs):
+                break
+            if coeffs[idx] == 0:
+                continue
+            g = bfv_add(g, bfv_scalar_mul(baby[j], coeffs[idx]))
+        groups.append(g)
+    result = groups.pop()
+    while groups:
+        g = groups.pop()
+        result = bfv_add(bfv_mul_and_relin(result, baby[k], rlk), g)
+    return result
+
+
+def eval_poly_homomorphic_batch(params: BfvParams, ct_x, poly_coeffs, rlk: RelinKey):
+    """The same evaluation on a device-resident batch ct_x [B, 2, n] (torch.int64 CUDA tensor): every baby /
+    giant step is ONE batched bfv_mul_and_relin launch sequence over the B independent ciphertexts, scalar
+    multiplications and additions are point-wise kernels (NTT of a constant polynomial is the constant
+    vector, so `poly_scalar_mul` equals the reference's bfv_plain_mul by a constant bit for bit)."""
+    import torch
+    from . import batch
+    coeffs = [int(c) for c in poly_coeffs]
+    q, p = params.ct_basis.moduli[0], params.plain_modulus
+    delta = q // p
+
+    def trivial(m):
+        t = torch.zeros_like(ct_x)
+        v = (m % p) * delta % q
+        t[:, 0, :] = v - (1 << 64) if v >= (1 << 63) else v
+        return t
+
+    d, k, num_groups = _ps_plan(len(coeffs))
+    if d == 0:
+        return trivial(coeffs[0])
+    baby = [trivial(1), ct_x]
+    for i in range(2, k + 1):
+        half = i // 2
+        baby.append(batch.bfv_mul_and_relin(params, baby[half], baby[i - half], rlk))
+    groups = []
+    for i in range(num_groups):
+        g = trivial(0)
+        for j in range(k):
+            idx = i * k + j
+            if idx >= len(coeffs):
+                break
+            if coeffs[idx] == 0:
+                continue
+            term = batch.poly_scalar_mul(params, 0, baby[j], coeffs[idx] % p)
+            g = batch.poly_add(params, 0, g, term)
+        groups.append(g)
+    result = groups.pop()
+    while groups:
+        g = groups.pop()
+        result = batch.poly_add(params, 0, batch.bfv_mul_and_relin(params, result, baby[k], rlk), g)
+    return result

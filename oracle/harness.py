@@ -211,3 +211,47 @@ def dbfv_decrypt_poly(setup: DbfvSetup, ct, s_ntt) -> np.ndarray:    # decrypt.r
     for i in range(n):
         out[i] = digit_recompose_signed([pl[i] for pl in polys], setup.base, setup.plain_modulus, t)
     return out
+
+
+# ---- Paterson-Stockmeyer evaluation (bootstrap/digit_extract.rs:100-197) on the oracle ------------------
+def trivial_encrypt(p: OracleParams, m: int) -> np.ndarray:          # :161-177
+    pt = np.zeros(p.n, np.uint64)
+    pt[0] = (m % p.plain_modulus) * (p.q // p.plain_modulus) % p.q
+    return np.stack([ntt_fwd(pt, p.q), np.zeros(p.n, np.uint64)])
+
+
+def bfv_scalar_mul(p: OracleParams, ct, scalar: int) -> np.ndarray:  # :192-197 + bfv/eval.rs:468-486
+    pt = np.zeros(p.n, np.uint64)
+    pt[0] = scalar % p.plain_modulus
+    pt_ntt = ntt_fwd(pt, p.q)
+    return np.stack([_mul(c, pt_ntt, p.q) for c in ct])
+
+
+def eval_poly_homomorphic(p: OracleParams, ct_x, poly_coeffs, rlk) -> np.ndarray:   # :100-157
+    import math
+    from . import bfv_add, bfv_mul_and_relin
+    coeffs = [int(c) for c in poly_coeffs]
+    d = max(len(coeffs) - 1, 0)
+    if d == 0:
+        return trivial_encrypt(p, coeffs[0])
+    k = max(int(math.ceil(math.sqrt(d + 1.0))), 2)
+    baby = [trivial_encrypt(p, 1), np.asarray(ct_x, dtype=np.uint64)]
+    for i in range(2, k + 1):
+        half = i // 2
+        baby.append(bfv_mul_and_relin(p, baby[half], baby[i - half], rlk))
+    groups = []
+    for i in range((d + k) // k):
+        g = trivial_encrypt(p, 0)
+        for j in range(k):
+            idx = i * k + j
+            if idx >= len(coeffs):
+                break
+            if coeffs[idx] == 0:
+                continue
+            g = bfv_add(p, g, bfv_scalar_mul(p, baby[j], coeffs[idx]))
+        groups.append(g)
+    result = groups.pop()
+    while groups:
+        g = groups.pop()
+        result = bfv_add(p, bfv_mul_and_relin(p, result, baby[k], rlk), g)
+    return result

@@ -265,3 +265,29 @@ def test_both_aux_basis_paths(monkeypatch):
             rlk = E.RelinKey(rlk_arr, params.bfv_params)
             out = E.dbfv_mul_batch(params, ct1[None], ct2[None], rlk)
             assert digest(out[0]) == str(g[f"{name}/dbfv_sha256"]), (name, mode)
+
+
+def test_eval_poly_homomorphic_paterson_stockmeyer():
+    """SURVEY row f-2: bootstrap/digit_extract.rs:100-157 as a sequence of hot-path multiplications;
+    single-ciphertext API and device-resident batch, bit-exact vs the oracle restatement + decrypt KAT."""
+    from exacto_b200 import batch
+    P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
+                       plain_modulus=17, gadget_base=256)       # p = 17: noise budget for depth 3
+    params = to_params(P)
+    rng = np.random.default_rng(7)
+    s = H.gen_secret_key(P, rng)
+    rlk_arr = H.gen_relin_key(P, s, rng)
+    rlk = E.RelinKey(rlk_arr, params)
+    coeffs = [1, 2, 3, 1, 0, 7]                                   # degree 5 -> k = 3, two baby + one giant step
+    xs = [5, 11, 16]
+    cts = np.stack([H.encrypt_sk(P, H.encode_scalar(P, x), s, rng) for x in xs])
+    want = np.stack([H.eval_poly_homomorphic(P, ct, coeffs, rlk_arr) for ct in cts])
+    one = E.eval_poly_homomorphic(E.BfvCiphertext.from_array(cts[0], params), coeffs, rlk)
+    assert np.array_equal(one.to_array(), want[0])
+    got = batch.to_host(E.eval_poly_homomorphic_batch(params, batch.to_device(cts), coeffs, rlk))
+    assert np.array_equal(got, want)
+    for x, ct in zip(xs, got):
+        assert int(H.decrypt(P, ct, s)[0]) == sum(c * x ** i for i, c in enumerate(coeffs)) % 17
+    assert np.array_equal(E.trivial_encrypt(100, params).to_array(), H.trivial_encrypt(P, 100))
+    assert np.array_equal(E.eval_poly_homomorphic(E.BfvCiphertext.from_array(cts[0], params), [42], rlk).to_array(),
+                          H.trivial_encrypt(P, 42))

@@ -167,3 +167,17 @@ def test_schoolbook_branch_small_params():
     ct1, ct2 = rng.integers(0, P.q, (2, 16), dtype=np.uint64), rng.integers(0, P.q, (2, 16), dtype=np.uint64)
     got = O.ntt_inv(O.bfv_mul_no_relin(P, O.ntt_fwd(ct1, P.q), O.ntt_fwd(ct2, P.q)), P.q)
     assert np.array_equal(got, np.array(D.bfv_mul_no_relin_coeff(ct1, ct2, P.q, 17), dtype=np.uint64))
+
+
+# ---- Paterson-Stockmeyer evaluation (bootstrap/digit_extract.rs:100-157), SURVEY row f-2 ---------------
+def test_eval_poly_homomorphic_oracle_decrypts():
+    """f(x) = 1 + 2x + 3x^2 + x^3 at x = 5 (mod 257) on HPS parameters with a deep noise budget."""
+    P = O.OracleParams(n=64, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
+                       plain_modulus=257, gadget_base=256)
+    rng = np.random.default_rng(7)
+    s = H.gen_secret_key(P, rng); rlk = H.gen_relin_key(P, s, rng)
+    ct = H.encrypt_sk(P, H.encode_scalar(P, 5), s, rng)
+    out = H.eval_poly_homomorphic(P, ct, [1, 2, 3, 1], rlk)
+    assert int(H.decrypt(P, out, s)[0]) == (1 + 10 + 75 + 125) % 257
+    assert int(H.decrypt(P, H.eval_poly_homomorphic(P, ct, [42], rlk), s)[0]) == 42
+    assert int(H.decrypt(P, H.trivial_encrypt(P, 100), s)[0]) == 100               # digit_extract.rs:271-288
