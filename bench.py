@@ -279,7 +279,12 @@ def run_gpu(args):
             "bfv_mul_and_relin_equiv_per_s": value * 64,
             "roofline": {"kernel": "tensor32_kernel (per product and component: point-wise tensor in q + 3 internal 30-bit primes, 4 INTT, hps_scale, gadget digits)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_fused_kernels.json
+                         # (ncu --set full on this command line; only valid for the default workload)
+                         "traffic": (1035571200 if (pairs == 148 and not args.all_products and
+                                                    os.environ.get("EXB_AUX_BASIS") != "reference") else None),
+                         "algorithmic_bytes": tensor_bytes * pairs,
                          "peak_source": peak_src, "share_of_step": stage_ms[1] / total_stage,
                          "note": "integer-pipe bound kernel: see DESIGN.md; HBM fraction is reported, not the target"},
             "stages": stages,

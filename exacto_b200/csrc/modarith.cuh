@@ -98,8 +98,8 @@ EXB_HD u64 mont_mul2_lazy(u64 a, u64 b, u64 c, u64 d, u64 m, u64 minv_neg) {
 // ---- Hand-scheduled Shoup multiply-accumulate for the NTT butterflies ----------------
 // Measured on B200 (tools/ubench2.cu): IMAD.LO ~1 issue cycle per warp, IMAD.WIDE ~2,
 // IMAD.HI ~2.5, a 64-bit compare + conditional subtract ~6.  So the butterfly uses an
-// *approximate* quotient  Q' = y1*s1 + hi32(y1*s0) + hi32(y0*s1)  in [Q-2, Q]
-// (1 WIDE + 2 HI instead of 4 WIDE + carries) and folds every addition into the IMAD
+// *approximate* quotient  Q' = hi64(y*s - y0*s0)  in [Q-1, Q]  (3 WIDE: only the y0*s0 partial
+// product is dropped; IMAD.HI would cost more and needs addend register pairs) and folds every addition into the IMAD
 // accumulate operands:  result = addend + y*w + Q' * (2^64 - m)  (mod 2^64)
 //                              = addend + T,   T = y*w mod m + e*m,  T in [0, 4m).
 // Valid for any y < 2^64 as long as addend + 4m < 2^64.
@@ -107,17 +107,20 @@ EXB_HD u64 shoup_mad4(u64 y, u64 w, u64 s, u64 neg_m, u64 addend) {
 #if defined(__CUDA_ARCH__)
     u64 r;
     asm("{\n\t"
-        ".reg .u64 qq, acc;\n\t"
-        ".reg .u32 y0, y1, w0, w1, s0, s1, n0, n1, q0, q1, t1, t2, lo, hi, x;\n\t"
+        ".reg .u64 qq, acc, c1, c2;\n\t"
+        ".reg .u32 y0, y1, w0, w1, s0, s1, n0, n1, q0, q1, t1, t2, l1, l2, lo, hi, x;\n\t"
         "mov.b64 {y0, y1}, %1;\n\t"
         "mov.b64 {w0, w1}, %2;\n\t"
         "mov.b64 {s0, s1}, %3;\n\t"
         "mov.b64 {n0, n1}, %4;\n\t"
         "mul.wide.u32 qq, y1, s1;\n\t"           // y1*s1
-        "mul.hi.u32 t1, y1, s0;\n\t"             // hi32(y1*s0)
-        "mul.hi.u32 t2, y0, s1;\n\t"             // hi32(y0*s1)
+        "mul.wide.u32 c1, y1, s0;\n\t"           // cross terms as full products: their low halves give
+        "mul.wide.u32 c2, y0, s1;\n\t"           // the exact carry, and no IMAD.HI addend pairs are needed
         "mov.b64 {q0, q1}, qq;\n\t"
-        "add.cc.u32 q0, q0, t1;\n\t"
+        "mov.b64 {l1, t1}, c1;\n\t"
+        "mov.b64 {l2, t2}, c2;\n\t"
+        "add.cc.u32 l1, l1, l2;\n\t"
+        "addc.cc.u32 q0, q0, t1;\n\t"
         "addc.u32 q1, q1, 0;\n\t"
         "add.cc.u32 q0, q0, t2;\n\t"
         "addc.u32 q1, q1, 0;\n\t"
@@ -136,7 +139,8 @@ EXB_HD u64 shoup_mad4(u64 y, u64 w, u64 s, u64 neg_m, u64 addend) {
     return r;
 #else
     const u64 y0 = (u32)y, y1 = y >> 32, s0 = (u32)s, s1 = s >> 32;
-    const u64 q = y1 * s1 + ((y1 * s0) >> 32) + ((y0 * s1) >> 32);
+    const u64 c1 = y1 * s0, c2 = y0 * s1;
+    const u64 q = y1 * s1 + (c1 >> 32) + (c2 >> 32) + (((c1 & 0xffffffffu) + (c2 & 0xffffffffu)) >> 32);
     return addend + y * w + q * neg_m;
 #endif
 }
