@@ -1,0 +1,281 @@
+// exacto_b200.hpp -- C++ host mirror of the reference's public surface for the
+// ciphertext-multiplication path, header-only, over the C ABI of exacto_b200.h.
+//
+// The reference is Rust; there is no Rust toolchain in this image, so the compiled-language host
+// side is C++: same type and function names, argument meaning, ownership (inputs borrowed, fresh
+// outputs sharing the parameter object) and error behaviour (ExactoError variants and the message
+// substrings the reference's tests pin).  Citations are into /root/reference/src/.
+//
+//   ring/    CoeffPoly (ring/poly.rs:6-9), NttPoly (ring/ntt.rs:11-15), RnsPoly (ring/rns.rs:14-17)
+//   params/  BfvParams + BfvParamsBuilder (params/mod.rs:11-124), DbfvParams (params/mod.rs:143-192),
+//            compact_bfv / compact_dbfv / u64_dbfv (params/presets.rs:24-98)
+//   bfv/     BfvCiphertext (bfv/mod.rs:19-24), RelinKey (bfv/keygen.rs:39-45),
+//            bfv_add (bfv/eval.rs:14-31), bfv_mul_and_relin (bfv/eval.rs:73-82)
+//   dbfv/    DbfvCiphertext (dbfv/ciphertext.rs:10-22), dbfv_add (dbfv/eval.rs:11-33), dbfv_mul (dbfv/eval.rs:82-149)
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "exacto_b200.h"
+
+namespace exacto {
+
+// ---- error.rs:4-31 ---------------------------------------------------------------------------
+class ExactoError : public std::runtime_error {
+public:
+    enum Kind { InvalidParam = 1, DimensionMismatch, ModulusMismatch, InvalidRingDegree, DecryptionError,
+                DecompositionError, LatticeError, MissingKey, NotImplemented, Cuda = 100 };
+    ExactoError(Kind k, const std::string &msg) : std::runtime_error(render(k, msg)), kind(k), detail(msg) {}
+    Kind kind;
+    std::string detail;
+private:
+    static std::string render(Kind k, const std::string &m) {
+        switch (k) {
+            case InvalidParam: return "invalid parameter: " + m;
+            case DimensionMismatch: return "dimension mismatch: " + m;
+            case ModulusMismatch: return "modulus mismatch";
+            case InvalidRingDegree: return m;
+            case NotImplemented: return "not yet implemented: " + m;
+            case Cuda: return "CUDA error: " + m;
+            default: return m;
+        }
+    }
+};
+
+inline void check(int rc) {
+    if (rc != EXB_OK) throw ExactoError(static_cast<ExactoError::Kind>(rc), exb_last_error());
+}
+
+// ---- params/ -----------------------------------------------------------------------------------
+struct BfvParams {                                   // params/mod.rs:11-27
+    size_t ring_degree = 4096;
+    uint64_t plain_modulus = 65537;
+    std::vector<uint64_t> ct_moduli, aux_moduli;
+    double sigma = 3.2;
+    uint64_t gadget_base = 0;
+    uint32_t gadget_digits = 0;
+
+    ~BfvParams() { if (ctx_) exb_context_destroy(ctx_); }
+    BfvParams() = default;
+    BfvParams(const BfvParams &) = delete;
+
+    // The GPU context (plans, HPS constants, workspace) is created on first use.
+    exb_context *context(int device = 0) const {
+        if (!ctx_) {
+            exb_bfv_params p{};
+            p.ring_degree = (uint32_t)ring_degree;
+            p.num_ct_moduli = (uint32_t)ct_moduli.size(); p.ct_moduli = ct_moduli.data();
+            p.num_aux_moduli = (uint32_t)aux_moduli.size(); p.aux_moduli = aux_moduli.data();
+            p.plain_modulus = plain_modulus; p.gadget_base = gadget_base; p.gadget_digits = gadget_digits;
+            check(exb_context_create(&p, device, &ctx_));
+        }
+        return ctx_;
+    }
+    uint64_t q() const { return ct_moduli.at(0); }
+private:
+    mutable exb_context *ctx_ = nullptr;
+};
+
+class BfvParamsBuilder {                             // params/mod.rs:29-124
+public:
+    BfvParamsBuilder &ring_degree(size_t n) { p_->ring_degree = n; return *this; }
+    BfvParamsBuilder &plain_modulus(uint64_t p) { p_->plain_modulus = p; return *this; }
+    BfvParamsBuilder &ct_moduli(std::vector<uint64_t> m) { p_->ct_moduli = std::move(m); return *this; }
+    BfvParamsBuilder &aux_moduli(std::vector<uint64_t> m) { p_->aux_moduli = std::move(m); return *this; }
+    BfvParamsBuilder &sigma(double s) { p_->sigma = s; return *this; }
+    BfvParamsBuilder &gadget_base(uint64_t b) { p_->gadget_base = b; return *this; }
+    // Validation (ring degree, moduli, plans) and the gadget-digit default run in exb_context_create,
+    // with the reference's error variants; build() forces it so errors surface here like in Rust.
+    std::shared_ptr<BfvParams> build() {
+        std::shared_ptr<BfvParams> out = p_;
+        exb_context *c = out->context();
+        uint64_t gb = 0; uint32_t gd = 0;
+        check(exb_context_gadget(c, &gb, &gd));
+        out->gadget_base = gb; out->gadget_digits = gd;
+        p_ = std::make_shared<BfvParams>();
+        return out;
+    }
+private:
+    std::shared_ptr<BfvParams> p_ = std::make_shared<BfvParams>();
+};
+
+struct DbfvParams {                                  // params/mod.rs:143-192
+    std::shared_ptr<BfvParams> bfv_params;
+    uint64_t base;
+    size_t num_digits;
+    uint64_t plain_modulus;                          // 0 == 2^64
+    static std::shared_ptr<DbfvParams> create(std::shared_ptr<BfvParams> bfv, uint64_t base, size_t d, uint64_t p) {
+        if (base < 2) throw ExactoError(ExactoError::InvalidParam, "base must be >= 2");
+        if (d < 1) throw ExactoError(ExactoError::InvalidParam, "num_digits must be >= 1");
+        unsigned __int128 bd = 1;
+        for (size_t i = 0; i < d; i++) { if (bd > (~(unsigned __int128)0) / base) { bd = ~(unsigned __int128)0; break; } bd *= base; }
+        const unsigned __int128 p128 = p == 0 ? ((unsigned __int128)1 << 64) : p;
+        if (bd < p128) throw ExactoError(ExactoError::InvalidParam, "base^digits < plain_modulus");
+        return std::make_shared<DbfvParams>(DbfvParams{std::move(bfv), base, d, p});
+    }
+};
+
+inline std::shared_ptr<BfvParams> compact_bfv() {    // params/presets.rs:24-35
+    return BfvParamsBuilder().ring_degree(1024).plain_modulus(257).ct_moduli({1099509805057ull})
+        .aux_moduli({562949953443841ull}).build();
+}
+inline std::shared_ptr<DbfvParams> compact_dbfv() {  // params/presets.rs:86-98
+    auto bfv = BfvParamsBuilder().ring_degree(1024).plain_modulus(929).ct_moduli({1099509805057ull})
+                   .aux_moduli({562949953443841ull}).build();
+    return DbfvParams::create(bfv, 16, 2, 256);
+}
+inline std::shared_ptr<DbfvParams> u64_dbfv() {      // params/presets.rs:61-75
+    auto bfv = BfvParamsBuilder().ring_degree(4096).plain_modulus(1040407).ct_moduli({1152921504606830593ull})
+                   .aux_moduli({18014398509998081ull, 36028797018972161ull}).gadget_base(256).build();
+    return DbfvParams::create(bfv, 256, 8, 0);
+}
+
+// ---- ring/ (single ciphertext prime: what the hot path uses) ---------------------------------------
+struct CoeffPoly {                                   // ring/poly.rs:6-9
+    std::vector<uint64_t> coeffs;
+    uint64_t modulus;
+};
+struct NttPoly {                                     // ring/ntt.rs:11-15 (the plan is the params' context)
+    std::vector<uint64_t> evals;
+    uint64_t modulus;
+    static NttPoly from_coeff_poly(const CoeffPoly &p, const BfvParams &params) {   // ring/ntt.rs:42-55
+        if (p.modulus != params.q()) throw ExactoError(ExactoError::ModulusMismatch, "");
+        NttPoly out{std::vector<uint64_t>(p.coeffs.size()), p.modulus};
+        check(exb_ntt_forward_host(params.context(), 0, p.coeffs.data(), out.evals.data(), 1));
+        return out;
+    }
+    CoeffPoly to_coeff_poly(const BfvParams &params) const {                        // ring/ntt.rs:58-67
+        CoeffPoly out{std::vector<uint64_t>(evals.size()), modulus};
+        check(exb_ntt_inverse_host(params.context(), 0, evals.data(), out.coeffs.data(), 1));
+        return out;
+    }
+};
+struct RnsPoly {                                     // ring/rns.rs:14-17
+    std::vector<NttPoly> components;
+    size_t ring_degree;
+};
+
+// ---- bfv/ --------------------------------------------------------------------------------------------
+struct BfvCiphertext {                               // bfv/mod.rs:19-24
+    std::vector<RnsPoly> c;
+    std::shared_ptr<BfvParams> params;
+    size_t degree() const { return c.size() - 1; }
+};
+
+class RelinKey {                                     // bfv/keygen.rs:39-45
+public:
+    std::vector<std::pair<RnsPoly, RnsPoly>> keys;
+    std::shared_ptr<BfvParams> params;
+    RelinKey(std::vector<std::pair<RnsPoly, RnsPoly>> k, std::shared_ptr<BfvParams> p) : keys(std::move(k)), params(std::move(p)) {}
+    RelinKey(const RelinKey &) = delete;
+    ~RelinKey() { if (dev_) exb_relin_key_destroy(dev_); }
+    const exb_relin_key *device() const {            // uploaded once, [G][2][n]
+        if (!dev_) {
+            const size_t n = params->ring_degree;
+            std::vector<uint64_t> flat;
+            flat.reserve(keys.size() * 2 * n);
+            for (const auto &k : keys) {
+                const auto &a = k.first.components.at(0).evals, &b = k.second.components.at(0).evals;
+                flat.insert(flat.end(), a.begin(), a.end());
+                flat.insert(flat.end(), b.begin(), b.end());
+            }
+            check(exb_relin_key_load(params->context(), flat.data(), (uint32_t)keys.size(), &dev_));
+        }
+        return dev_;
+    }
+private:
+    mutable exb_relin_key *dev_ = nullptr;
+};
+
+namespace detail {
+inline void flatten(const BfvCiphertext &ct, std::vector<uint64_t> &out) {
+    for (const RnsPoly &p : ct.c) {
+        const auto &e = p.components.at(0).evals;
+        out.insert(out.end(), e.begin(), e.end());
+    }
+}
+inline BfvCiphertext unflatten(const uint64_t *src, size_t polys, const std::shared_ptr<BfvParams> &params) {
+    const size_t n = params->ring_degree;
+    BfvCiphertext ct{{}, params};
+    for (size_t i = 0; i < polys; i++)
+        ct.c.push_back(RnsPoly{{NttPoly{std::vector<uint64_t>(src + i * n, src + (i + 1) * n), params->q()}}, n});
+    return ct;
+}
+}  // namespace detail
+
+inline BfvCiphertext bfv_add(const BfvCiphertext &ct1, const BfvCiphertext &ct2) {   // bfv/eval.rs:14-31
+    if (ct1.c.size() != 2 || ct2.c.size() != 2)
+        throw ExactoError(ExactoError::NotImplemented, "C++ mirror adds degree-1 ciphertexts only");
+    std::vector<uint64_t> a, b;
+    detail::flatten(ct1, a); detail::flatten(ct2, b);
+    exb_context *ctx = ct1.params->context();
+    void *da = nullptr, *db = nullptr;
+    const size_t bytes = a.size() * 8;
+    check(exb_device_alloc(ctx, bytes, &da)); check(exb_device_alloc(ctx, bytes, &db));
+    check(exb_copy_to_device(ctx, da, a.data(), bytes, nullptr)); check(exb_copy_to_device(ctx, db, b.data(), bytes, nullptr));
+    check(exb_bfv_add(ctx, (const uint64_t *)da, (const uint64_t *)db, (uint64_t *)da, 1, nullptr));
+    check(exb_copy_to_host(ctx, a.data(), da, bytes, nullptr)); check(exb_synchronize(ctx, nullptr));
+    exb_device_free(ctx, da); exb_device_free(ctx, db);
+    return detail::unflatten(a.data(), 2, ct1.params);
+}
+
+inline BfvCiphertext bfv_mul_and_relin(const BfvCiphertext &ct1, const BfvCiphertext &ct2, const RelinKey &rlk) {   // bfv/eval.rs:73-82
+    if (ct1.c.size() != 2 || ct2.c.size() != 2)                                                                     // :93-97
+        throw ExactoError(ExactoError::InvalidParam, "multiplication requires degree-1 ciphertexts");
+    std::vector<uint64_t> a, b;
+    detail::flatten(ct1, a); detail::flatten(ct2, b);
+    std::vector<uint64_t> out(a.size());
+    check(exb_bfv_mul_and_relin_host(ct1.params->context(), a.data(), b.data(), rlk.device(), out.data(), 1));
+    return detail::unflatten(out.data(), 2, ct1.params);
+}
+
+// ---- dbfv/ -----------------------------------------------------------------------------------------------
+struct DbfvCiphertext {                              // dbfv/ciphertext.rs:10-22
+    std::vector<BfvCiphertext> limbs;
+    size_t degree;
+    size_t mul_depth;
+    std::shared_ptr<DbfvParams> params;
+    size_t num_limbs() const { return limbs.size(); }
+    bool needs_reduction() const { return degree > params->num_digits; }
+};
+
+inline DbfvCiphertext dbfv_add(const DbfvCiphertext &ct1, const DbfvCiphertext &ct2) {   // dbfv/eval.rs:11-33
+    if (ct1.num_limbs() != ct2.num_limbs())
+        throw ExactoError(ExactoError::DimensionMismatch, "expected " + std::to_string(ct1.num_limbs()) + ", got " + std::to_string(ct2.num_limbs()));
+    DbfvCiphertext out{{}, std::max(ct1.degree, ct2.degree), std::max(ct1.mul_depth, ct2.mul_depth), ct1.params};
+    for (size_t i = 0; i < ct1.num_limbs(); i++) out.limbs.push_back(bfv_add(ct1.limbs[i], ct2.limbs[i]));
+    return out;
+}
+
+inline DbfvCiphertext dbfv_mul(const DbfvCiphertext &ct1, const DbfvCiphertext &ct2, const RelinKey &rlk) {   // dbfv/eval.rs:82-149
+    const auto &params = ct1.params;
+    const size_t d = params->num_digits;
+    if (ct1.num_limbs() != d || ct2.num_limbs() != d)                                                         // :90-94
+        throw ExactoError(ExactoError::InvalidParam, "multiplication requires d-limb ciphertexts");
+    const size_t next_depth = std::max(ct1.mul_depth, ct2.mul_depth) + 1;
+    if (next_depth > 1)                                                                                       // :96-102
+        throw ExactoError(ExactoError::NotImplemented,
+                          "chained dBFV multiplication requires ciphertext-level lattice reduction (paper §4.6.2)");
+    std::vector<uint64_t> a, b;
+    for (const auto &l : ct1.limbs) {
+        if (l.c.size() != 2) throw ExactoError(ExactoError::InvalidParam, "multiplication requires degree-1 ciphertexts");
+        detail::flatten(l, a);
+    }
+    for (const auto &l : ct2.limbs) {
+        if (l.c.size() != 2) throw ExactoError(ExactoError::InvalidParam, "multiplication requires degree-1 ciphertexts");
+        detail::flatten(l, b);
+    }
+    std::vector<uint64_t> out(a.size());
+    check(exb_dbfv_mul_host(params->bfv_params->context(), params->base, (uint32_t)d, params->plain_modulus, a.data(), b.data(),
+                            rlk.device(), out.data(), 1, 0));       // the d^2 products, per-k sums and reduce() in one batched sequence
+    DbfvCiphertext res{{}, d, next_depth, params};                   // :138-146, reduction.rs:54-59
+    const size_t n = params->bfv_params->ring_degree;
+    for (size_t i = 0; i < d; i++) res.limbs.push_back(detail::unflatten(out.data() + i * 2 * n, 2, params->bfv_params));
+    return res;
+}
+
+}  // namespace exacto

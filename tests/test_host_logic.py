@@ -171,3 +171,12 @@ def test_gloo_world2_sharding(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_cpp_host_mirror_builds_and_links(native_lib):
+    """include/exacto_b200.hpp compiles against the C ABI and the driver links the in-tree library."""
+    import subprocess
+    import __graft_entry__ as g
+    exe = g.build_cpp_driver()
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 2 and "usage" in res.stderr
