@@ -430,7 +430,9 @@ static int mul_precheck(exb_context *c, const exb_relin_key *rlk) {
 static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G) {
     size_t eb, rb, db, xb;
     const size_t per = ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
-    size_t chunk = ((size_t)4 << 30) / (per ? per : 1);
+    // EXB_DEVICE_CHUNK_BYTES (tests only) forces small chunks so the chunk loop is exercised
+    static const size_t budget = getenv("EXB_DEVICE_CHUNK_BYTES") ? (size_t)atoll(getenv("EXB_DEVICE_CHUNK_BYTES")) : ((size_t)4 << 30);
+    size_t chunk = budget / (per ? per : 1);
     return chunk ? chunk : 1;
 }
 

@@ -9,6 +9,10 @@ from common import CASES, H, O, digest, golden, golden_inputs, to_dbfv_params, t
 
 pytestmark = pytest.mark.gpu
 
+import os as _os
+TESTS_DIR = _os.path.dirname(_os.path.abspath(__file__))
+ROOT_DIR = _os.path.dirname(TESTS_DIR)
+
 torch = pytest.importorskip("torch")
 
 
@@ -318,3 +322,42 @@ def test_cpp_host_mirror(preset, tmp_path):
     want_sum = np.array((ct1.astype(object) + ct2.astype(object)) % P.q, dtype=np.uint64)
     assert np.array_equal(out[lim + 2 * P.n:2 * lim + 2 * P.n].reshape(S.d, 2, P.n), want_sum)
     assert np.array_equal(out[2 * lim + 2 * P.n:], O.ntt_inv(ct1[0, 0], P.q))
+
+
+def test_device_api_chunk_loop():
+    """exb_dbfv_mul splits large batches into workspace-bounded chunks; force tiny chunks (env is read once
+    per process, so this runs in a subprocess) and compare with the oracle."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import exacto_b200 as E, oracle as O
+        from exacto_b200 import batch
+        from common import CASES, to_dbfv_params
+        P, base, d, pm, seed, _ = CASES["n64_a2_rep"]
+        rng = np.random.default_rng(3)
+        ct1 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64); ct2 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64)
+        rk = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+        params = to_dbfv_params(P, base, d, pm)
+        got = batch.to_host(batch.dbfv_mul(params, batch.to_device(ct1), batch.to_device(ct2), E.RelinKey(rk, params.bfv_params)))
+        want = np.stack([O.dbfv_mul(P, base, d, pm, a, b, rk) for a, b in zip(ct1, ct2)])
+        assert np.array_equal(got, want); print("chunk loop ok")
+    """) % (ROOT_DIR, TESTS_DIR)
+    env = dict(__import__("os").environ, EXB_DEVICE_CHUNK_BYTES=str(2 * 40000))   # ~2 pairs per chunk at n=64
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert res.returncode == 0 and "chunk loop ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("n", [16, 2048, 8192])
+def test_generic_ring_degrees(n):
+    """Ring degrees other than 4096 take the generic shared-memory path (any n <= 8192)."""
+    P = O.OracleParams(n=n, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
+                       plain_modulus=1040407, gadget_base=256)
+    rng = np.random.default_rng(n)
+    ct1 = rng.integers(0, P.q, (2, 2, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (2, 2, 2, n), dtype=np.uint64)
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    params = to_dbfv_params(P, 256, 2, 65536)
+    got = E.dbfv_mul_batch(params, ct1, ct2, E.RelinKey(rlk_arr, params.bfv_params))
+    want = np.stack([O.dbfv_mul(P, 256, 2, 65536, a, b, rlk_arr, threads=O.max_threads()) for a, b in zip(ct1, ct2)])
+    assert np.array_equal(got, want)
