@@ -351,8 +351,9 @@ def test_device_api_chunk_loop():
 @pytest.mark.parametrize("n", [16, 2048, 8192])
 def test_generic_ring_degrees(n):
     """Ring degrees other than 4096 take the generic shared-memory path (any n <= 8192)."""
-    P = O.OracleParams(n=n, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
-                       plain_modulus=1040407, gadget_base=256)
+    # n = 8192 needs aux primes = 1 mod 16384 (the u64-profile pair is only = 1 mod 8192)
+    aux = (36028797019389953, 36028797019488257) if n == 8192 else (18014398509998081, 36028797018972161)
+    P = O.OracleParams(n=n, q=1152921504606830593, aux=aux, plain_modulus=1040407, gadget_base=256)
     rng = np.random.default_rng(n)
     ct1 = rng.integers(0, P.q, (2, 2, 2, n), dtype=np.uint64)
     ct2 = rng.integers(0, P.q, (2, 2, 2, n), dtype=np.uint64)
