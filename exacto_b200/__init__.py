@@ -5,8 +5,9 @@ and error behaviour) over the C ABI of ``libexacto_b200.so`` (include/exacto_b20
 
     ring/      CoeffPoly, NttPoly, RnsPoly, RnsBasis, make_plan
     params/    BfvParamsBuilder, BfvParams, DbfvParams, compact_bfv, compact_dbfv, u64_dbfv
-    bfv/       BfvCiphertext, RelinKey, bfv_mul_and_relin, bfv_add, bfv_sub, bfv_neg
-    dbfv/      DbfvCiphertext, dbfv_mul, dbfv_add, dbfv_sub, dbfv_neg
+    bfv/       BfvCiphertext, RelinKey, bfv_mul_and_relin, bfv_add, bfv_sub, bfv_neg,
+               GaloisKey, bfv_apply_automorphism, bfv_trace, bfv_inner_product
+    dbfv/      DbfvCiphertext, dbfv_mul, dbfv_add, dbfv_sub, dbfv_neg, dbfv_apply_automorphism
     bootstrap/ dbfv_mul_then_bootstrap, dbfv_mul_chain_then_bootstrap (orchestration only),
                eval_poly_homomorphic (Paterson-Stockmeyer over the hot-path multiplications)
 
@@ -16,9 +17,10 @@ from .error import ExactoError
 from .params import (BfvParams, BfvParamsBuilder, DbfvParams, RnsBasis, cfg3_prime_dbfv, compact_bfv,
                      compact_dbfv, compute_gadget_digits, set_default_device, small_bfv, u64_dbfv)
 from .ring import CoeffPoly, NttPoly, Plan, RnsPoly, make_plan
-from .bfv import (BfvCiphertext, RelinKey, bfv_add, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_neg, bfv_plain_add,
-                  bfv_plain_mul, bfv_scalar_mul, bfv_sub, scale_plaintext, trivial_encrypt)
-from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
+from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automorphism, bfv_apply_automorphism_batch,
+                  bfv_inner_product, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_neg, bfv_plain_add, bfv_plain_mul,
+                  bfv_scalar_mul, bfv_sub, bfv_trace, scale_plaintext, trivial_encrypt)
+from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_apply_automorphism, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
 from .bootstrap import (BootstrapKey, dbfv_bootstrap, dbfv_mul_chain_then_bootstrap, dbfv_mul_then_bootstrap,
                         eval_poly_homomorphic, eval_poly_homomorphic_batch)
 

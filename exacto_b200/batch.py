@@ -90,6 +90,18 @@ def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: Reli
     return out
 
 
+def bfv_apply_automorphism(params: BfvParams, ct: torch.Tensor, gk, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bfv/eval.rs:512-561 over [B, 2, n] (or [B, d, 2, n]: every limb, dbfv/advanced.rs:15-30); ``gk`` is a
+    GaloisKey.  ``out`` must not alias ``ct``."""
+    n = params.ring_degree
+    _check(ct, (2, n), "ct")
+    out = torch.empty_like(ct) if out is None else out
+    ctx = params.context(ct.device.index)
+    _native.check(_native.lib().exb_bfv_apply_automorphism(ctx.handle, ct.data_ptr(), gk.element, gk.native(ctx),
+                                                           out.data_ptr(), ct.numel() // (2 * n), _stream(ct)))
+    return out
+
+
 def _poly_binary(name: str, params: BfvParams, index: int, a: torch.Tensor, b: Optional[torch.Tensor],
                  out: Optional[torch.Tensor], scalar: int = 0) -> torch.Tensor:
     _check(a, (params.ring_degree,), name)

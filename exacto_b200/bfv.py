@@ -4,6 +4,8 @@ behaviour; the arithmetic runs in libexacto_b200.so on the GPU.
 
     bfv_mul_and_relin(ct1, ct2, rlk)   bfv/eval.rs:73-82
     bfv_add / bfv_sub / bfv_neg        bfv/eval.rs:14-62
+    bfv_apply_automorphism / bfv_trace bfv/eval.rs:512-588 (Galois automorphism + key switch)
+    bfv_inner_product                  bfv/eval.rs:593-606
     relinearize passthrough rules      bfv/keyswitch.rs:59-70
 """
 from __future__ import annotations
@@ -80,6 +82,15 @@ class RelinKey:
             pass
 
 
+class GaloisKey(RelinKey):
+    """bfv/keygen.rs:47-54: key-switch key from s(X^element) to s(X); same [G][2][n] layout as a
+    RelinKey, plus the Galois element."""
+
+    def __init__(self, keys, element: int, params: BfvParams):
+        super().__init__(keys, params)
+        self.element = int(element)
+
+
 def _zip_op(ct1: BfvCiphertext, ct2: BfvCiphertext, op: str, lone_rhs) -> BfvCiphertext:
     c = []
     for i in range(max(len(ct1.c), len(ct2.c))):
@@ -134,6 +145,49 @@ def bfv_mul_and_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray,
     _native.check(_native.lib().exb_bfv_mul_and_relin_host(ctx.handle, _ptr(ct1), _ptr(ct2), rlk.native(ctx),
                                                            _ptr(out), ct1.shape[0]))
     return out
+
+
+# ---- Galois automorphism + key switch --------------------------------------------------------------
+def bfv_apply_automorphism(ct: BfvCiphertext, gk: GaloisKey) -> BfvCiphertext:
+    """bfv/eval.rs:512-561: sigma_k on (c0, c1), then key-switch c1 back to s with the Galois key."""
+    if len(ct.c) != 2:                                                   # :516-520
+        raise InvalidParam("automorphism requires degree-1 ciphertext")
+    out = bfv_apply_automorphism_batch(ct.params, ct.to_array()[None], gk)
+    return BfvCiphertext.from_array(out[0], ct.params)
+
+
+def bfv_apply_automorphism_batch(params: BfvParams, ct: np.ndarray, gk: GaloisKey,
+                                 device: Optional[int] = None) -> np.ndarray:
+    """Batched host-buffer form: ct [B][2][n] -> [B][2][n] (exb_bfv_apply_automorphism_host)."""
+    ct = _u64(ct)
+    if ct.ndim != 3 or ct.shape[1:] != (2, params.ring_degree):
+        raise InvalidParam("automorphism requires degree-1 ciphertext")
+    ctx = params.context(device)
+    out = np.empty_like(ct)
+    _native.check(_native.lib().exb_bfv_apply_automorphism_host(ctx.handle, _ptr(ct), gk.element, gk.native(ctx),
+                                                                _ptr(out), ct.shape[0]))
+    return out
+
+
+def bfv_trace(ct: BfvCiphertext, galois_elements: Sequence[int], galois_keys) -> BfvCiphertext:
+    """bfv/eval.rs:573-588: result <- result + sigma_k(result) for each k in order."""
+    result = ct
+    for k in galois_elements:
+        gk = galois_keys.get(k)
+        if gk is None:
+            raise InvalidParam(f"missing Galois key for element {k}")
+        result = bfv_add(result, bfv_apply_automorphism(result, gk))
+    return result
+
+
+def bfv_inner_product(cts: Sequence[BfvCiphertext], pts) -> BfvCiphertext:
+    """bfv/eval.rs:593-606: sum_i pt_i * ct_i."""
+    if len(cts) == 0 or len(cts) != len(pts):
+        raise InvalidParam("mismatched ct/pt lengths")
+    acc = bfv_plain_mul(cts[0], pts[0])
+    for ct, pt in zip(cts[1:], pts[1:]):
+        acc = bfv_add(acc, bfv_plain_mul(ct, pt))
+    return acc
 
 
 # ---- plaintext operations used by the polynomial evaluator (bootstrap/digit_extract.rs) -------------

@@ -78,6 +78,18 @@ static int grow(void **p, size_t *have, size_t want) {
     return EXB_OK;
 }
 
+// in2 and out share the growth bookkeeping of out_b
+static int grow_in2_out(Workspace &w, size_t want) {
+    if (w.out_b >= want) return EXB_OK;
+    if (w.in2) EXB_CUDA(cudaFree(w.in2));
+    if (w.out) EXB_CUDA(cudaFree(w.out));
+    w.in2 = w.out = nullptr; w.out_b = 0;
+    EXB_CUDA(cudaMalloc((void **)&w.in2, want));
+    EXB_CUDA(cudaMalloc((void **)&w.out, want));
+    w.out_b = want;
+    return EXB_OK;
+}
+
 extern "C" const char *exb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *exb_version(void) { return "exacto_b200 0.1 (sm_100a)"; }
 extern "C" unsigned long long exb_launch_count(void) { return exb::g_launch_count; }
@@ -487,15 +499,7 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
         const size_t bytes = cnt * stride * 8;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
-        // in2 and out share the growth bookkeeping of out_b
-        if (w.out_b < chunk * stride * 8) {
-            if (w.in2) EXB_CUDA(cudaFree(w.in2));
-            if (w.out) EXB_CUDA(cudaFree(w.out));
-            w.in2 = w.out = nullptr; w.out_b = 0;
-            EXB_CUDA(cudaMalloc((void **)&w.in2, chunk * stride * 8));
-            EXB_CUDA(cudaMalloc((void **)&w.out, chunk * stride * 8));
-            w.out_b = chunk * stride * 8;
-        }
+        if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream))) return rc;
@@ -508,4 +512,52 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
 extern "C" int exb_bfv_mul_and_relin_host(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
                                           const exb_relin_key *rlk, uint64_t *out, size_t batch) {
     return exb_dbfv_mul_host(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0);
+}
+
+// ---- Galois automorphism + key switch (bfv/eval.rs:512-561) -------------------------------------
+static int galois_precheck(exb_context *c, const exb_relin_key *gk, uint64_t element) {
+    if (!c || !gk) return fail(EXB_INVALID_PARAM, "null argument");
+    if (gk->ctx != c) return fail(EXB_INVALID_PARAM, "Galois key belongs to another context");
+    if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "automorphism on the device path needs a single ciphertext prime");
+    if (!(element & 1))   // sigma_k is a ring automorphism only for odd k (bfv/keygen.rs:216-217)
+        return fail(EXB_INVALID_PARAM, "Galois element must be odd");
+    if (gk->num_keys < c->gadget_digits)
+        return fail(EXB_INVALID_PARAM, "Galois key holds fewer than gadget_digits key pairs");
+    return EXB_OK;
+}
+
+extern "C" int exb_bfv_apply_automorphism(exb_context *c, const uint64_t *ct, uint64_t element,
+                                          const exb_relin_key *gk, uint64_t *out, size_t batch, void *stream) {
+    int rc = galois_precheck(c, gk, element);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    const size_t words = batch * 2 * (size_t)c->n;
+    if (ct < out + words && out < ct + words) return fail(EXB_INVALID_PARAM, "automorphism output must not alias its input");
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_galois(c->P, ct, gk->d_mont, (u32)(element % (2 * (uint64_t)c->n)), out, batch, (cudaStream_t)stream);
+    return check_launch("galois");
+}
+
+extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *ct, uint64_t element,
+                                               const exb_relin_key *gk, uint64_t *out, size_t batch) {
+    int rc = galois_precheck(c, gk, element);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    const size_t stride = 2 * (size_t)c->n;
+    size_t chunk = 1024;                                   // 64 MiB of ciphertexts at n = 4096
+    if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
+    size_t ci = 0;
+    for (size_t off = 0; off < batch; off += chunk, ci++) {
+        Workspace &w = c->ws[ci % kSlots];
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
+        if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
+        EXB_CUDA(cudaMemcpyAsync(w.in1, ct + off * stride, cnt * stride * 8, cudaMemcpyHostToDevice, w.stream));
+        launch_galois(c->P, w.in1, gk->d_mont, (u32)(element % (2 * (uint64_t)c->n)), w.out, cnt, w.stream);
+        if ((rc = check_launch("galois"))) return rc;
+        EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, cnt * stride * 8, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
+    return EXB_OK;
 }

@@ -822,6 +822,66 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
     stg_u64x4(dst + n + e0, v); stg_u64x4(dst + n + e0 + 4, v + 4);
 }
 
+// ---------------------------------------------------------------------------------
+// Galois automorphism + key switch (bfv/eval.rs:512-561).  One CTA per ciphertext:
+//   c0' = NTT(sigma_k(INTT c0)) + sum_g NTT(digit_g(sigma_k(INTT c1))) * gk0_g
+//   c1' =                         sum_g NTT(digit_g(sigma_k(INTT c1))) * gk1_g
+// sigma_k (bfv/keygen.rs:218-239) is a signed permutation for odd k, applied as the scatter
+// out of the inverse transform.  The running `remaining` of gadget_decompose
+// (bfv/keyswitch.rs:24-44) lives in shared memory as i64; c1' accumulates in `out` itself
+// (each thread re-visits only its own words).
+// ---------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
+galois_kernel(const __grid_constant__ DeviceParams P, const u64 *__restrict__ ct,
+              const u64 *__restrict__ gk_mont, u32 k, u64 *__restrict__ out) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = P.n, G = P.gadget_digits, mask2n = 2 * n - 1;
+    const Modulus &mq = P.mod[0];
+    const u64 q = mq.m, half_q = q >> 1;
+    u64 *work = smem, *acc0 = smem + n;
+    i64 *remaining = reinterpret_cast<i64 *>(smem + 2 * (size_t)n);
+    const u64 *src = ct + (size_t)blockIdx.x * 2 * n;
+    u64 *dst = out + (size_t)blockIdx.x * 2 * n;
+
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) work[Lay<LOGN>::at(e)] = ld_stream(src + e);
+    inv_sm<LOGN>(work, P.twi[0], P.headi[0], mq, P.logn);
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 c = work[Lay<LOGN>::at(e)];
+        const u32 j = (e * k) & mask2n;
+        acc0[Lay<LOGN>::at(j & (n - 1))] = j < n ? c : mod_neg(c, q);
+    }
+    fwd_sm<LOGN>(acc0, P.twf[0], P.headf[0], mq, P.logn);
+
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) work[Lay<LOGN>::at(e)] = ld_stream(src + n + e);
+    inv_sm<LOGN>(work, P.twi[0], P.headi[0], mq, P.logn);
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 c = work[Lay<LOGN>::at(e)];
+        const u32 j = (e * k) & mask2n;
+        remaining[j & (n - 1)] = center_i64(j < n ? c : mod_neg(c, q), q, half_q);
+    }
+    __syncthreads();
+    for (u32 g = 0; g < G; g++) {
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            i64 r = remaining[e];
+            const i64 dg = P.gadget_log2 ? gadget_digit_pow2(r, P.gadget_log2)
+                                         : gadget_digit_general(r, (i64)P.gadget_base);
+            remaining[e] = r;
+            work[Lay<LOGN>::at(e)] = signed_to_mod(dg, q);
+        }
+        fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
+        const u64 *k0 = gk_mont + ((size_t)g * 2) * n, *k1 = k0 + n;
+        for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+            const u64 x = work[Lay<LOGN>::at(e)];
+            const u32 a = Lay<LOGN>::at(e);
+            acc0[a] = mod_add(acc0[a], csub(mont_mul_lazy(x, k0[e], q, mq.minv_neg), q), q);
+            const u64 y = csub(mont_mul_lazy(x, k1[e], q, mq.minv_neg), q);
+            dst[n + e] = g ? mod_add(dst[n + e], y, q) : y;
+        }
+    }
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = acc0[Lay<LOGN>::at(e)];
+}
+
 // out_limb += (+/-) s * excess_limb over 2n words per pair (dbfv/reduction.rs:34-52, :65-93).
 __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const u64 *__restrict__ excess_limb,
                                   u64 s_mont, int negative, size_t out_stride, size_t excess_stride,
@@ -997,6 +1057,21 @@ void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const
     if (pairs == 0) return;
     if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s);
     else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s);
+}
+
+void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32 element, u64 *out,
+                   size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    const size_t sm = (size_t)P.n * 8 * 3;
+    const u32 k = element & (2 * P.n - 1);
+    if (P.logn == 12) {
+        set_smem(galois_kernel<12>, sm);
+        galois_kernel<12><<<(unsigned)count, kThreads12, sm, s>>>(P, ct, gk_mont, k, out);
+    } else {
+        set_smem(galois_kernel<0>, sm);
+        galois_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(P, ct, gk_mont, k, out);
+    }
+    g_launch_count++;
 }
 
 void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_limb, u64 abs_scalar_mod_q,

@@ -38,6 +38,11 @@ void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_l
                        bool negative, size_t out_stride, size_t excess_stride, size_t pairs,
                        cudaStream_t s);
 
+// Galois automorphism + key switch on `count` degree-1 ciphertexts [count][2][n] (bfv/eval.rs:512-561);
+// gk_mont [G][2][n] in Montgomery form, element odd.  `out` must not alias `ct`.
+void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32 element, u64 *out,
+                   size_t count, cudaStream_t s);
+
 #endif  // EXB_HOST_EMUL
 
 // Count of kernels launched by this library (bench.py's gpu_launches).

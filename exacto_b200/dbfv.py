@@ -10,7 +10,8 @@ from typing import List, Optional
 import numpy as np
 
 from . import _native
-from .bfv import BfvCiphertext, RelinKey, bfv_add, bfv_neg, bfv_sub
+from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automorphism_batch, bfv_neg,
+                  bfv_sub)
 from .error import DimensionMismatch, InvalidParam, NotImplementedErr
 from .params import DbfvParams
 from .ring import _ptr, _u64
@@ -95,6 +96,16 @@ def dbfv_mul_batch(params: DbfvParams, ct1: np.ndarray, ct2: np.ndarray, rlk: Re
     _native.check(_native.lib().exb_dbfv_mul_host(ctx.handle, params.base, d, params.plain_modulus, _ptr(ct1),
                                                   _ptr(ct2), rlk.native(ctx), _ptr(out), ct1.shape[0], flags))
     return out
+
+
+def dbfv_apply_automorphism(ct: DbfvCiphertext, gk: GaloisKey) -> DbfvCiphertext:
+    """dbfv/advanced.rs:15-30: the BFV automorphism + key switch on every limb (one batched launch);
+    degree and mul_depth carry over."""
+    for limb in ct.limbs:
+        if len(limb.c) != 2:                                             # bfv/eval.rs:516-520
+            raise InvalidParam("automorphism requires degree-1 ciphertext")
+    out = bfv_apply_automorphism_batch(ct.params.bfv_params, ct.to_array(), gk)
+    return DbfvCiphertext.from_array(out, ct.params, degree=ct.degree, mul_depth=ct.mul_depth)
 
 
 def small_reps(base: int, d: int, plain_modulus: int) -> np.ndarray:

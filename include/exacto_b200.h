@@ -151,6 +151,17 @@ int exb_bfv_mul_and_relin_host(exb_context *ctx, const uint64_t *ct1_host, const
 int exb_bfv_add(exb_context *ctx, const uint64_t *a_dev, const uint64_t *b_dev, uint64_t *out_dev,
                 size_t batch, void *stream);
 
+/* ---- bfv_apply_automorphism (bfv/eval.rs:512-561): sigma_k: X -> X^k (bfv/keygen.rs:218-239) on
+ * both components followed by the key switch from s(X^k) back to s, batched over independent
+ * degree-1 ciphertexts [batch][2][n].  A GaloisKey (bfv/keygen.rs:47-54, keys[g] = (ks0_g, a_g),
+ * [G][2][n] NTT domain) is loaded with exb_relin_key_load: it is the same key-switch key layout.
+ * `element` must be odd (EXB_INVALID_PARAM otherwise; the "degree-1 ciphertext" guard :516-520
+ * reads ciphertext metadata and lives in the host wrapper).  out must not alias ct. */
+int exb_bfv_apply_automorphism(exb_context *ctx, const uint64_t *ct_dev, uint64_t element,
+                               const exb_relin_key *gk, uint64_t *out_dev, size_t batch, void *stream);
+int exb_bfv_apply_automorphism_host(exb_context *ctx, const uint64_t *ct_host, uint64_t element,
+                                    const exb_relin_key *gk, uint64_t *out_host, size_t batch);
+
 /* ---- dbfv_mul (dbfv/eval.rs:82-149) incl. reduction::reduce (dbfv/reduction.rs:15-60),
  * batched.  `base`, `num_digits`, `dbfv_plain_modulus` are DbfvParams (params/mod.rs:143-192;
  * 0 = 2^64).  The limb-count and mul_depth guards (dbfv/eval.rs:90-102) read ciphertext

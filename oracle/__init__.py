@@ -125,6 +125,9 @@ def lib():
         L.exo_bfv_mul_no_relin.argtypes = [pp, p64, p64, p64]
         L.exo_bfv_mul_and_relin.argtypes = [pp, p64, p64, p64, p64]
         L.exo_bfv_mul_and_relin_batch.argtypes = [pp, p64, p64, p64, p64, ctypes.c_size_t, ctypes.c_int]
+        L.exo_apply_automorphism.argtypes = [u32, u64, p64, u64, p64]
+        L.exo_apply_automorphism.restype = None
+        L.exo_bfv_apply_automorphism_batch.argtypes = [pp, p64, p64, u64, p64, ctypes.c_size_t, ctypes.c_int]
         L.exo_small_reps.argtypes = [u64, u32, u64, p64]
         L.exo_small_reps.restype = None
         L.exo_dbfv_mul.argtypes = [pp, u64, u32, u64, p64, p64, p64, p64, ctypes.c_int]
@@ -235,6 +238,26 @@ def bfv_mul_and_relin(p: OracleParams, ct1, ct2, rlk, threads: int = 1) -> np.nd
     batch = ct1.size // (2 * p.n)
     _check(lib().exo_bfv_mul_and_relin_batch(ctypes.byref(p._c), _ptr(ct1), _ptr(ct2), _ptr(rlk),
                                              _ptr(out), batch, threads))
+    return out
+
+
+# ---- Galois automorphism + key switch ----------------------------------------
+def apply_automorphism(coeffs, q: int, k: int) -> np.ndarray:
+    """bfv/keygen.rs:218-239 on one coefficient-domain poly."""
+    a = _u64(coeffs)
+    out = np.zeros_like(a)
+    lib().exo_apply_automorphism(a.shape[-1], q, _ptr(a), k, _ptr(out))
+    return out
+
+
+def bfv_apply_automorphism(p: OracleParams, ct, gk, k: int, threads: int = 1) -> np.ndarray:
+    """bfv/eval.rs:512-561.  ct [..,2,n] NTT domain, gk [G,2,n] -> [..,2,n]."""
+    ct = _u64(ct)
+    gk = _u64(gk, (p.gadget_digits, 2, p.n))
+    assert ct.shape[-2:] == (2, p.n)
+    out = np.zeros_like(ct)
+    _check(lib().exo_bfv_apply_automorphism_batch(ctypes.byref(p._c), _ptr(ct), _ptr(gk), k, _ptr(out),
+                                                  ct.size // (2 * p.n), threads))
     return out
 
 

@@ -622,6 +622,71 @@ int exo_bfv_mul_and_relin_batch(const exo_params *p, const u64 *ct1, const u64 *
 }
 
 /* ------------------------------------------------------------------------ */
+/* Galois automorphism + key switch                            */
+/* ------------------------------------------------------------------------ */
+
+/* apply_automorphism bfv/keygen.rs:218-239: X^i -> X^(i*k) mod (X^n + 1), a
+ * signed scatter with mod_add / mod_sub accumulation (zero coefficients skipped). */
+void exo_apply_automorphism(uint32_t n, u64 q, const u64 *in, uint64_t k, u64 *out) {
+    memset(out, 0, sizeof(u64) * n);
+    for (uint32_t i = 0; i < n; i++) {
+        u64 c = in[i];
+        if (c == 0) continue;
+        u64 new_exp = (u64)(((u128)i * k) % (2 * (u64)n));
+        if (new_exp < n) out[new_exp] = exo_mod_add(out[new_exp], c, q);
+        else out[new_exp - n] = exo_mod_sub(out[new_exp - n], c, q);
+    }
+}
+
+/* bfv_apply_automorphism bfv/eval.rs:512-561.  ct [2][n], gk [G][2][n] (NTT domain),
+ * out [2][n]. */
+int exo_bfv_apply_automorphism(const exo_params *p, const u64 *ct, const u64 *gk, uint64_t k,
+                               u64 *out) {
+    const plan *pq = get_plan(p->n, p->q);
+    if (!pq) return fail(EXO_INVALID_PARAM, "cannot create NTT plan");
+    const uint32_t n = p->n, G = p->gadget_digits;
+    const u64 q = p->q;
+    u64 *c0 = (u64 *)malloc(sizeof(u64) * n), *c1 = (u64 *)malloc(sizeof(u64) * n);
+    u64 *a0 = (u64 *)malloc(sizeof(u64) * n), *a1 = (u64 *)malloc(sizeof(u64) * n);
+    u64 *digits = (u64 *)malloc(sizeof(u64) * n * G), *prod = (u64 *)malloc(sizeof(u64) * n);
+    memcpy(c0, ct, sizeof(u64) * n);
+    memcpy(c1, ct + n, sizeof(u64) * n);
+    ntt_inv(pq, c0);                                                  /* :527 */
+    ntt_inv(pq, c1);                                                  /* :528 */
+    exo_apply_automorphism(n, q, c0, k, a0);                          /* :530 */
+    exo_apply_automorphism(n, q, c1, k, a1);                          /* :531 */
+    ntt_fwd(pq, a0);                                                  /* :533 */
+    exo_gadget_decompose(n, q, a1, p->gadget_base, G, digits);        /* :538 */
+    memcpy(out, a0, sizeof(u64) * n);
+    memset(out + n, 0, sizeof(u64) * n);
+    for (uint32_t g = 0; g < G; g++) {                                /* :543-555 */
+        u64 *dg = digits + (size_t)g * n;
+        ntt_fwd(pq, dg);
+        pw_mul(n, q, dg, gk + ((size_t)g * 2 + 0) * n, prod);
+        pw_add(n, q, out, prod, out);
+        pw_mul(n, q, dg, gk + ((size_t)g * 2 + 1) * n, prod);
+        pw_add(n, q, out + n, prod, out + n);
+    }
+    free(c0); free(c1); free(a0); free(a1); free(digits); free(prod);
+    return EXO_OK;
+}
+
+int exo_bfv_apply_automorphism_batch(const exo_params *p, const u64 *ct, const u64 *gk, uint64_t k,
+                                     u64 *out, size_t batch, int threads) {
+    int rc = EXO_OK;
+    if (!get_plan(p->n, p->q)) return fail(EXO_INVALID_PARAM, "cannot create NTT plan");
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic)
+    for (size_t b = 0; b < batch; b++) {
+        int r = exo_bfv_apply_automorphism(p, ct + b * 2 * (size_t)p->n, gk, k, out + b * 2 * (size_t)p->n);
+        if (r != EXO_OK) {
+#pragma omp critical
+            rc = r;
+        }
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------------ */
 /* dbfv/                                                                     */
 /* ------------------------------------------------------------------------ */
 

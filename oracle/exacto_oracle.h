@@ -99,6 +99,15 @@ int exo_bfv_mul_and_relin(const exo_params *p, const uint64_t *ct1, const uint64
 int exo_bfv_mul_and_relin_batch(const exo_params *p, const uint64_t *ct1, const uint64_t *ct2,
                                 const uint64_t *rlk, uint64_t *out, size_t batch, int threads);
 
+/* ---- Galois automorphism + key switch ------------------------------------ */
+/* apply_automorphism bfv/keygen.rs:218-239.                                 */
+void exo_apply_automorphism(uint32_t n, uint64_t q, const uint64_t *in, uint64_t k, uint64_t *out);
+/* bfv_apply_automorphism bfv/eval.rs:512-561. ct [2][n], gk [G][2][n], out [2][n]. */
+int exo_bfv_apply_automorphism(const exo_params *p, const uint64_t *ct, const uint64_t *gk,
+                               uint64_t k, uint64_t *out);
+int exo_bfv_apply_automorphism_batch(const exo_params *p, const uint64_t *ct, const uint64_t *gk,
+                                     uint64_t k, uint64_t *out, size_t batch, int threads);
+
 /* ---- dbfv/ --------------------------------------------------------------- */
 /* SmallReps::compute_simple lattice.rs:104-122. reps is [(d-1)][d] int64.   */
 void exo_small_reps(uint64_t base, uint32_t d, uint64_t plain_modulus, int64_t *reps);

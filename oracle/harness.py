@@ -114,6 +114,22 @@ def gen_relin_key(p: OracleParams, s_ntt: np.ndarray, rng, sigma: float = 3.2) -
     return keys
 
 
+def gen_galois_key(p: OracleParams, s_ntt: np.ndarray, element: int, rng, sigma: float = 3.2) -> np.ndarray:
+    """bfv/keygen.rs:170-210: key-switch key from s(X^element) to s(X), [G][2][n] NTT domain."""
+    from . import apply_automorphism
+    q = p.q
+    gadget_s_auto = ntt_fwd(apply_automorphism(ntt_inv(s_ntt, q), q, element), q)
+    keys = np.zeros((p.gadget_digits, 2, p.n), np.uint64)
+    for g in range(p.gadget_digits):
+        a = ntt_fwd(sample_uniform(p.n, q, rng), q)
+        e = ntt_fwd(sample_gaussian(p.n, q, sigma, rng), q)
+        keys[g, 0] = _add(_neg(_add(_mul(a, s_ntt, q), e, q), q), gadget_s_auto, q)
+        keys[g, 1] = a
+        if g + 1 < p.gadget_digits:
+            gadget_s_auto = _mul(gadget_s_auto, np.full(p.n, p.gadget_base % q, np.uint64), q)
+    return keys
+
+
 # ---- BFV encrypt / decrypt (bfv/encrypt.rs) ------------------------------------
 def encrypt_sk(p: OracleParams, pt_coeffs, s_ntt, rng, sigma: float = 3.2) -> np.ndarray:      # :79-106
     q = p.q

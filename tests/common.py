@@ -56,6 +56,7 @@ class Emulator:
         L.emu_poly_op.argtypes = [vp, u32, ctypes.c_int, vp, vp, u64, vp, ctypes.c_size_t]
         L.emu_small_primes.argtypes = [vp, vp]
         L.emu_dbfv_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, u32, u32]
+        L.emu_bfv_apply_automorphism.argtypes = [vp, vp, u64, vp, vp, ctypes.c_size_t]
         self.L = L
 
     @staticmethod
@@ -97,6 +98,12 @@ class Emulator:
         bb = np.ascontiguousarray(b if b is not None else a, np.uint64)
         out = np.zeros_like(a)
         self.L.emu_poly_op(h, base, op, self._p(a), self._p(bb), scalar, self._p(out), a.size)
+        return out
+
+    def bfv_apply_automorphism(self, h, ct, element, gk):
+        ct, gk = np.ascontiguousarray(ct, np.uint64), np.ascontiguousarray(gk, np.uint64)
+        out = np.zeros_like(ct)
+        self.L.emu_bfv_apply_automorphism(h, self._p(ct), element, self._p(gk), self._p(out), ct.size // (2 * ct.shape[-1]))
         return out
 
     def dbfv_mul(self, h, base, d, pm, ct1, ct2, rlk, flags=0, limb_mask=0, out=None):

@@ -238,4 +238,20 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     return 0;
 }
 
+// Same launch as launch_galois() in exacto_b200/csrc/kernels.cu.
+int emu_bfv_apply_automorphism(emu_ctx *c, const uint64_t *ct, uint64_t element, const uint64_t *gk,
+                               uint64_t *out, size_t count) {
+    HostSetup &hs = c->hs;
+    const DeviceParams &P = hs.P;
+    const size_t n = hs.n, kw = (size_t)hs.gadget_digits * 2 * n;
+    std::vector<u64> gk_mont(kw + 1);
+    const Modulus mq = P.mod[0];
+    emu_launch(4, 64, 0, [&]() { poly_op_kernel(mq, OP_TO_MONT, gk, nullptr, 0, gk_mont.data(), kw); });
+    const u64 *gm = gk_mont.data();
+    const u32 k = (u32)(element % (2 * n));
+    if (P.logn == 12) emu_launch((unsigned)count, kThreads12, n * 24, [&]() { galois_kernel<12>(P, ct, gm, k, out); });
+    else emu_launch((unsigned)count, emu_block_threads(P), n * 24, [&]() { galois_kernel<0>(P, ct, gm, k, out); });
+    return 0;
+}
+
 }  // extern "C"

@@ -158,3 +158,26 @@ def test_small_basis_adversarial_inputs(emu):
     rc, got, err = emu.dbfv_mul(h, 2, 1, 0, ct1[:, None], ct2[:, None], rlk)
     assert rc == 0, err
     assert np.array_equal(got[:, 0], O.bfv_mul_and_relin(P, ct1, ct2, rlk, threads=4))
+
+
+# ---- Galois automorphism + key switch -------------------------------------------------
+@pytest.mark.parametrize("preset,elements", [("toy16", [3, 5, 31]), ("compact", [3, 2047]), ("u64", [3, 8191]),
+                                             ("cfg3", [4097])])
+def test_galois_kernel_matches_oracle(emu, preset, elements):
+    """galois_kernel (generic and n = 4096 paths; power-of-two gadget bases 2^8 / 2^16 and a general
+    base) against the literal restatement of bfv/eval.rs:512-561 on uniform and edge inputs."""
+    P = {"toy16": O.OracleParams(n=16, q=1152921504606830593, aux=(18014398509998081,), plain_modulus=17,
+                                 gadget_base=10),
+         "compact": H.compact_bfv(), "u64": H.u64_dbfv().bfv, "cfg3": H.cfg3_prime().bfv}[preset]
+    h = emu.from_oracle(P)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(n)
+    gk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    ct = rng.integers(0, q, (3, 2, n), dtype=np.uint64)
+    edge = np.zeros(n, np.uint64)
+    edge[:6] = [0, 1, q - 1, q // 2, q // 2 + 1, 2]
+    ct[1, 0] = O.ntt_fwd(edge, q); ct[1, 1] = O.ntt_fwd(edge[::-1].copy(), q)
+    ct[2] = 0
+    for k in elements:
+        got = emu.bfv_apply_automorphism(h, ct, k, gk)
+        assert np.array_equal(got, O.bfv_apply_automorphism(P, ct, gk, k, threads=4)), (preset, k)

@@ -362,3 +362,82 @@ def test_generic_ring_degrees(n):
     got = E.dbfv_mul_batch(params, ct1, ct2, E.RelinKey(rlk_arr, params.bfv_params))
     want = np.stack([O.dbfv_mul(P, 256, 2, 65536, a, b, rlk_arr, threads=O.max_threads()) for a, b in zip(ct1, ct2)])
     assert np.array_equal(got, want)
+
+
+# ---- Galois automorphism + key switch ------------------------------------------------------
+def test_automorphism_kats():
+    """bfv/eval.rs:929-976 (sigma_3 keeps the scalar 10; 1 + 2X -> 1 + 2X^3) and
+    dbfv/advanced.rs:182-193 (dBFV value 42 through sigma_3), with valid keys."""
+    P, params = H.compact_bfv(), E.compact_bfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(P, rng)
+    gk = E.GaloisKey(H.gen_galois_key(P, s, 3, rng), 3, params)
+    ct = E.BfvCiphertext.from_array(H.encrypt_sk(P, H.encode_scalar(P, 10), s, rng), params)
+    assert int(H.decrypt(P, E.bfv_apply_automorphism(ct, gk).to_array(), s)[0]) == 10
+    pt = np.zeros(P.n, np.uint64); pt[:2] = [1, 2]
+    ct = E.BfvCiphertext.from_array(H.encrypt_sk(P, pt, s, rng), params)
+    dec = H.decrypt(P, E.bfv_apply_automorphism(ct, gk).to_array(), s)
+    assert dec[:4].tolist() == [1, 0, 0, 2] and np.count_nonzero(dec) == 2
+    # trace over {3}: m + sigma_3(m) = 2 + 2X + 2X^3 (bfv/eval.rs:573-588)
+    dec = H.decrypt(P, E.bfv_trace(ct, [3], {3: gk}).to_array(), s)
+    assert dec[:4].tolist() == [2, 2, 0, 2]
+    with pytest.raises(E.ExactoError, match="missing Galois key for element 5"):
+        E.bfv_trace(ct, [5], {3: gk})
+    with pytest.raises(E.ExactoError, match="automorphism requires degree-1 ciphertext"):
+        E.bfv_apply_automorphism(E.BfvCiphertext(ct.c + ct.c[:1], params), gk)
+    with pytest.raises(E.ExactoError, match="Galois element must be odd"):
+        E.bfv_apply_automorphism(ct, E.GaloisKey(gk.array, 4, params))
+    # inner product 3*ct_a + 5*ct_b (bfv/eval.rs:593-606)
+    enc = lambda m: E.BfvCiphertext.from_array(H.encrypt_sk(P, H.encode_scalar(P, m), s, rng), params)
+    const = lambda v: E.CoeffPoly.from_coeffs(np.array([v] + [0] * (P.n - 1)), P.plain_modulus)
+    assert int(H.decrypt(P, E.bfv_inner_product([enc(2), enc(7)], [const(3), const(5)]).to_array(), s)[0]) == 41
+    with pytest.raises(E.ExactoError, match="mismatched ct/pt lengths"):
+        E.bfv_inner_product([enc(2)], [])
+
+    S, dparams = H.compact_dbfv(), E.compact_dbfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(S.bfv, rng)
+    gk = E.GaloisKey(H.gen_galois_key(S.bfv, s, 3, rng), 3, dparams.bfv_params)
+    dct = E.DbfvCiphertext.from_array(H.dbfv_encrypt_sk(S, 42, s, rng), dparams)
+    auto = E.dbfv_apply_automorphism(dct, gk)
+    assert H.dbfv_decrypt(S, auto.to_array(), s) == 42 and (auto.degree, auto.mul_depth) == (dct.degree, dct.mul_depth)
+
+
+@pytest.mark.parametrize("preset,elements", [("compact", [3, 5, 2047]), ("u64", [3, 4097, 8191]), ("cfg3", [5]),
+                                             ("n16", [3, 31]), ("n8192", [3, 16383])])
+def test_automorphism_vs_oracle(preset, elements):
+    """Word-for-word parity of exb_bfv_apply_automorphism (host and device entry points) with the
+    literal restatement of bfv/eval.rs:512-561 on uniform, edge and zero ciphertexts."""
+    from exacto_b200 import batch
+    P = {"compact": H.compact_bfv(), "u64": H.u64_dbfv().bfv, "cfg3": H.cfg3_prime().bfv,
+         "n16": O.OracleParams(n=16, q=1152921504606830593, aux=(18014398509998081,), plain_modulus=17, gadget_base=10),
+         "n8192": O.OracleParams(n=8192, q=1152921504606830593, aux=(36028797019389953, 36028797019488257),
+                                 plain_modulus=1040407, gadget_base=256)}[preset]
+    params = to_params(P)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(n + 1)
+    B = 9
+    ct = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    edge = np.zeros(n, np.uint64)
+    edge[:6] = [0, 1, q - 1, q // 2, q // 2 + 1, 2]
+    ct[1, 0] = O.ntt_fwd(edge, q); ct[1, 1] = O.ntt_fwd(edge[::-1].copy(), q)
+    ct[2] = 0
+    ct[3] = O.ntt_fwd(np.full((2, n), q - 1, np.uint64), q)
+    ct[4] = O.ntt_fwd(np.full((2, n), q // 2 + 1, np.uint64), q)
+    karr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    for k in elements:
+        gk = E.GaloisKey(karr, k, params)
+        want = O.bfv_apply_automorphism(P, ct, karr, k, threads=O.max_threads())
+        assert np.array_equal(E.bfv_apply_automorphism_batch(params, ct, gk), want), (preset, k, "host")
+        dev = batch.bfv_apply_automorphism(params, batch.to_device(ct), gk)
+        assert np.array_equal(batch.to_host(dev), want), (preset, k, "device")
+    # sigma_a o sigma_b = sigma_ab on ciphertext components when the key switch is the identity gadget:
+    # with an all-zero key only c0' = NTT(sigma(INTT c0)) survives -> compose and compare
+    zero = E.GaloisKey(np.zeros_like(karr), 3, params)
+    a = E.bfv_apply_automorphism_batch(params, ct, zero)
+    ab = E.bfv_apply_automorphism_batch(params, a, E.GaloisKey(np.zeros_like(karr), 5, params))
+    direct = E.bfv_apply_automorphism_batch(params, ct, E.GaloisKey(np.zeros_like(karr), 15, params))
+    assert np.array_equal(ab[:, 0], direct[:, 0]) and not ab[:, 1].any()
+    with pytest.raises(E.ExactoError, match="must not alias"):
+        d = batch.to_device(ct)
+        batch.bfv_apply_automorphism(params, d, zero, out=d)

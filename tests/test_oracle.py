@@ -181,3 +181,45 @@ def test_eval_poly_homomorphic_oracle_decrypts():
     assert int(H.decrypt(P, out, s)[0]) == (1 + 10 + 75 + 125) % 257
     assert int(H.decrypt(P, H.eval_poly_homomorphic(P, ct, [42], rlk), s)[0]) == 42
     assert int(H.decrypt(P, H.trivial_encrypt(P, 100), s)[0]) == 100               # digit_extract.rs:271-288
+
+
+# ---- Galois automorphism + key switch ------------------------------------------------
+def test_apply_automorphism_signed_permutation():
+    """bfv/keygen.rs:218-239: X^i -> X^(ik) with X^n = -1; composition sigma_a(sigma_b) = sigma_ab."""
+    q, n = 65537, 16
+    x = np.zeros(n, np.uint64); x[1] = 5
+    y = O.apply_automorphism(x, q, 3)
+    assert y[3] == 5 and y.sum() == 5
+    x = np.zeros(n, np.uint64); x[7] = 2                          # 7*3 = 21 = n + 5 -> -2 X^5
+    y = O.apply_automorphism(x, q, 3)
+    assert y[5] == q - 2 and np.count_nonzero(y) == 1
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, q, n, dtype=np.uint64)
+    assert np.array_equal(O.apply_automorphism(O.apply_automorphism(x, q, 3), q, 5), O.apply_automorphism(x, q, 15))
+    # ring homomorphism: sigma(a*b) = sigma(a)*sigma(b)
+    a, b = rng.integers(0, q, n, dtype=np.uint64), rng.integers(0, q, n, dtype=np.uint64)
+    assert np.array_equal(O.apply_automorphism(O.poly_mul_naive(a, b, q), q, 7),
+                          O.poly_mul_naive(O.apply_automorphism(a, q, 7), O.apply_automorphism(b, q, 7), q))
+
+
+def test_bfv_apply_automorphism_decrypts():
+    """bfv/eval.rs:929-976: sigma_3 keeps a scalar, maps 1 + 2X to 1 + 2X^3."""
+    P = H.compact_bfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(P, rng)
+    gk = H.gen_galois_key(P, s, 3, rng)
+    ct = H.encrypt_sk(P, H.encode_scalar(P, 10), s, rng)
+    assert int(H.decrypt(P, O.bfv_apply_automorphism(P, ct, gk, 3), s)[0]) == 10
+    pt = np.zeros(P.n, np.uint64); pt[:2] = [1, 2]
+    dec = H.decrypt(P, O.bfv_apply_automorphism(P, H.encrypt_sk(P, pt, s, rng), gk, 3), s)
+    assert dec[:4].tolist() == [1, 0, 0, 2] and np.count_nonzero(dec) == 2
+
+
+def test_dbfv_apply_automorphism_scalar_decrypts():
+    """dbfv/advanced.rs:182-193: every limb through sigma_3, value 42 preserved."""
+    S = H.compact_dbfv()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(S.bfv, rng)
+    gk = H.gen_galois_key(S.bfv, s, 3, rng)
+    ct = H.dbfv_encrypt_sk(S, 42, s, rng)
+    assert H.dbfv_decrypt(S, O.bfv_apply_automorphism(S.bfv, ct, gk, 3), s) == 42
