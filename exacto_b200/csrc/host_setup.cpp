@@ -235,7 +235,7 @@ static int fill_scale_consts(HostSetup *c, std::string *err) {
     return EXB_OK;
 }
 
-// ---- internal 30-bit auxiliary basis (ntt32_core.cuh, hps32.cuh) ---------------------------
+// ---- internal 27-bit auxiliary basis (ntt32_core.cuh, hps32.cuh) ---------------------------
 static int build_mod32(u32 n, u32 logn, u32 p, Mod32 *m, std::vector<Tw32> *twf, std::vector<Tw32> *twi) {
     const u64 e = (p - 1) / (2ull * n);
     u64 psi = 0;
@@ -255,7 +255,7 @@ static int build_mod32(u32 n, u32 logn, u32 p, Mod32 *m, std::vector<Tw32> *twf,
         pw = pw * psi % p; ipw = ipw * psi_inv % p;
     }
     memset(m, 0, sizeof *m);
-    m->p = p; m->two_p = 2 * p; m->neg_p = (u32)0 - p;
+    m->p = p; m->two_p = 2 * p; m->neg_p = (u32)0 - p; m->four_p = 4 * p;
     u32 inv = p;
     for (int i = 0; i < 5; i++) inv *= 2 - p * inv;
     m->pinv_neg = (u32)0 - inv;
@@ -286,9 +286,10 @@ static void build_small_basis(HostSetup *c) {
     std::vector<u32> primes;
     u128 prod = 1;
     const u128 need = mmax << 8;
-    for (u64 cand = (((u64)1 << 30) - 1) / (2ull * n) * (2ull * n) + 1; cand > ((u64)1 << 29) && prod < need;
-         cand -= 2ull * n) {
-        if (cand >= ((u64)1 << 30) || !h_is_prime(cand) || cand == q) continue;
+    // primes in (2^26, 2^27): 32p fits a u32 (lazy NTT ranges, ntt32_core.cuh) and 2^57 / p fits a u32
+    constexpr u64 top = (u64)1 << kSmallPrimeBits;
+    for (u64 cand = (top - 1) / (2ull * n) * (2ull * n) + 1; cand > top / 2 && prod < need; cand -= 2ull * n) {
+        if (cand >= top || !h_is_prime(cand) || cand == q) continue;
         bool clash = false;
         for (u64 a : c->aux_moduli) clash |= (a == cand);
         if (clash) continue;
@@ -308,13 +309,26 @@ static void build_small_basis(HostSetup *c) {
         const u128 cof = prod / pi;                            // P'/p_i
         u64 inv = 0;
         if (!h_inv((u64)((u128)(q % pi) * (u64)(cof % pi) % pi), pi, &inv)) return;
-        s.Kp[i] = (u32)inv; s.Kp_s[i] = (u32)((inv << 32) / pi);
-        s.g[i] = (u32)(((u64)1 << 60) / pi);
+        auto sh32 = [&](u64 w) { return (u32)((w << 32) / pi); };
+        s.Kp[i] = (u32)inv; s.Kp_s[i] = sh32(inv);
+        const u64 rk = (((u64)1 << 32) % pi) * inv % pi;
+        s.RK[i] = (u32)rk; s.RK_s[i] = sh32(rk);
+        s.QK[i] = (u32)((q % pi) * inv % pi);
+        // the inverse transforms of this basis only feed hps_scale32_coeff: fold Kp_i into n^-1
+        Mod32 &m = s.m[i];
+        const u64 nk = (u64)m.ninv * inv % pi, nwk = (u64)m.ninv_w * inv % pi;
+        m.ninv = (u32)nk; m.ninv_s = sh32(nk);
+        m.ninv_w = (u32)nwk; m.ninv_w_s = sh32(nwk);
+        s.g[i] = (u32)(((u64)1 << 57) / pi);
         s.C[i] = h_mul(p % q, (u64)(cof % q), q);
-        s.C_s[i] = shoup_of(s.C[i], q);
     }
     const u64 pp = h_mul(p % q, (u64)(prod % q), q);
-    for (u32 a = 0; a <= K; a++) s.CP[a] = (u64)((u128)pp * a % q);
+    for (u32 a = 0; a <= K; a++) s.CPn[a] = q - (u64)((u128)pp * a % q);
+    u32 bits = 0;
+    while (bits < 64 && (q >> bits)) bits++;
+    s.sh = bits - 2;
+    s.rq = (u32)((((u128)1) << (32 + s.sh)) / q);
+    s.plain32 = (p < ((u64)1 << 32) && c->P.sc.plain_s < ((u64)1 << 32)) ? 1u : 0u;
     c->small_primes.assign(primes.begin(), primes.end());
     sb.K = K;
     sb.enabled = 1;

@@ -20,7 +20,7 @@ constexpr int kMaxDigits = 16;                 // dBFV digits d
 constexpr int kMaxProducts = kMaxDigits * kMaxDigits;
 constexpr int kMaxLimbs = 2 * kMaxDigits - 1;
 
-// Internal 30-bit auxiliary basis (see ntt32_core.cuh / hps32.cuh): replaces the reference's aux
+// Internal 27-bit auxiliary basis (see ntt32_core.cuh / hps32.cuh): replaces the reference's aux
 // primes inside the lift / tensor kernels when that is provably result-identical.
 struct SmallBasis {
     u32 enabled, K;

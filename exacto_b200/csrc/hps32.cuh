@@ -1,12 +1,14 @@
-// hps32.cuh -- hps_scale (bfv/eval.rs:257-413) on the internal 30-bit auxiliary basis.
+// hps32.cuh -- hps_scale (bfv/eval.rs:257-413) on the internal 27-bit auxiliary basis.
 //
 // With a = t mod q (canonical) and b_i = t mod p_i for the small primes p_i (P' = prod p_i),
 //   M = (t - a_c) / q           (exact integer, |M| <= n*q/2 + 1  <<  P'/2)
 //   out = round(p * a_c / q) + p * M   (mod q)            -- bfv/eval.rs:323-331 / :390-403
 // M is recovered without big integers (HPS "exact alpha"):
-//   m'_i = (b_i - [a_c]_{p_i}) * (q * P'/p_i)^-1  mod p_i,
+//   m'_i = (b_i - [a_c]_{p_i}) * Kp_i  mod p_i,   Kp_i = (q * P'/p_i)^-1 mod p_i
+//        (b_i * Kp_i comes out of the inverse transform: Kp_i is folded into its n^-1 scaling),
 //   M    = sum_i m'_i * (P'/p_i)  -  alpha * P',   alpha = round(sum_i m'_i / p_i)
-// and alpha is exact in 2^-60 fixed point (error < 2^-28) because |M| / P' < 2^-8 (checked on the host).
+// and alpha is exact in 2^-57 fixed point (error < 3 * 2^27 * 2^-57 < 2^-28) because |M| / P' < 2^-8
+// (checked on the host).
 // The result equals the reference's for every input because the reference's own centred CRT of m
 // cannot wrap for the parameter sets this path is enabled for (host_setup.cpp: small_basis_ok).
 #pragma once
@@ -19,12 +21,16 @@ constexpr int kMaxSmall = 4;
 
 struct Scale32Consts {
     u32 K;                       // number of small primes
-    u32 pad_;
-    Mod32 m[kMaxSmall];
-    u32 Kp[kMaxSmall], Kp_s[kMaxSmall];   // (q * P'/p_i)^-1 mod p_i  + Shoup32 companion
-    u32 g[kMaxSmall];                     // floor(2^60 / p_i)
-    u64 C[kMaxSmall], C_s[kMaxSmall];     // p * (P'/p_i) mod q       + Shoup64 companion
-    u64 CP[kMaxSmall + 1];                // alpha * p * P' mod q, alpha = 0..K
+    u32 sh;                      // bitlen(q) - 2  (q >> sh in [2, 4))
+    u32 rq;                      // floor(2^(32 + sh) / q): Barrett companion for the final reduction
+    u32 plain32;                 // 1 when p and floor(p * 2^64 / q) both fit 32 bits
+    Mod32 m[kMaxSmall];          // ninv* hold n^-1 * Kp_i: the inverse transforms deliver b_i * Kp_i
+    u32 Kp[kMaxSmall], Kp_s[kMaxSmall];   // Kp_i = (q * P'/p_i)^-1 mod p_i  + Shoup32 companion
+    u32 RK[kMaxSmall], RK_s[kMaxSmall];   // 2^32 * Kp_i mod p_i             + Shoup32 companion
+    u32 QK[kMaxSmall];                    // q * Kp_i mod p_i
+    u32 g[kMaxSmall];                     // floor(2^57 / p_i)  (p_i > 2^26)
+    u64 C[kMaxSmall];                     // p * (P'/p_i) mod q
+    u64 CPn[kMaxSmall + 1];               // q - (alpha * p * P' mod q), alpha = 0..K
 };
 
 // Centred value of a (mod q) reduced to [0, p_i): the ext rule of bfv/eval.rs:230-240.
@@ -34,31 +40,61 @@ EXB_HD u32 ext32_centered(u64 a, u64 q, u64 half_q, const Mod32 &m) {
     return (neg && r != 0) ? m.p - r : r;
 }
 
-// addend + x * w mod q (+ up to 3q) for a 32-bit x: approximate Shoup quotient hi32(x * s1).
-EXB_HD u64 shoup_small_mad(u32 x, u64 w, u64 s, u64 neg_q, u64 addend) {
-    const u32 qh = mulhi32(x, (u32)(s >> 32));                // in [Q-2, Q]
-    return addend + (u64)x * w + (u64)qh * neg_q;
+// round_term (hps.cuh) when p and its Shoup companion fit 32 bits: same k and r, half the multiplies.
+EXB_HD u64 round_term32(u64 a, const ScaleConsts &c) {
+    const bool neg = a > c.half_q;
+    const u64 av = neg ? c.q - a : a;
+    const u32 a1 = (u32)(av >> 32), a0 = (u32)av, s = (u32)c.plain_s, p = (u32)c.plain;
+    const u32 k = (u32)(((u64)a1 * s + (((u64)a0 * s) >> 32)) >> 32);        // floor(av * s / 2^64)
+    const u64 avp = (u64)a0 * p + ((u64)(a1 * p) << 32);                      // av * p   mod 2^64
+    const u64 kq = (u64)k * (u32)c.q + ((u64)(k * (u32)(c.q >> 32)) << 32);   // k * q    mod 2^64
+    const u64 r = avp - kq;                                                   // [0, 2q)
+    const u64 rh = r + c.half_q;
+    const u64 rr = (u64)k + (rh >= c.q ? 1u : 0u) + (rh >= 2 * c.q ? 1u : 0u);
+    return neg ? mod_neg(rr, c.q) : rr;
 }
 
-// a = t mod q, b[i] = t mod p_i (all canonical).  Needs q < 2^60.
-EXB_HD u64 hps_scale32_coeff(u64 a, const u32 *b, const ScaleConsts &c, const Scale32Consts &s,
-                             const LazyC &lq) {
-    u64 acc = round_term(a, c);                               // [0, q)
+// a = t mod q (canonical), bk[i] = (t mod p_i) * Kp_i mod p_i (canonical).  Needs 2^36 <= q < 2^60.
+//   m'_i = bk_i - a_c * Kp_i  mod p_i,  a_c = a - [a > q/2] q
+//   out  = rnd + sum_i m'_i * C_i - alpha * p * P'   (mod q),  accumulated exactly in 96 bits and
+//          reduced once (Barrett on the top 32 bits: quotient estimate within 2, remainder < 3q).
+EXB_HD u64 hps_scale32_coeff(u64 a, const u32 *bk, const ScaleConsts &c, const Scale32Consts &s) {
+    const u64 rnd = s.plain32 ? round_term32(a, c) : round_term(a, c);      // [0, q)
+    const bool neg = a > c.half_q;
+    const u32 a1 = (u32)(a >> 32), a0 = (u32)a;
     u64 frac = 0;
+    u64 lo = rnd;                // 96-bit accumulator hi:lo
+    u32 hi = 0;
 #pragma unroll
     for (u32 i = 0; i < (u32)kMaxSmall; i++) {
         if (i < s.K) {
             const Mod32 &m = s.m[i];
-            const u32 ae = ext32_centered(a, c.q, c.half_q, m);
-            const u32 d = b[i] >= ae ? b[i] - ae : b[i] + m.p - ae;
-            const u32 mp = shoup32(d, s.Kp[i], s.Kp_s[i], m.p);
+            const u32 u = shoup32_lazy(a1, s.RK[i], s.RK_s[i], m.p) + shoup32_lazy(a0, s.Kp[i], s.Kp_s[i], m.p);   // [0,4p)
+            const u32 t = bk[i] + m.four_p - u + (neg ? s.QK[i] : 0u);                                              // (0,6p)
+            const u32 mp = csub32(csub32(csub32(t, m.four_p), m.two_p), m.p);
             frac += (u64)mp * s.g[i];
-            acc = shoup_small_mad(mp, s.C[i], s.C_s[i], lq.neg_q, acc);   // + [0, 4q)
+            const u64 p0 = (u64)mp * (u32)s.C[i], p1 = (u64)mp * (u32)(s.C[i] >> 32);
+            u64 nl = lo + p0;
+            hi += nl < lo ? 1u : 0u;
+            lo = nl;
+            nl = lo + (p1 << 32);
+            hi += (u32)(p1 >> 32) + (nl < lo ? 1u : 0u);
+            lo = nl;
         }
     }
-    const u32 alpha = (u32)((frac + ((u64)1 << 59)) >> 60);
-    acc += c.q - s.CP[alpha];                                 // total < (2 + 4K) q <= 14 q < 2^64
-    return reduce_full(acc, lq);
+    const u32 alpha = (u32)((frac + ((u64)1 << 56)) >> 57);
+    {
+        const u64 nl = lo + s.CPn[alpha];
+        hi += nl < lo ? 1u : 0u;
+        lo = nl;
+    }
+    // T = hi:lo < (K * 2^27 + 2) q;  Th = floor(T / 2^sh) < 2^32
+    const u64 mid = ((u64)hi << 32) | (lo >> 32);
+    const u32 th = (u32)(mid >> (s.sh - 32));
+    const u32 k = mulhi32(th, s.rq);
+    const u64 kq = (u64)k * (u32)c.q + ((u64)(k * (u32)(c.q >> 32)) << 32);
+    const u64 r = lo - kq;                                                  // [0, 3q)
+    return csub(csub(r, 2 * c.q), c.q);
 }
 
 }  // namespace exb

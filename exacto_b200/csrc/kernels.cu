@@ -117,6 +117,7 @@ __device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, con
 }
 
 // 32-bit transforms of the internal auxiliary basis (n = 4096, 512 threads x 8 values).
+// Forward: canonical inputs, outputs in [0, 2p) (lazy: the point-wise Montgomery products accept them).
 __device__ __forceinline__ void fwd32_sm(u32 *sm, const Tw32 *__restrict__ tw, const TwHead32 &head, const Mod32 &m) {
     const u32 t = threadIdx.x;
     u32 v[8];
@@ -129,11 +130,11 @@ __device__ __forceinline__ void fwd32_sm(u32 *sm, const Tw32 *__restrict__ tw, c
     __syncthreads();
     load_vals32<3, 0>(v, sm, t); fwd_pass32<12, 0, 3>(v, tw, t, m);
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = csub32(csub32(v[k], m.two_p), m.p);
+    for (int k = 0; k < 8; k++) v[k] = fold32(v[k], m);      // < 25p -> [0, 2p)
     store_vals32<3, 0>(v, sm, t);
     __syncthreads();
 }
-// Inputs in [0, 2p); outputs canonical.
+// Inputs in [0, 4p); outputs canonical.
 __device__ __forceinline__ void inv32_sm(u32 *sm, const Tw32 *__restrict__ tw, const TwHead32 &head, const Mod32 &m) {
     const u32 t = threadIdx.x;
     u32 v[8];
@@ -146,6 +147,56 @@ __device__ __forceinline__ void inv32_sm(u32 *sm, const Tw32 *__restrict__ tw, c
     __syncthreads();
     load_vals32<3, 9>(v, sm, t); inv_pass32<12, 9, 3, true>(v, head, t, m); store_vals32<3, 9>(v, sm, t);
     __syncthreads();
+}
+
+// KK small primes at once: the KK independent 8-value butterfly networks of a thread are
+// interleaved by the compiler (3x the ILP per barrier of one transform at a time).  Image i
+// lives at sm + i * 4096.
+template <int KK>
+__device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb) {
+    const u32 t = threadIdx.x;
+    u32 v[KK][8];
+    __syncthreads();
+#define EXB_PASS(S, TW)                                                                               \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) load_vals32<3, S>(v[i], sm + i * 4096, t);          \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) fwd_pass32<12, S, 3>(v[i], sb.TW[i], t, sb.sc.m[i]);
+    EXB_PASS(9, headf)
+#pragma unroll
+    for (int i = 0; i < KK; i++) store_vals32<3, 9>(v[i], sm + i * 4096, t);
+    __syncthreads();
+    EXB_PASS(6, twf)
+#pragma unroll
+    for (int i = 0; i < KK; i++) store_vals32<3, 6>(v[i], sm + i * 4096, t);
+    __syncthreads();
+    EXB_PASS(3, twf)
+#pragma unroll
+    for (int i = 0; i < KK; i++) store_vals32<3, 3>(v[i], sm + i * 4096, t);
+    __syncthreads();
+    EXB_PASS(0, twf)
+#undef EXB_PASS
+#pragma unroll
+    for (int i = 0; i < KK; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[i][k] = fold32(v[i][k], sb.sc.m[i]);
+        store_vals32<3, 0>(v[i], sm + i * 4096, t);
+    }
+    __syncthreads();
+}
+template <int KK>
+__device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb) {
+    const u32 t = threadIdx.x;
+    u32 v[KK][8];
+    __syncthreads();
+#define EXB_PASS(S, LAST, TW)                                                                         \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) load_vals32<3, S>(v[i], sm + i * 4096, t);          \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) inv_pass32<12, S, 3, LAST>(v[i], sb.TW[i], t, sb.sc.m[i]); \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) store_vals32<3, S>(v[i], sm + i * 4096, t);         \
+    __syncthreads();
+    EXB_PASS(0, false, twi)
+    EXB_PASS(3, false, twi)
+    EXB_PASS(6, false, twi)
+    EXB_PASS(9, true, headi)
+#undef EXB_PASS
 }
 
 template <int LOGN>
@@ -544,10 +595,10 @@ __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
 }
 
 // ---------------------------------------------------------------------------------
-// K4' / K5': lift and tensor+scale on the internal 30-bit auxiliary basis (n = 4096 only;
+// K4' / K5': lift and tensor+scale on the internal 27-bit auxiliary basis (n = 4096 only;
 // see ntt32_core.cuh for why this is result-identical).  Layouts:
 //   ext_q : [pair][limb][comp][n] u64      right operand mod q in Montgomery form
-//   ext_s : [pair][side][limb][comp][K][n] u32   both operands mod the small primes
+//   ext_s : [pair][side][limb][comp][K][n] u32   both operands mod the small primes, in [0, 2p)
 //           (right operand in Montgomery form, R = 2^32)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads12, 2)
@@ -579,16 +630,20 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restri
     inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12);
     lds_u64x4(coef, e0, x); lds_u64x4(coef, e0 + 4, x + 4);      // canonical coefficients stay in registers
     for (u32 i = 0; i < K; i++) {
-        const Mod32 &m = P.sb.sc.m[i];
         u32 y[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) y[k] = ext32_centered(x[k], mq.m, P.sc.half_q, m);
-        sts_u32x8(work, e0, y);
-        fwd32_sm(work, P.sb.twf[i], P.sb.headf[i], m);
-        lds_u32x8(work, e0, y);
+        for (int k = 0; k < 8; k++) y[k] = ext32_centered(x[k], mq.m, P.sc.half_q, P.sb.sc.m[i]);
+        sts_u32x8(work + (size_t)i * n, e0, y);
+    }
+    if (K == 3) fwd32_smK<3>(work, P.sb);
+    else for (u32 i = 0; i < K; i++) fwd32_sm(work + (size_t)i * n, P.sb.twf[i], P.sb.headf[i], P.sb.sc.m[i]);
+    for (u32 i = 0; i < K; i++) {
+        const Mod32 &m = P.sb.sc.m[i];
+        u32 y[8];
+        lds_u32x8(work + (size_t)i * n, e0, y);
         if (side) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) y[k] = shoup32(y[k], m.r_mod, m.r_mod_s, m.p);
+            for (int k = 0; k < 8; k++) y[k] = shoup32_lazy(y[k], m.r_mod, m.r_mod_s, m.p);
         }
         stg_u32x8(ds + (size_t)i * n + e0, y);
     }
@@ -632,7 +687,7 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         }
         inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
     }
-    for (u32 i = 0; i < K; i++) {   // small primes: 32-bit Montgomery point-wise + INTT
+    for (u32 i = 0; i < K; i++) {   // small primes: 32-bit Montgomery point-wise, then the K INTTs together
         const Mod32 &m = P.sb.sc.m[i];
         const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + li) * 2) * (size_t)K + i) * n, *l1 = l0 + (size_t)K * n;
         const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + lj) * 2) * (size_t)K + i) * n, *r1 = r0 + (size_t)K * n;
@@ -648,9 +703,9 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             for (int k = 0; k < 8; k++) v[k] = mont32_redc_lazy((u64)a[k] * b[k], m.p, m.pinv_neg);
         }
         sts_u32x8(bs + (size_t)i * n, e0, v);
-        inv32_sm(bs + (size_t)i * n, P.sb.twi[i], P.sb.headi[i], m);
     }
-    const LazyC lq = make_lazyc(P.mod[0]);
+    if (K == 3) inv32_smK<3>(bs, P.sb);
+    else for (u32 i = 0; i < K; i++) inv32_sm(bs + (size_t)i * n, P.sb.twi[i], P.sb.headi[i], P.sb.sc.m[i]);
     const u32 G = P.gadget_digits;
     u64 av[8];
     u32 bv[kMaxSmall][8];
@@ -663,7 +718,7 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         u32 b[kMaxSmall];
 #pragma unroll
         for (u32 i = 0; i < (u32)kMaxSmall; i++) b[i] = i < K ? bv[i][k] : 0u;
-        av[k] = hps_scale32_coeff(av[k], b, P.sc, P.sb.sc, lq);
+        av[k] = hps_scale32_coeff(av[k], b, P.sc, P.sb.sc);
     }
     if (comp < 2) {
         u64 *o01 = r01 + ((pair * NP + prod) * 2 + comp) * (size_t)n;
@@ -988,7 +1043,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
                  size_t pairs, cudaStream_t s) {
     if (pairs == 0) return;
     if (P.sb.enabled && P.logn == 12) {
-        const size_t sm32 = 4096 * 8 + 4096 * 4;
+        const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
         set_smem(lift32_kernel, sm32);
         lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext,
                                                                            ext_small_part(P, M, ext, pairs));

@@ -183,7 +183,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     const u64 *rk = rlk_mont.data();
     if (small) {
         u32 *exts = reinterpret_cast<u32 *>(extp + pairs * d * 2 * n);
-        emu_launch((unsigned)(pairs * 4 * d), thr, n * 12, [&]() { lift32_kernel(P, d, ct1, ct2, extp, exts); });
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, extp, exts); });
         const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
         if (hs.digits32) {
             int32_t *dg = dig32.data();

@@ -120,12 +120,12 @@ def test_dispatch_errors(emu):
 
 
 def test_internal_small_basis_selection(emu, monkeypatch):
-    """The 30-bit internal auxiliary basis is used exactly when it is provably result-identical
+    """The 27-bit internal auxiliary basis is used exactly when it is provably result-identical
     (n = 4096 fast path, two-aux configs where the reference's centred CRT cannot wrap)."""
     for name in ("cfg3p_dbfv", "u64_dbfv"):
         P = CASES[name][0]
         primes = emu.small_primes(emu.from_oracle(P))
-        assert len(primes) == 3 and all(p < 2 ** 30 and p % 8192 == 1 and O.is_prime(p) for p in primes)
+        assert len(primes) == 3 and all(2 ** 26 < p < 2 ** 27 and p % 8192 == 1 and O.is_prime(p) for p in primes)
         prod = primes[0] * primes[1] * primes[2]
         assert prod >= (P.n * P.q // 2 + 2) << 8
     assert emu.small_primes(emu.from_oracle(CASES["compact_dbfv"][0])) == []          # n = 1024: generic path

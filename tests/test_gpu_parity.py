@@ -257,7 +257,7 @@ def test_smoke_entry():
 
 
 def test_both_aux_basis_paths(monkeypatch):
-    """cfg 3' and cfg 4 through both tensor paths: the internal 30-bit auxiliary basis (default when it is
+    """cfg 3' and cfg 4 through both tensor paths: the internal 27-bit auxiliary basis (default when it is
     provably result-identical) and the reference's own aux primes (EXB_AUX_BASIS=reference)."""
     g = golden()
     for name in ("cfg3p_dbfv", "u64_dbfv"):
