@@ -60,6 +60,8 @@ SYMBOLS = {
     "exb_bfv_mul_and_relin": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "exb_bfv_mul_and_relin_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz]),
     "exb_bfv_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "exb_bfv_decrypt": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_sz, c_vp]),
+    "exb_bfv_decrypt_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_sz]),
     "exb_bfv_apply_automorphism": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_sz, c_vp]),
     "exb_bfv_apply_automorphism_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_sz]),
     "exb_dbfv_mul": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, c_sz, c_u32, c_u32, c_vp]),

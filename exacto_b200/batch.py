@@ -102,6 +102,20 @@ def bfv_apply_automorphism(params: BfvParams, ct: torch.Tensor, gk, out: Optiona
     return out
 
 
+def bfv_decrypt(params: BfvParams, ct: torch.Tensor, sk_ntt: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bfv/encrypt.rs:111-178 over [B, k, n] ciphertexts with the secret key [n] in the NTT domain -> [B, n]
+    plaintext coefficients mod p."""
+    n = params.ring_degree
+    _check(ct, (n,), "ct"); _check(sk_ntt, (n,), "sk_ntt")
+    if ct.dim() != 3:
+        raise InvalidParam("ct: need [batch, components, n]")
+    out = torch.empty((ct.shape[0], n), dtype=torch.int64, device=ct.device) if out is None else out
+    ctx = params.context(ct.device.index)
+    _native.check(_native.lib().exb_bfv_decrypt(ctx.handle, ct.data_ptr(), ct.shape[1], sk_ntt.data_ptr(), out.data_ptr(),
+                                                ct.shape[0], _stream(ct)))
+    return out
+
+
 def _poly_binary(name: str, params: BfvParams, index: int, a: torch.Tensor, b: Optional[torch.Tensor],
                  out: Optional[torch.Tensor], scalar: int = 0) -> torch.Tensor:
     _check(a, (params.ring_degree,), name)

@@ -234,7 +234,7 @@ static int check_launch(const char *what) {
 
 static int check_base(const exb_context *c, u32 idx) {
     if (!c) return fail(EXB_INVALID_PARAM, "null context");
-    const u32 A = (u32)c->aux_moduli.size();
+    const u32 A = c->user_aux;                       // an internal auxiliary pair is not addressable
     if (idx != 0 && (A > (u32)kMaxAux || idx > A))
         return fail(EXB_MODULUS_MISMATCH, "modulus index " + std::to_string(idx) + " has no device plan");
     return EXB_OK;
@@ -559,5 +559,43 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
         EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, cnt * stride * 8, cudaMemcpyDeviceToHost, w.stream));
     }
     for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
+    return EXB_OK;
+}
+
+// ---- decrypt (bfv/encrypt.rs:111-178) -------------------------------------------------------------
+static int decrypt_precheck(exb_context *c, uint32_t ncomp) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null argument");
+    if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "decrypt on the device path needs a single ciphertext prime");
+    if (ncomp < 1) return fail(EXB_INVALID_PARAM, "ciphertext has no components");
+    if (c->plain >= c->ct_moduli[0]) return fail(EXB_NOT_IMPLEMENTED, "decrypt on the device path needs plain_modulus < q");
+    return EXB_OK;
+}
+
+extern "C" int exb_bfv_decrypt(exb_context *c, const uint64_t *ct, uint32_t ncomp, const uint64_t *sk_ntt,
+                               uint64_t *out, size_t batch, void *stream) {
+    int rc = decrypt_precheck(c, ncomp);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_decrypt(c->P, ct, ncomp, sk_ntt, out, batch, (cudaStream_t)stream);
+    return check_launch("decrypt");
+}
+
+extern "C" int exb_bfv_decrypt_host(exb_context *c, const uint64_t *ct, uint32_t ncomp, const uint64_t *sk_ntt,
+                                    uint64_t *out, size_t batch) {
+    int rc = decrypt_precheck(c, ncomp);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    Workspace &w = c->ws[0];
+    const size_t n = c->n, in_bytes = batch * ncomp * n * 8, out_bytes = batch * n * 8;
+    if ((rc = grow((void **)&w.in1, &w.in_b, in_bytes))) return rc;
+    if ((rc = grow_in2_out(w, out_bytes > n * 8 ? out_bytes : n * 8))) return rc;
+    EXB_CUDA(cudaMemcpyAsync(w.in1, ct, in_bytes, cudaMemcpyHostToDevice, w.stream));
+    EXB_CUDA(cudaMemcpyAsync(w.in2, sk_ntt, n * 8, cudaMemcpyHostToDevice, w.stream));
+    launch_decrypt(c->P, w.in1, ncomp, w.in2, w.out, batch, w.stream);
+    if ((rc = check_launch("decrypt"))) return rc;
+    EXB_CUDA(cudaMemcpyAsync(out, w.out, out_bytes, cudaMemcpyDeviceToHost, w.stream));
+    EXB_CUDA(cudaStreamSynchronize(w.stream));
     return EXB_OK;
 }

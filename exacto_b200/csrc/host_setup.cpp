@@ -198,6 +198,7 @@ static int fill_scale_consts(HostSetup *c, std::string *err) {
     const u32 A = (u32)c->aux_moduli.size();
     const u64 q = c->ct_moduli[0], p = c->plain;
     s.q = q; s.half_q = q / 2; s.num_aux = A;
+    if (p < q) { s.plain = p; s.plain_s = shoup_of(p, q); }   // decrypt needs these without an aux basis
     if (A == 0 || A > 2 || p >= q) return EXB_OK;      // multiplication is refused by decide_mul_support
     u128 big_p = 1;
     for (u32 j = 0; j < A; j++) {
@@ -352,6 +353,22 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
     c->aux_moduli.clear();
     if (p->num_aux_moduli) c->aux_moduli.assign(p->aux_moduli, p->aux_moduli + p->num_aux_moduli);
     c->plain = p->plain_modulus;
+    c->user_aux = (u32)c->aux_moduli.size();
+    c->internal_aux = false;
+    // No auxiliary basis: the reference multiplies by exact i128 schoolbook convolution and rounds
+    // round(p * t / q) per coefficient (bfv/eval.rs:415-464), refusing when i128 could overflow
+    // (:457-464).  That result is the HPS closed form with ANY auxiliary basis large enough to hold
+    // m = (t - [t]_q) / q without wrapping (q is an odd prime that divides neither 2p nor a non-multiple t,
+    // so the rounding never ties), so the device synthesises two 61-bit NTT primes (P ~ 2^122 >> n*q) and runs
+    // its HPS pipeline; tests compare it with the literal O(n^2) restatement.
+    if (c->user_aux == 0 && c->ct_moduli.size() == 1 && n >= 2 && c->plain < c->ct_moduli[0] &&
+        !schoolbook_overflow_risk(c->plain, c->ct_moduli[0], n)) {
+        const u64 step = 2ull * n, top = (u64)1 << 61;
+        for (u64 cand = (top - 1) / step * step + 1; cand > top / 2 && c->aux_moduli.size() < 2; cand -= step)
+            if (cand != c->ct_moduli[0] && h_is_prime(cand)) c->aux_moduli.push_back(cand);
+        if (c->aux_moduli.size() == 2) c->internal_aux = true;
+        else c->aux_moduli.clear();
+    }
     // gadget parameters: params/mod.rs:98-112, compute_gadget_digits :126-140
     c->gadget_base = p->gadget_base ? p->gadget_base : (1ull << 16);
     if (p->gadget_digits) {

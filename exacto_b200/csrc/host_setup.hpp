@@ -63,6 +63,8 @@ struct MulPlan {
 struct HostSetup {
     u32 n = 0, logn = 0;
     std::vector<u64> ct_moduli, aux_moduli;
+    u32 user_aux = 0;                        // aux primes supplied by the caller (0: aux_moduli may hold the internal pair)
+    bool internal_aux = false;               // aux_moduli were synthesised (reference would run its schoolbook branch)
     std::vector<u64> psi;                    // per modulus index (0 = q_0, 1..A = aux, then q_1..)
     u64 plain = 0, gadget_base = 0;
     u32 gadget_digits = 0;

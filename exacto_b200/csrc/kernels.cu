@@ -937,6 +937,42 @@ galois_kernel(const __grid_constant__ DeviceParams P, const u64 *__restrict__ ct
     for (u32 e = threadIdx.x; e < n; e += blockDim.x) dst[e] = acc0[Lay<LOGN>::at(e)];
 }
 
+// ---------------------------------------------------------------------------------
+// decrypt (bfv/encrypt.rs:111-178, single ciphertext prime).  One CTA per ciphertext:
+//   phase = c0 + c1 s + c2 s^2 + ...  (NTT domain),  x = INTT(phase),
+//   m = floor((p x + floor(q/2)) / q) mod p     with x in [0, q)  (the reference does not centre x).
+// p x = k q + r by Shoup (k = mulhi(x, p_s), r in [0, 2q)), so the floor is k + [r+h >= q] + [r+h >= 2q].
+// ---------------------------------------------------------------------------------
+template <int LOGN>
+__global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
+decrypt_kernel(const __grid_constant__ DeviceParams P, const u64 *__restrict__ ct, u32 ncomp,
+               const u64 *__restrict__ sk_ntt, u64 *__restrict__ out) {
+    EXB_DYN_SMEM(smem);
+    const u32 n = P.n;
+    const Modulus &mq = P.mod[0];
+    const u64 q = mq.m, half_q = q >> 1, p = P.sc.plain, p_s = P.sc.plain_s;
+    const u64 *src = ct + (size_t)blockIdx.x * ncomp * n;
+    u64 *dst = out + (size_t)blockIdx.x * n;
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 s_m = csub(mont_mul_lazy(sk_ntt[e], mq.r2_mod, q, mq.minv_neg), q);      // s * 2^64
+        u64 phase = ld_stream(src + e), spow = s_m;
+        for (u32 i = 1; i < ncomp; i++) {
+            phase = mod_add(phase, csub(mont_mul_lazy(ld_stream(src + (size_t)i * n + e), spow, q, mq.minv_neg), q), q);
+            if (i + 1 < ncomp) spow = csub(mont_mul_lazy(spow, s_m, q, mq.minv_neg), q);
+        }
+        smem[Lay<LOGN>::at(e)] = phase;
+    }
+    inv_sm<LOGN>(smem, P.twi[0], P.headi[0], mq, P.logn);
+    for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
+        const u64 x = smem[Lay<LOGN>::at(e)];
+        const u64 k = mulhi64(x, p_s);
+        const u64 r = x * p - k * q;
+        const u64 rh = r + half_q;
+        const u64 m = k + (rh >= q ? 1u : 0u) + (rh >= 2 * q ? 1u : 0u);                    // <= p
+        dst[e] = m >= p ? m - p : m;
+    }
+}
+
 // out_limb += (+/-) s * excess_limb over 2n words per pair (dbfv/reduction.rs:34-52, :65-93).
 __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const u64 *__restrict__ excess_limb,
                                   u64 s_mont, int negative, size_t out_stride, size_t excess_stride,
@@ -1125,6 +1161,20 @@ void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32
     } else {
         set_smem(galois_kernel<0>, sm);
         galois_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(P, ct, gk_mont, k, out);
+    }
+    g_launch_count++;
+}
+
+void launch_decrypt(const DeviceParams &P, const u64 *ct, u32 ncomp, const u64 *sk_ntt, u64 *out, size_t count,
+                    cudaStream_t s) {
+    if (count == 0) return;
+    const size_t sm = (size_t)P.n * 8;
+    if (P.logn == 12) {
+        set_smem(decrypt_kernel<12>, sm);
+        decrypt_kernel<12><<<(unsigned)count, kThreads12, sm, s>>>(P, ct, ncomp, sk_ntt, out);
+    } else {
+        set_smem(decrypt_kernel<0>, sm);
+        decrypt_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(P, ct, ncomp, sk_ntt, out);
     }
     g_launch_count++;
 }

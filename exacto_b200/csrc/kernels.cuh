@@ -43,6 +43,11 @@ void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_l
 void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32 element, u64 *out,
                    size_t count, cudaStream_t s);
 
+// decrypt (bfv/encrypt.rs:111-178) of `count` ciphertexts [count][ncomp][n] with the secret key in the
+// NTT domain -> plaintext coefficients mod p, [count][n].  Needs p < q.
+void launch_decrypt(const DeviceParams &P, const u64 *ct, u32 ncomp, const u64 *sk_ntt, u64 *out, size_t count,
+                    cudaStream_t s);
+
 #endif  // EXB_HOST_EMUL
 
 // Count of kernels launched by this library (bench.py's gpu_launches).

@@ -162,6 +162,16 @@ int exb_bfv_apply_automorphism(exb_context *ctx, const uint64_t *ct_dev, uint64_
 int exb_bfv_apply_automorphism_host(exb_context *ctx, const uint64_t *ct_host, uint64_t element,
                                     const exb_relin_key *gk, uint64_t *out_host, size_t batch);
 
+/* ---- decrypt (bfv/encrypt.rs:111-178), batched: phase = c0 + c1 s + c2 s^2 + ..., then
+ * m = floor((p * INTT(phase) + floor(q/2)) / q) mod p per coefficient.  ct [batch][num_components][n]
+ * (NTT domain), sk_ntt [n] = SecretKey.poly (NTT domain), out [batch][n] coefficients mod p.
+ * Needs a single ciphertext prime and p < q (EXB_NOT_IMPLEMENTED otherwise: the reference's
+ * BigUint CRT path is outside the device path). */
+int exb_bfv_decrypt(exb_context *ctx, const uint64_t *ct_dev, uint32_t num_components, const uint64_t *sk_ntt_dev,
+                    uint64_t *out_dev, size_t batch, void *stream);
+int exb_bfv_decrypt_host(exb_context *ctx, const uint64_t *ct_host, uint32_t num_components,
+                         const uint64_t *sk_ntt_host, uint64_t *out_host, size_t batch);
+
 /* ---- dbfv_mul (dbfv/eval.rs:82-149) incl. reduction::reduce (dbfv/reduction.rs:15-60),
  * batched.  `base`, `num_digits`, `dbfv_plain_modulus` are DbfvParams (params/mod.rs:143-192;
  * 0 = 2^64).  The limb-count and mul_depth guards (dbfv/eval.rs:90-102) read ciphertext

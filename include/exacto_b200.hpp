@@ -14,6 +14,7 @@
 //   dbfv/    DbfvCiphertext (dbfv/ciphertext.rs:10-22), dbfv_add (dbfv/eval.rs:11-33), dbfv_mul (dbfv/eval.rs:82-149)
 #pragma once
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -191,6 +192,13 @@ private:
     mutable exb_relin_key *dev_ = nullptr;
 };
 
+class GaloisKey : public RelinKey {                  // bfv/keygen.rs:47-54: key switch s(X^element) -> s(X)
+public:
+    size_t element;
+    GaloisKey(std::vector<std::pair<RnsPoly, RnsPoly>> k, size_t elem, std::shared_ptr<BfvParams> p)
+        : RelinKey(std::move(k), std::move(p)), element(elem) {}
+};
+
 namespace detail {
 inline void flatten(const BfvCiphertext &ct, std::vector<uint64_t> &out) {
     for (const RnsPoly &p : ct.c) {
@@ -231,6 +239,29 @@ inline BfvCiphertext bfv_mul_and_relin(const BfvCiphertext &ct1, const BfvCipher
     std::vector<uint64_t> out(a.size());
     check(exb_bfv_mul_and_relin_host(ct1.params->context(), a.data(), b.data(), rlk.device(), out.data(), 1));
     return detail::unflatten(out.data(), 2, ct1.params);
+}
+
+inline BfvCiphertext bfv_apply_automorphism(const BfvCiphertext &ct, const GaloisKey &gk) {   // bfv/eval.rs:512-561
+    if (ct.c.size() != 2)                                                                     // :516-520
+        throw ExactoError(ExactoError::InvalidParam, "automorphism requires degree-1 ciphertext");
+    std::vector<uint64_t> a;
+    detail::flatten(ct, a);
+    std::vector<uint64_t> out(a.size());
+    check(exb_bfv_apply_automorphism_host(ct.params->context(), a.data(), gk.element, gk.device(), out.data(), 1));
+    return detail::unflatten(out.data(), 2, ct.params);
+}
+
+// bfv/eval.rs:573-588: result <- result + sigma_k(result) for each k in order.
+inline BfvCiphertext bfv_trace(const BfvCiphertext &ct, const std::vector<size_t> &galois_elements,
+                               const std::map<size_t, std::shared_ptr<GaloisKey>> &galois_keys) {
+    BfvCiphertext result = ct;
+    for (size_t k : galois_elements) {
+        auto it = galois_keys.find(k);
+        if (it == galois_keys.end())
+            throw ExactoError(ExactoError::InvalidParam, "missing Galois key for element " + std::to_string(k));
+        result = bfv_add(result, bfv_apply_automorphism(result, *it->second));
+    }
+    return result;
 }
 
 // ---- dbfv/ -----------------------------------------------------------------------------------------------
@@ -275,6 +306,22 @@ inline DbfvCiphertext dbfv_mul(const DbfvCiphertext &ct1, const DbfvCiphertext &
     DbfvCiphertext res{{}, d, next_depth, params};                   // :138-146, reduction.rs:54-59
     const size_t n = params->bfv_params->ring_degree;
     for (size_t i = 0; i < d; i++) res.limbs.push_back(detail::unflatten(out.data() + i * 2 * n, 2, params->bfv_params));
+    return res;
+}
+
+// dbfv/advanced.rs:15-30: the BFV automorphism + key switch on every limb, one batched call.
+inline DbfvCiphertext dbfv_apply_automorphism(const DbfvCiphertext &ct, const GaloisKey &gk) {
+    std::vector<uint64_t> a;
+    for (const auto &l : ct.limbs) {
+        if (l.c.size() != 2) throw ExactoError(ExactoError::InvalidParam, "automorphism requires degree-1 ciphertext");
+        detail::flatten(l, a);
+    }
+    std::vector<uint64_t> out(a.size());
+    const auto &bfv = ct.params->bfv_params;
+    check(exb_bfv_apply_automorphism_host(bfv->context(), a.data(), gk.element, gk.device(), out.data(), ct.num_limbs()));
+    DbfvCiphertext res{{}, ct.degree, ct.mul_depth, ct.params};
+    const size_t n = bfv->ring_degree;
+    for (size_t i = 0; i < ct.num_limbs(); i++) res.limbs.push_back(detail::unflatten(out.data() + i * 2 * n, 2, bfv));
     return res;
 }
 

@@ -57,6 +57,7 @@ class Emulator:
         L.emu_small_primes.argtypes = [vp, vp]
         L.emu_dbfv_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, u32, u32]
         L.emu_bfv_apply_automorphism.argtypes = [vp, vp, u64, vp, vp, ctypes.c_size_t]
+        L.emu_bfv_decrypt.argtypes = [vp, vp, u32, vp, vp, ctypes.c_size_t]
         self.L = L
 
     @staticmethod
@@ -104,6 +105,12 @@ class Emulator:
         ct, gk = np.ascontiguousarray(ct, np.uint64), np.ascontiguousarray(gk, np.uint64)
         out = np.zeros_like(ct)
         self.L.emu_bfv_apply_automorphism(h, self._p(ct), element, self._p(gk), self._p(out), ct.size // (2 * ct.shape[-1]))
+        return out
+
+    def bfv_decrypt(self, h, ct, sk_ntt):
+        ct, sk_ntt = np.ascontiguousarray(ct, np.uint64), np.ascontiguousarray(sk_ntt, np.uint64)
+        out = np.zeros(ct.shape[:-2] + ct.shape[-1:], np.uint64)
+        self.L.emu_bfv_decrypt(h, self._p(ct), ct.shape[-2], self._p(sk_ntt), self._p(out), out.size // ct.shape[-1])
         return out
 
     def dbfv_mul(self, h, base, d, pm, ct1, ct2, rlk, flags=0, limb_mask=0, out=None):

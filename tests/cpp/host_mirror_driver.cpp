@@ -2,7 +2,8 @@
 // Usage: host_mirror_driver <preset: compact_dbfv|u64_dbfv> <in.bin> <out.bin>
 //   in.bin : ct1 [d][2][n] | ct2 [d][2][n] | rlk [G][2][n]   (u64, NTT domain)
 //   out.bin: dbfv_mul limbs [d][2][n] | bfv_mul_and_relin(limb0, limb0) [2][n] | dbfv_add [d][2][n]
-//            | NTT round trip of ct1 limb 0 comp 0 [n]
+//            | NTT round trip of ct1 limb 0 comp 0 [n] | dbfv_apply_automorphism(ct1, sigma_3 with rlk as key) [d][2][n]
+//            | bfv_trace(ct1 limb 0, {3}) [2][n]
 // Prints "guards ok" after checking the reference's error behaviour (dbfv/eval.rs:90-102, bfv/eval.rs:93-97).
 #include <cstdio>
 #include <cstring>
@@ -47,6 +48,7 @@ int main(int argc, char **argv) {
             BfvCiphertext k = make_ct(pk + g * 2 * n, 2, bfv);
             keys.emplace_back(k.c[0], k.c[1]);
         }
+        auto gk = std::make_shared<GaloisKey>(keys, 3, bfv);              // same [G][2][n] words as a Galois key
         RelinKey rlk(std::move(keys), bfv);
 
         const DbfvCiphertext prod = dbfv_mul(a, b, rlk);
@@ -73,6 +75,11 @@ int main(int argc, char **argv) {
                  BfvCiphertext z = detail::unflatten(std::vector<uint64_t>(2 * 4096, 0).data(), 2, p);
                  bfv_mul_and_relin(z, z, empty);
              });
+        const DbfvCiphertext rot = dbfv_apply_automorphism(a, *gk);
+        const BfvCiphertext tr = bfv_trace(a.limbs[0], {3}, {{3, gk}});
+        ok = ok && rot.degree == a.degree && rot.mul_depth == a.mul_depth && rot.num_limbs() == d;
+        ok = ok && throws(ExactoError::InvalidParam, "automorphism requires degree-1 ciphertext", [&] { bfv_apply_automorphism(deg2, *gk); });
+        ok = ok && throws(ExactoError::InvalidParam, "missing Galois key for element 5", [&] { bfv_trace(a.limbs[0], {5}, {{3, gk}}); });
         std::puts(ok ? "guards ok" : "guards FAILED");
 
         std::ofstream out(argv[3], std::ios::binary);
@@ -81,6 +88,8 @@ int main(int argc, char **argv) {
         dump(one);
         for (const auto &l : sum.limbs) dump(l);
         out.write(reinterpret_cast<const char *>(back.coeffs.data()), (std::streamsize)(n * 8));
+        for (const auto &l : rot.limbs) dump(l);
+        dump(tr);
         return ok ? 0 : 4;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -254,4 +254,13 @@ int emu_bfv_apply_automorphism(emu_ctx *c, const uint64_t *ct, uint64_t element,
     return 0;
 }
 
+// Same launch as launch_decrypt() in exacto_b200/csrc/kernels.cu.
+int emu_bfv_decrypt(emu_ctx *c, const uint64_t *ct, uint32_t ncomp, const uint64_t *sk_ntt, uint64_t *out, size_t count) {
+    const DeviceParams &P = c->hs.P;
+    const size_t n = c->hs.n;
+    if (P.logn == 12) emu_launch((unsigned)count, kThreads12, n * 8, [&]() { decrypt_kernel<12>(P, ct, ncomp, sk_ntt, out); });
+    else emu_launch((unsigned)count, emu_block_threads(P), n * 8, [&]() { decrypt_kernel<0>(P, ct, ncomp, sk_ntt, out); });
+    return 0;
+}
+
 }  // extern "C"

@@ -181,3 +181,79 @@ def test_galois_kernel_matches_oracle(emu, preset, elements):
     for k in elements:
         got = emu.bfv_apply_automorphism(h, ct, k, gk)
         assert np.array_equal(got, O.bfv_apply_automorphism(P, ct, gk, k, threads=4)), (preset, k)
+
+
+# ---- decrypt --------------------------------------------------------------------------
+@pytest.mark.parametrize("preset", ["compact", "u64", "toy16"])
+def test_decrypt_kernel_matches_definition(emu, preset):
+    """decrypt_kernel against the big-int restatement of bfv/encrypt.rs:111-178 (oracle/harness.py:decrypt) on
+    real encryptions (degree 1), a degree-2 product and uniform / edge phases."""
+    P = {"compact": H.compact_bfv(), "u64": H.u64_dbfv().bfv,
+         "toy16": O.OracleParams(n=16, q=1152921504606830593, aux=(18014398509998081,), plain_modulus=17,
+                                 gadget_base=10)}[preset]
+    h = emu.from_oracle(P)
+    q, n, t = P.q, P.n, P.plain_modulus
+    rng = np.random.default_rng(5)
+    s = H.gen_secret_key(P, rng)
+    pt = rng.integers(0, t, n, dtype=np.uint64)
+    ct = np.stack([H.encrypt_sk(P, pt, s, rng), rng.integers(0, q, (2, n), dtype=np.uint64)])
+    got = emu.bfv_decrypt(h, ct, s)
+    assert np.array_equal(got[0], pt) and np.array_equal(got[0], H.decrypt(P, ct[0], s))
+    assert np.array_equal(got[1], H.decrypt(P, ct[1], s))
+    edge = np.zeros(n, np.uint64)
+    edge[:8] = [0, 1, q - 1, q // 2, q // 2 + 1, q // t, q - q // (2 * t), q - q // (2 * t) - 1]
+    c0 = np.stack([O.ntt_fwd(edge, q), np.zeros(n, np.uint64)])[None]
+    assert np.array_equal(emu.bfv_decrypt(h, c0, s)[0], H.decrypt(P, c0[0], s))
+    if preset != "toy16":
+        c3 = O.bfv_mul_no_relin(P, ct[0], H.encrypt_sk(P, pt, s, rng))[None]       # degree 2: c0 + c1 s + c2 s^2
+        assert np.array_equal(emu.bfv_decrypt(h, c3, s)[0], H.decrypt(P, c3[0], s))
+
+
+# ---- parameter sets without an auxiliary basis (the reference's schoolbook branch) --------------------
+NO_AUX = {
+    "boot_orig": dict(P=O.OracleParams(n=16, q=65537, aux=(), plain_modulus=5), dbfv=None),
+    "boot_scheme": dict(P=O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8), dbfv=None),
+    "boot_dbfv": dict(P=O.OracleParams(n=16, q=65537, aux=(), plain_modulus=97, gadget_base=8), dbfv=(4, 2, 16)),
+    "n256_q40": dict(P=O.OracleParams(n=256, q=1099509805057, aux=(), plain_modulus=257), dbfv=(16, 2, 256)),
+    "n4096_q50": dict(P=O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=65537, gadget_base=256), dbfv=None),
+}
+
+
+@pytest.mark.parametrize("name", list(NO_AUX))
+def test_no_aux_params_match_schoolbook(emu, name):
+    """bfv/eval.rs:415-464: without an auxiliary basis the reference convolves exactly in i128 and rounds.  The
+    device runs its HPS pipeline on an internal auxiliary basis (two 61-bit primes, or the 27-bit basis at
+    n = 4096); the result must equal the literal O(n^2) restatement word for word (bootstrap test parameter
+    sets of bootstrap/bfv_host.rs:345-386 included)."""
+    P, dbfv = NO_AUX[name]["P"], NO_AUX[name]["dbfv"]
+    h = emu.from_oracle(P)
+    assert emu.info(h)[2] == 0, emu.info(h)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(len(name))
+    rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    B = 2 if n == 4096 else 4
+    ct1 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    edge = np.full(n, q // 2, np.uint64); edge[::2] = q // 2 + 1
+    ct1[0] = O.ntt_fwd(np.stack([edge, edge[::-1].copy()]), q)           # worst-case |t| coefficients
+    ct2[0] = O.ntt_fwd(np.stack([edge, edge]), q)
+    rc, got, err = emu.dbfv_mul(h, 2, 1, 0, ct1[:, None], ct2[:, None], rlk)
+    assert rc == 0, err
+    assert np.array_equal(got[:, 0], O.bfv_mul_and_relin(P, ct1, ct2, rlk, threads=4))
+    if dbfv:
+        b, d, pm = dbfv
+        a = rng.integers(0, q, (d, 2, n), dtype=np.uint64); c = rng.integers(0, q, (d, 2, n), dtype=np.uint64)
+        rc, got, err = emu.dbfv_mul(h, b, d, pm, a[None], c[None], rlk)
+        assert rc == 0, err
+        assert np.array_equal(got[0], O.dbfv_mul(P, b, d, pm, a, c, rlk, threads=4))
+
+
+def test_no_aux_overflow_risk_still_refused(emu):
+    """README config 3 (n = 4096, 59-bit q, no aux): the reference errors (bfv/eval.rs:426-431); so do we."""
+    P = O.OracleParams(n=4096, q=576460752308273153, aux=(), plain_modulus=65537)
+    h = emu.from_oracle(P)
+    info = emu.info(h)
+    assert info[2] == 9
+    rc, _, err = emu.dbfv_mul(h, 2, 1, 0, np.zeros((1, 1, 2, 4096), np.uint64), np.zeros((1, 1, 2, 4096), np.uint64),
+                              np.zeros((P.gadget_digits, 2, 4096), np.uint64))
+    assert rc == 9 and "schoolbook BFV multiplication can overflow i128" in err

@@ -300,7 +300,8 @@ def test_eval_poly_homomorphic_paterson_stockmeyer():
 @pytest.mark.parametrize("preset", ["compact_dbfv", "u64_dbfv"])
 def test_cpp_host_mirror(preset, tmp_path):
     """The C++ host mirror (include/exacto_b200.hpp: same names / guards as the reference) end to end:
-    dbfv_mul, bfv_mul_and_relin, dbfv_add, NTT round trip and the error pins, bit-compared with the oracle."""
+    dbfv_mul, bfv_mul_and_relin, dbfv_add, NTT round trip, dbfv_apply_automorphism, bfv_trace and the error pins,
+    bit-compared with the oracle."""
     import subprocess
     import __graft_entry__ as g
     exe = g.build_cpp_driver()
@@ -321,7 +322,11 @@ def test_cpp_host_mirror(preset, tmp_path):
     assert np.array_equal(out[lim:lim + 2 * P.n].reshape(2, P.n), O.bfv_mul_and_relin(P, ct1[0], ct2[0], rlk))
     want_sum = np.array((ct1.astype(object) + ct2.astype(object)) % P.q, dtype=np.uint64)
     assert np.array_equal(out[lim + 2 * P.n:2 * lim + 2 * P.n].reshape(S.d, 2, P.n), want_sum)
-    assert np.array_equal(out[2 * lim + 2 * P.n:], O.ntt_inv(ct1[0, 0], P.q))
+    off = 2 * lim + 2 * P.n
+    assert np.array_equal(out[off:off + P.n], O.ntt_inv(ct1[0, 0], P.q))
+    rot = O.bfv_apply_automorphism(P, ct1, rlk, 3, threads=O.max_threads())
+    assert np.array_equal(out[off + P.n:off + P.n + lim].reshape(S.d, 2, P.n), rot)
+    assert np.array_equal(out[off + P.n + lim:].reshape(2, P.n), O.bfv_add(P, ct1[0], rot[0]))
 
 
 def test_device_api_chunk_loop():
@@ -441,3 +446,191 @@ def test_automorphism_vs_oracle(preset, elements):
     with pytest.raises(E.ExactoError, match="must not alias"):
         d = batch.to_device(ct)
         batch.bfv_apply_automorphism(params, d, zero, out=d)
+
+
+# ---- keygen / encrypt / decrypt around the path ---------------------------------------------
+class NpSampler:
+    """The harness samplers behind exacto_b200's sampler protocol (same rng consumption order as the oracle)."""
+
+    def __init__(self, rng):
+        self.rng = rng
+
+    def ternary(self, n, q): return H.sample_ternary(n, q, self.rng)
+    def uniform(self, n, q): return H.sample_uniform(n, q, self.rng)
+    def gaussian(self, n, q, sigma): return H.sample_gaussian(n, q, sigma, self.rng)
+
+
+@pytest.mark.parametrize("preset", ["compact", "u64"])
+def test_keygen_encrypt_decrypt_parity(preset):
+    """Keys and ciphertexts are bit-exact functions of the sampled polynomials (bfv/keygen.rs:64-210,
+    bfv/encrypt.rs:79-106); decrypt (bfv/encrypt.rs:111-178) matches the big-int restatement for degree-1 and
+    degree-2 ciphertexts, host and device entry points; dBFV encrypt/decrypt round trip (dbfv/decrypt.rs tests)."""
+    from exacto_b200 import batch
+    S = H.compact_dbfv() if preset == "compact" else H.u64_dbfv()
+    P = S.bfv
+    dparams = to_dbfv_params(P, S.base, S.d, S.plain_modulus)
+    params = dparams.bfv_params
+    r1, r2 = np.random.default_rng(9), np.random.default_rng(9)
+    s_ref = H.gen_secret_key(P, r1)
+    rlk_ref = H.gen_relin_key(P, s_ref, r1)
+    gk_ref = H.gen_galois_key(P, s_ref, 5, r1)
+    smp = NpSampler(r2)
+    sk = E.gen_secret_key_with_sampler(params, smp)
+    rlk = E.gen_relin_key_with_sampler(sk, smp)
+    gk = E.gen_galois_key_with_sampler(sk, 5, smp)
+    assert np.array_equal(sk.ntt_array(), s_ref)
+    assert np.array_equal(rlk.array, rlk_ref) and np.array_equal(gk.array, gk_ref) and gk.element == 5
+    pt = r1.integers(0, P.plain_modulus, P.n, dtype=np.uint64); r2.integers(0, P.plain_modulus, P.n, dtype=np.uint64)
+    ct_ref = H.encrypt_sk(P, pt, s_ref, r1)
+    a = E.CoeffPoly(smp.uniform(P.n, P.q), P.q); e = E.CoeffPoly(smp.gaussian(P.n, P.q, 3.2), P.q)
+    ct = E.encrypt_sk_with_samples(E.CoeffPoly(pt, P.plain_modulus), sk, params, a, e)
+    assert np.array_equal(ct.to_array(), ct_ref)
+    assert np.array_equal(E.decrypt(ct, sk).coeffs, pt)
+    prod3 = O.bfv_mul_no_relin(P, ct_ref, ct_ref)                                  # degree 2
+    rnd = r1.integers(0, P.q, (3, 3, P.n), dtype=np.uint64)
+    rnd[0] = prod3
+    want = np.stack([H.decrypt(P, c, s_ref) for c in rnd])
+    assert np.array_equal(E.decrypt_batch(params, rnd, sk), want)
+    dev = batch.bfv_decrypt(params, batch.to_device(rnd), batch.to_device(s_ref))
+    assert np.array_equal(batch.to_host(dev), want)
+    for value in [0, 1, 42, 255]:                                                   # dbfv/decrypt.rs:96-108
+        smp2 = [(E.CoeffPoly(smp.uniform(P.n, P.q), P.q), E.CoeffPoly(smp.gaussian(P.n, P.q, 3.2), P.q)) for _ in range(S.d)]
+        dct = E.dbfv_encrypt_sk_with_samples(value, sk, dparams, [x[0] for x in smp2], [x[1] for x in smp2])
+        assert E.dbfv_decrypt(dct, sk) == value
+    with pytest.raises(E.ExactoError, match="plaintext 1000000000 >= plain_modulus"):
+        E.encode_scalar(1000000000, params)
+
+
+NO_AUX_GPU = {
+    "boot_orig": (O.OracleParams(n=16, q=65537, aux=(), plain_modulus=5), None),
+    "boot_scheme": (O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8), None),
+    "boot_dbfv": (O.OracleParams(n=16, q=65537, aux=(), plain_modulus=97, gadget_base=8), (4, 2, 16)),
+    "n1024_q40": (O.OracleParams(n=1024, q=1099509805057, aux=(), plain_modulus=257), (16, 2, 256)),
+    "n4096_q50": (O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=65537, gadget_base=256), None),
+}
+
+
+@pytest.mark.parametrize("name", list(NO_AUX_GPU))
+def test_no_aux_params_match_schoolbook(name):
+    """Parameter sets without an auxiliary basis: the reference's exact i128 schoolbook branch
+    (bfv/eval.rs:415-464) vs the device's HPS pipeline on an internal auxiliary basis -- word for word."""
+    P, dbfv = NO_AUX_GPU[name]
+    params = to_params(P)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(len(name))
+    rlk_arr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, params)
+    ct1 = rng.integers(0, q, (3, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (3, 2, n), dtype=np.uint64)
+    edge = np.full(n, q // 2, np.uint64); edge[::2] = q // 2 + 1
+    ct1[0] = O.ntt_fwd(np.stack([edge, edge[::-1].copy()]), q)
+    ct2[0] = O.ntt_fwd(np.stack([edge, edge]), q)
+    assert np.array_equal(E.bfv_mul_and_relin_batch(params, ct1, ct2, rlk),
+                          O.bfv_mul_and_relin(P, ct1, ct2, rlk_arr, threads=O.max_threads()))
+    if dbfv:
+        b, d, pm = dbfv
+        dp = to_dbfv_params(P, b, d, pm)
+        a = rng.integers(0, q, (2, d, 2, n), dtype=np.uint64); c = rng.integers(0, q, (2, d, 2, n), dtype=np.uint64)
+        want = np.stack([O.dbfv_mul(P, b, d, pm, x, y, rlk_arr, threads=O.max_threads()) for x, y in zip(a, c)])
+        assert np.array_equal(E.dbfv_mul_batch(dp, a, c, E.RelinKey(rlk_arr, dp.bfv_params)), want)
+    with pytest.raises(E.ExactoError, match="schoolbook BFV multiplication can overflow i128"):   # README config 3
+        p3 = to_params(O.OracleParams(n=4096, q=576460752308273153, aux=(), plain_modulus=65537))
+        z = np.zeros((1, 2, 4096), np.uint64)
+        E.bfv_mul_and_relin_batch(p3, z, z, E.RelinKey(np.zeros((4, 2, 4096), np.uint64), p3))
+
+
+# ---- bootstrap (bootstrap/bfv_host.rs:134-288, tests :345-560): SURVEY 8(f)1, BASELINE config 5 ----------------
+def _product_bootstrap_key(bk, boot_params):
+    return E.BootstrapKey(boot_params, E.RelinKey(bk.boot_rlk, boot_params),
+                          bsk=E.BfvCiphertext.from_array(bk.bsk, boot_params),
+                          galois_keys={k: E.GaloisKey(v, k, boot_params) for k, v in bk.galois_keys.items()},
+                          rounding_poly=bk.rounding_poly, t_orig=bk.t_orig, q_prime=bk.q_prime)
+
+
+def test_bootstrap_single_and_ring():
+    """bfv_host.rs:398-453 on the reference's toy parameter sets: trivial ciphertexts m = 0..4 decode to m after
+    the refresh; a real encryption takes the full ring path (CoeffsToSlots, rounding polynomial per slot,
+    SlotsToCoeffs) and must equal the oracle pipeline word for word; on a parameter set that fits the noise
+    budget the ring path must also equal the clear-text model of the bootstrap for all n coefficients."""
+    from oracle import bootstrap_ref as B
+    from test_oracle import _boot_params, expected_ring_bootstrap
+    orig, boot, qp = _boot_params()
+    op, bp = to_params(orig), to_params(boot)
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(orig, rng)
+    bk = B.gen_bootstrap_key(orig, boot, s, qp, orig.plain_modulus, rng)
+    pk = _product_bootstrap_key(bk, bp)
+    sk = E.SecretKey.from_ntt(s, op)
+    boot_sk = E.create_boot_sk(sk, bp)
+    assert np.array_equal(boot_sk.ntt_array(), B.create_boot_sk(orig, boot, s))
+    assert E.compute_rounding_poly(5, 25, 29) == bk.rounding_poly
+    for m in range(5):
+        out = E.bfv_bootstrap(E.trivial_encrypt(m, op), pk)
+        assert out.params is bp and E.decode_scalar(E.decrypt(out, boot_sk)) % 5 == m
+        assert np.array_equal(out.to_array(), B.bfv_bootstrap(orig, H.trivial_encrypt(orig, m), bk))
+    ct = H.encrypt_sk(orig, H.encode_scalar(orig, 3), s, rng)
+    got = E.bfv_bootstrap(E.BfvCiphertext.from_array(ct, op), pk)
+    assert np.array_equal(got.to_array(), B.bfv_bootstrap(orig, ct, bk))
+    with pytest.raises(E.ExactoError, match="bootstrap requires degree-1 ciphertext"):
+        E.bfv_bootstrap(E.BfvCiphertext.from_array(np.zeros((3, 16), np.uint64), op), pk)
+    # coefficient extraction / packing on their own (coeffs_to_slots.rs tests)
+    pt = rng.integers(0, boot.plain_modulus, boot.n, dtype=np.uint64)
+    cte = E.BfvCiphertext.from_array(H.encrypt_sk(boot, pt, boot_sk.ntt_array(), rng), bp)
+    slots = E.coeffs_to_slots(cte, pk.galois_keys)
+    assert [E.decode_scalar(E.decrypt(sl, boot_sk)) for sl in slots] == [int(v) for v in pt]
+    assert np.array_equal(E.decrypt(E.slots_to_coeffs(slots), boot_sk).coeffs, pt)
+    assert np.array_equal(slots[5].to_array(), B.extract_coefficient(boot, cte.to_array(), 5, bk.galois_keys))
+
+    orig2 = O.OracleParams(n=16, q=65537, aux=(), plain_modulus=2)
+    boot2 = O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=5, gadget_base=8)
+    op2, bp2 = to_params(orig2), to_params(boot2)
+    r1, r2 = np.random.default_rng(3), np.random.default_rng(3)
+    s2 = H.gen_secret_key(orig2, r1)
+    sk2 = E.gen_secret_key_with_sampler(op2, NpSampler(r2))
+    bk2 = B.gen_bootstrap_key(orig2, boot2, s2, 4, 2, r1)
+    pk2 = E.gen_bootstrap_key_with_sampler(sk2, bp2, 4, 2, NpSampler(r2))          # same stream -> same key material
+    assert np.array_equal(pk2.bsk.to_array(), bk2.bsk) and np.array_equal(pk2.boot_rlk.array, bk2.boot_rlk)
+    assert sorted(pk2.galois_keys) == sorted(bk2.galois_keys)
+    assert all(np.array_equal(pk2.galois_keys[k].array, bk2.galois_keys[k]) for k in bk2.galois_keys)
+    ct2 = H.encrypt_sk(orig2, r1.integers(0, 2, 16, dtype=np.uint64), s2, r1)
+    out2 = E.bfv_bootstrap(E.BfvCiphertext.from_array(ct2, op2), pk2)
+    assert np.array_equal(out2.to_array(), B.bfv_bootstrap(orig2, ct2, bk2))
+    assert np.array_equal(E.decrypt(out2, E.create_boot_sk(sk2, bp2)).coeffs, expected_ring_bootstrap(orig2, boot2, 4, ct2, s2))
+
+
+def test_dbfv_mul_then_bootstrap_and_chain():
+    """bfv_host.rs:455-560: dbfv_mul_then_bootstrap resets mul_depth and swaps in the boot parameter set, the
+    refreshed ciphertext multiplies again under the boot key material, the chain helper folds three inputs;
+    every ciphertext equals the oracle pipeline's word for word."""
+    from oracle import bootstrap_ref as B
+    from test_oracle import _dbfv_boot_params
+    S, boot, qp = _dbfv_boot_params()
+    dp = to_dbfv_params(S.bfv, S.base, S.d, S.plain_modulus)
+    bp = to_params(boot)
+    rng = np.random.default_rng(777)
+    s = H.gen_secret_key(S.bfv, rng)
+    rlk_arr = H.gen_relin_key(S.bfv, s, rng)
+    bk = B.gen_bootstrap_key(S.bfv, boot, s, qp, S.bfv.plain_modulus, rng)
+    pk = _product_bootstrap_key(bk, bp)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    boot_sk = E.create_boot_sk(E.SecretKey.from_ntt(s, dp.bfv_params), bp)
+    pa = np.zeros(16, np.uint64); pa[:2] = [3, 1]
+    pb = np.zeros(16, np.uint64); pb[0] = 2
+    ca, cb = H.dbfv_encrypt_poly_sk(S, pa, s, rng), H.dbfv_encrypt_poly_sk(S, pb, s, rng)
+    refreshed = E.dbfv_mul_then_bootstrap(E.DbfvCiphertext.from_array(ca, dp), E.DbfvCiphertext.from_array(cb, dp), rlk, pk)
+    S2, want = B.dbfv_mul_then_bootstrap(S, ca, cb, rlk_arr, bk)
+    assert refreshed.mul_depth == 0 and refreshed.params.bfv_params.plain_modulus == 257 and refreshed.degree == 2
+    assert np.array_equal(refreshed.to_array(), want)
+    c3 = H.dbfv_encrypt_poly_sk(S2, pb, boot_sk.ntt_array(), rng)
+    nxt = E.dbfv_mul(refreshed, E.DbfvCiphertext.from_array(c3, refreshed.params), pk.boot_rlk)
+    assert nxt.mul_depth == 1
+    assert np.array_equal(nxt.to_array(), O.dbfv_mul(S2.bfv, S2.base, S2.d, S2.plain_modulus, want, c3, bk.boot_rlk))
+    dec = E.dbfv_decrypt_poly(nxt, boot_sk)
+    assert dec.modulus == 16 and len(dec) == 16 and isinstance(E.dbfv_decrypt(nxt, boot_sk), int)
+    mk = lambda m: H.dbfv_encrypt_poly_sk(S, np.array([m % 16] + [0] * 15, np.uint64), s, rng)
+    arrs = [mk(3), mk(2), mk(5)]
+    chained = E.dbfv_mul_chain_then_bootstrap([E.DbfvCiphertext.from_array(a, dp) for a in arrs], rlk, pk)
+    S3, want_chain = B.dbfv_mul_chain_then_bootstrap([(S, a) for a in arrs], rlk_arr, bk)
+    assert chained.mul_depth == 0 and chained.params.bfv_params.plain_modulus == 257
+    assert np.array_equal(chained.to_array(), want_chain)
+    assert len(E.dbfv_decrypt_poly(chained, boot_sk)) == 16

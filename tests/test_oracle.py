@@ -223,3 +223,110 @@ def test_dbfv_apply_automorphism_scalar_decrypts():
     gk = H.gen_galois_key(S.bfv, s, 3, rng)
     ct = H.dbfv_encrypt_sk(S, 42, s, rng)
     assert H.dbfv_decrypt(S, O.bfv_apply_automorphism(S.bfv, ct, gk, 3), s) == 42
+
+
+# ---- bootstrap pipeline (bootstrap/bfv_host.rs tests :345-560), SURVEY row f-1 / BASELINE config 5 --------
+def _boot_params():
+    orig = O.OracleParams(n=16, q=65537, aux=(), plain_modulus=5)                          # :351-357
+    boot = O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8)   # :359-365
+    return orig, boot, 25
+
+
+def _dbfv_boot_params():
+    orig = H.DbfvSetup(O.OracleParams(n=16, q=65537, aux=(), plain_modulus=97, gadget_base=8), 4, 2, 16)   # :372-380
+    boot = O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=257, gadget_base=8)              # :382-388
+    return orig, boot, 64
+
+
+def expected_ring_bootstrap(orig, boot, qp, ct, s_ntt):
+    """Clear-text model of bfv_bootstrap's ring path: mod-switch, phase mod t_boot, rounding function."""
+    q, t, tb, n = orig.q, orig.plain_modulus, boot.plain_modulus, orig.n
+    sw = lambda v: ((qp * int(v) + q // 2) // q) % qp % tb
+    c0 = [sw(v) for v in O.ntt_inv(ct[0], q)]
+    c1 = [sw(v) for v in O.ntt_inv(ct[1], q)]
+    sc = [int(v) if int(v) <= q // 2 else int(v) - q for v in O.ntt_inv(s_ntt, q)]
+    out = []
+    for j in range(n):
+        acc = c0[j]
+        for i in range(n):
+            k = j - i
+            acc += c1[i] * sc[k] if k >= 0 else -c1[i] * sc[k + n]
+        x = acc % tb
+        out.append(((t * (x % qp) + qp // 2) // qp) % t)
+    return np.array(out, dtype=np.uint64)
+
+
+def test_rounding_poly_interpolates():
+    """digit_extract.rs:19-29: f(x) = round(t x' / q') mod t on x' = x mod q' for every x in Z_{t_boot}."""
+    from oracle import bootstrap_ref as B
+    poly = B.compute_rounding_poly(5, 25, 29)
+    assert len(poly) == 29
+    for x in range(29):
+        val = sum(c * pow(x, k, 29) for k, c in enumerate(poly)) % 29
+        assert val == ((5 * (x % 25) + 12) // 25) % 5
+
+
+def test_coeffs_to_slots_roundtrip_oracle():
+    """coeffs_to_slots.rs tests: every coefficient extracted as a constant, then packed back."""
+    from oracle import bootstrap_ref as B
+    _, boot, _ = _boot_params()
+    rng = np.random.default_rng(7)
+    s = H.gen_secret_key(boot, rng)
+    gks = B.gen_trace_galois_keys(boot, s, rng)
+    assert sorted(gks) == list(range(3, 32, 2))
+    pt = rng.integers(0, boot.plain_modulus, boot.n, dtype=np.uint64)
+    ct = H.encrypt_sk(boot, pt, s, rng)
+    slots = B.coeffs_to_slots(boot, ct, gks)
+    for j, sl in enumerate(slots):
+        dec = H.decrypt(boot, sl, s)
+        assert int(dec[0]) == int(pt[j]) and not dec[1:].any()
+    assert np.array_equal(H.decrypt(boot, B.slots_to_coeffs(boot, slots), s), pt)
+
+
+def test_bootstrap_single_and_ring_oracle():
+    """bfv_host.rs:398-453: trivial ciphertexts m = 0..4 (fast path) and a real encryption of 3 (ring path)."""
+    from oracle import bootstrap_ref as B
+    orig, boot, qp = _boot_params()
+    rng = np.random.default_rng(42)
+    s = H.gen_secret_key(orig, rng)
+    bk = B.gen_bootstrap_key(orig, boot, s, qp, orig.plain_modulus, rng)
+    boot_sk = B.create_boot_sk(orig, boot, s)
+    for m in range(5):
+        out = B.bfv_bootstrap(orig, H.trivial_encrypt(orig, m), bk)
+        assert int(H.decrypt(boot, out, boot_sk)[0]) % 5 == m
+    # Ring path (:428-453).  With the reference's toy sizes the degree-28 rounding polynomial needs ~8
+    # multiplicative levels (~7.5 bits each, measured) on a 44-bit budget, and the integer phase
+    # c0' + c1' s leaves [0, t_boot): the reference's `== 3` holds for its ChaCha20 stream only (sampling is
+    # outside this path).  The pipeline itself is pinned on a parameter set that fits the budget, against a
+    # clear-text model of every step (mod-switch, phase mod t_boot, rounding function), all n coefficients.
+    orig2 = O.OracleParams(n=16, q=65537, aux=(), plain_modulus=2)
+    boot2 = O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=5, gadget_base=8)
+    s2 = H.gen_secret_key(orig2, rng)
+    bk2 = B.gen_bootstrap_key(orig2, boot2, s2, 4, 2, rng)
+    ct = H.encrypt_sk(orig2, rng.integers(0, 2, 16, dtype=np.uint64), s2, rng)
+    out = B.bfv_bootstrap(orig2, ct, bk2)
+    assert np.array_equal(H.decrypt(boot2, out, B.create_boot_sk(orig2, boot2, s2)),
+                          expected_ring_bootstrap(orig2, boot2, 4, ct, s2))
+
+
+def test_dbfv_mul_then_bootstrap_and_chain_oracle():
+    """bfv_host.rs:455-560: metadata contract (params swapped to the boot set), a second multiplication
+    under boot key material, decryptability under the boot key."""
+    from oracle import bootstrap_ref as B
+    S, boot, qp = _dbfv_boot_params()
+    rng = np.random.default_rng(777)
+    s = H.gen_secret_key(S.bfv, rng)
+    rlk = H.gen_relin_key(S.bfv, s, rng)
+    bk = B.gen_bootstrap_key(S.bfv, boot, s, qp, S.bfv.plain_modulus, rng)
+    boot_sk = B.create_boot_sk(S.bfv, boot, s)
+    pa = np.zeros(16, np.uint64); pa[:2] = [3, 1]
+    pb = np.zeros(16, np.uint64); pb[0] = 2
+    ca, cb = H.dbfv_encrypt_poly_sk(S, pa, s, rng), H.dbfv_encrypt_poly_sk(S, pb, s, rng)
+    S2, refreshed = B.dbfv_mul_then_bootstrap(S, ca, cb, rlk, bk)
+    assert S2.bfv.plain_modulus == 257 and refreshed.shape == (2, 2, 16)
+    c3 = H.dbfv_encrypt_poly_sk(S2, pb, boot_sk, rng)
+    nxt = O.dbfv_mul(S2.bfv, S2.base, S2.d, S2.plain_modulus, refreshed, c3, bk.boot_rlk)
+    assert H.dbfv_decrypt_poly(S2, nxt, boot_sk).shape == (16,)
+    mk = lambda m: H.dbfv_encrypt_poly_sk(S, np.array([m % 16] + [0] * 15, np.uint64), s, rng)
+    S3, chained = B.dbfv_mul_chain_then_bootstrap([(S, mk(3)), (S, mk(2)), (S, mk(5))], rlk, bk)
+    assert S3.bfv.plain_modulus == 257 and H.dbfv_decrypt_poly(S3, chained, boot_sk).shape == (16,)
