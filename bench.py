@@ -281,7 +281,7 @@ def run_gpu(args):
         if os.environ.get("EXB_AUX_BASIS") == "reference":
             in_bytes = 2 * D * 2 * (1 + A) * N * 8                      # q + two 64-bit aux bases
         else:
-            in_bytes = 2 * D * 2 * N * 8 + 2 * D * 2 * 3 * N * 4        # q (u64) + three 30-bit internal primes (u32)
+            in_bytes = 2 * D * 2 * N * 8 + 2 * D * 2 * 3 * N * 4        # q (u64) + three 27-bit internal primes (u32)
         tensor_bytes = in_bytes + n_products * (2 * N * 8 + G * N * 2)
         t_ms = stage_ms[1] / max(stage_n[1], 1)
         achieved = tensor_bytes * pairs / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
@@ -305,7 +305,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": e2e_pairs * ct_bytes, "pairs_per_step": e2e_pairs, "result_checksum": checksum},
             "gpu_launches": int(launches),
             "bfv_mul_and_relin_equiv_per_s": value * 64,
-            "roofline": {"kernel": "tensor32_kernel (per product and component: point-wise tensor in q + 3 internal 30-bit primes, 4 INTT, hps_scale, gadget digits)",
+            "roofline": {"kernel": "tensor32_kernel (per product and component: point-wise tensor in q + 3 internal 27-bit primes, 4 INTT, hps_scale, gadget digits)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_fused_kernels.json
@@ -320,6 +320,7 @@ def run_gpu(args):
         }
         if not args.no_ntt:
             line["ntt"] = bench_ntt(torch, batch, P, peak, peak_src, args)
+            line["widened"] = bench_widened(torch, batch, P, peak, args)
         if world == 1 and not args.no_cpu:
             threads = host_threads()
             work = CpuWork()
@@ -363,6 +364,35 @@ def bench_ntt(torch, batch, P, peak, peak_src, args):
     worst = min(v["frac"] for k, v in res.items() if isinstance(v, dict))
     res["roofline"] = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                        "frac_min": worst, "frac_max": best, "target_frac": 0.60}
+    return res
+
+
+def bench_widened(torch, batch, P, peak, args):
+    """The SURVEY 8(f) rows that got their own kernels: Galois automorphism + key switch (bfv/eval.rs:512-561) and
+    decrypt (bfv/encrypt.rs:111-178), batched at n=4096 on the u64 profile's BFV parameters (inputs > L2)."""
+    import exacto_b200 as E
+    rng = np.random.default_rng(0xA070)
+    q = P.modulus(0)
+    count = 2048
+    ct = batch.to_device(rng.integers(0, q, (count, 2, N), dtype=np.uint64))
+    gk = E.GaloisKey(rng.integers(0, q, (G, 2, N), dtype=np.uint64), 3, P)
+    sk = batch.to_device(rng.integers(0, q, N, dtype=np.uint64))
+    out = torch.empty_like(ct)
+    dec = torch.empty((count, N), dtype=torch.int64, device=ct.device)
+    res = {"count": count}
+    for name, fn, nbytes in (("automorphism_keyswitch", lambda: batch.bfv_apply_automorphism(P, ct, gk, out=out), 4 * 8 * N),
+                             ("decrypt", lambda: batch.bfv_decrypt(P, ct, sk, out=dec), 3 * 8 * N)):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(args.ntt_reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
+        res[name] = {"per_s": count / (ms * 1e-3), "ms": ms, "algorithmic_bytes_each": nbytes,
+                     "hbm_frac": count * nbytes / (ms * 1e-3) / 1e9 / peak}
     return res
 
 

@@ -2,6 +2,7 @@
 
     python tools/prof.py ntt  [count]     # batched forward+inverse NTT, n=4096, prime q
     python tools/prof.py mul  [pairs]     # u64-profile dbfv_mul, device resident
+    python tools/prof.py all  [pairs]     # dbfv_mul twice, then automorphism+key switch and decrypt twice each
 """
 import os
 import sys
@@ -32,5 +33,12 @@ else:
     rlk = E.RelinKey(rng.integers(0, q, (8, 2, 4096), dtype=np.uint64), P)
     for _ in range(2):
         batch.dbfv_mul(params, a, b, rlk)
+    if what == "all":
+        ct = batch.to_device(rng.integers(0, q, (2048, 2, 4096), dtype=np.uint64))
+        gk = E.GaloisKey(rng.integers(0, q, (8, 2, 4096), dtype=np.uint64), 3, P)
+        sk = batch.to_device(rng.integers(0, q, 4096, dtype=np.uint64))
+        for _ in range(2):
+            batch.bfv_apply_automorphism(P, ct, gk)
+            batch.bfv_decrypt(P, ct, sk)
 torch.cuda.synchronize()
 print("done", what)
