@@ -489,14 +489,21 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
     const size_t stride = (size_t)d * 2 * c->n;
     // chunk size: enough CTAs to fill the GPU a few times, small enough that H2D / kernels / D2H of
     // consecutive chunks overlap on the three streams (EXB_HOST_CHUNK_PRODUCTS overrides, lab only)
-    static const size_t chunk_products = getenv("EXB_HOST_CHUNK_PRODUCTS") ? (size_t)atol(getenv("EXB_HOST_CHUNK_PRODUCTS")) : 512;
+    static const size_t chunk_products = getenv("EXB_HOST_CHUNK_PRODUCTS") ? (size_t)atol(getenv("EXB_HOST_CHUNK_PRODUCTS")) : 1024;
     size_t chunk = chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
     if (chunk < 1) chunk = 1;
     if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
+    // the call is synchronous, so the first chunk's H2D and the last chunk's kernels + D2H are exposed:
+    // taper both ends (half-size first chunk, remainder split over the last two)
     size_t ci = 0;
-    for (size_t off = 0; off < batch; off += chunk, ci++) {
+    for (size_t off = 0; off < batch; ci++) {
         Workspace &w = c->ws[ci % kSlots];
-        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        const size_t left = batch - off;
+        size_t cnt = chunk;
+        if (ci == 0 && batch > 2 * chunk) cnt = (chunk + 1) / 2;
+        else if (left <= chunk) cnt = left;
+        else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
+        if (cnt > chunk) cnt = chunk;
         const size_t bytes = cnt * stride * 8;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
@@ -504,6 +511,7 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
         EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream))) return rc;
         EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
+        off += cnt;
     }
     for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
     return EXB_OK;

@@ -24,6 +24,7 @@ constexpr int kMaxLimbs = 2 * kMaxDigits - 1;
 // primes inside the lift / tensor kernels when that is provably result-identical.
 struct SmallBasis {
     u32 enabled, K;
+    u32 max_terms, pad_;          // most products a limb may sum in tensor01_kernel (0: per-product kernel only)
     const Tw32 *twf[kMaxSmall];
     const Tw32 *twi[kMaxSmall];
     TwHead32 headf[kMaxSmall], headi[kMaxSmall];

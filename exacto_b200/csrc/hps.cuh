@@ -51,6 +51,17 @@ EXB_HD u64 round_term(u64 a, const ScaleConsts &c) {
     return neg ? mod_neg(rr, c.q) : rr;
 }
 
+// The same rounding term as a signed integer (|value| <= p/2 + 1), for sums over products.
+EXB_HD i64 round_term_signed(u64 a, const ScaleConsts &c) {
+    const bool neg = a > c.half_q;
+    const u64 av = neg ? c.q - a : a;
+    const u64 k = mulhi64(av, c.plain_s);
+    const u64 r = av * c.plain - k * c.q;
+    const u64 rh = r + c.half_q;
+    const i64 rr = (i64)(k + (rh >= c.q ? 1u : 0u) + (rh >= 2 * c.q ? 1u : 0u));
+    return neg ? -rr : rr;
+}
+
 // hps_scale, one coefficient.  a = t mod q, b0/b1 = t mod p_j (all canonical).
 EXB_HD u64 hps_scale_coeff(u64 a, u64 b0, u64 b1, const ScaleConsts &c) {
     const u64 q = c.q;

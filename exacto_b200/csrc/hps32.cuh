@@ -54,6 +54,60 @@ EXB_HD u64 round_term32(u64 a, const ScaleConsts &c) {
     return neg ? mod_neg(rr, c.q) : rr;
 }
 
+EXB_HD i64 round_term32_signed(u64 a, const ScaleConsts &c) {
+    const bool neg = a > c.half_q;
+    const u64 av = neg ? c.q - a : a;
+    const u32 a1 = (u32)(av >> 32), a0 = (u32)av, s = (u32)c.plain_s, p = (u32)c.plain;
+    const u32 k = (u32)(((u64)a1 * s + (((u64)a0 * s) >> 32)) >> 32);
+    const u64 avp = (u64)a0 * p + ((u64)(a1 * p) << 32);
+    const u64 kq = (u64)k * (u32)c.q + ((u64)(k * (u32)(c.q >> 32)) << 32);
+    const u64 rh = avp - kq + c.half_q;
+    const i64 rr = (i64)((u64)k + (rh >= c.q ? 1u : 0u) + (rh >= 2 * c.q ? 1u : 0u));
+    return neg ? -rr : rr;
+}
+
+// Sum over the products of one output limb (tensor01_kernel):
+//   rsum = sum_ij round(p a_ij / q) as a signed integer (|rsum| < q),  ssum = sum_ij a_ij (centred, |ssum| < 2^62),
+//   bk[i] = (T mod p_i) * Kp_i mod p_i with T = sum_ij t_ij.  M = (T - ssum) / q = sum_ij m_ij, so
+//   out = rsum + p * M  (mod q)  =  sum_ij [ round(p a_ij / q) + p m_ij ]  (mod q).
+EXB_HD u64 hps_scale32_sum(i64 rsum, i64 ssum, const u32 *bk, const ScaleConsts &c, const Scale32Consts &s) {
+    const bool neg = ssum < 0;
+    const u64 sa = neg ? (u64)(-ssum) : (u64)ssum;
+    const u32 a1 = (u32)(sa >> 32), a0 = (u32)sa;
+    u64 frac = 0;
+    u64 lo = rsum < 0 ? c.q - (u64)(-rsum) : (u64)rsum;
+    u32 hi = 0;
+#pragma unroll
+    for (u32 i = 0; i < (u32)kMaxSmall; i++) {
+        if (i < s.K) {
+            const Mod32 &m = s.m[i];
+            const u32 u = shoup32_lazy(a1, s.RK[i], s.RK_s[i], m.p) + shoup32_lazy(a0, s.Kp[i], s.Kp_s[i], m.p);   // |S| Kp, [0,4p)
+            const u32 t = neg ? bk[i] + u : bk[i] + m.four_p - u;                                                    // [0,5p)
+            const u32 mp = csub32(csub32(csub32(t, m.four_p), m.two_p), m.p);
+            frac += (u64)mp * s.g[i];
+            const u64 p0 = (u64)mp * (u32)s.C[i], p1 = (u64)mp * (u32)(s.C[i] >> 32);
+            u64 nl = lo + p0;
+            hi += nl < lo ? 1u : 0u;
+            lo = nl;
+            nl = lo + (p1 << 32);
+            hi += (u32)(p1 >> 32) + (nl < lo ? 1u : 0u);
+            lo = nl;
+        }
+    }
+    const u32 alpha = (u32)((frac + ((u64)1 << 56)) >> 57);
+    {
+        const u64 nl = lo + s.CPn[alpha];
+        hi += nl < lo ? 1u : 0u;
+        lo = nl;
+    }
+    const u64 mid = ((u64)hi << 32) | (lo >> 32);
+    const u32 th = (u32)(mid >> (s.sh - 32));
+    const u32 k = mulhi32(th, s.rq);
+    const u64 kq = (u64)k * (u32)c.q + ((u64)(k * (u32)(c.q >> 32)) << 32);
+    const u64 r = lo - kq;
+    return csub(csub(r, 2 * c.q), c.q);
+}
+
 // a = t mod q (canonical), bk[i] = (t mod p_i) * Kp_i mod p_i (canonical).  Needs 2^36 <= q < 2^60.
 //   m'_i = bk_i - a_c * Kp_i  mod p_i,  a_c = a - [a > q/2] q
 //   out  = rnd + sum_i m'_i * C_i - alpha * p * P'   (mod q),  accumulated exactly in 96 bits and

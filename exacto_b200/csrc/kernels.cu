@@ -653,14 +653,15 @@ template <typename DigT>
 __global__ void __launch_bounds__(kThreads12, 2)
 tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
                 const u64 *__restrict__ ct1, const u64 *__restrict__ ext_q, const u32 *__restrict__ ext_s,
-                u64 *__restrict__ r01, DigT *__restrict__ digits) {
+                u64 *__restrict__ r01, DigT *__restrict__ digits, u32 only_c2) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
     const u32 K = P.sb.K, d = M.d, NP = M.num_products;
     const u32 idx = blockIdx.x;
-    const u32 comp = idx % 3u;
-    const u32 prod = (idx / 3u) % NP;
-    const size_t pair = idx / (3u * NP);
+    // only_c2: components 0 and 1 are produced per output limb by tensor01_kernel
+    const u32 comp = only_c2 ? 2u : idx % 3u;
+    const u32 prod = only_c2 ? idx % NP : (idx / 3u) % NP;
+    const size_t pair = only_c2 ? idx / NP : idx / (3u * NP);
     const u32 li = M.prod_i[prod], lj = M.prod_j[prod];
     u64 *bq = smem;
     u32 *bs = reinterpret_cast<u32 *>(smem + n);
@@ -740,6 +741,131 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------
+// K5'' : components 0 and 1 per OUTPUT LIMB (n = 4096, internal basis).  relinearize only needs
+//   sum_{i+j=k} [ round(p a_ij / q) + p m_ij ]  (mod q),   a_ij = t_ij mod q (centred),  m_ij = (t_ij - a_ij) / q,
+// and sum_ij m_ij = (T_k - sum_ij a_ij) / q with T_k = sum_ij t_ij is LINEAR in the tensor, so the
+// small-prime point-wise products are summed in the NTT domain and inverse-transformed once per limb
+// instead of once per product; only the base-q transform and the rounding term stay per product
+// (the rounding is the non-linear part).  Exact while cnt * q < 2^63 and P' >= 2^5 * cnt * |m|max
+// (checked on the host: SmallBasis::max_terms).  Component 2 keeps the per-product kernel: its gadget
+// digits are a non-linear function of each product.
+// One CTA per (pair, computed limb, component in {0, 1}); output r01s [pair][limb][2][n], coefficient domain.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads12, 2)
+tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+                const u64 *__restrict__ ct1, const u64 *__restrict__ ext_q, const u32 *__restrict__ ext_s,
+                u64 *__restrict__ r01s) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const u32 K = P.sb.K, d = M.d, NL = M.num_limbs;
+    const u32 comp = blockIdx.x & 1u;
+    const u32 limb = (blockIdx.x >> 1) % NL;
+    const size_t pair = (blockIdx.x >> 1) / NL;
+    const u32 k = M.limb_k[limb];
+    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+    i64 *racc = reinterpret_cast<i64 *>(smem);                 // sum of signed rounding terms
+    i64 *sacc = reinterpret_cast<i64 *>(smem + n);             // sum of centred a_ij
+    u64 *bq = smem + 2 * (size_t)n;                            // base-q work image, later the K u32 images
+    u32 *bs = reinterpret_cast<u32 *>(bq);
+    const Modulus &mb = P.mod[0];
+    const ScaleConsts &c = P.sc;
+    const Scale32Consts &sc = P.sb.sc;
+    const u32 e0 = 8 * threadIdx.x;
+
+    for (u32 i = i_lo; i <= i_hi; i++) {   // base q: Montgomery point-wise + INTT per product
+        const u32 j = k - i;
+        const u64 *l0 = ct1 + ((pair * d + i) * 2) * (size_t)n, *l1 = l0 + n;
+        const u64 *r0 = ext_q + ((pair * d + j) * 2) * (size_t)n, *r1 = r0 + n;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 eh = e0 + 4 * h;
+            u64 a[4], b[4], v[4];
+            if (comp == 1) {
+                u64 cc[4], dd[4];
+                ldg_u64x4(l0 + eh, a); ldg_u64x4(r1 + eh, b); ldg_u64x4(l1 + eh, cc); ldg_u64x4(r0 + eh, dd);
+#pragma unroll
+                for (int t = 0; t < 4; t++) v[t] = mont_mul2_lazy(a[t], b[t], cc[t], dd[t], mb.m, mb.minv_neg);
+            } else {
+                ldg_u64x4(l0 + eh, a); ldg_u64x4(r0 + eh, b);
+#pragma unroll
+                for (int t = 0; t < 4; t++) v[t] = mont_mul_lazy(a[t], b[t], mb.m, mb.minv_neg);
+            }
+            sts_u64x4(bq, eh, v);
+        }
+        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const u32 eh = e0 + 4 * h;
+            u64 a[4];
+            i64 r[4], sv[4];
+            lds_u64x4(bq, eh, a);
+            if (i != i_lo) {
+                lds_u64x4(reinterpret_cast<const u64 *>(racc), eh, reinterpret_cast<u64 *>(r));
+                lds_u64x4(reinterpret_cast<const u64 *>(sacc), eh, reinterpret_cast<u64 *>(sv));
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; t++) r[t] = sv[t] = 0;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                r[t] += sc.plain32 ? round_term32_signed(a[t], c) : round_term_signed(a[t], c);
+                sv[t] += center_i64(a[t], c.q, c.half_q);
+            }
+            sts_u64x4(reinterpret_cast<u64 *>(racc), eh, reinterpret_cast<const u64 *>(r));
+            sts_u64x4(reinterpret_cast<u64 *>(sacc), eh, reinterpret_cast<const u64 *>(sv));
+        }
+        __syncthreads();                   // bq is rewritten by the next product / the small-prime images
+    }
+    for (u32 pi = 0; pi < K; pi++) {       // small primes: point-wise products summed over the limb's products
+        const Mod32 &m = sc.m[pi];
+        u32 acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) acc[t] = 0;
+        for (u32 i = i_lo; i <= i_hi; i++) {
+            const u32 j = k - i;
+            const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + i) * 2) * (size_t)K + pi) * n, *l1 = l0 + (size_t)K * n;
+            const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + j) * 2) * (size_t)K + pi) * n, *r1 = r0 + (size_t)K * n;
+            u32 a[8], b[8];
+            if (comp == 1) {
+                u32 cc[8], dd[8];
+                ldg_u32x8(l0 + e0, a); ldg_u32x8(r1 + e0, b); ldg_u32x8(l1 + e0, cc); ldg_u32x8(r0 + e0, dd);
+#pragma unroll
+                for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t] + (u64)cc[t] * dd[t], m.p, m.pinv_neg);
+            } else {
+                ldg_u32x8(l0 + e0, a); ldg_u32x8(r0 + e0, b);
+#pragma unroll
+                for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t], m.p, m.pinv_neg);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // < 16 * 2p -> [0, 2p)
+        sts_u32x8(bs + (size_t)pi * n, e0, acc);
+    }
+    if (K == 3) inv32_smK<3>(bs, P.sb);
+    else for (u32 pi = 0; pi < K; pi++) inv32_sm(bs + (size_t)pi * n, P.sb.twi[pi], P.sb.headi[pi], sc.m[pi]);
+    u64 *o = r01s + ((pair * NL + limb) * 2 + comp) * (size_t)n;
+    u32 bv[kMaxSmall][8];
+#pragma unroll
+    for (u32 pi = 0; pi < (u32)kMaxSmall; pi++)
+        if (pi < K) lds_u32x8(bs + (size_t)pi * n, e0, bv[pi]);
+    u64 res[8];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        i64 r[4], sv[4];
+        lds_u64x4(reinterpret_cast<const u64 *>(racc), e0 + 4 * h, reinterpret_cast<u64 *>(r));
+        lds_u64x4(reinterpret_cast<const u64 *>(sacc), e0 + 4 * h, reinterpret_cast<u64 *>(sv));
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            u32 b[kMaxSmall];
+#pragma unroll
+            for (u32 pi = 0; pi < (u32)kMaxSmall; pi++) b[pi] = pi < K ? bv[pi][4 * h + t] : 0u;
+            res[4 * h + t] = hps_scale32_sum(r[t], sv[t], b, c, sc);
+        }
+    }
+    stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
+}
+
+// ---------------------------------------------------------------------------------
 // K6+K7: relinearise + per-k accumulation.  One CTA per (pair, output limb k):
 //   c0 = NTT(sum r0) + sum_g NTT(sum digits_g) * rlk0_g     (likewise c1)
 // All sums are exact mod q, so any association is bit-equal to the reference's
@@ -807,7 +933,7 @@ template <typename DigT>
 __global__ void __launch_bounds__(kThreads12, 2)
 relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
                const u64 *__restrict__ r01, const DigT *__restrict__ digits,
-               const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess) {
+               const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess, u32 r01_summed) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
     const u32 d = M.d, NP = M.num_products, NL = M.num_limbs, G = P.gadget_digits;
@@ -822,13 +948,18 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
 
     for (u32 comp = 0; comp < 2; comp++) {
         u64 sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (u32 i = i_lo; i <= i_hi; i++) {
-            const size_t pr = (size_t)M.prod_of[i][k - i];
-            const u64 *src = r01 + ((pair * NP + pr) * 2 + comp) * n + e0;
-            u64 v[8];
-            ldg_u64x4(src, v); ldg_u64x4(src + 4, v + 4);
+        if (r01_summed) {                  // tensor01_kernel already summed the limb's products
+            const u64 *src = r01 + ((pair * NL + limb) * 2 + comp) * n + e0;
+            ldg_u64x4(src, sum); ldg_u64x4(src + 4, sum + 4);
+        } else {
+            for (u32 i = i_lo; i <= i_hi; i++) {
+                const size_t pr = (size_t)M.prod_of[i][k - i];
+                const u64 *src = r01 + ((pair * NP + pr) * 2 + comp) * n + e0;
+                u64 v[8];
+                ldg_u64x4(src, v); ldg_u64x4(src + 4, v + 4);
 #pragma unroll
-            for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
+                for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
+            }
         }
         sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
         fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
@@ -989,6 +1120,21 @@ __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const
     }
 }
 
+// Components 0/1 can be produced per output limb (tensor01_kernel) when the internal basis is on and
+// every limb sums at most SmallBasis::max_terms products.
+bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M) {
+    if (!P.sb.enabled || P.logn != 12) return false;
+    static const bool off = getenv("EXB_TENSOR_PER_PRODUCT") != nullptr;   // lab switch: the per-product kernel only
+    if (off) return false;
+    u32 worst = 0;
+    for (u32 l = 0; l < M.num_limbs; l++) {
+        const u32 k = M.limb_k[l];
+        const u32 cnt = (k < M.d ? k : M.d - 1) - (k >= M.d ? k - M.d + 1 : 0) + 1;
+        worst = cnt > worst ? cnt : worst;
+    }
+    return worst <= P.sb.max_terms;
+}
+
 #ifndef EXB_HOST_EMUL
 // ---------------------------------------------------------------------------------
 // Launchers
@@ -1105,9 +1251,19 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
+        const u32 *ext_s = ext_small_part(P, M, const_cast<u64 *>(ext), pairs);
         set_smem(tensor32_kernel<DigT>, sm32);
-        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(
-            P, M, ct1, ext, ext_small_part(P, M, const_cast<u64 *>(ext), pairs), r01, digits);
+        if (tensor_sums_per_limb(P, M)) {
+            // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
+            const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
+            set_smem(tensor01_kernel, sm01);
+            tensor01_kernel<<<(unsigned)(pairs * M.num_limbs * 2), kThreads12, sm01, s>>>(P, M, ct1, ext, ext_s, r01);
+            tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01,
+                                                                                             digits, 1u);
+            g_launch_count += 2;
+            return;
+        }
+        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01, digits, 0u);
         g_launch_count++;
         return;
     }
@@ -1135,7 +1291,8 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     const unsigned grid = (unsigned)(pairs * M.num_limbs);
     if (P.logn == 12) {
         set_smem(relin12_kernel<DigT>, sm);
-        relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+        relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess,
+                                                          tensor_sums_per_limb(P, M) ? 1u : 0u);
     } else {
         set_smem(relin_kernel<0, DigT>, sm);
         relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);

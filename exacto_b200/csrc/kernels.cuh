@@ -30,6 +30,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
                  size_t pairs, cudaStream_t s);
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
                    void *digits, bool digits32, size_t pairs, cudaStream_t s);
+bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M);   // r01 is [pairs][limbs][2][n] when true
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
                   bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
                   cudaStream_t s);

@@ -58,6 +58,7 @@ class Emulator:
         L.emu_dbfv_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, u32, u32]
         L.emu_bfv_apply_automorphism.argtypes = [vp, vp, u64, vp, vp, ctypes.c_size_t]
         L.emu_bfv_decrypt.argtypes = [vp, vp, u32, vp, vp, ctypes.c_size_t]
+        L.emu_tensor_per_limb.argtypes = [vp, u64, u32, u64, u32, u32]
         self.L = L
 
     @staticmethod
@@ -106,6 +107,9 @@ class Emulator:
         out = np.zeros_like(ct)
         self.L.emu_bfv_apply_automorphism(h, self._p(ct), element, self._p(gk), self._p(out), ct.size // (2 * ct.shape[-1]))
         return out
+
+    def tensor_per_limb(self, h, base, d, pm, flags=0, limb_mask=0):
+        return self.L.emu_tensor_per_limb(h, base, d, pm, flags, limb_mask)
 
     def bfv_decrypt(self, h, ct, sk_ntt):
         ct, sk_ntt = np.ascontiguousarray(ct, np.uint64), np.ascontiguousarray(sk_ntt, np.uint64)

@@ -185,25 +185,32 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         u32 *exts = reinterpret_cast<u32 *>(extp + pairs * d * 2 * n);
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, extp, exts); });
         const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
+        const bool per_limb = tensor_sums_per_limb(P, M);
+        const u32 c2 = per_limb ? 1u : 0u;
+        const unsigned tgrid = (unsigned)(pairs * M.num_products * (per_limb ? 1 : 3));
+        if (per_limb) {
+            const size_t sm01 = 2 * n * 8 + (sm32 > n * 16 ? sm32 - n * 8 : n * 8);
+            emu_launch((unsigned)(pairs * M.num_limbs * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, extp, exts, r01p); });
+        }
         if (hs.digits32) {
             int32_t *dg = dig32.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, extp, exts, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, extp, exts, r01p, dg, c2); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, c2); });
         } else {
             int16_t *dg = dig16.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, extp, exts, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, extp, exts, r01p, dg, c2); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, c2); });
         }
     } else if (P.logn == 12) {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         } else {
             int16_t *dg = dig16.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         }
     } else {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, ct1, ct2, extp); });
@@ -236,6 +243,13 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         }
     }
     return 0;
+}
+
+// 1 when dbfv_mul with this plan takes the per-limb tensor01_kernel for components 0/1.
+int emu_tensor_per_limb(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, uint32_t flags, uint32_t limb_mask) {
+    HostPlan hp;
+    if (host_build_plan(d, base, pm, flags, limb_mask, &hp, &g_emu_err)) return -1;
+    return tensor_sums_per_limb(c->hs.P, hp.M) ? 1 : 0;
 }
 
 // Same launch as launch_galois() in exacto_b200/csrc/kernels.cu.

@@ -257,3 +257,29 @@ def test_no_aux_overflow_risk_still_refused(emu):
     rc, _, err = emu.dbfv_mul(h, 2, 1, 0, np.zeros((1, 1, 2, 4096), np.uint64), np.zeros((1, 1, 2, 4096), np.uint64),
                               np.zeros((P.gadget_digits, 2, 4096), np.uint64))
     assert rc == 9 and "schoolbook BFV multiplication can overflow i128" in err
+
+
+def test_per_limb_tensor_path_is_taken_and_exact(emu):
+    """tensor01_kernel (components 0/1 summed per output limb before ONE small-prime inverse transform) is what
+    the n = 4096 presets run, including with all 64 products (limbs k >= d sum up to d-1 products), limb masks
+    and worst-case inputs: every |t_ij| at its bound with equal signs maximises |sum m_ij|."""
+    S = H.u64_dbfv()
+    P = S.bfv
+    h = emu.from_oracle(P)
+    assert emu.tensor_per_limb(h, S.base, S.d, 0) == 1 and emu.tensor_per_limb(h, S.base, S.d, 0, flags=1) == 1
+    assert emu.tensor_per_limb(h, 256, 2, 65536) == 1
+    assert emu.tensor_per_limb(emu.from_oracle(H.compact_bfv()), 16, 2, 256) == 0        # n = 1024: generic kernels
+    q, n = P.q, P.n
+    rng = np.random.default_rng(77)
+    rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    half = np.full(n, q // 2, np.uint64)
+    a = np.stack([np.stack([O.ntt_fwd(half, q), O.ntt_fwd(half, q)]) for _ in range(S.d)])
+    b = a.copy()
+    b[::2] = np.stack([O.ntt_fwd(half + np.uint64(1), q)] * 2)                       # -q/2 rows: mixed signs too
+    for flags, mask in [(0, 0), (1, 0), (0, 0b10100000)]:
+        want = O.dbfv_mul(P, S.base, S.d, S.plain_modulus, a, b, rlk, threads=8)
+        init = np.zeros_like(a[None])
+        rc, got, err = emu.dbfv_mul(h, S.base, S.d, S.plain_modulus, a[None], b[None], rlk, flags=flags, limb_mask=mask, out=init)
+        assert rc == 0, err
+        ks = [k for k in range(S.d) if not mask or (mask >> k) & 1]
+        assert np.array_equal(got[0][ks], want[ks]), (flags, mask)
