@@ -38,6 +38,9 @@ PUBLISHED_MS_PER_DBFV_MUL = 31.395      # reports/paper_reproduction.md:9 (hardw
 WORKLOAD = ("paper_repro u64 profile: dbfv_mul, n=4096, q=1152921504606830593 (60 bit), aux "
             "18014398509998081 & 36028797018972161, BFV p=1040407, gadget B=256 G=8, dBFV p=2^64 b=256 d=8")
 N, D, A, G = 4096, 8, 2, 8
+# dram__bytes_read.sum + dram__bytes_write.sum of one tensor01_kernel launch at the default workload (148 pairs),
+# from profiles/r01_ncu_fused_kernels_final.json (ncu --set full on tools/prof.py mul 148)
+TENSOR01_DRAM_BYTES = 398925568 + 72187648
 
 
 def measured_peaks():
@@ -230,8 +233,8 @@ def run_gpu(args):
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = batch.launch_count() - launches0
-    stage_ms = (ctypes.c_double * 4)()
-    stage_n = (ctypes.c_ulonglong * 4)()
+    stage_ms = (ctypes.c_double * 5)()
+    stage_n = (ctypes.c_ulonglong * 5)()
     _native.check(L.exb_profile_read(ctx.handle, stage_ms, stage_n))
     _native.check(L.exb_profile_enable(ctx.handle, 0))
     clocks = sampler.stop() if sampler else None
@@ -276,18 +279,28 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         n_products = 64 if args.all_products else 36
-        # algorithmic bytes of the tensor+scale kernel per pair: unique inputs
-        # (both operands in every base it reads) + its outputs (r0, r1 u64; G digit planes int16)
-        if os.environ.get("EXB_AUX_BASIS") == "reference":
+        n_limbs = 15 if args.all_products else 8
+        small = os.environ.get("EXB_AUX_BASIS") != "reference"
+        per_limb = small and stage_n[2] > 0          # tensor01_kernel (comps 0/1 per output limb) + per-product comp 2
+        # algorithmic bytes per pair of the dominant kernel: unique inputs (both operands in
+        # every base it reads) + its outputs
+        if not small:
             in_bytes = 2 * D * 2 * (1 + A) * N * 8                      # q + two 64-bit aux bases
         else:
             in_bytes = 2 * D * 2 * N * 8 + 2 * D * 2 * 3 * N * 4        # q (u64) + three 27-bit internal primes (u32)
-        tensor_bytes = in_bytes + n_products * (2 * N * 8 + G * N * 2)
+        if per_limb:
+            kernel_name = ("tensor01_kernel (components 0/1 per output limb: per product point-wise tensor mod q + INTT + "
+                           "rounding term; per limb the summed 27-bit point-wise tensors, 3 INTT32 and the exact m recombination)")
+            tensor_bytes = in_bytes + n_limbs * 2 * N * 8
+        else:
+            kernel_name = ("tensor32_kernel" if small else "tensor_kernel") + " (per product and component: point-wise tensor, INTTs, hps_scale, gadget digits)"
+            tensor_bytes = in_bytes + n_products * (2 * N * 8 + G * N * 2)
         t_ms = stage_ms[1] / max(stage_n[1], 1)
         achieved = tensor_bytes * pairs / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         stages = {nm: {"ms_per_launch": stage_ms[i] / max(stage_n[i], 1), "launches": int(stage_n[i])}
-                  for i, nm in enumerate(["lift", "tensor_scale", "relin", "reduce"]) if stage_n[i]}
-        total_stage = sum(stage_ms[i] for i in range(4)) or 1.0
+                  for i, nm in enumerate(["lift", "tensor01_per_limb" if per_limb else "tensor_scale", "tensor_c2_per_product",
+                                          "relin", "reduce"]) if stage_n[i]}
+        total_stage = sum(stage_ms[i] for i in range(5)) or 1.0
         line = {
             "metric": "dbfv_mul_per_s", "value": value, "unit": "dbfv_mul/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1),
@@ -305,13 +318,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": e2e_pairs * ct_bytes, "pairs_per_step": e2e_pairs, "result_checksum": checksum},
             "gpu_launches": int(launches),
             "bfv_mul_and_relin_equiv_per_s": value * 64,
-            "roofline": {"kernel": "tensor32_kernel (per product and component: point-wise tensor in q + 3 internal 27-bit primes, 4 INTT, hps_scale, gadget digits)",
+            "roofline": {"kernel": kernel_name,
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_ncu_fused_kernels.json
-                         # (ncu --set full on this command line; only valid for the default workload)
-                         "traffic": (1035571200 if (pairs == 148 and not args.all_products and
-                                                    os.environ.get("EXB_AUX_BASIS") != "reference") else None),
+                         "traffic": (TENSOR01_DRAM_BYTES if (pairs == 148 and per_limb and not args.all_products) else None),
                          "algorithmic_bytes": tensor_bytes * pairs,
                          "peak_source": peak_src, "share_of_step": stage_ms[1] / total_stage,
                          "note": "integer-pipe bound kernel: see DESIGN.md; HBM fraction is reported, not the target"},

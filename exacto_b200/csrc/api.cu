@@ -51,8 +51,8 @@ struct Workspace {
 };
 
 struct StageEvents {
-    cudaEvent_t ev[5];
-    bool has_reduce;
+    cudaEvent_t ev[6];
+    bool has_reduce, has_c2;
 };
 
 struct exb_context : HostSetup {
@@ -166,11 +166,11 @@ extern "C" int exb_profile_read(exb_context *c, double *ms, unsigned long long *
     if (!c || !ms || !launches) return fail(EXB_INVALID_PARAM, "null argument");
     EXB_CUDA(cudaSetDevice(c->device));
     for (StageEvents &se : c->events) {
-        EXB_CUDA(cudaEventSynchronize(se.ev[4]));
-        for (int k = 0; k < 4; k++) {
+        EXB_CUDA(cudaEventSynchronize(se.ev[5]));
+        for (int k = 0; k < 5; k++) {
             float t = 0.f;
             EXB_CUDA(cudaEventElapsedTime(&t, se.ev[k], se.ev[k + 1]));
-            if (k < 3 || se.has_reduce) { ms[k] += t; launches[k] += 1; }
+            if ((k != 2 || se.has_c2) && (k != 4 || se.has_reduce)) { ms[k] += t; launches[k] += 1; }
         }
         for (auto &e : se.ev) cudaEventDestroy(e);
     }
@@ -403,10 +403,11 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     }
     launch_lift(P, hp.M, ct1, ct2, w.ext, pairs, stream);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[1], stream));
-    launch_tensor(P, hp.M, ct1, w.ext, w.r01, w.digits, c->digits32, pairs, stream);
-    if (prof) EXB_CUDA(cudaEventRecord(se.ev[2], stream));
-    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);
+    se.has_c2 = tensor_sums_per_limb(P, hp.M);
+    launch_tensor(P, hp.M, ct1, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
+    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);
+    if (prof) EXB_CUDA(cudaEventRecord(se.ev[4], stream));
     // reduction::reduce for non-zero small representatives (dbfv/reduction.rs:34-52)
     const u32 d = hp.M.d;
     const size_t n = c->n, nx = hp.M.num_limbs - hp.num_low;
@@ -426,7 +427,7 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
         }
     }
     if (prof) {
-        EXB_CUDA(cudaEventRecord(se.ev[4], stream));
+        EXB_CUDA(cudaEventRecord(se.ev[5], stream));
         c->events.push_back(se);
     }
     return check_launch("ct-mul pipeline");

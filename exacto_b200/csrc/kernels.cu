@@ -1246,7 +1246,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 
 template <typename DigT>
 static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
-                            DigT *digits, size_t pairs, cudaStream_t s) {
+                            DigT *digits, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
     const size_t sm = (size_t)P.n * 8 * (1 + P.num_aux);
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
     if (P.sb.enabled && P.logn == 12) {
@@ -1258,12 +1258,14 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
             set_smem(tensor01_kernel, sm01);
             tensor01_kernel<<<(unsigned)(pairs * M.num_limbs * 2), kThreads12, sm01, s>>>(P, M, ct1, ext, ext_s, r01);
+            if (mid) cudaEventRecord(mid, s);
             tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01,
                                                                                              digits, 1u);
             g_launch_count += 2;
             return;
         }
         tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01, digits, 0u);
+        if (mid) cudaEventRecord(mid, s);
         g_launch_count++;
         return;
     }
@@ -1274,14 +1276,15 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
         set_smem(tensor_kernel<0, DigT>, sm);
         tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits);
     }
+    if (mid) cudaEventRecord(mid, s);
     g_launch_count++;
 }
 
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
-                   void *digits, bool digits32, size_t pairs, cudaStream_t s) {
-    if (pairs == 0) return;
-    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ext, r01, (int32_t *)digits, pairs, s);
-    else launch_tensor_t<int16_t>(P, M, ct1, ext, r01, (int16_t *)digits, pairs, s);
+                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
+    if (pairs == 0) { if (mid) cudaEventRecord(mid, s); return; }
+    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ext, r01, (int32_t *)digits, pairs, s, mid);
+    else launch_tensor_t<int16_t>(P, M, ct1, ext, r01, (int16_t *)digits, pairs, s, mid);
 }
 
 template <typename DigT>

@@ -28,8 +28,10 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
 //   out      : [pairs][d][2][n];  excess: [pairs][num_limbs - d'][2][n] for k >= d
 void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
                  size_t pairs, cudaStream_t s);
+// `mid` (optional) is recorded after the first of the two tensor kernels (per-limb components 0/1), or after
+// the only one.
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
-                   void *digits, bool digits32, size_t pairs, cudaStream_t s);
+                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr);
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M);   // r01 is [pairs][limbs][2][n] when true
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
                   bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,

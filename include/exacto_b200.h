@@ -92,9 +92,12 @@ int exb_context_psi(const exb_context *ctx, uint32_t modulus_index, uint64_t *ps
 unsigned long long exb_launch_count(void);
 
 /* Per-kernel device timing of the ct-mul pipeline (CUDA events recorded on the launching stream
- * between the kernels; no extra synchronisation).  stage: 0 = lift, 1 = tensor+scale, 2 = relin,
- * 3 = reduce.  exb_profile_read synchronises the recorded events, adds their times (ms) and launch
- * counts into the arrays (4 entries each) and clears the record. */
+ * between the kernels; no extra synchronisation).  stage: 0 = lift, 1 = tensor+scale (components 0/1
+ * per output limb when that kernel is used, otherwise all three components per product), 2 = tensor+scale
+ * of component 2 per product (0 launches when stage 1 covered it), 3 = relin, 4 = reduce.
+ * exb_profile_read synchronises the recorded events, adds their times (ms) and launch counts into the
+ * arrays (EXB_PROFILE_STAGES = 5 entries each) and clears the record. */
+#define EXB_PROFILE_STAGES 5
 int exb_profile_enable(exb_context *ctx, int on);
 int exb_profile_read(exb_context *ctx, double *stage_ms, unsigned long long *stage_launches);
 
