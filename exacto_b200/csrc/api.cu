@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,6 +49,8 @@ struct Workspace {
     size_t ext_b = 0, r01_b = 0, excess_b = 0, digits_b = 0;
     u64 *in1 = nullptr, *in2 = nullptr, *out = nullptr;   // staging for the *_host entry points
     size_t in_b = 0, out_b = 0;
+    cudaStream_t last = nullptr;                          // stream of the work that used this slot last
+    bool used = false;
 };
 
 struct StageEvents {
@@ -61,7 +64,18 @@ struct exb_context : HostSetup {
     std::vector<StageEvents> events;
     std::vector<Tw *> d_tables;       // owned device twiddle tables
     Workspace ws[kSlots];
+    // Entry points that touch the workspaces are serialised per context (the reference's functions are
+    // re-entrant; callers may share one context between host threads).
+    std::recursive_mutex mu;
 };
+
+// A workspace slot is reused by work on another stream only after the earlier work has finished.
+static int claim(Workspace &w, cudaStream_t stream) {
+    if (w.used && w.last != stream) EXB_CUDA(cudaStreamSynchronize(w.last));
+    w.last = stream;
+    w.used = true;
+    return EXB_OK;
+}
 
 struct exb_relin_key {
     exb_context *ctx = nullptr;
@@ -164,6 +178,7 @@ extern "C" int exb_profile_enable(exb_context *c, int on) {
 
 extern "C" int exb_profile_read(exb_context *c, double *ms, unsigned long long *launches) {
     if (!c || !ms || !launches) return fail(EXB_INVALID_PARAM, "null argument");
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     EXB_CUDA(cudaSetDevice(c->device));
     for (StageEvents &se : c->events) {
         EXB_CUDA(cudaEventSynchronize(se.ev[5]));
@@ -263,9 +278,11 @@ extern "C" int exb_ntt_inverse(exb_context *c, uint32_t idx, const uint64_t *in,
 static int ntt_host(exb_context *c, u32 idx, const u64 *in, u64 *out, size_t count, bool fwd) {
     int rc = check_base(c, idx);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (count == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     Workspace &w = c->ws[0];
+    if ((rc = claim(w, w.stream))) return rc;
     const size_t bytes = count * c->n * sizeof(u64);
     rc = grow((void **)&w.in1, &w.in_b, bytes);
     if (rc) return rc;
@@ -390,6 +407,7 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     size_t eb, rb, db, xb;
     ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
     int rc;
+    if ((rc = claim(w, stream))) return rc;
     if ((rc = grow((void **)&w.ext, &w.ext_b, eb * pairs))) return rc;
     if ((rc = grow((void **)&w.r01, &w.r01_b, rb * pairs))) return rc;
     if ((rc = grow(&w.digits, &w.digits_b, db * pairs))) return rc;
@@ -454,6 +472,7 @@ extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t 
                             uint32_t flags, uint32_t limb_mask, void *stream) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, limb_mask, &hp))) return rc;
@@ -482,6 +501,7 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
                                  uint32_t flags) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, 0, &hp))) return rc;
@@ -506,6 +526,7 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
         else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
         if (cnt > chunk) cnt = chunk;
         const size_t bytes = cnt * stride * 8;
+        if ((rc = claim(w, w.stream))) return rc;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
@@ -551,6 +572,7 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
                                                const exb_relin_key *gk, uint64_t *out, size_t batch) {
     int rc = galois_precheck(c, gk, element);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     const size_t stride = 2 * (size_t)c->n;
@@ -560,6 +582,7 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
     for (size_t off = 0; off < batch; off += chunk, ci++) {
         Workspace &w = c->ws[ci % kSlots];
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        if ((rc = claim(w, w.stream))) return rc;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct + off * stride, cnt * stride * 8, cudaMemcpyHostToDevice, w.stream));
@@ -594,9 +617,11 @@ extern "C" int exb_bfv_decrypt_host(exb_context *c, const uint64_t *ct, uint32_t
                                     uint64_t *out, size_t batch) {
     int rc = decrypt_precheck(c, ncomp);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     Workspace &w = c->ws[0];
+    if ((rc = claim(w, w.stream))) return rc;
     const size_t n = c->n, in_bytes = batch * ncomp * n * 8, out_bytes = batch * n * 8;
     if ((rc = grow((void **)&w.in1, &w.in_b, in_bytes))) return rc;
     if ((rc = grow_in2_out(w, out_bytes > n * 8 ? out_bytes : n * 8))) return rc;

@@ -66,6 +66,10 @@ typedef struct exb_bfv_params {
     uint32_t gadget_digits;        /* 0 = compute_gadget_digits (params/mod.rs:126) */
 } exb_bfv_params;
 
+/* Threading: the reference's functions are re-entrant; here a context may be shared by host threads --
+ * entry points that use its workspaces serialise on a per-context lock, and a workspace slot waits for the
+ * stream that used it last, so device-resident calls on different streams stay correct (they do not overlap;
+ * use one context per stream for concurrency).  exb_last_error() is thread-local. */
 typedef struct exb_context exb_context;       /* BfvParams + plans + workspace on one GPU */
 typedef struct exb_relin_key exb_relin_key;   /* device-resident RelinKey                 */
 

@@ -634,3 +634,43 @@ def test_dbfv_mul_then_bootstrap_and_chain():
     assert chained.mul_depth == 0 and chained.params.bfv_params.plain_modulus == 257
     assert np.array_equal(chained.to_array(), want_chain)
     assert len(E.dbfv_decrypt_poly(chained, boot_sk)) == 16
+
+
+def test_shared_context_from_host_threads_and_streams():
+    """The reference's functions are re-entrant (no global state).  One context shared by host threads
+    (ctypes drops the GIL) and by device-resident calls on different CUDA streams must still give the oracle's
+    words: entry points serialise on the context and a workspace slot waits for its previous stream."""
+    import threading
+    from exacto_b200 import batch
+    S = H.cfg3_prime()
+    P = S.bfv
+    dp = to_dbfv_params(P, S.base, S.d, S.plain_modulus)
+    rng = np.random.default_rng(99)
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    ins = [(rng.integers(0, P.q, (3, S.d, 2, P.n), dtype=np.uint64), rng.integers(0, P.q, (3, S.d, 2, P.n), dtype=np.uint64))
+           for _ in range(4)]
+    want = [np.stack([O.dbfv_mul(P, S.base, S.d, S.plain_modulus, x, y, rlk_arr, threads=O.max_threads()) for x, y in zip(a, b)])
+            for a, b in ins]
+    rlk.native(dp.bfv_params.context())                    # upload once before the threads start
+    got, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = E.dbfv_mul_batch(dp, ins[i][0], ins[i][1], rlk)
+        except Exception as exc:                           # pragma: no cover
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errs, errs
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for i, st in enumerate(streams * 2):
+        with torch.cuda.stream(st):
+            a, b = batch.to_device(ins[i][0]), batch.to_device(ins[i][1])
+            outs.append(batch.dbfv_mul(dp, a, b, rlk))
+    torch.cuda.synchronize()
+    assert all(np.array_equal(batch.to_host(o), w) for o, w in zip(outs, want))
