@@ -54,4 +54,18 @@ for name, bfv, dbfv in cfgs:
         rows[str(B)] = {"ms": ms, "per_s": B / (ms * 1e-3)}
         del a, b, o
     out[name] = rows
+# batched NTT at the three SURVEY 8(d) batch sizes (inputs 128 MiB .. 2 GiB, all > L2), u64-profile primes
+P = E.u64_dbfv().bfv_params
+ntt = {}
+for count in (4096, 16384, 65536):
+    for idx in range(3):
+        q = P.modulus(idx)
+        x = batch.to_device(rng.integers(0, q, (count, 4096), dtype=np.uint64))
+        y = torch.empty_like(x)
+        for nm, fn in (("fwd", batch.ntt_forward), ("inv", batch.ntt_inverse)):
+            ms = timed(lambda: fn(P, idx, x, out=y))
+            ntt[f"{nm}_prime{idx}_x{count}"] = {"ms": ms, "ntt_per_s": count / (ms * 1e-3),
+                                                 "gbs": count * 65536 / (ms * 1e-3) / 1e9}
+        del x, y
+out["ntt_n4096"] = ntt
 print(json.dumps(out))
