@@ -391,7 +391,7 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
                                 size_t *dig_b, size_t *exc_b) {
     const size_t n = c->n, A = c->aux_moduli.size(), d = hp.M.d;
     *ext_b = 2 * d * 2 * (1 + A) * n * 8;
-    if (c->P.sb.enabled && c->logn == 12) *ext_b = d * 2 * n * 8 + 2 * d * 2 * (size_t)c->P.sb.K * n * 4;
+    if (c->P.sb.enabled && c->logn == 12) *ext_b = 2 * d * 2 * (size_t)c->P.sb.K * n * 4;
     *r01_b = (size_t)hp.M.num_products * 2 * n * 8;
     *dig_b = (size_t)hp.M.num_products * (G ? G : 1) * n * (c->digits32 ? 4 : 2);
     *exc_b = (size_t)(hp.M.num_limbs - hp.num_low) * 2 * n * 8;
@@ -422,7 +422,7 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     launch_lift(P, hp.M, ct1, ct2, w.ext, pairs, stream);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[1], stream));
     se.has_c2 = tensor_sums_per_limb(P, hp.M);
-    launch_tensor(P, hp.M, ct1, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
+    launch_tensor(P, hp.M, ct1, ct2, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
     launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[4], stream));

@@ -262,6 +262,7 @@ static int build_mod32(u32 n, u32 logn, u32 p, Mod32 *m, std::vector<Tw32> *twf,
     m->pinv_neg = (u32)0 - inv;
     m->r_mod = (u32)(((u64)1 << 32) % p); m->r_mod_s = sh(m->r_mod);
     m->one_s = (u32)(((u64)1 << 32) / p);
+    m->c28 = (u32)(((u64)1 << 28) % p); m->c28_s = sh(m->c28);
     m->ninv = (u32)ninv; m->ninv_s = sh(ninv);
     m->ninv_w = (u32)(ninv * (*twi)[1].w % p); m->ninv_w_s = sh(m->ninv_w);
     return EXB_OK;
@@ -317,7 +318,9 @@ static void build_small_basis(HostSetup *c) {
         s.QK[i] = (u32)((q % pi) * inv % pi);
         // the inverse transforms of this basis only feed hps_scale32_coeff: fold Kp_i into n^-1
         Mod32 &m = s.m[i];
-        const u64 nk = (u64)m.ninv * inv % pi, nwk = (u64)m.ninv_w * inv % pi;
+        // ... and 2^32: the point-wise products are plain REDCs of operands that are not in Montgomery form
+        const u64 r32 = ((u64)1 << 32) % pi;
+        const u64 nk = (u64)m.ninv * inv % pi * r32 % pi, nwk = (u64)m.ninv_w * inv % pi * r32 % pi;
         m.ninv = (u32)nk; m.ninv_s = sh32(nk);
         m.ninv_w = (u32)nwk; m.ninv_w_s = sh32(nwk);
         s.g[i] = (u32)(((u64)1 << 57) / pi);
@@ -341,6 +344,12 @@ static void build_small_basis(HostSetup *c) {
         mt = cnt;
     }
     sb.max_terms = mt;
+    sb.mq_r = c->P.mod[0];
+    {
+        const u64 r64 = (u64)((((u128)1) << 64) % q);
+        sb.mq_r.ninv = h_mul(c->P.mod[0].ninv, r64, q);     sb.mq_r.ninv_s = shoup_of(sb.mq_r.ninv, q);
+        sb.mq_r.ninv_w = h_mul(c->P.mod[0].ninv_w, r64, q); sb.mq_r.ninv_w_s = shoup_of(sb.mq_r.ninv_w, q);
+    }
     c->small_primes.assign(primes.begin(), primes.end());
     sb.K = K;
     sb.enabled = 1;

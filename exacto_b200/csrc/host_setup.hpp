@@ -29,6 +29,7 @@ struct SmallBasis {
     const Tw32 *twi[kMaxSmall];
     TwHead32 headf[kMaxSmall], headi[kMaxSmall];
     Scale32Consts sc;
+    Modulus mq_r;                 // mod[0] with n^-1 * 2^64 in the ninv fields (inverse transforms after a plain REDC)
 };
 
 // Everything a fused kernel needs about the parameter set (passed by value).

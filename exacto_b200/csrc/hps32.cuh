@@ -40,6 +40,16 @@ EXB_HD u32 ext32_centered(u64 a, u64 q, u64 half_q, const Mod32 &m) {
     return (neg && r != 0) ? m.p - r : r;
 }
 
+// The same value up to a multiple of p, in [0, 2p], with ONE 32-bit Shoup multiply: |a_c| < 2^59 is split at bit 28,
+// top * (2^28 mod p) + low < 2p + 2^28 < 6p (p > 2^26).  Feeds the lazy forward transform (which accepts it).
+EXB_HD u32 ext32_centered_lazy(u64 a, u64 q, u64 half_q, const Mod32 &m) {
+    const bool neg = a > half_q;
+    const u64 v = neg ? q - a : a;
+    const u32 u = shoup32_lazy((u32)(v >> 28), m.c28, m.c28_s, m.p) + ((u32)v & 0x0fffffffu);
+    const u32 r = csub32(csub32(u, m.four_p), m.two_p);                  // [0, 2p)
+    return neg ? m.two_p - r : r;
+}
+
 // round_term (hps.cuh) when p and its Shoup companion fit 32 bits: same k and r, half the multiplies.
 EXB_HD u64 round_term32(u64 a, const ScaleConsts &c) {
     const bool neg = a > c.half_q;

@@ -597,13 +597,13 @@ __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
 // ---------------------------------------------------------------------------------
 // K4' / K5': lift and tensor+scale on the internal 27-bit auxiliary basis (n = 4096 only;
 // see ntt32_core.cuh for why this is result-identical).  Layouts:
-//   ext_q : [pair][limb][comp][n] u64      right operand mod q in Montgomery form
 //   ext_s : [pair][side][limb][comp][K][n] u32   both operands mod the small primes, in [0, 2p)
-//           (right operand in Montgomery form, R = 2^32)
+// No operand is converted to Montgomery form: the point-wise REDC leaves a*b*R^-1 and R is folded into the
+// n^-1 constants of the inverse transforms that follow (SmallBasis::mq_r for q, Mod32::ninv for the small primes).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads12, 2)
 lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
-              const u64 *__restrict__ ct2, u64 *__restrict__ ext_q, u32 *__restrict__ ext_s) {
+              const u64 *__restrict__ ct2, u32 *__restrict__ ext_s) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
     const u32 K = P.sb.K;
@@ -615,36 +615,25 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restri
     const u32 side = (idx / (2 * d)) & 1u;
     const size_t pair = idx / (4 * d);
     const u64 *src = (side ? ct2 : ct1) + ((pair * d + limb) * 2 + comp) * (size_t)n;
-    u64 *dq = ext_q + ((pair * d + limb) * 2 + comp) * (size_t)n;
     u32 *ds = ext_s + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)K) * n;
     const Modulus &mq = P.mod[0];
     const u32 e0 = 8 * threadIdx.x;
     u64 x[8];
     ldg_u64x4(src + e0, x); ldg_u64x4(src + e0 + 4, x + 4);
     sts_u64x4(coef, e0, x); sts_u64x4(coef, e0 + 4, x + 4);
-    if (side) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) x[k] = shoup(x[k], mq.r_mod, mq.r_mod_s, mq.m);
-        stg_u64x4(dq + e0, x); stg_u64x4(dq + e0 + 4, x + 4);
-    }
     inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12);
     lds_u64x4(coef, e0, x); lds_u64x4(coef, e0 + 4, x + 4);      // canonical coefficients stay in registers
     for (u32 i = 0; i < K; i++) {
         u32 y[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) y[k] = ext32_centered(x[k], mq.m, P.sc.half_q, P.sb.sc.m[i]);
+        for (int k = 0; k < 8; k++) y[k] = ext32_centered_lazy(x[k], mq.m, P.sc.half_q, P.sb.sc.m[i]);
         sts_u32x8(work + (size_t)i * n, e0, y);
     }
     if (K == 3) fwd32_smK<3>(work, P.sb);
     else for (u32 i = 0; i < K; i++) fwd32_sm(work + (size_t)i * n, P.sb.twf[i], P.sb.headf[i], P.sb.sc.m[i]);
     for (u32 i = 0; i < K; i++) {
-        const Mod32 &m = P.sb.sc.m[i];
         u32 y[8];
         lds_u32x8(work + (size_t)i * n, e0, y);
-        if (side) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) y[k] = shoup32_lazy(y[k], m.r_mod, m.r_mod_s, m.p);
-        }
         stg_u32x8(ds + (size_t)i * n + e0, y);
     }
 }
@@ -652,7 +641,7 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restri
 template <typename DigT>
 __global__ void __launch_bounds__(kThreads12, 2)
 tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
-                const u64 *__restrict__ ct1, const u64 *__restrict__ ext_q, const u32 *__restrict__ ext_s,
+                const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, const u32 *__restrict__ ext_s,
                 u64 *__restrict__ r01, DigT *__restrict__ digits, u32 only_c2) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
@@ -667,9 +656,9 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     u32 *bs = reinterpret_cast<u32 *>(smem + n);
     const u32 e0 = 8 * threadIdx.x;
     {   // base q: 64-bit Montgomery point-wise + INTT (two halves of 4 coefficients: register budget)
-        const Modulus &mb = P.mod[0];
+        const Modulus &mb = P.sb.mq_r;               // q with n^-1 * 2^64 as the inverse transform's scaling
         const u64 *l0 = ct1 + ((pair * d + li) * 2) * (size_t)n, *l1 = l0 + n;
-        const u64 *r0 = ext_q + ((pair * d + lj) * 2) * (size_t)n, *r1 = r0 + n;
+        const u64 *r0 = ct2 + ((pair * d + lj) * 2) * (size_t)n, *r1 = r0 + n;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
@@ -753,7 +742,7 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads12, 2)
 tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
-                const u64 *__restrict__ ct1, const u64 *__restrict__ ext_q, const u32 *__restrict__ ext_s,
+                const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, const u32 *__restrict__ ext_s,
                 u64 *__restrict__ r01s) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
@@ -767,7 +756,7 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     i64 *sacc = reinterpret_cast<i64 *>(smem + n);             // sum of centred a_ij
     u64 *bq = smem + 2 * (size_t)n;                            // base-q work image, later the K u32 images
     u32 *bs = reinterpret_cast<u32 *>(bq);
-    const Modulus &mb = P.mod[0];
+    const Modulus &mb = P.sb.mq_r;                   // q with n^-1 * 2^64 as the inverse transform's scaling
     const ScaleConsts &c = P.sc;
     const Scale32Consts &sc = P.sb.sc;
     const u32 e0 = 8 * threadIdx.x;
@@ -775,7 +764,7 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     for (u32 i = i_lo; i <= i_hi; i++) {   // base q: Montgomery point-wise + INTT per product
         const u32 j = k - i;
         const u64 *l0 = ct1 + ((pair * d + i) * 2) * (size_t)n, *l1 = l0 + n;
-        const u64 *r0 = ext_q + ((pair * d + j) * 2) * (size_t)n, *r1 = r0 + n;
+        const u64 *r0 = ct2 + ((pair * d + j) * 2) * (size_t)n, *r1 = r0 + n;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
@@ -1216,10 +1205,8 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
     g_launch_count++;
 }
 
-// ext points at ext_q followed by ext_s when the internal small basis is enabled.
-static inline u32 *ext_small_part(const DeviceParams &P, const MulPlan &M, u64 *ext, size_t pairs) {
-    return reinterpret_cast<u32 *>(ext + pairs * M.d * 2 * (size_t)P.n);
-}
+// With the internal small basis the lift workspace holds ext_s only.
+static inline u32 *ext_small_part(u64 *ext) { return reinterpret_cast<u32 *>(ext); }
 
 void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
                  size_t pairs, cudaStream_t s) {
@@ -1227,8 +1214,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
         set_smem(lift32_kernel, sm32);
-        lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext,
-                                                                           ext_small_part(P, M, ext, pairs));
+        lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext_small_part(ext));
         g_launch_count++;
         return;
     }
@@ -1245,26 +1231,26 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 }
 
 template <typename DigT>
-static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
-                            DigT *digits, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
+static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext,
+                            u64 *r01, DigT *digits, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
     const size_t sm = (size_t)P.n * 8 * (1 + P.num_aux);
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
-        const u32 *ext_s = ext_small_part(P, M, const_cast<u64 *>(ext), pairs);
+        const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
         set_smem(tensor32_kernel<DigT>, sm32);
         if (tensor_sums_per_limb(P, M)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
             set_smem(tensor01_kernel, sm01);
-            tensor01_kernel<<<(unsigned)(pairs * M.num_limbs * 2), kThreads12, sm01, s>>>(P, M, ct1, ext, ext_s, r01);
+            tensor01_kernel<<<(unsigned)(pairs * M.num_limbs * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
             if (mid) cudaEventRecord(mid, s);
-            tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01,
+            tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01,
                                                                                              digits, 1u);
             g_launch_count += 2;
             return;
         }
-        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ext, ext_s, r01, digits, 0u);
+        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01, digits, 0u);
         if (mid) cudaEventRecord(mid, s);
         g_launch_count++;
         return;
@@ -1280,11 +1266,11 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
     g_launch_count++;
 }
 
-void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
+void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
                    void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
     if (pairs == 0) { if (mid) cudaEventRecord(mid, s); return; }
-    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ext, r01, (int32_t *)digits, pairs, s, mid);
-    else launch_tensor_t<int16_t>(P, M, ct1, ext, r01, (int16_t *)digits, pairs, s, mid);
+    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ct2, ext, r01, (int32_t *)digits, pairs, s, mid);
+    else launch_tensor_t<int16_t>(P, M, ct1, ct2, ext, r01, (int16_t *)digits, pairs, s, mid);
 }
 
 template <typename DigT>

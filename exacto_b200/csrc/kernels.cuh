@@ -21,7 +21,7 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
 
 // Fused ciphertext-multiplication pipeline.
 //   ct1, ct2 : [pairs][d][2][n]  NTT domain, canonical mod q
-//   ext      : [pairs][2 sides][d][2][1+A][n]  (workspace)
+//   ext      : [pairs][2 sides][d][2][1+A][n] u64, or [pairs][2 sides][d][2][K][n] u32 with the internal basis  (workspace)
 //   r01      : [pairs][products][2][n] u64      (workspace, coefficient domain)
 //   digits   : [pairs][products][G][n] int16|int32 (workspace)
 //   rlk_mont : [G][2][n] relin key in Montgomery form
@@ -30,7 +30,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
                  size_t pairs, cudaStream_t s);
 // `mid` (optional) is recorded after the first of the two tensor kernels (per-limb components 0/1), or after
 // the only one.
-void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ext, u64 *r01,
+void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
                    void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr);
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M);   // r01 is [pairs][limbs][2][n] when true
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,

@@ -33,6 +33,7 @@ struct Mod32 {
     u32 pinv_neg;             // -p^-1 mod 2^32 (Montgomery, R = 2^32)
     u32 r_mod, r_mod_s;       // 2^32 mod p and its Shoup companion (to-Montgomery / high-word fold)
     u32 one_s;                // floor(2^32 / p): Shoup companion of 1 (reduces any u32 to [0,2p))
+    u32 c28, c28_s;           // 2^28 mod p and its Shoup companion (60-bit -> p reduction with one multiply)
     u32 ninv, ninv_s, ninv_w, ninv_w_s;
 };
 

@@ -166,7 +166,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     const MulPlan &M = hp.M;
     const size_t nx = M.num_limbs - hp.num_low;
     const bool small = P.sb.enabled && P.logn == 12;
-    std::vector<u64> ext(small ? pairs * d * 2 * n + (pairs * 2 * d * 2 * P.sb.K * n + 1) / 2 + 2
+    std::vector<u64> ext(small ? (pairs * 2 * d * 2 * P.sb.K * n + 1) / 2 + 2
                                : pairs * 2 * d * 2 * (1 + A) * n),
         r01(pairs * M.num_products * 2 * n + 1);
     std::vector<u64> excess(pairs * nx * 2 * n + 1), rlk_mont((size_t)num_keys * 2 * n + 1);
@@ -182,23 +182,23 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     u64 *extp = ext.data(), *r01p = r01.data(), *xp = excess.data();
     const u64 *rk = rlk_mont.data();
     if (small) {
-        u32 *exts = reinterpret_cast<u32 *>(extp + pairs * d * 2 * n);
-        emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, extp, exts); });
+        u32 *exts = reinterpret_cast<u32 *>(extp);
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, exts); });
         const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
         const bool per_limb = tensor_sums_per_limb(P, M);
         const u32 c2 = per_limb ? 1u : 0u;
         const unsigned tgrid = (unsigned)(pairs * M.num_products * (per_limb ? 1 : 3));
         if (per_limb) {
             const size_t sm01 = 2 * n * 8 + (sm32 > n * 16 ? sm32 - n * 8 : n * 8);
-            emu_launch((unsigned)(pairs * M.num_limbs * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, extp, exts, r01p); });
+            emu_launch((unsigned)(pairs * M.num_limbs * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, ct2, exts, r01p); });
         }
         if (hs.digits32) {
             int32_t *dg = dig32.data();
-            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, extp, exts, r01p, dg, c2); });
+            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
             emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, c2); });
         } else {
             int16_t *dg = dig16.data();
-            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, extp, exts, r01p, dg, c2); });
+            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
             emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, c2); });
         }
     } else if (P.logn == 12) {
