@@ -208,16 +208,34 @@ __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const
         else if (mod.lazy == 1) fwd_sm12<1>(sm, tw, head, mod);
         else fwd_sm12<0>(sm, tw, head, mod);
     } else {
+        // generic path: two butterfly stages per shared-memory round trip (radix 4 on four register values),
+        // one radix-2 stage first when logn is odd
         const u32 n = 1u << logn;
-        u32 len = n;
-        for (u32 m = 1; m < n; m <<= 1) {
+        u32 len = n, m = 1;
+        if (logn & 1u) {
             len >>= 1;
             __syncthreads();
             for (u32 b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-                const u32 i = b / len, j = b - i * len;
-                u64 *x = sm + 2 * i * len + j;
-                ct_bfly(x[0], x[len], tw[m + i], q, q2);
+                u64 *x = sm + b;                                     // m = 1: one block, j = b
+                ct_bfly(x[0], x[len], tw[1], q, q2);
             }
+            m = 2;
+        }
+        for (; m < n; m <<= 2) {
+            const u32 L = len >> 1, H = L >> 1;                      // stage distances L and H
+            __syncthreads();
+            for (u32 b = threadIdx.x; b < (n >> 2); b += blockDim.x) {
+                const u32 i = b / H, j = b - i * H;
+                u64 *x = sm + 2 * i * L + j;
+                u64 v0 = x[0], v1 = x[H], v2 = x[L], v3 = x[L + H];
+                const Tw w = tw[m + i];
+                ct_bfly(v0, v2, w, q, q2);
+                ct_bfly(v1, v3, w, q, q2);
+                ct_bfly(v0, v1, tw[2 * m + 2 * i], q, q2);
+                ct_bfly(v2, v3, tw[2 * m + 2 * i + 1], q, q2);
+                x[0] = v0; x[H] = v1; x[L] = v2; x[L + H] = v3;
+            }
+            len >>= 2;
         }
         __syncthreads();
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) sm[e] = reduce4(sm[e], q, q2);
@@ -235,23 +253,48 @@ __device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const
         else if (mod.lazy == 1) inv_sm12<1>(sm, tw, head, mod);
         else inv_sm12<0>(sm, tw, head, mod);
     } else {
+        // generic path: two stages per shared-memory round trip; one radix-2 stage first when logn is odd;
+        // the very last stage folds n^-1 (plan.normalize, ring/ntt.rs:62)
         const u32 n = 1u << logn;
-        u32 len = 1;
-        for (u32 m = n; m > 1; m >>= 1) {
+        u32 len = 1, m = n;
+        if (logn & 1u) {
             const u32 h = m >> 1;
             __syncthreads();
             for (u32 b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-                const u32 i = b / len, j = b - i * len;
-                u64 *x = sm + 2 * i * len + j;
-                if (h == 1) {  // last stage: fold n^-1 (plan.normalize, ring/ntt.rs:62)
-                    const u64 s2 = x[0] + x[len], dd = x[0] - x[len] + q2;
+                u64 *x = sm + 2 * b;
+                if (h == 1) {                                         // n = 2
+                    const u64 s2 = x[0] + x[1], dd = x[0] - x[1] + q2;
                     x[0] = shoup_lazy(s2, mod.ninv, mod.ninv_s, q);
-                    x[len] = shoup_lazy(dd, mod.ninv_w, mod.ninv_w_s, q);
+                    x[1] = shoup_lazy(dd, mod.ninv_w, mod.ninv_w_s, q);
                 } else {
-                    gs_bfly(x[0], x[len], tw[h + i], q, q2);
+                    gs_bfly(x[0], x[1], tw[h + b], q, q2);
                 }
             }
-            len <<= 1;
+            len = 2; m >>= 1;
+        }
+        for (; m > 1; m >>= 2) {
+            const u32 h = m >> 1, h2 = m >> 2;                        // twiddle bases of the two stages
+            __syncthreads();
+            for (u32 b = threadIdx.x; b < (n >> 2); b += blockDim.x) {
+                const u32 i = b / len, j = b - i * len;
+                u64 *x = sm + 4 * i * len + j;
+                u64 v0 = x[0], v1 = x[len], v2 = x[2 * len], v3 = x[3 * len];
+                gs_bfly(v0, v1, tw[h + 2 * i], q, q2);
+                gs_bfly(v2, v3, tw[h + 2 * i + 1], q, q2);
+                if (h2 == 1) {                                        // last stage
+                    const u64 s02 = v0 + v2, d02 = v0 - v2 + q2, s13 = v1 + v3, d13 = v1 - v3 + q2;
+                    v0 = shoup_lazy(s02, mod.ninv, mod.ninv_s, q);
+                    v2 = shoup_lazy(d02, mod.ninv_w, mod.ninv_w_s, q);
+                    v1 = shoup_lazy(s13, mod.ninv, mod.ninv_s, q);
+                    v3 = shoup_lazy(d13, mod.ninv_w, mod.ninv_w_s, q);
+                } else {
+                    const Tw w = tw[h2 + i];
+                    gs_bfly(v0, v2, w, q, q2);
+                    gs_bfly(v1, v3, w, q, q2);
+                }
+                x[0] = v0; x[len] = v1; x[2 * len] = v2; x[3 * len] = v3;
+            }
+            len <<= 2;
         }
         __syncthreads();
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) sm[e] = csub(sm[e], q);

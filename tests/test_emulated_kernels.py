@@ -13,7 +13,8 @@ def emu():
     return Emulator()
 
 
-@pytest.mark.parametrize("n,moduli", [(16, [65537]), (64, [1152921504606830593, 18014398509998081]),
+@pytest.mark.parametrize("n,moduli", [(8, [65537]), (16, [65537]), (32, [65537, 1152921504606830593]), (128, [1099509805057]),
+                                      (64, [1152921504606830593, 18014398509998081]),
                                       (1024, [1099509805057, 562949953443841]),
                                       (4096, [1152921504606830593, 18014398509998081, 36028797018972161])])
 def test_ntt_kernels(emu, n, moduli):
