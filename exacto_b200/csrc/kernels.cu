@@ -55,7 +55,9 @@ struct Lay<12> {
 constexpr int kNB = 3;                       // values-per-thread exponent used by the fused kernels
 constexpr int kThreads12 = 4096 >> kNB;
 
-template <int NB, int LAZY>
+// CANON = false leaves the outputs lazily reduced (any u64 below the transform's growth bound): enough for a
+// consumer that feeds them to a Montgomery REDC, which accepts any x < 2^64 against a canonical multiplier.
+template <int NB, int LAZY, bool CANON = true>
 __device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head,
                                            const LazyC &c, const u32 t) {
     u64 v[1 << NB];
@@ -74,8 +76,10 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, c
         __syncthreads();
         load_vals<3, 0>(v, sm, t); fwd_pass<12, 0, 3, LAZY>(v, tw, t, c);
     }
+    if constexpr (CANON) {
 #pragma unroll
-    for (int k = 0; k < (1 << NB); k++) v[k] = fwd_final<LAZY>(v[k], c);
+        for (int k = 0; k < (1 << NB); k++) v[k] = fwd_final<LAZY>(v[k], c);
+    }
     store_vals<NB, 0>(v, sm, t);
 }
 
@@ -101,11 +105,11 @@ __device__ __forceinline__ void inv_body12(u64 *sm, const Tw *__restrict__ tw, c
     }
 }
 
-template <int LAZY>
+template <int LAZY, bool CANON = true>
 __device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
     const LazyC c = make_lazyc(mod);
     __syncthreads();
-    fwd_body12<kNB, LAZY>(sm, tw, head, c, threadIdx.x);
+    fwd_body12<kNB, LAZY, CANON>(sm, tw, head, c, threadIdx.x);
     __syncthreads();
 }
 template <int LAZY>
@@ -199,14 +203,14 @@ __device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb) {
 #undef EXB_PASS
 }
 
-template <int LOGN>
+template <int LOGN, bool CANON = true>
 __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
                                        u32 logn) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        if (mod.lazy == 2) fwd_sm12<2>(sm, tw, head, mod);
-        else if (mod.lazy == 1) fwd_sm12<1>(sm, tw, head, mod);
-        else fwd_sm12<0>(sm, tw, head, mod);
+        if (mod.lazy == 2) fwd_sm12<2, CANON>(sm, tw, head, mod);
+        else if (mod.lazy == 1) fwd_sm12<1, CANON>(sm, tw, head, mod);
+        else fwd_sm12<0, CANON>(sm, tw, head, mod);
     } else {
         // generic path: two butterfly stages per shared-memory round trip (radix 4 on four register values),
         // one radix-2 stage first when logn is odd
@@ -1013,7 +1017,7 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
             v[j] = (ds[j] < 0 && r) ? q - r : r;
         }
         sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
-        fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+        fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);       // lazy outputs: they only feed the REDCs below
         const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -1087,7 +1091,7 @@ galois_kernel(const __grid_constant__ DeviceParams P, const u64 *__restrict__ ct
             remaining[e] = r;
             work[Lay<LOGN>::at(e)] = signed_to_mod(dg, q);
         }
-        fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
+        fwd_sm<LOGN, false>(work, P.twf[0], P.headf[0], mq, P.logn);      // lazy outputs feed the REDCs below
         const u64 *k0 = gk_mont + ((size_t)g * 2) * n, *k1 = k0 + n;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
             const u64 x = work[Lay<LOGN>::at(e)];
