@@ -421,7 +421,7 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     }
     launch_lift(P, hp.M, ct1, ct2, w.ext, pairs, stream);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[1], stream));
-    se.has_c2 = tensor_sums_per_limb(P, hp.M);
+    se.has_c2 = tensor_sums_per_limb(P, hp.M, pairs);
     launch_tensor(P, hp.M, ct1, ct2, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
     launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);

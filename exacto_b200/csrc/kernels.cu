@@ -1158,7 +1158,7 @@ __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const
 
 // Components 0/1 can be produced per output limb (tensor01_kernel) when the internal basis is on and
 // every limb sums at most SmallBasis::max_terms products.
-bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M) {
+bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs) {
     if (!P.sb.enabled || P.logn != 12) return false;
     static const bool off = getenv("EXB_TENSOR_PER_PRODUCT") != nullptr;   // lab switch: the per-product kernel only
     if (off) return false;
@@ -1168,7 +1168,10 @@ bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M) {
         const u32 cnt = (k < M.d ? k : M.d - 1) - (k >= M.d ? k - M.d + 1 : 0) + 1;
         worst = cnt > worst ? cnt : worst;
     }
-    return worst <= P.sb.max_terms;
+    if (worst > P.sb.max_terms) return false;
+    // It pays when limbs sum several products (fewer small-prime inverse transforms) and the per-limb CTAs
+    // (1..d products each) still fill the GPU; small batches keep the finer-grained per-product kernel.
+    return M.num_products > M.num_limbs && pairs * M.num_limbs * 2 >= 2 * 148;
 }
 
 #ifndef EXB_HOST_EMUL
@@ -1286,7 +1289,7 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
         const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
         set_smem(tensor32_kernel<DigT>, sm32);
-        if (tensor_sums_per_limb(P, M)) {
+        if (tensor_sums_per_limb(P, M, pairs)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
             set_smem(tensor01_kernel, sm01);
@@ -1328,7 +1331,7 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     if (P.logn == 12) {
         set_smem(relin12_kernel<DigT>, sm);
         relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess,
-                                                          tensor_sums_per_limb(P, M) ? 1u : 0u);
+                                                          tensor_sums_per_limb(P, M, pairs) ? 1u : 0u);
     } else {
         set_smem(relin_kernel<0, DigT>, sm);
         relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);

@@ -32,7 +32,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 // the only one.
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
                    void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr);
-bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M);   // r01 is [pairs][limbs][2][n] when true
+bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs);   // r01 is [pairs][limbs][2][n] when true
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
                   bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
                   cudaStream_t s);

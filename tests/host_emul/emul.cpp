@@ -154,6 +154,8 @@ int emu_poly_op(emu_ctx *c, uint32_t base, int op, const uint64_t *a, const uint
 int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1, const uint64_t *ct2,
                  const uint64_t *rlk, uint32_t num_keys, uint64_t *out, size_t pairs, uint32_t flags,
                  uint32_t limb_mask) {
+    const bool per_product = (flags & 0x80000000u) != 0;   // emulator-only flag
+    flags &= 0x7fffffffu;
     HostSetup &hs = c->hs;
     if (hs.mul_status != EXB_OK) { g_emu_err = hs.mul_error; return hs.mul_status; }
     HostPlan hp;
@@ -185,7 +187,9 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         u32 *exts = reinterpret_cast<u32 *>(extp);
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, exts); });
         const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
-        const bool per_limb = tensor_sums_per_limb(P, M);
+        // the emulator always takes the per-limb kernel when it is legal (large-batch decision), so the CPU tier
+        // covers it on small inputs; `per_product` forces the other kernel
+        const bool per_limb = !per_product && tensor_sums_per_limb(P, M, (size_t)1 << 20);
         const u32 c2 = per_limb ? 1u : 0u;
         const unsigned tgrid = (unsigned)(pairs * M.num_products * (per_limb ? 1 : 3));
         if (per_limb) {
@@ -249,7 +253,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
 int emu_tensor_per_limb(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, uint32_t flags, uint32_t limb_mask) {
     HostPlan hp;
     if (host_build_plan(d, base, pm, flags, limb_mask, &hp, &g_emu_err)) return -1;
-    return tensor_sums_per_limb(c->hs.P, hp.M) ? 1 : 0;
+    return tensor_sums_per_limb(c->hs.P, hp.M, (size_t)1 << 20) ? 1 : 0;
 }
 
 // Same launch as launch_galois() in exacto_b200/csrc/kernels.cu.

@@ -270,6 +270,7 @@ def test_per_limb_tensor_path_is_taken_and_exact(emu):
     assert emu.tensor_per_limb(h, S.base, S.d, 0) == 1 and emu.tensor_per_limb(h, S.base, S.d, 0, flags=1) == 1
     assert emu.tensor_per_limb(h, 256, 2, 65536) == 1
     assert emu.tensor_per_limb(emu.from_oracle(H.compact_bfv()), 16, 2, 256) == 0        # n = 1024: generic kernels
+    assert emu.tensor_per_limb(h, 2, 1, 0) == 0                                          # d = 1: nothing to hoist
     q, n = P.q, P.n
     rng = np.random.default_rng(77)
     rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
@@ -284,3 +285,6 @@ def test_per_limb_tensor_path_is_taken_and_exact(emu):
         assert rc == 0, err
         ks = [k for k in range(S.d) if not mask or (mask >> k) & 1]
         assert np.array_equal(got[0][ks], want[ks]), (flags, mask)
+    # the per-product kernel (what small batches run on the GPU) on the same worst-case inputs
+    rc, got, err = emu.dbfv_mul(h, S.base, S.d, S.plain_modulus, a[None], b[None], rlk, flags=0x80000000)
+    assert rc == 0 and np.array_equal(got[0], want), err

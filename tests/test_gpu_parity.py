@@ -674,3 +674,39 @@ def test_shared_context_from_host_threads_and_streams():
             outs.append(batch.dbfv_mul(dp, a, b, rlk))
     torch.cuda.synchronize()
     assert all(np.array_equal(batch.to_host(o), w) for o, w in zip(outs, want))
+
+
+def test_per_limb_tensor_path_on_gpu():
+    """Batches large enough for tensor01_kernel (components 0/1 summed per output limb) vs the oracle, device and
+    host entry points, and the same batch through the per-product kernel only (EXB_TENSOR_PER_PRODUCT, read once per
+    process: subprocess)."""
+    import subprocess, sys, tempfile
+    from exacto_b200 import batch
+    S = H.u64_dbfv()
+    P = S.bfv
+    dp = E.u64_dbfv()
+    rng = np.random.default_rng(2024)
+    B = 20                                              # 20 pairs x 8 limbs x 2 components = 320 CTAs >= 2 x 148
+    ct1 = rng.integers(0, P.q, (B, S.d, 2, P.n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (B, S.d, 2, P.n), dtype=np.uint64)
+    half = O.ntt_fwd(np.full(P.n, P.q // 2, np.uint64), P.q)
+    ct1[0] = half; ct2[0] = half                       # every |t_ij| at its bound, equal signs
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    want = np.stack([O.dbfv_mul(P, S.base, S.d, S.plain_modulus, a, b, rlk_arr, threads=O.max_threads()) for a, b in zip(ct1, ct2)])
+    got = batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk))
+    assert np.array_equal(got, want)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savez(f"{tmp}/in.npz", ct1=ct1, ct2=ct2, rlk=rlk_arr)
+        code = "\n".join([
+            f"import sys; sys.path.insert(0, {ROOT_DIR!r})",
+            "import numpy as np, exacto_b200 as E",
+            "from exacto_b200 import batch",
+            f"d = np.load({tmp!r} + '/in.npz'); dp = E.u64_dbfv()",
+            "rlk = E.RelinKey(d['rlk'], dp.bfv_params)",
+            "out = batch.to_host(batch.dbfv_mul(dp, batch.to_device(d['ct1']), batch.to_device(d['ct2']), rlk))",
+            f"np.save({tmp!r} + '/out.npy', out)"])
+        env = dict(_os.environ, EXB_TENSOR_PER_PRODUCT="1")
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert np.array_equal(np.load(f"{tmp}/out.npy"), want)
