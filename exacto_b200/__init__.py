@@ -26,9 +26,10 @@ from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automor
 from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_apply_automorphism, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
 from .encrypt import (SecretKey, decode_scalar, decrypt, decrypt_batch, dbfv_decrypt, dbfv_decrypt_poly,
                       dbfv_encrypt_poly_sk_with_samples, dbfv_encrypt_sk_with_samples, digit_decompose,
-                      digit_recompose_signed, encode_scalar, encrypt_sk_with_samples)
-from .keygen import (apply_automorphism, gen_galois_key_with_sampler, gen_relin_key_with_sampler,
-                     gen_secret_key_with_sampler)
+                      digit_recompose_signed, encode_scalar, encrypt_sk_with_samples, encrypt_sk_with_sampler,
+                      encrypt_pk_with_sampler, dbfv_encrypt_sk_with_sampler, dbfv_encrypt_with_sampler)
+from .keygen import (PublicKey, apply_automorphism, gen_galois_key_with_sampler, gen_public_key_with_sampler,
+                     gen_relin_key_with_sampler, gen_secret_key_with_sampler)
 from .bootstrap import (BootstrapKey, bfv_bootstrap, bfv_monomial_mul, coeffs_to_slots, compute_rounding_poly,
                         create_boot_sk, dbfv_bootstrap, dbfv_mul_chain_then_bootstrap, dbfv_mul_then_bootstrap,
                         eval_poly_homomorphic, eval_poly_homomorphic_batch, extract_coefficient,

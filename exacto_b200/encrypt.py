@@ -72,6 +72,24 @@ def encrypt_sk_with_samples(plaintext: CoeffPoly, sk: SecretKey, params: BfvPara
     return BfvCiphertext([c0, a_ntt], params)
 
 
+def encrypt_sk_with_sampler(plaintext: CoeffPoly, sk: SecretKey, params: BfvParams, sampler) -> BfvCiphertext:
+    """bfv/encrypt.rs:79-106 drawing (a, e) from ``sampler`` in the reference's order (see keygen.py)."""
+    q, n = params.ct_basis.moduli[0], params.ring_degree
+    a = CoeffPoly(sampler.uniform(n, q), q)
+    e = CoeffPoly(sampler.gaussian(n, q, params.sigma), q)
+    return encrypt_sk_with_samples(plaintext, sk, params, a, e)
+
+
+def encrypt_pk_with_sampler(plaintext: CoeffPoly, pk, params: BfvParams, sampler) -> BfvCiphertext:
+    """bfv/encrypt.rs:29-64: ct = (pk0 u + e1 + Delta m, pk1 u + e2), u binary; sampling order u, e1, e2."""
+    q, n = params.ct_basis.moduli[0], params.ring_degree
+    delta_m = scale_plaintext(plaintext, params)
+    u = RnsPoly.from_coeff_poly(CoeffPoly(sampler.binary(n, q), q), params)
+    e1 = RnsPoly.from_coeff_poly(CoeffPoly(sampler.gaussian(n, q, params.sigma), q), params)
+    e2 = RnsPoly.from_coeff_poly(CoeffPoly(sampler.gaussian(n, q, params.sigma), q), params)
+    return BfvCiphertext([pk.pk0.mul(u).add(e1).add(delta_m), pk.pk1.mul(u).add(e2)], params)
+
+
 def decrypt(ct: BfvCiphertext, sk: SecretKey) -> CoeffPoly:
     """bfv/encrypt.rs:111-178: m = round(p (c0 + c1 s + c2 s^2 + ...) / q) mod p, any ciphertext degree."""
     params = ct.params
@@ -147,6 +165,43 @@ def dbfv_encrypt_poly_sk_with_samples(plaintext: CoeffPoly, sk: SecretKey, param
         for k, dg in enumerate(digit_decompose(int(c) % params.plain_modulus, params.base, params.num_digits)):
             polys[k, i] = dg
     return _encrypt_digit_polys(list(polys), sk, params, a_samples, e_samples)
+
+
+def _digit_polys(value_or_poly, params: DbfvParams, poly: bool):
+    n = params.bfv_params.ring_degree
+    if not poly:
+        reduced = value_or_poly % (1 << 64) if params.plain_modulus == 0 else value_or_poly % params.plain_modulus
+        out = []
+        for dg in digit_decompose(reduced, params.base, params.num_digits):
+            c = np.zeros(n, np.uint64)
+            c[0] = dg
+            out.append(c)
+        return out
+    if params.plain_modulus == 0:
+        raise InvalidParam("polynomial dBFV plaintext requires finite plain_modulus (plain_modulus=0 is scalar-only)")
+    if len(value_or_poly) != n:
+        raise InvalidParam("plaintext length must equal the ring degree")
+    polys = np.zeros((params.num_digits, n), np.uint64)
+    for i, c in enumerate(value_or_poly.coeffs):
+        for k, dg in enumerate(digit_decompose(int(c) % params.plain_modulus, params.base, params.num_digits)):
+            polys[k, i] = dg
+    return list(polys)
+
+
+def dbfv_encrypt_sk_with_sampler(plaintext, sk: SecretKey, params: DbfvParams, sampler, poly: bool = False) -> DbfvCiphertext:
+    """dbfv/encrypt.rs:73-104 (scalar, or a Z_p[X]/(X^n+1) CoeffPoly with poly=True): one BFV encryption per digit."""
+    bfv = params.bfv_params
+    limbs = [encrypt_sk_with_sampler(CoeffPoly(dp, bfv.plain_modulus), sk, bfv, sampler)
+             for dp in _digit_polys(plaintext, params, poly)]
+    return DbfvCiphertext(limbs, params.num_digits, 0, params)
+
+
+def dbfv_encrypt_with_sampler(plaintext, pk, params: DbfvParams, sampler, poly: bool = False) -> DbfvCiphertext:
+    """dbfv/encrypt.rs:17-60: public-key encryption of every digit polynomial."""
+    bfv = params.bfv_params
+    limbs = [encrypt_pk_with_sampler(CoeffPoly(dp, bfv.plain_modulus), pk, bfv, sampler)
+             for dp in _digit_polys(plaintext, params, poly)]
+    return DbfvCiphertext(limbs, params.num_digits, 0, params)
 
 
 def _decrypt_limbs(ct: DbfvCiphertext, sk: SecretKey, count: int) -> np.ndarray:

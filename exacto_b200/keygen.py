@@ -5,11 +5,13 @@ takes a ``sampler`` with
     sampler.ternary(n, q)          -> coefficients in {0, 1, q-1}     (sampling/uniform.rs:29-46)
     sampler.uniform(n, q)          -> coefficients uniform in [0, q)  (sampling/uniform.rs:5-26)
     sampler.gaussian(n, q, sigma)  -> centred Gaussian mod q          (sampling/gaussian.rs:15-70)
+    sampler.binary(n, q)           -> coefficients in {0, 1}          (sampling/uniform.rs, encrypt_pk only)
 
 and calls it in the reference's order, so the keys are bit-exact functions of the sampled
 polynomials; all transforms and products run on the GPU.
 
     gen_secret_key_with_sampler   bfv/keygen.rs:64-80
+    gen_public_key_with_sampler   bfv/keygen.rs:89-121
     gen_relin_key_with_sampler    bfv/keygen.rs:123-162
     gen_galois_key_with_sampler   bfv/keygen.rs:170-210
     apply_automorphism            bfv/keygen.rs:218-239 (coefficient polynomial, host)
@@ -43,6 +45,21 @@ def apply_automorphism(poly: CoeffPoly, k: int) -> CoeffPoly:
 def gen_secret_key_with_sampler(params: BfvParams, sampler) -> SecretKey:
     q = params.ct_basis.moduli[0]
     return SecretKey.from_coeffs(sampler.ternary(params.ring_degree, q), params)
+
+
+class PublicKey:
+    """bfv/keygen.rs:30-34: (pk0, pk1) = (-(a s + e), a)."""
+
+    def __init__(self, pk0: RnsPoly, pk1: RnsPoly, params: BfvParams):
+        self.pk0, self.pk1, self.params = pk0, pk1, params
+
+
+def gen_public_key_with_sampler(sk: SecretKey, sampler) -> PublicKey:
+    params = sk.params
+    n, q = params.ring_degree, params.ct_basis.moduli[0]
+    a = RnsPoly.from_coeff_poly(CoeffPoly(sampler.uniform(n, q), q), params)
+    e = RnsPoly.from_coeff_poly(CoeffPoly(sampler.gaussian(n, q, params.sigma), q), params)
+    return PublicKey(a.mul(sk.poly).add(e).neg(), a, params)
 
 
 def _key_switch_key(sk: SecretKey, target: RnsPoly, sampler):

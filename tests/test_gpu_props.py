@@ -125,3 +125,23 @@ def test_prop_dbfv_poly_mul_sparse(a_terms, b_terms, seed):                     
     agg = lambda ts: [(i, int(v)) for i, v in enumerate(_terms_to_poly(ts, n, p)) if v]
     got = E.dbfv_decrypt_poly(E.dbfv_mul(ca, cb, rlk), sk).coeffs
     assert [int(v) for v in got] == _sparse_negacyclic_mul(agg(a_terms), agg(b_terms), n, p)
+
+
+def _binary(self, n, q):
+    return self.rng.integers(0, 2, n).astype(np.uint64)
+
+
+NpSampler.binary = _binary
+
+
+@CASES
+@given(value=st.integers(0, 255), seed=st.integers(0, 2**32))
+def test_prop_public_key_roundtrip(value, seed):            # bfv/encrypt.rs tests + dbfv/decrypt.rs:110-124
+    dp, smp = E.compact_dbfv(), NpSampler(seed)
+    P = dp.bfv_params
+    sk = E.gen_secret_key_with_sampler(P, smp)
+    pk = E.gen_public_key_with_sampler(sk, smp)
+    m = value % P.plain_modulus
+    assert E.decode_scalar(E.decrypt(E.encrypt_pk_with_sampler(E.encode_scalar(m, P), pk, P, smp), sk)) == m
+    assert E.dbfv_decrypt(E.dbfv_encrypt_with_sampler(value, pk, dp, smp), sk) == value
+    assert E.dbfv_decrypt(E.dbfv_encrypt_sk_with_sampler(value, sk, dp, smp), sk) == value
