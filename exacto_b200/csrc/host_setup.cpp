@@ -501,6 +501,18 @@ int host_build_plan(u32 d, u64 base, u64 pm, u32 flags, u32 limb_mask, HostPlan 
             }
         }
     M.num_products = np;
+    {   // pair the computed limbs heaviest-with-lightest (a limb k sums min(k, d-1) - max(0, k-d+1) + 1 products)
+        auto cnt = [&](u32 l) { const u32 k = M.limb_k[l]; return (k < d ? k : d - 1) - (k >= d ? k - d + 1 : 0) + 1; };
+        std::vector<u32> order(nl);
+        for (u32 l = 0; l < nl; l++) order[l] = l;
+        for (u32 a = 1; a < nl; a++)
+            for (u32 b = a; b > 0 && cnt(order[b]) > cnt(order[b - 1]); b--) { const u32 t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+        M.num_duos = (nl + 1) / 2;
+        for (u32 i = 0; i < M.num_duos; i++) {
+            M.duo_a[i] = (uint8_t)order[i];
+            M.duo_b[i] = (nl - 1 - i > i) ? (uint8_t)order[nl - 1 - i] : (uint8_t)0xFF;
+        }
+    }
     return EXB_OK;
 }
 

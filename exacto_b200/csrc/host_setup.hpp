@@ -59,6 +59,11 @@ struct MulPlan {
     uint8_t prod_j[kMaxProducts];            // product -> rhs limb j
     uint8_t limb_k[kMaxLimbs];               // computed limb index -> k
     uint8_t pad2_;
+    // tensor01_kernel work items: two computed limbs per CTA (heaviest with lightest, 0xFF = none) so that
+    // every CTA runs about the same number of products
+    uint8_t duo_a[kMaxLimbs], duo_b[kMaxLimbs];
+    uint8_t pad3_[2];
+    u32 num_duos;
     int16_t prod_of[kMaxDigits][kMaxDigits]; // (i, j) -> product index or -1
 };
 

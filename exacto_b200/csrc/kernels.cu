@@ -785,7 +785,7 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 // (the rounding is the non-linear part).  Exact while cnt * q < 2^63 and P' >= 2^5 * cnt * |m|max
 // (checked on the host: SmallBasis::max_terms).  Component 2 keeps the per-product kernel: its gadget
 // digits are a non-linear function of each product.
-// One CTA per (pair, computed limb, component in {0, 1}); output r01s [pair][limb][2][n], coefficient domain.
+// One CTA per (pair, two computed limbs, component in {0, 1}); output r01s [pair][limb][2][n], coefficient domain.
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads12, 2)
 tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
@@ -793,12 +793,10 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
                 u64 *__restrict__ r01s) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
-    const u32 K = P.sb.K, d = M.d, NL = M.num_limbs;
+    const u32 K = P.sb.K, d = M.d, NL = M.num_limbs, ND = M.num_duos;
     const u32 comp = blockIdx.x & 1u;
-    const u32 limb = (blockIdx.x >> 1) % NL;
-    const size_t pair = (blockIdx.x >> 1) / NL;
-    const u32 k = M.limb_k[limb];
-    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+    const u32 duo = (blockIdx.x >> 1) % ND;
+    const size_t pair = (blockIdx.x >> 1) / ND;
     i64 *racc = reinterpret_cast<i64 *>(smem);                 // sum of signed rounding terms
     i64 *sacc = reinterpret_cast<i64 *>(smem + n);             // sum of centred a_ij
     u64 *bq = smem + 2 * (size_t)n;                            // base-q work image, later the K u32 images
@@ -807,6 +805,13 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     const ScaleConsts &c = P.sc;
     const Scale32Consts &sc = P.sb.sc;
     const u32 e0 = 8 * threadIdx.x;
+  // two limbs per CTA (heaviest with lightest: every CTA runs about d + 1 products)
+  for (u32 part = 0; part < 2; part++) {
+    const u32 limb = part ? M.duo_b[duo] : M.duo_a[duo];
+    if (limb == 0xFFu) break;
+    const u32 k = M.limb_k[limb];
+    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+    __syncthreads();                       // the previous limb's images are dead
 
     for (u32 i = i_lo; i <= i_hi; i++) {   // base q: Montgomery point-wise + INTT per product
         const u32 j = k - i;
@@ -899,6 +904,7 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         }
     }
     stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -1171,7 +1177,7 @@ bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs)
     if (worst > P.sb.max_terms) return false;
     // It pays when limbs sum several products (fewer small-prime inverse transforms) and the per-limb CTAs
     // (1..d products each) still fill the GPU; small batches keep the finer-grained per-product kernel.
-    return M.num_products > M.num_limbs && pairs * M.num_limbs * 2 >= 2 * 148;
+    return M.num_products > M.num_limbs && pairs * M.num_duos * 2 >= 148;
 }
 
 #ifndef EXB_HOST_EMUL
@@ -1293,7 +1299,7 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
             set_smem(tensor01_kernel, sm01);
-            tensor01_kernel<<<(unsigned)(pairs * M.num_limbs * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
+            tensor01_kernel<<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
             if (mid) cudaEventRecord(mid, s);
             tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01,
                                                                                              digits, 1u);
