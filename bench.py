@@ -341,7 +341,11 @@ def run_gpu(args):
                          "traffic": (TENSOR01_DRAM_BYTES if (pairs == 148 and per_limb and not args.all_products) else None),
                          "algorithmic_bytes": tensor_bytes * pairs,
                          "peak_source": peak_src, "share_of_step": stage_ms[1] / total_stage,
-                         "note": "integer-pipe bound kernel: see DESIGN.md; HBM fraction is reported, not the target"},
+                         "note": "integer-pipe bound kernel: see DESIGN.md; HBM fraction is reported, not the target",
+                         # what actually bounds it (ncu --set full of this kernel at this workload,
+                         # profiles/r01_ncu_fused_kernels_final.json): the integer-multiply pipe
+                         "binding_pipe": ({"metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                                           "busy_frac": 0.523, "issue_active_frac": 0.502} if per_limb else None)},
             "stages": stages,
             "published_anchor_ms_per_dbfv_mul": PUBLISHED_MS_PER_DBFV_MUL,
         }
