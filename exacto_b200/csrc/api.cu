@@ -44,9 +44,9 @@ static const int kSlots = 3;
 
 struct Workspace {
     cudaStream_t stream = nullptr;
-    u64 *ext = nullptr, *r01 = nullptr, *excess = nullptr;
+    u64 *ext = nullptr, *r01 = nullptr, *excess = nullptr, *wide = nullptr;
     void *digits = nullptr;
-    size_t ext_b = 0, r01_b = 0, excess_b = 0, digits_b = 0;
+    size_t ext_b = 0, r01_b = 0, excess_b = 0, digits_b = 0, wide_b = 0;
     u64 *in1 = nullptr, *in2 = nullptr, *out = nullptr;   // staging for the *_host entry points
     size_t in_b = 0, out_b = 0;
     cudaStream_t last = nullptr;                          // stream of the work that used this slot last
@@ -114,7 +114,7 @@ extern "C" void exb_context_destroy(exb_context *c) {
     for (StageEvents &se : c->events) for (auto &e : se.ev) cudaEventDestroy(e);
     for (Tw *t : c->d_tables) cudaFree(t);
     for (Workspace &w : c->ws) {
-        cudaFree(w.ext); cudaFree(w.r01); cudaFree(w.excess); cudaFree(w.digits);
+        cudaFree(w.ext); cudaFree(w.r01); cudaFree(w.excess); cudaFree(w.digits); cudaFree(w.wide);
         cudaFree(w.in1); cudaFree(w.in2); cudaFree(w.out);
         if (w.stream) cudaStreamDestroy(w.stream);
     }
@@ -424,7 +424,12 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     se.has_c2 = tensor_sums_per_limb(P, hp.M, pairs);
     launch_tensor(P, hp.M, ct1, ct2, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
-    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream);
+    u64 *wide = nullptr;
+    if (relin_goes_wide(P, hp.M, pairs)) {
+        if ((rc = grow((void **)&w.wide, &w.wide_b, relin_wide_scratch_bytes(P, hp.M, pairs)))) return rc;
+        wide = w.wide;
+    }
+    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream, wide);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[4], stream));
     // reduction::reduce for non-zero small representatives (dbfv/reduction.rs:34-52)
     const u32 d = hp.M.d;

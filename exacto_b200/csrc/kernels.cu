@@ -1051,6 +1051,109 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
 }
 
 // ---------------------------------------------------------------------------------
+// K6+K7 for small batches: relin12_kernel runs (2 + G) transforms back to back in one CTA per output limb,
+// which leaves most SMs idle when pairs * limbs < #SMs (a single dbfv_mul has 8 such CTAs).  The wide form
+// gives every transform its own CTA -- role g < G: digit plane g (sum over the limb's products, NTT, times
+// rlk0_g and rlk1_g); role G: the r0 / r1 sums -- writing 2 polynomials each, and relin_reduce_kernel adds
+// the G + 1 partial pairs mod q.  Same sums in another order: exact.
+//   partial : [pair][limb][G + 1][2][n]
+// ---------------------------------------------------------------------------------
+template <typename DigT>
+__global__ void __launch_bounds__(kThreads12, 2)
+relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+                    const u64 *__restrict__ r01, const DigT *__restrict__ digits,
+                    const u64 *__restrict__ rlk_mont, u64 *__restrict__ partial, u32 r01_summed) {
+    EXB_DYN_SMEM(smem);
+    constexpr u32 n = 4096;
+    const u32 d = M.d, NP = M.num_products, NL = M.num_limbs, G = P.gadget_digits;
+    const Modulus &mq = P.mod[0];
+    const u64 q = mq.m;
+    u64 *work = smem;
+    const u32 role = blockIdx.x % (G + 1);
+    const u32 limb = (blockIdx.x / (G + 1)) % NL;
+    const size_t pair = blockIdx.x / ((G + 1) * NL);
+    const u32 k = M.limb_k[limb];
+    const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
+    const u32 e0 = 8 * threadIdx.x;
+    u64 *dst = partial + (((pair * NL + limb) * (G + 1) + role) * 2) * (size_t)n;
+    if (role == G) {
+        for (u32 comp = 0; comp < 2; comp++) {
+            u64 sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (r01_summed) {
+                const u64 *src = r01 + ((pair * NL + limb) * 2 + comp) * n + e0;
+                ldg_u64x4(src, sum); ldg_u64x4(src + 4, sum + 4);
+            } else {
+                for (u32 i = i_lo; i <= i_hi; i++) {
+                    const size_t pr = (size_t)M.prod_of[i][k - i];
+                    const u64 *src = r01 + ((pair * NP + pr) * 2 + comp) * n + e0;
+                    u64 v[8];
+                    ldg_u64x4(src, v); ldg_u64x4(src + 4, v + 4);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
+                }
+            }
+            sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+            lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+            stg_u64x4(dst + comp * n + e0, sum); stg_u64x4(dst + comp * n + e0 + 4, sum + 4);
+            __syncthreads();
+        }
+        return;
+    }
+    const u32 g = role;
+    i64 ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (u32 i = i_lo; i <= i_hi; i++) {
+        const size_t pr = (size_t)M.prod_of[i][k - i];
+        ldg_dig8<DigT>(digits + ((pair * NP + pr) * G + g) * n + e0, ds);
+    }
+    u64 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const u64 mag = ds[j] < 0 ? (u64)(-ds[j]) : (u64)ds[j];
+        const u64 r = mag < q ? mag : mag % q;
+        v[j] = (ds[j] < 0 && r) ? q - r : r;
+    }
+    sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
+    fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);           // lazy outputs: they only feed the REDCs below
+    const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        u64 x[4], kk[4], a[4];
+        lds_u64x4(work, e0 + 4 * h, x);
+        ldg_u64x4(k0 + 4 * h, kk);
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q);
+        stg_u64x4(dst + e0 + 4 * h, a);
+        ldg_u64x4(k1 + 4 * h, kk);
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q);
+        stg_u64x4(dst + n + e0 + 4 * h, a);
+    }
+}
+
+// out (or excess) limb = sum of the G + 1 partial pairs of relin12_wide_kernel, mod q.
+__global__ void relin_reduce_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
+                                    const u64 *__restrict__ partial, u64 *__restrict__ out, u64 *__restrict__ excess,
+                                    size_t pairs) {
+    const u32 n = P.n, d = M.d, NL = M.num_limbs, R = P.gadget_digits + 1;
+    const u64 q = P.mod[0].m;
+    const size_t total = pairs * NL * 2 * (size_t)n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const u32 e = (u32)(idx % (2 * (size_t)n));
+        const size_t pl = idx / (2 * (size_t)n);
+        const u32 limb = (u32)(pl % NL);
+        const size_t pair = pl / NL;
+        const u64 *src = partial + (pl * R * 2) * (size_t)n + e;
+        u64 acc = 0;
+        for (u32 r = 0; r < R; r++) acc = mod_add(acc, src[(size_t)r * 2 * n], q);
+        const u32 k = M.limb_k[limb];
+        u64 *dst = k < d ? out + ((pair * d + k) * 2) * (size_t)n
+                         : excess + ((pair * (NL - M.num_low) + (limb - M.num_low)) * 2) * (size_t)n;
+        dst[e] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Galois automorphism + key switch (bfv/eval.rs:512-561).  One CTA per ciphertext:
 //   c0' = NTT(sigma_k(INTT c0)) + sum_g NTT(digit_g(sigma_k(INTT c1))) * gk0_g
 //   c1' =                         sum_g NTT(digit_g(sigma_k(INTT c1))) * gk1_g
@@ -1178,6 +1281,15 @@ bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs)
     // It pays when limbs sum several products (fewer small-prime inverse transforms) and the per-limb CTAs
     // (1..d products each) still fill the GPU; small batches keep the finer-grained per-product kernel.
     return M.num_products > M.num_limbs && pairs * M.num_duos * 2 >= 148;
+}
+
+// Small batches at n = 4096: one CTA per transform instead of one per output limb (relin12_wide_kernel).
+bool relin_goes_wide(const DeviceParams &P, const MulPlan &M, size_t pairs) {
+    static const bool off = getenv("EXB_RELIN_NARROW") != nullptr;         // lab switch
+    return !off && P.logn == 12 && P.gadget_digits > 0 && pairs * M.num_limbs < 148;
+}
+size_t relin_wide_scratch_bytes(const DeviceParams &P, const MulPlan &M, size_t pairs) {
+    return pairs * M.num_limbs * (size_t)(P.gadget_digits + 1) * 2 * P.n * sizeof(u64);
 }
 
 #ifndef EXB_HOST_EMUL
@@ -1331,9 +1443,20 @@ void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, cons
 
 template <typename DigT>
 static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r01, const DigT *digits,
-                           const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s) {
+                           const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch) {
     const size_t sm = (size_t)P.n * 8 * 3;
     const unsigned grid = (unsigned)(pairs * M.num_limbs);
+    if (wide_scratch && relin_goes_wide(P, M, pairs)) {
+        const u32 summed = tensor_sums_per_limb(P, M, pairs) ? 1u : 0u;
+        set_smem(relin12_wide_kernel<DigT>, (size_t)P.n * 8);
+        relin12_wide_kernel<DigT><<<grid * (P.gadget_digits + 1), kThreads12, (size_t)P.n * 8, s>>>(
+            P, M, r01, digits, rlk_mont, wide_scratch, summed);
+        size_t blocks = (pairs * M.num_limbs * 2 * (size_t)P.n + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        relin_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, M, wide_scratch, out, excess, pairs);
+        g_launch_count += 2;
+        return;
+    }
     if (P.logn == 12) {
         set_smem(relin12_kernel<DigT>, sm);
         relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess,
@@ -1346,10 +1469,10 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
 }
 
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits, bool digits32,
-                  const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s) {
+                  const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch) {
     if (pairs == 0) return;
-    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s);
-    else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s);
+    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch);
+    else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch);
 }
 
 void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32 element, u64 *out,

@@ -33,9 +33,12 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
                    void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr);
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs);   // r01 is [pairs][limbs][2][n] when true
+// `wide_scratch` (relin_wide_scratch_bytes, optional): lets small batches use one CTA per transform.
+bool relin_goes_wide(const DeviceParams &P, const MulPlan &M, size_t pairs);
+size_t relin_wide_scratch_bytes(const DeviceParams &P, const MulPlan &M, size_t pairs);
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
                   bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
-                  cudaStream_t s);
+                  cudaStream_t s, u64 *wide_scratch = nullptr);
 // out[pairs][d][2][n] limb i += rep * excess limb (signed scalar, reduction.rs:34-52)
 void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_limb, u64 abs_scalar_mod_q,
                        bool negative, size_t out_stride, size_t excess_stride, size_t pairs,

@@ -154,8 +154,9 @@ int emu_poly_op(emu_ctx *c, uint32_t base, int op, const uint64_t *a, const uint
 int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1, const uint64_t *ct2,
                  const uint64_t *rlk, uint32_t num_keys, uint64_t *out, size_t pairs, uint32_t flags,
                  uint32_t limb_mask) {
-    const bool per_product = (flags & 0x80000000u) != 0;   // emulator-only flag
-    flags &= 0x7fffffffu;
+    const bool per_product = (flags & 0x80000000u) != 0;   // emulator-only flags
+    const bool wide_relin = (flags & 0x40000000u) != 0;
+    flags &= 0x3fffffffu;
     HostSetup &hs = c->hs;
     if (hs.mul_status != EXB_OK) { g_emu_err = hs.mul_error; return hs.mul_status; }
     HostPlan hp;
@@ -196,15 +197,21 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
             const size_t sm01 = 2 * n * 8 + (sm32 > n * 16 ? sm32 - n * 8 : n * 8);
             emu_launch((unsigned)(pairs * M.num_duos * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, ct2, exts, r01p); });
         }
+        std::vector<u64> wide(wide_relin ? relin_wide_scratch_bytes(P, M, pairs) / 8 + 1 : 1);
+        u64 *wp = wide.data();
+        const unsigned rgrid = (unsigned)(pairs * M.num_limbs);
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, c2); });
+            if (wide_relin) emu_launch(rgrid * (G + 1), thr, n * 8, [&]() { relin12_wide_kernel<int32_t>(P, M, r01p, dg, rk, wp, c2); });
+            else emu_launch(rgrid, thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, c2); });
         } else {
             int16_t *dg = dig16.data();
             emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, c2); });
+            if (wide_relin) emu_launch(rgrid * (G + 1), thr, n * 8, [&]() { relin12_wide_kernel<int16_t>(P, M, r01p, dg, rk, wp, c2); });
+            else emu_launch(rgrid, thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, c2); });
         }
+        if (wide_relin) emu_launch(4, 256, 0, [&]() { relin_reduce_kernel(P, M, wp, out, xp, pairs); });
     } else if (P.logn == 12) {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {

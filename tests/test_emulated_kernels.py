@@ -285,6 +285,8 @@ def test_per_limb_tensor_path_is_taken_and_exact(emu):
         assert rc == 0, err
         ks = [k for k in range(S.d) if not mask or (mask >> k) & 1]
         assert np.array_equal(got[0][ks], want[ks]), (flags, mask)
-    # the per-product kernel (what small batches run on the GPU) on the same worst-case inputs
-    rc, got, err = emu.dbfv_mul(h, S.base, S.d, S.plain_modulus, a[None], b[None], rlk, flags=0x80000000)
-    assert rc == 0 and np.array_equal(got[0], want), err
+    # the per-product kernel (what small batches run on the GPU) on the same worst-case inputs, also with the
+    # one-CTA-per-transform relinearisation of small batches (relin12_wide_kernel + relin_reduce_kernel)
+    for fl in (0x80000000, 0xC0000000, 0x40000000, 0x40000001):
+        rc, got, err = emu.dbfv_mul(h, S.base, S.d, S.plain_modulus, a[None], b[None], rlk, flags=fl)
+        assert rc == 0 and np.array_equal(got[0], want), (hex(fl), err)
