@@ -352,6 +352,16 @@ def run_gpu(args):
         if not args.no_ntt:
             line["ntt"] = bench_ntt(torch, batch, P, peak, peak_src, args)
             line["widened"] = bench_widened(torch, batch, P, peak, args)
+            # one dbfv_mul alone (what src/bin/paper_repro.rs times on the CPU: 31.395 ms published)
+            lat = []
+            a1, b1, o1 = ct1[:1].contiguous(), ct2[:1].contiguous(), torch.empty_like(ct1[:1])
+            for i in range(args.ntt_reps + 3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); batch.dbfv_mul(params, a1, b1, rlk, out=o1); e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    lat.append(e0.elapsed_time(e1))
+            line["single_call"] = {"dbfv_mul_ms": statistics.median(lat), "published_reference_ms": PUBLISHED_MS_PER_DBFV_MUL}
         if world == 1 and not args.no_cpu:
             threads = host_threads()
             work = CpuWork()
