@@ -1,14 +1,18 @@
-// kernels.cu -- sm_100a kernels of the ciphertext-multiplication hot path.
+// kernels.cu -- sm_100a kernels of the ciphertext-multiplication hot path and its callers.
 //
-//   K1/K2  ntt_fwd_kernel / ntt_inv_kernel   ring/ntt.rs:42-67 (concrete-ntt fwd / inv+normalize)
-//   K3     poly_op_kernel                    ring/ntt.rs:75-139, ring/rns.rs:159-217
-//   K4     lift_kernel                       bfv/eval.rs:217-247 base_extend_centered (once per limb)
-//   K3+K5  tensor_kernel                     bfv/eval.rs:187-203 tensor + hps_scale, keyswitch.rs:11-52 digits
-//   K6+K7  relin_kernel                      bfv/keyswitch.rs:83-95 + dbfv/eval.rs:125-132 per-k sums
-//          reduce_mac_kernel                 dbfv/reduction.rs:34-52 (general rep != 0 case)
+//   K1/K2  ntt12_persist_kernel, ntt_*_kernel   ring/ntt.rs:42-67 (concrete-ntt fwd / inv+normalize)
+//   K3     poly_op_kernel                       ring/ntt.rs:75-139, ring/rns.rs:159-217
+//   K4     lift32_kernel / lift_kernel          bfv/eval.rs:217-247 base_extend_centered (once per limb)
+//   K5     tensor01_kernel                      bfv/eval.rs:187-203 tensor + hps_scale, components 0/1 per output limb
+//          tensor32_kernel / tensor_kernel      the same per product (component 2: keyswitch.rs:11-52 digits)
+//   K6+K7  relin12_kernel / relin_kernel        bfv/keyswitch.rs:83-95 + dbfv/eval.rs:125-132 per-k sums
+//          relin12_wide_kernel + relin_reduce_kernel   the same with one CTA per transform (small batches)
+//          reduce_mac_kernel                    dbfv/reduction.rs:34-52 (general rep != 0 case)
+//          galois_kernel                        bfv/eval.rs:512-561 automorphism + key switch
+//          decrypt_kernel                       bfv/encrypt.rs:111-178
 //
-// No tensor cores: nothing here is a dense contraction; the work is 64-bit modular
-// arithmetic on the integer pipes, staged through shared memory.
+// No tensor cores: nothing here is a dense contraction; the work is 64-bit (and, on the internal auxiliary
+// basis, 32-bit) modular arithmetic on the integer pipes, staged through shared memory.
 #include "kernels.cuh"
 
 #include <cstdlib>
