@@ -1,0 +1,100 @@
+"""GPU tier: differential fuzz over parameter sets -- ring degree, prime sizes (every lazy-reduction class of the
+64-bit transforms), 0 / 1 / 2 auxiliary primes, plaintext modulus, power-of-two and general gadget bases, dBFV
+digit counts -- against the literal oracle: dbfv_mul (host and device entry points), automorphism + key switch,
+decrypt.  Deterministic (seeded); the parameter sets are derived, not hand-picked."""
+import numpy as np
+import pytest
+
+import exacto_b200 as E
+from common import H, O, to_dbfv_params, to_params
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(native_lib):
+    assert torch.cuda.is_available(), "the gpu tier needs a CUDA device"
+
+
+def ntt_prime(bits: int, n: int, skip=()):
+    """Largest prime < 2^bits with p = 1 mod 2n that is not in `skip`."""
+    step = 2 * n
+    c = ((1 << bits) - 1) // step * step + 1
+    while c > (1 << (bits - 1)):
+        if c not in skip and O.is_prime(c):
+            return c
+        c -= step
+    raise AssertionError("no prime")
+
+
+def overflow_risk(p, q, n):                      # bfv/eval.rs:457-464
+    mc = q // 2
+    mt = n * mc * mc
+    return mt > (1 << 127) - 1 or mt * p > (1 << 127) - 1
+
+
+def make_cases():
+    rng = np.random.default_rng(20241018)
+    cases = []
+    qbits = [20, 31, 36, 40, 47, 52, 55, 57, 59, 60, 61, 62]
+    for idx in range(36):
+        logn = int(rng.integers(4, 14))
+        if idx % 6 == 0:
+            logn = 12                                    # the tuned path gets its share
+        n = 1 << logn
+        qb = max(qbits[idx % len(qbits)], logn + 3)
+        q = ntt_prime(qb, n)
+        p = int(rng.integers(2, min(q, 1 << int(rng.integers(2, 21)))))
+        A = idx % 3
+        aux = ()
+        if A == 1:
+            need = (n * q) // 2 + 1
+            ab = max(need.bit_length() + 1, 30)
+            if ab > 62:
+                A = 2
+            else:
+                aux = (ntt_prime(ab, n, skip=(q,)),)
+        if A == 2:
+            a0 = ntt_prime(int(rng.integers(50, 62)), n, skip=(q,))
+            aux = (a0, ntt_prime(int(rng.integers(50, 62)), n, skip=(q, a0)))
+        if A == 0 and overflow_risk(p, q, n):
+            a0 = ntt_prime(61, n, skip=(q,))
+            aux = (a0, ntt_prime(60, n, skip=(q, a0)))
+        gb = [16, 256, 1 << 16, 10, 1000, 1 << 20][idx % 6]
+        d = [1, 2, 3, 2][idx % 4]
+        b = [4, 16, 256][idx % 3]
+        pm = max(2, b ** d - 3) if idx % 5 == 0 else b ** d        # b^d - 3: non-zero small representatives (reduce)
+        cases.append((idx, O.OracleParams(n=n, q=q, aux=aux, plain_modulus=p, gadget_base=gb), b, d, pm))
+    return cases
+
+
+CASES = make_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-n{c[1].n}-q{c[1].q.bit_length()}-A{len(c[1].aux)}-B{c[1].gadget_base}-d{c[3]}")
+def test_fuzz_parameter_sets(case):
+    from exacto_b200 import batch
+    idx, P, b, d, pm = case
+    dp = to_dbfv_params(P, b, d, pm)
+    params = dp.bfv_params
+    q, n = P.q, P.n
+    rng = np.random.default_rng(idx)
+    B = 3
+    ct1 = rng.integers(0, q, (B, d, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (B, d, 2, n), dtype=np.uint64)
+    edge = np.full(n, q // 2, np.uint64); edge[::3] = q // 2 + 1; edge[1::5] = q - 1; edge[2::7] = 0
+    ct1[0] = O.ntt_fwd(edge, q); ct2[0] = O.ntt_fwd(edge[::-1].copy(), q)
+    karr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    rlk = E.RelinKey(karr, params)
+    want = np.stack([O.dbfv_mul(P, b, d, pm, x, y, karr, threads=O.max_threads()) for x, y in zip(ct1, ct2)])
+    assert np.array_equal(E.dbfv_mul_batch(dp, ct1, ct2, rlk), want)
+    assert np.array_equal(batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk)), want)
+    # automorphism + key switch on the limbs of the first operand, decrypt of products under a random "key"
+    k = int(rng.integers(1, n)) * 2 + 1
+    flat = ct1.reshape(B * d, 2, n)
+    assert np.array_equal(E.bfv_apply_automorphism_batch(params, flat, E.GaloisKey(karr, k, params)),
+                          O.bfv_apply_automorphism(P, flat, karr, k, threads=O.max_threads()))
+    s = rng.integers(0, q, n, dtype=np.uint64)
+    got = E.decrypt_batch(params, flat[:2], E.SecretKey.from_ntt(s, params))
+    assert np.array_equal(got, np.stack([H.decrypt(P, c, s) for c in flat[:2]]))
