@@ -21,9 +21,10 @@ from .params import (BfvParams, BfvParamsBuilder, DbfvParams, RnsBasis, cfg3_pri
                      compact_dbfv, compute_gadget_digits, set_default_device, small_bfv, u64_dbfv)
 from .ring import CoeffPoly, NttPoly, Plan, RnsPoly, make_plan
 from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automorphism, bfv_apply_automorphism_batch,
-                  bfv_inner_product, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_neg, bfv_plain_add, bfv_plain_mul,
+                  bfv_inner_product, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_mul_no_relin, bfv_mul_no_relin_batch,
+                  gadget_decompose, relinearize, relinearize_batch, bfv_neg, bfv_plain_add, bfv_plain_mul,
                   bfv_scalar_mul, bfv_sub, bfv_trace, scale_plaintext, trivial_encrypt)
-from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_apply_automorphism, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
+from .dbfv import (DbfvCiphertext, dbfv_add, dbfv_apply_automorphism, dbfv_relinearize, dbfv_mul, dbfv_mul_batch, dbfv_neg, dbfv_sub, small_reps)
 from .encrypt import (SecretKey, decode_scalar, decrypt, decrypt_batch, dbfv_decrypt, dbfv_decrypt_poly,
                       dbfv_encrypt_poly_sk_with_samples, dbfv_encrypt_sk_with_samples, digit_decompose,
                       digit_recompose_signed, encode_scalar, encrypt_sk_with_samples, encrypt_sk_with_sampler,

@@ -60,6 +60,9 @@ SYMBOLS = {
     "exb_bfv_mul_and_relin": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "exb_bfv_mul_and_relin_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz]),
     "exb_bfv_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "exb_bfv_mul_no_relin": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "exb_bfv_relinearize": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_sz, c_vp]),
+    "exb_gadget_decompose": (ctypes.c_int, [c_vp, c_vp, c_vp, c_sz, c_vp]),
     "exb_bfv_decrypt": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_sz, c_vp]),
     "exb_bfv_decrypt_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_sz]),
     "exb_bfv_apply_automorphism": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_sz, c_vp]),

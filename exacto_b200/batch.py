@@ -90,6 +90,32 @@ def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: Reli
     return out
 
 
+def bfv_mul_no_relin(params: BfvParams, ct1: torch.Tensor, ct2: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bfv/eval.rs:89-108 over [B, 2, n] -> [B, 3, n]."""
+    n = params.ring_degree
+    _check(ct1, (2, n), "ct1"); _check(ct2, (2, n), "ct2")
+    if ct1.shape != ct2.shape or ct1.dim() != 3:
+        raise InvalidParam("ct1/ct2: need matching [batch, 2, n]")
+    out = torch.empty((ct1.shape[0], 3, n), dtype=torch.int64, device=ct1.device) if out is None else out
+    ctx = params.context(ct1.device.index)
+    _native.check(_native.lib().exb_bfv_mul_no_relin(ctx.handle, ct1.data_ptr(), ct2.data_ptr(), out.data_ptr(), ct1.shape[0],
+                                                     _stream(ct1)))
+    return out
+
+
+def relinearize(params: BfvParams, ct3: torch.Tensor, rlk: RelinKey, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bfv/keyswitch.rs:59-101 over [B, 3, n] -> [B, 2, n]."""
+    n = params.ring_degree
+    _check(ct3, (3, n), "ct3")
+    if ct3.dim() != 3:
+        raise InvalidParam("ct3: need [batch, 3, n]")
+    out = torch.empty((ct3.shape[0], 2, n), dtype=torch.int64, device=ct3.device) if out is None else out
+    ctx = params.context(ct3.device.index)
+    _native.check(_native.lib().exb_bfv_relinearize(ctx.handle, ct3.data_ptr(), 3, rlk.native(ctx), out.data_ptr(), ct3.shape[0],
+                                                    _stream(ct3)))
+    return out
+
+
 def bfv_apply_automorphism(params: BfvParams, ct: torch.Tensor, gk, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bfv/eval.rs:512-561 over [B, 2, n] (or [B, d, 2, n]: every limb, dbfv/advanced.rs:15-30); ``gk`` is a
     GaloisKey.  ``out`` must not alias ``ct``."""

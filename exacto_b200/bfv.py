@@ -3,6 +3,9 @@ on the ciphertext-multiplication hot path, with the reference's signatures and e
 behaviour; the arithmetic runs in libexacto_b200.so on the GPU.
 
     bfv_mul_and_relin(ct1, ct2, rlk)   bfv/eval.rs:73-82
+    bfv_mul_no_relin(ct1, ct2)         bfv/eval.rs:89-108
+    relinearize(ct, rlk)               bfv/keyswitch.rs:59-101
+    gadget_decompose(poly, base, G)    bfv/keyswitch.rs:11-52
     bfv_add / bfv_sub / bfv_neg        bfv/eval.rs:14-62
     bfv_apply_automorphism / bfv_trace bfv/eval.rs:512-588 (Galois automorphism + key switch)
     bfv_inner_product                  bfv/eval.rs:593-606
@@ -145,6 +148,72 @@ def bfv_mul_and_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray,
     _native.check(_native.lib().exb_bfv_mul_and_relin_host(ctx.handle, _ptr(ct1), _ptr(ct2), rlk.native(ctx),
                                                            _ptr(out), ct1.shape[0]))
     return out
+
+
+def _dev_call(params: BfvParams, fn, *arrays, out_shape, extra=()):
+    """Device round trip for the stand-alone halves: host arrays -> HBM -> kernel sequence -> host array."""
+    import torch  # noqa: F401  (device memory plumbing only)
+    from . import batch
+    devs = [batch.to_device(a) for a in arrays]
+    out = batch.to_device(np.zeros(out_shape, np.uint64))
+    ctx = params.context(devs[0].device.index)
+    _native.check(fn(ctx, devs, out))
+    return batch.to_host(out)
+
+
+def bfv_mul_no_relin(ct1: BfvCiphertext, ct2: BfvCiphertext) -> BfvCiphertext:
+    """bfv/eval.rs:89-108: the degree-2 product (c0 d0, c0 d1 + c1 d0, c1 d1), scaled and rounded."""
+    _check_degree1(ct1, ct2)
+    params = ct1.params
+    out = bfv_mul_no_relin_batch(params, ct1.to_array()[None], ct2.to_array()[None])
+    return BfvCiphertext.from_array(out[0], params)
+
+
+def bfv_mul_no_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray) -> np.ndarray:
+    """ct [B][2][n] x2 -> [B][3][n] (exb_bfv_mul_no_relin)."""
+    ct1, ct2 = _u64(ct1), _u64(ct2)
+    n = params.ring_degree
+    if ct1.shape != ct2.shape or ct1.shape[1:] != (2, n):
+        raise InvalidParam("multiplication requires degree-1 ciphertexts")
+    L = _native.lib()
+    return _dev_call(params, lambda ctx, d, o: L.exb_bfv_mul_no_relin(ctx.handle, d[0].data_ptr(), d[1].data_ptr(), o.data_ptr(),
+                                                                      ct1.shape[0], None),
+                     ct1, ct2, out_shape=(ct1.shape[0], 3, n))
+
+
+def relinearize(ct: BfvCiphertext, rlk: RelinKey) -> BfvCiphertext:
+    """bfv/keyswitch.rs:59-101: degree-2 -> degree-1 with the relinearisation key; fewer than three components
+    are returned unchanged (:63-65), more than three are rejected (:66-70)."""
+    if len(ct.c) < 3:
+        return ct
+    if len(ct.c) > 3:
+        raise InvalidParam("relinearization only supports degree-2 ciphertexts")
+    out = relinearize_batch(ct.params, ct.to_array()[None], rlk)
+    return BfvCiphertext.from_array(out[0], ct.params)
+
+
+def relinearize_batch(params: BfvParams, ct3: np.ndarray, rlk: RelinKey) -> np.ndarray:
+    """ct [B][3][n] -> [B][2][n] (exb_bfv_relinearize)."""
+    ct3 = _u64(ct3)
+    n = params.ring_degree
+    if ct3.ndim != 3 or ct3.shape[1:] != (3, n):
+        raise InvalidParam("relinearization only supports degree-2 ciphertexts")
+    L = _native.lib()
+    return _dev_call(params, lambda ctx, d, o: L.exb_bfv_relinearize(ctx.handle, d[0].data_ptr(), 3, rlk.native(ctx), o.data_ptr(),
+                                                                     ct3.shape[0], None),
+                     ct3, out_shape=(ct3.shape[0], 2, n))
+
+
+def gadget_decompose(poly, params: BfvParams) -> list:
+    """bfv/keyswitch.rs:11-52 with the context's gadget base and digit count: balanced base-B digits of the centred
+    coefficients, each digit polynomial stored mod q."""
+    from .ring import CoeffPoly
+    q, n, G = params.ct_basis.moduli[0], params.ring_degree, params.gadget_digits
+    coeffs = _u64(poly.coeffs)[None]
+    L = _native.lib()
+    out = _dev_call(params, lambda ctx, d, o: L.exb_gadget_decompose(ctx.handle, d[0].data_ptr(), o.data_ptr(), 1, None),
+                    coeffs, out_shape=(1, G, n))
+    return [CoeffPoly(out[0, g], q) for g in range(G)]
 
 
 # ---- Galois automorphism + key switch --------------------------------------------------------------

@@ -638,3 +638,94 @@ extern "C" int exb_bfv_decrypt_host(exb_context *c, const uint64_t *ct, uint32_t
     EXB_CUDA(cudaStreamSynchronize(w.stream));
     return EXB_OK;
 }
+
+// ---- bfv_mul_no_relin (bfv/eval.rs:89-108), relinearize (bfv/keyswitch.rs:59-101), gadget_decompose (:11-52)
+// as stand-alone entry points (the fused pipeline above is what bfv_mul_and_relin / dbfv_mul use) ----------
+extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out3,
+                                    size_t batch, void *stream) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null argument");
+    if (c->mul_status != EXB_OK) return fail(c->mul_status, c->mul_error);
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    HostPlan hp;
+    int rc = build_plan(1, 2, 0, 0, 0, &hp);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace &w = c->ws[0];
+    const size_t n = c->n;
+    size_t eb, rb, db, xb;
+    ws_bytes_per_pair(c, hp, c->gadget_digits, &eb, &rb, &db, &xb);
+    const size_t per = eb + 3 * n * 8;
+    size_t chunk = ((size_t)4 << 30) / per;
+    if (chunk < 1) chunk = 1;
+    for (size_t off = 0; off < batch; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        if ((rc = claim(w, st))) return rc;
+        if ((rc = grow((void **)&w.ext, &w.ext_b, eb * cnt))) return rc;
+        if ((rc = grow((void **)&w.r01, &w.r01_b, 3 * n * 8 * cnt))) return rc;
+        launch_lift(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, cnt, st);
+        launch_tensor(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, w.r01, nullptr, c->digits32, cnt, st, nullptr, true);
+        launch_ntt_fwd(c->P, 0, w.r01, out3 + off * 3 * n, 3 * cnt, st);      // hps_scale ends with from_coeff_poly (:412)
+    }
+    return check_launch("bfv_mul_no_relin");
+}
+
+extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t ncomp, const exb_relin_key *rlk,
+                                   uint64_t *out, size_t batch, void *stream) {
+    if (!c || !rlk) return fail(EXB_INVALID_PARAM, "null argument");
+    if (rlk->ctx != c) return fail(EXB_INVALID_PARAM, "relinearisation key belongs to another context");
+    if (ncomp > 3) return fail(EXB_INVALID_PARAM, "relinearization only supports degree-2 ciphertexts");   // :66-70
+    if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "relinearize on the device path needs a single ciphertext prime");
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = c->n;
+    if (ncomp < 3) {                                                           // :63-65 already degree 1: unchanged
+        if (out != ct) EXB_CUDA(cudaMemcpyAsync(out, ct, batch * ncomp * n * 8, cudaMemcpyDeviceToDevice, st));
+        return EXB_OK;
+    }
+    if (c->gadget_base < 2 || c->gadget_base > (1ull << 32))
+        return fail(EXB_NOT_IMPLEMENTED, "device path supports gadget bases in [2, 2^32]");
+    HostPlan hp;
+    int rc = build_plan(1, 2, 0, 0, 0, &hp);
+    if (rc) return rc;
+    DeviceParams P = c->P;
+    const u32 G = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;                    // :86-89
+    P.gadget_digits = G;
+    Workspace &w = c->ws[0];
+    const size_t dig_b = (size_t)(G ? G : 1) * n * (c->digits32 ? 4 : 2);
+    const size_t per = n * 8 + 2 * n * 8 + dig_b + (size_t)(G + 1) * 2 * n * 8;
+    size_t chunk = ((size_t)4 << 30) / per;
+    if (chunk < 1) chunk = 1;
+    for (size_t off = 0; off < batch; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        if ((rc = claim(w, st))) return rc;
+        if ((rc = grow((void **)&w.ext, &w.ext_b, cnt * n * 8))) return rc;    // c2 in the coefficient domain
+        if ((rc = grow((void **)&w.r01, &w.r01_b, cnt * 2 * n * 8))) return rc;
+        if ((rc = grow(&w.digits, &w.digits_b, cnt * dig_b))) return rc;
+        const uint64_t *src = ct + off * 3 * n;
+        EXB_CUDA(cudaMemcpy2DAsync(w.r01, 2 * n * 8, src, 3 * n * 8, 2 * n * 8, cnt, cudaMemcpyDeviceToDevice, st));
+        EXB_CUDA(cudaMemcpy2DAsync(w.ext, n * 8, src + 2 * n, 3 * n * 8, n * 8, cnt, cudaMemcpyDeviceToDevice, st));
+        launch_ntt_inv(P, 0, w.ext, w.ext, cnt, st);                           // :76
+        launch_gadget_digits(P, w.ext, w.digits, c->digits32 ? 1 : 0, cnt, st);   // :79
+        u64 *wide = nullptr;
+        if (relin_goes_wide(P, hp.M, cnt)) {
+            if ((rc = grow((void **)&w.wide, &w.wide_b, relin_wide_scratch_bytes(P, hp.M, cnt)))) return rc;
+            wide = w.wide;
+        }
+        launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out + off * 2 * n, nullptr, cnt, st, wide, true);
+    }
+    return check_launch("relinearize");
+}
+
+extern "C" int exb_gadget_decompose(exb_context *c, const uint64_t *coeffs, uint64_t *out, size_t count, void *stream) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null argument");
+    if (c->gadget_base < 2 || c->gadget_base > (1ull << 32))
+        return fail(EXB_NOT_IMPLEMENTED, "device path supports gadget bases in [2, 2^32]");
+    if (count == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    launch_gadget_digits(c->P, coeffs, out, 2, count, (cudaStream_t)stream);
+    return check_launch("gadget_decompose");
+}

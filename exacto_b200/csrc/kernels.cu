@@ -505,7 +505,7 @@ template <int LOGN, typename DigT>
 __global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
 tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
               const u64 *__restrict__ ct1, const u64 *__restrict__ ext, u64 *__restrict__ r01,
-              DigT *__restrict__ digits) {
+              DigT *__restrict__ digits, u32 raw3) {
     EXB_DYN_SMEM(smem);
     const u32 n = P.n, A = P.num_aux, d = M.d, NP = M.num_products;
     const u32 idx = blockIdx.x;
@@ -539,8 +539,8 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
     }
 
     const u64 *ba = smem, *b0 = smem + n, *b1 = smem + 2 * (size_t)n;
-    if (comp < 2) {
-        u64 *o = r01 + ((pair * NP + prod) * 2 + comp) * (size_t)n;
+    if (comp < 2 || raw3) {                // raw3 (bfv_mul_no_relin): all three scaled components, [pair][prod][3][n]
+        u64 *o = r01 + ((pair * NP + prod) * (raw3 ? 3 : 2) + comp) * (size_t)n;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) {
             const u32 p = Lay<LOGN>::at(e);
             o[e] = hps_scale_coeff(ba[p], b0[p], A == 2 ? b1[p] : 0, P.sc);
@@ -698,7 +698,10 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     constexpr u32 n = 4096;
     const u32 K = P.sb.K, d = M.d, NP = M.num_products;
     const u32 idx = blockIdx.x;
-    // only_c2: components 0 and 1 are produced per output limb by tensor01_kernel
+    // mode bit 0 (only_c2): components 0 and 1 are produced per output limb by tensor01_kernel;
+    // mode bit 1 (raw3, bfv_mul_no_relin): all three scaled components go to r01 as [pair][prod][3][n]
+    const u32 raw3 = only_c2 & 2u;
+    only_c2 &= 1u;
     const u32 comp = only_c2 ? 2u : idx % 3u;
     const u32 prod = only_c2 ? idx % NP : (idx / 3u) % NP;
     const size_t pair = only_c2 ? idx / NP : idx / (3u * NP);
@@ -761,8 +764,8 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         for (u32 i = 0; i < (u32)kMaxSmall; i++) b[i] = i < K ? bv[i][k] : 0u;
         av[k] = hps_scale32_coeff(av[k], b, P.sc, P.sb.sc);
     }
-    if (comp < 2) {
-        u64 *o01 = r01 + ((pair * NP + prod) * 2 + comp) * (size_t)n;
+    if (comp < 2 || raw3) {
+        u64 *o01 = r01 + ((pair * NP + prod) * (raw3 ? 3 : 2) + comp) * (size_t)n;
         stg_u64x4(o01 + e0, av); stg_u64x4(o01 + e0 + 4, av + 4);
     } else {
         DigT *od = digits + ((pair * NP + prod) * (size_t)G) * n;
@@ -912,6 +915,29 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------
+// gadget_decompose (bfv/keyswitch.rs:11-52) on coefficient-domain polynomials [count][n]:
+//   digits_kernel     signed digits (DigT) in the layout the relin kernels read, [count][G][n]
+//   gadget_kernel     the reference's return value: each digit reduced mod q, [count][G][n] u64
+// ---------------------------------------------------------------------------------
+template <typename OutT, bool MOD_Q>
+__global__ void gadget_digits_kernel(const __grid_constant__ DeviceParams P, const u64 *__restrict__ coeffs,
+                                     OutT *__restrict__ out, size_t count) {
+    const u32 n = P.n, G = P.gadget_digits;
+    const u64 q = P.mod[0].m, half_q = q >> 1;
+    const size_t total = count * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = idx / n;
+        const u32 e = (u32)(idx - poly * n);
+        i64 rem = center_i64(coeffs[idx], q, half_q);
+        for (u32 g = 0; g < G; g++) {
+            const i64 dg = P.gadget_log2 ? gadget_digit_pow2(rem, P.gadget_log2) : gadget_digit_general(rem, (i64)P.gadget_base);
+            if constexpr (MOD_Q) out[(poly * G + g) * n + e] = signed_to_mod(dg, q);
+            else out[(poly * G + g) * n + e] = (OutT)dg;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // K6+K7: relinearise + per-k accumulation.  One CTA per (pair, output limb k):
 //   c0 = NTT(sum r0) + sum_g NTT(sum digits_g) * rlk0_g     (likewise c1)
 // All sums are exact mod q, so any association is bit-equal to the reference's
@@ -921,7 +947,7 @@ template <int LOGN, typename DigT>
 __global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
 relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
              const u64 *__restrict__ r01, const DigT *__restrict__ digits,
-             const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess) {
+             const u64 *__restrict__ rlk_mont, u64 *__restrict__ out, u64 *__restrict__ excess, u32 r01_ntt) {
     EXB_DYN_SMEM(smem);
     const u32 n = P.n, d = M.d, NP = M.num_products, NL = M.num_limbs, G = P.gadget_digits;
     const Modulus &mq = P.mod[0];
@@ -941,7 +967,8 @@ relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mul
             }
             work[Lay<LOGN>::at(e)] = s;
         }
-        fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
+        if (r01_ntt) __syncthreads();      // r0 / r1 already in the NTT domain (standalone relinearize)
+        else fwd_sm<LOGN>(work, P.twf[0], P.headf[0], mq, P.logn);
         u64 *acc = comp ? acc1 : acc0;
         for (u32 e = threadIdx.x; e < n; e += blockDim.x) acc[e] = work[Lay<LOGN>::at(e)];
     }
@@ -994,7 +1021,7 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
 
     for (u32 comp = 0; comp < 2; comp++) {
         u64 sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (r01_summed) {                  // tensor01_kernel already summed the limb's products
+        if (r01_summed & 1u) {             // tensor01_kernel already summed the limb's products
             const u64 *src = r01 + ((pair * NL + limb) * 2 + comp) * n + e0;
             ldg_u64x4(src, sum); ldg_u64x4(src + 4, sum + 4);
         } else {
@@ -1007,10 +1034,12 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
                 for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
             }
         }
-        sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
-        fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
         u64 *acc = comp ? acc1 : acc0;
-        lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+        if (!(r01_summed & 2u)) {          // bit 1: r0 / r1 are already in the NTT domain (standalone relinearize)
+            sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+            lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+        }
         sts_u64x4(acc, e0, sum); sts_u64x4(acc, e0 + 4, sum + 4);
     }
     for (u32 g = 0; g < G; g++) {
@@ -1083,7 +1112,7 @@ relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constan
     if (role == G) {
         for (u32 comp = 0; comp < 2; comp++) {
             u64 sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (r01_summed) {
+            if (r01_summed & 1u) {
                 const u64 *src = r01 + ((pair * NL + limb) * 2 + comp) * n + e0;
                 ldg_u64x4(src, sum); ldg_u64x4(src + 4, sum + 4);
             } else {
@@ -1096,9 +1125,11 @@ relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constan
                     for (int j = 0; j < 8; j++) sum[j] = mod_add(sum[j], v[j], q);
                 }
             }
-            sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
-            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
-            lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+            if (!(r01_summed & 2u)) {
+                sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+                fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
+                lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+            }
             stg_u64x4(dst + comp * n + e0, sum); stg_u64x4(dst + comp * n + e0 + 4, sum + 4);
             __syncthreads();
         }
@@ -1404,14 +1435,14 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 
 template <typename DigT>
 static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext,
-                            u64 *r01, DigT *digits, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
+                            u64 *r01, DigT *digits, size_t pairs, cudaStream_t s, cudaEvent_t mid, bool raw3) {
     const size_t sm = (size_t)P.n * 8 * (1 + P.num_aux);
     const unsigned grid = (unsigned)(pairs * M.num_products * 3);
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
         const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
         set_smem(tensor32_kernel<DigT>, sm32);
-        if (tensor_sums_per_limb(P, M, pairs)) {
+        if (!raw3 && tensor_sums_per_limb(P, M, pairs)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
             set_smem(tensor01_kernel, sm01);
@@ -1422,36 +1453,49 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
             g_launch_count += 2;
             return;
         }
-        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01, digits, 0u);
+        tensor32_kernel<DigT><<<grid, kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01, digits, raw3 ? 2u : 0u);
         if (mid) cudaEventRecord(mid, s);
         g_launch_count++;
         return;
     }
     if (P.logn == 12) {
         set_smem(tensor_kernel<12, DigT>, sm);
-        tensor_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, ct1, ext, r01, digits);
+        tensor_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, ct1, ext, r01, digits, raw3 ? 1u : 0u);
     } else {
         set_smem(tensor_kernel<0, DigT>, sm);
-        tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits);
+        tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits, raw3 ? 1u : 0u);
     }
     if (mid) cudaEventRecord(mid, s);
     g_launch_count++;
 }
 
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
-                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid) {
+                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid, bool raw3) {
     if (pairs == 0) { if (mid) cudaEventRecord(mid, s); return; }
-    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ct2, ext, r01, (int32_t *)digits, pairs, s, mid);
-    else launch_tensor_t<int16_t>(P, M, ct1, ct2, ext, r01, (int16_t *)digits, pairs, s, mid);
+    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ct2, ext, r01, (int32_t *)digits, pairs, s, mid, raw3);
+    else launch_tensor_t<int16_t>(P, M, ct1, ct2, ext, r01, (int16_t *)digits, pairs, s, mid, raw3);
+}
+
+void launch_gadget_digits(const DeviceParams &P, const u64 *coeffs, void *out, int out_kind, size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    size_t blocks = (count * P.n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (out_kind == 0) gadget_digits_kernel<int16_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int16_t *)out, count);
+    else if (out_kind == 1) gadget_digits_kernel<int32_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int32_t *)out, count);
+    else gadget_digits_kernel<u64, true><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (u64 *)out, count);
+    g_launch_count++;
 }
 
 template <typename DigT>
 static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r01, const DigT *digits,
-                           const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch) {
+                           const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch,
+                           bool r01_ntt) {
     const size_t sm = (size_t)P.n * 8 * 3;
     const unsigned grid = (unsigned)(pairs * M.num_limbs);
+    // flags: bit 0 = r01 is [pair][limb][2][n] (per-limb sums), bit 1 = r0 / r1 already in the NTT domain
+    const u32 flags12 = r01_ntt ? 3u : (tensor_sums_per_limb(P, M, pairs) ? 1u : 0u);
     if (wide_scratch && relin_goes_wide(P, M, pairs)) {
-        const u32 summed = tensor_sums_per_limb(P, M, pairs) ? 1u : 0u;
+        const u32 summed = flags12;
         set_smem(relin12_wide_kernel<DigT>, (size_t)P.n * 8);
         relin12_wide_kernel<DigT><<<grid * (P.gadget_digits + 1), kThreads12, (size_t)P.n * 8, s>>>(
             P, M, r01, digits, rlk_mont, wide_scratch, summed);
@@ -1463,20 +1507,20 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     }
     if (P.logn == 12) {
         set_smem(relin12_kernel<DigT>, sm);
-        relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess,
-                                                          tensor_sums_per_limb(P, M, pairs) ? 1u : 0u);
+        relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess, flags12);
     } else {
         set_smem(relin_kernel<0, DigT>, sm);
-        relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess);
+        relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess, r01_ntt ? 1u : 0u);
     }
     g_launch_count++;
 }
 
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits, bool digits32,
-                  const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch) {
+                  const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch,
+                  bool r01_ntt) {
     if (pairs == 0) return;
-    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch);
-    else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch);
+    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
+    else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
 }
 
 void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32 element, u64 *out,

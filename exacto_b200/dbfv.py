@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _native
 from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automorphism_batch, bfv_neg,
-                  bfv_sub)
+                  bfv_sub, relinearize)
 from .error import DimensionMismatch, InvalidParam, NotImplementedErr
 from .params import DbfvParams
 from .ring import _ptr, _u64
@@ -96,6 +96,11 @@ def dbfv_mul_batch(params: DbfvParams, ct1: np.ndarray, ct2: np.ndarray, rlk: Re
     _native.check(_native.lib().exb_dbfv_mul_host(ctx.handle, params.base, d, params.plain_modulus, _ptr(ct1),
                                                   _ptr(ct2), rlk.native(ctx), _ptr(out), ct1.shape[0], flags))
     return out
+
+
+def dbfv_relinearize(ct: DbfvCiphertext, rlk: RelinKey) -> DbfvCiphertext:
+    """dbfv/keyswitch.rs:9-23: BFV relinearisation of every limb; metadata unchanged."""
+    return DbfvCiphertext([relinearize(l, rlk) for l in ct.limbs], ct.degree, ct.mul_depth, ct.params)
 
 
 def dbfv_apply_automorphism(ct: DbfvCiphertext, gk: GaloisKey) -> DbfvCiphertext:

@@ -154,6 +154,18 @@ int exb_bfv_mul_and_relin(exb_context *ctx, const uint64_t *ct1_dev, const uint6
                           const exb_relin_key *rlk, uint64_t *out_dev, size_t batch, void *stream);
 int exb_bfv_mul_and_relin_host(exb_context *ctx, const uint64_t *ct1_host, const uint64_t *ct2_host,
                                const exb_relin_key *rlk, uint64_t *out_host, size_t batch);
+/* The two halves of bfv_mul_and_relin as the reference exposes them, device-resident:
+ *   bfv_mul_no_relin (bfv/eval.rs:89-108): ct [batch][2][n] x2 -> degree-2 ciphertexts [batch][3][n] (NTT domain);
+ *   relinearize (bfv/keyswitch.rs:59-101): ct [batch][num_components][n] -> [batch][2][n]; fewer than 3
+ *     components are returned unchanged ([batch][num_components][n], :63-65), more than 3 ->
+ *     EXB_INVALID_PARAM "relinearization only supports degree-2 ciphertexts" (:66-70);
+ *   gadget_decompose (bfv/keyswitch.rs:11-52): coefficient-domain polynomials [count][n] -> balanced base-B digits,
+ *     each stored mod q, [count][gadget_digits][n] (gadget base and digit count of the context). */
+int exb_bfv_mul_no_relin(exb_context *ctx, const uint64_t *ct1_dev, const uint64_t *ct2_dev, uint64_t *out3_dev,
+                         size_t batch, void *stream);
+int exb_bfv_relinearize(exb_context *ctx, const uint64_t *ct_dev, uint32_t num_components, const exb_relin_key *rlk,
+                        uint64_t *out_dev, size_t batch, void *stream);
+int exb_gadget_decompose(exb_context *ctx, const uint64_t *coeffs_dev, uint64_t *out_dev, size_t count, void *stream);
 /* bfv_add (bfv/eval.rs:14-31) on degree-1 ciphertexts. */
 int exb_bfv_add(exb_context *ctx, const uint64_t *a_dev, const uint64_t *b_dev, uint64_t *out_dev,
                 size_t batch, void *stream);

@@ -241,6 +241,56 @@ inline BfvCiphertext bfv_mul_and_relin(const BfvCiphertext &ct1, const BfvCipher
     return detail::unflatten(out.data(), 2, ct1.params);
 }
 
+namespace detail {
+// host vector -> HBM -> `fn(device in..., device out)` -> host vector (device memory through the C ABI only)
+template <typename F>
+inline std::vector<uint64_t> device_round_trip(exb_context *ctx, const std::vector<const std::vector<uint64_t> *> &ins,
+                                               size_t out_words, F fn) {
+    std::vector<void *> dev(ins.size() + 1, nullptr);
+    auto release = [&] { for (void *p : dev) if (p) exb_device_free(ctx, p); };
+    try {
+        for (size_t i = 0; i < ins.size(); i++) {
+            check(exb_device_alloc(ctx, ins[i]->size() * 8, &dev[i]));
+            check(exb_copy_to_device(ctx, dev[i], ins[i]->data(), ins[i]->size() * 8, nullptr));
+        }
+        check(exb_device_alloc(ctx, out_words * 8, &dev.back()));
+        check(fn(dev));
+        std::vector<uint64_t> out(out_words);
+        check(exb_copy_to_host(ctx, out.data(), dev.back(), out_words * 8, nullptr));
+        check(exb_synchronize(ctx, nullptr));
+        release();
+        return out;
+    } catch (...) { release(); throw; }
+}
+}  // namespace detail
+
+inline BfvCiphertext bfv_mul_no_relin(const BfvCiphertext &ct1, const BfvCiphertext &ct2) {   // bfv/eval.rs:89-108
+    if (ct1.c.size() != 2 || ct2.c.size() != 2)                                               // :93-97
+        throw ExactoError(ExactoError::InvalidParam, "multiplication requires degree-1 ciphertexts");
+    std::vector<uint64_t> a, b;
+    detail::flatten(ct1, a); detail::flatten(ct2, b);
+    exb_context *ctx = ct1.params->context();
+    const size_t n = ct1.params->ring_degree;
+    auto out = detail::device_round_trip(ctx, {&a, &b}, 3 * n, [&](std::vector<void *> &d) {
+        return exb_bfv_mul_no_relin(ctx, (const uint64_t *)d[0], (const uint64_t *)d[1], (uint64_t *)d[2], 1, nullptr);
+    });
+    return detail::unflatten(out.data(), 3, ct1.params);
+}
+
+inline BfvCiphertext relinearize(const BfvCiphertext &ct, const RelinKey &rlk) {              // bfv/keyswitch.rs:59-101
+    if (ct.c.size() < 3) return ct;                                                           // :63-65
+    if (ct.c.size() > 3)                                                                      // :66-70
+        throw ExactoError(ExactoError::InvalidParam, "relinearization only supports degree-2 ciphertexts");
+    std::vector<uint64_t> a;
+    detail::flatten(ct, a);
+    exb_context *ctx = ct.params->context();
+    const size_t n = ct.params->ring_degree;
+    auto out = detail::device_round_trip(ctx, {&a}, 2 * n, [&](std::vector<void *> &d) {
+        return exb_bfv_relinearize(ctx, (const uint64_t *)d[0], 3, rlk.device(), (uint64_t *)d[1], 1, nullptr);
+    });
+    return detail::unflatten(out.data(), 2, ct.params);
+}
+
 inline BfvCiphertext bfv_apply_automorphism(const BfvCiphertext &ct, const GaloisKey &gk) {   // bfv/eval.rs:512-561
     if (ct.c.size() != 2)                                                                     // :516-520
         throw ExactoError(ExactoError::InvalidParam, "automorphism requires degree-1 ciphertext");

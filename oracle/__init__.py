@@ -128,6 +128,7 @@ def lib():
         L.exo_apply_automorphism.argtypes = [u32, u64, p64, u64, p64]
         L.exo_apply_automorphism.restype = None
         L.exo_bfv_apply_automorphism_batch.argtypes = [pp, p64, p64, u64, p64, ctypes.c_size_t, ctypes.c_int]
+        L.exo_relinearize.argtypes = [pp, p64, p64, p64]
         L.exo_small_reps.argtypes = [u64, u32, u64, p64]
         L.exo_small_reps.restype = None
         L.exo_dbfv_mul.argtypes = [pp, u64, u32, u64, p64, p64, p64, p64, ctypes.c_int]
@@ -239,6 +240,17 @@ def bfv_mul_and_relin(p: OracleParams, ct1, ct2, rlk, threads: int = 1) -> np.nd
     _check(lib().exo_bfv_mul_and_relin_batch(ctypes.byref(p._c), _ptr(ct1), _ptr(ct2), _ptr(rlk),
                                              _ptr(out), batch, threads))
     return out
+
+
+def relinearize(p: OracleParams, ct3, rlk) -> np.ndarray:
+    """bfv/keyswitch.rs:59-101: ct3 [..,3,n] NTT domain -> [..,2,n]."""
+    ct3 = _u64(ct3)
+    rlk = _u64(rlk, (p.gadget_digits, 2, p.n))
+    flat = ct3.reshape(-1, 3, p.n)
+    out = np.zeros((flat.shape[0], 2, p.n), np.uint64)
+    for i in range(flat.shape[0]):
+        _check(lib().exo_relinearize(ctypes.byref(p._c), _ptr(np.ascontiguousarray(flat[i])), _ptr(rlk), _ptr(out[i])))
+    return out.reshape(ct3.shape[:-2] + (2, p.n))
 
 
 # ---- Galois automorphism + key switch ----------------------------------------

@@ -331,6 +331,13 @@ static int relinearize(const exo_params *p, const plan *pq, const u64 *c3, const
     return EXO_OK;
 }
 
+/* relinearize :59-101 as a public entry: c3 [3][n] -> out [2][n]. */
+int exo_relinearize(const exo_params *p, const u64 *c3, const u64 *rlk, u64 *out) {
+    const plan *pq = get_plan(p->n, p->q);
+    if (!pq) return fail(EXO_INVALID_PARAM, "cannot create NTT plan");
+    return relinearize(p, pq, c3, rlk, out);
+}
+
 /* ------------------------------------------------------------------------ */
 /* bfv/eval.rs                                                               */
 /* ------------------------------------------------------------------------ */

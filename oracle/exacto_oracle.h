@@ -87,6 +87,9 @@ void exo_poly_mul_naive(uint32_t n, uint64_t q, const uint64_t *a, const uint64_
 void exo_gadget_decompose(uint32_t n, uint64_t q, const uint64_t *coeffs, uint64_t base,
                           uint32_t num_digits, uint64_t *out);
 
+/* relinearize :59-101 on one degree-2 ciphertext c3 [3][n] (NTT domain), rlk [G][2][n] -> out [2][n]. */
+int exo_relinearize(const exo_params *p, const uint64_t *c3, const uint64_t *rlk, uint64_t *out);
+
 /* ---- bfv/eval.rs --------------------------------------------------------- */
 /* bfv_add :14-31 on two degree-1 ciphertexts [2][n].                        */
 void exo_bfv_add(const exo_params *p, const uint64_t *a, const uint64_t *b, uint64_t *out);

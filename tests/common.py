@@ -59,6 +59,9 @@ class Emulator:
         L.emu_bfv_apply_automorphism.argtypes = [vp, vp, u64, vp, vp, ctypes.c_size_t]
         L.emu_bfv_decrypt.argtypes = [vp, vp, u32, vp, vp, ctypes.c_size_t]
         L.emu_tensor_per_limb.argtypes = [vp, u64, u32, u64, u32, u32]
+        L.emu_bfv_mul_no_relin.argtypes = [vp, vp, vp, vp, ctypes.c_size_t]
+        L.emu_bfv_relinearize.argtypes = [vp, vp, vp, u32, vp, ctypes.c_size_t, ctypes.c_int]
+        L.emu_gadget_decompose.argtypes = [vp, vp, vp, ctypes.c_size_t]
         self.L = L
 
     @staticmethod
@@ -106,6 +109,25 @@ class Emulator:
         ct, gk = np.ascontiguousarray(ct, np.uint64), np.ascontiguousarray(gk, np.uint64)
         out = np.zeros_like(ct)
         self.L.emu_bfv_apply_automorphism(h, self._p(ct), element, self._p(gk), self._p(out), ct.size // (2 * ct.shape[-1]))
+        return out
+
+    def bfv_mul_no_relin(self, h, ct1, ct2):
+        ct1, ct2 = np.ascontiguousarray(ct1, np.uint64), np.ascontiguousarray(ct2, np.uint64)
+        out = np.zeros(ct1.shape[:-2] + (3, ct1.shape[-1]), np.uint64)
+        rc = self.L.emu_bfv_mul_no_relin(h, self._p(ct1), self._p(ct2), self._p(out), ct1.size // (2 * ct1.shape[-1]))
+        return rc, out, self.L.emu_last_error().decode()
+
+    def bfv_relinearize(self, h, ct3, rlk, wide=False):
+        ct3, rlk = np.ascontiguousarray(ct3, np.uint64), np.ascontiguousarray(rlk, np.uint64)
+        out = np.zeros(ct3.shape[:-2] + (2, ct3.shape[-1]), np.uint64)
+        rc = self.L.emu_bfv_relinearize(h, self._p(ct3), self._p(rlk), rlk.shape[0], self._p(out),
+                                        ct3.size // (3 * ct3.shape[-1]), 1 if wide else 0)
+        return rc, out
+
+    def gadget_decompose(self, h, coeffs, G):
+        coeffs = np.ascontiguousarray(coeffs, np.uint64)
+        out = np.zeros(coeffs.shape[:-1] + (G, coeffs.shape[-1]), np.uint64)
+        self.L.emu_gadget_decompose(h, self._p(coeffs), self._p(out), coeffs.size // coeffs.shape[-1])
         return out
 
     def tensor_per_limb(self, h, base, d, pm, flags=0, limb_mask=0):

@@ -75,6 +75,10 @@ int main(int argc, char **argv) {
                  BfvCiphertext z = detail::unflatten(std::vector<uint64_t>(2 * 4096, 0).data(), 2, p);
                  bfv_mul_and_relin(z, z, empty);
              });
+        const BfvCiphertext two_step = relinearize(bfv_mul_no_relin(a.limbs[0], b.limbs[0]), rlk);   // == bfv_mul_and_relin
+        ok = ok && two_step.c.size() == 2 && two_step.c[0].components[0].evals == one.c[0].components[0].evals &&
+             two_step.c[1].components[0].evals == one.c[1].components[0].evals;
+        ok = ok && relinearize(a.limbs[0], rlk).c.size() == 2;
         const DbfvCiphertext rot = dbfv_apply_automorphism(a, *gk);
         const BfvCiphertext tr = bfv_trace(a.limbs[0], {3}, {{3, gk}});
         ok = ok && rot.degree == a.degree && rot.mul_depth == a.mul_depth && rot.num_limbs() == d;

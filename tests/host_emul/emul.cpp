@@ -216,23 +216,23 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
             emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         } else {
             int16_t *dg = dig16.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg); });
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg, 0u); });
             emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         }
     } else {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int32_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         } else {
             int16_t *dg = dig16.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, dg); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, xp); });
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, dg, 0u); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         }
     }
     const u64 q = hs.ct_moduli[0];
@@ -253,6 +253,83 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
             });
         }
     }
+    return 0;
+}
+
+// Same launch sequences as exb_bfv_mul_no_relin / exb_bfv_relinearize / exb_gadget_decompose in api.cu.
+int emu_bfv_mul_no_relin(emu_ctx *c, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out3, size_t pairs) {
+    HostSetup &hs = c->hs;
+    if (hs.mul_status != EXB_OK) { g_emu_err = hs.mul_error; return hs.mul_status; }
+    HostPlan hp;
+    int rc = host_build_plan(1, 2, 0, 0, 0, &hp, &g_emu_err);
+    if (rc) return rc;
+    const DeviceParams P = hs.P;
+    const MulPlan &M = hp.M;
+    const size_t n = hs.n, A = hs.aux_moduli.size();
+    const bool small = P.sb.enabled && P.logn == 12;
+    std::vector<u64> ext(small ? (pairs * 2 * 2 * P.sb.K * n + 1) / 2 + 2 : pairs * 2 * 2 * (1 + A) * n), r01(pairs * 3 * n + 1);
+    u64 *extp = ext.data(), *r01p = r01.data();
+    const unsigned thr = emu_block_threads(P);
+    int16_t *nodig = nullptr;
+    if (small) {
+        u32 *exts = reinterpret_cast<u32 *>(extp);
+        emu_launch((unsigned)(pairs * 4), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, 1, ct1, ct2, exts); });
+        emu_launch((unsigned)(pairs * 3), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { tensor32_kernel<int16_t>(P, M, ct1, ct2, exts, r01p, nodig, 2u); });
+    } else if (P.logn == 12) {
+        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<12>(P, 1, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, nodig, 1u); });
+    } else {
+        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<0>(P, 1, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, nodig, 1u); });
+    }
+    return emu_ntt(c, 0, 1, r01p, out3, pairs * 3);
+}
+
+int emu_bfv_relinearize(emu_ctx *c, const uint64_t *ct, const uint64_t *rlk, uint32_t num_keys, uint64_t *out,
+                        size_t pairs, int wide) {
+    HostSetup &hs = c->hs;
+    HostPlan hp;
+    int rc = host_build_plan(1, 2, 0, 0, 0, &hp, &g_emu_err);
+    if (rc) return rc;
+    DeviceParams P = hs.P;
+    const uint32_t G = num_keys < hs.gadget_digits ? num_keys : hs.gadget_digits;
+    P.gadget_digits = G;
+    const MulPlan &M = hp.M;
+    const size_t n = hs.n, kw = (size_t)num_keys * 2 * n;
+    std::vector<u64> r01(pairs * 2 * n + 1), c2(pairs * n + 1), rlk_mont(kw + 1), widebuf(wide ? relin_wide_scratch_bytes(P, M, pairs) / 8 + 1 : 1);
+    for (size_t b = 0; b < pairs; b++) {
+        memcpy(r01.data() + b * 2 * n, ct + b * 3 * n, 2 * n * 8);
+        memcpy(c2.data() + b * n, ct + b * 3 * n + 2 * n, n * 8);
+    }
+    const Modulus mq = P.mod[0];
+    if (kw) emu_launch(4, 64, 0, [&]() { poly_op_kernel(mq, OP_TO_MONT, rlk, nullptr, 0, rlk_mont.data(), kw); });
+    if ((rc = emu_ntt(c, 0, 0, c2.data(), c2.data(), pairs))) return rc;
+    std::vector<int32_t> dig32; std::vector<int16_t> dig16;
+    const u64 *c2p = c2.data(), *r01p = r01.data(), *rk = rlk_mont.data();
+    u64 *wp = widebuf.data(), *none = nullptr;
+    const unsigned thr = emu_block_threads(P);
+    if (hs.digits32) {
+        dig32.resize(pairs * (G ? G : 1) * n);
+        int32_t *dg = dig32.data();
+        emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<int32_t, false>(P, c2p, dg, pairs); });
+        if (P.logn == 12 && wide) emu_launch((unsigned)(pairs * (G + 1)), thr, n * 8, [&]() { relin12_wide_kernel<int32_t>(P, M, r01p, dg, rk, wp, 3u); });
+        else if (P.logn == 12) emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, none, 3u); });
+        else emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, none, 1u); });
+    } else {
+        dig16.resize(pairs * (G ? G : 1) * n);
+        int16_t *dg = dig16.data();
+        emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<int16_t, false>(P, c2p, dg, pairs); });
+        if (P.logn == 12 && wide) emu_launch((unsigned)(pairs * (G + 1)), thr, n * 8, [&]() { relin12_wide_kernel<int16_t>(P, M, r01p, dg, rk, wp, 3u); });
+        else if (P.logn == 12) emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, none, 3u); });
+        else emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, none, 1u); });
+    }
+    if (P.logn == 12 && wide) emu_launch(4, 256, 0, [&]() { relin_reduce_kernel(P, M, wp, out, none, pairs); });
+    return 0;
+}
+
+int emu_gadget_decompose(emu_ctx *c, const uint64_t *coeffs, uint64_t *out, size_t count) {
+    const DeviceParams P = c->hs.P;
+    emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<u64, true>(P, coeffs, out, count); });
     return 0;
 }
 

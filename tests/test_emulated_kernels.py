@@ -290,3 +290,39 @@ def test_per_limb_tensor_path_is_taken_and_exact(emu):
     for fl in (0x80000000, 0xC0000000, 0x40000000, 0x40000001):
         rc, got, err = emu.dbfv_mul(h, S.base, S.d, S.plain_modulus, a[None], b[None], rlk, flags=fl)
         assert rc == 0 and np.array_equal(got[0], want), (hex(fl), err)
+
+
+# ---- the halves of bfv_mul_and_relin as stand-alone entry points ---------------------------------------
+@pytest.mark.parametrize("preset", ["compact", "u64", "cfg3", "toy16_noaux", "n64_base10"])
+def test_mul_no_relin_relinearize_gadget_decompose(emu, preset):
+    """bfv_mul_no_relin (bfv/eval.rs:89-108), relinearize (bfv/keyswitch.rs:59-101) and gadget_decompose (:11-52)
+    against the literal restatement, and relinearize(mul_no_relin(a, b)) == bfv_mul_and_relin(a, b) word for word."""
+    P = {"compact": H.compact_bfv(), "u64": H.u64_dbfv().bfv, "cfg3": H.cfg3_prime().bfv,
+         "toy16_noaux": O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8),
+         "n64_base10": O.OracleParams(n=64, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
+                                      plain_modulus=257, gadget_base=10)}[preset]
+    h = emu.from_oracle(P)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(n + 5)
+    B = 2
+    ct1 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    edge = np.full(n, q // 2, np.uint64); edge[::2] = q // 2 + 1
+    ct1[0] = O.ntt_fwd(np.stack([edge, edge[::-1].copy()]), q)
+    rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    rc, c3, err = emu.bfv_mul_no_relin(h, ct1, ct2)
+    assert rc == 0, err
+    want3 = np.stack([O.bfv_mul_no_relin(P, a, b) for a, b in zip(ct1, ct2)])
+    assert np.array_equal(c3, want3)
+    want2 = O.relinearize(P, want3, rlk)
+    for wide in (False, True):
+        rc, got2 = emu.bfv_relinearize(h, want3, rlk, wide=wide)
+        assert rc == 0 and np.array_equal(got2, want2), wide
+    assert np.array_equal(want2, O.bfv_mul_and_relin(P, ct1, ct2, rlk))
+    rnd3 = rng.integers(0, q, (B, 3, n), dtype=np.uint64)                  # any degree-2 input, not only products
+    rc, got = emu.bfv_relinearize(h, rnd3, rlk)
+    assert rc == 0 and np.array_equal(got, O.relinearize(P, rnd3, rlk))
+    coeffs = rng.integers(0, q, (2, n), dtype=np.uint64)
+    coeffs[0, :6] = [0, 1, q - 1, q // 2, q // 2 + 1, 42]
+    want_d = np.stack([O.gadget_decompose(c, q, P.gadget_base, P.gadget_digits) for c in coeffs])
+    assert np.array_equal(emu.gadget_decompose(h, coeffs, P.gadget_digits), want_d)

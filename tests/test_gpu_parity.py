@@ -710,3 +710,51 @@ def test_per_limb_tensor_path_on_gpu():
         res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
         assert np.array_equal(np.load(f"{tmp}/out.npy"), want)
+
+
+@pytest.mark.parametrize("preset", ["compact", "u64", "cfg3", "toy16_noaux", "n64_base10"])
+def test_mul_no_relin_relinearize_gadget_decompose(preset):
+    """The halves of bfv_mul_and_relin as the reference exposes them (bfv/eval.rs:89-108, bfv/keyswitch.rs:11-101):
+    word-for-word against the oracle, relinearize(mul_no_relin) == bfv_mul_and_relin, the degree-2 product decrypts
+    (c0 + c1 s + c2 s^2), the reference's gadget KAT and guards."""
+    from exacto_b200 import batch
+    P = {"compact": H.compact_bfv(), "u64": H.u64_dbfv().bfv, "cfg3": H.cfg3_prime().bfv,
+         "toy16_noaux": O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8),
+         "n64_base10": O.OracleParams(n=64, q=1152921504606830593, aux=(18014398509998081, 36028797018972161),
+                                      plain_modulus=257, gadget_base=10)}[preset]
+    params = to_params(P)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(n + 5)
+    s = H.gen_secret_key(P, rng)
+    rlk_arr = H.gen_relin_key(P, s, rng)
+    rlk = E.RelinKey(rlk_arr, params)
+    B = 24 if n == 4096 else 3                         # n = 4096: enough limbs for the one-CTA-per-limb relin kernel too
+    ct1 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (B, 2, n), dtype=np.uint64)
+    ct1[0] = H.encrypt_sk(P, H.encode_scalar(P, 3), s, rng); ct2[0] = H.encrypt_sk(P, H.encode_scalar(P, 7), s, rng)
+    want3 = np.stack([O.bfv_mul_no_relin(P, a, b) for a, b in zip(ct1, ct2)])
+    got3 = E.bfv_mul_no_relin_batch(params, ct1, ct2)
+    assert np.array_equal(got3, want3)
+    want2 = O.relinearize(P, want3, rlk_arr)
+    assert np.array_equal(E.relinearize_batch(params, want3, rlk), want2)
+    assert np.array_equal(E.relinearize_batch(params, want3[:2], rlk), want2[:2])          # small batch: wide relin
+    assert np.array_equal(want2, E.bfv_mul_and_relin_batch(params, ct1, ct2, rlk))
+    d3 = batch.bfv_mul_no_relin(params, batch.to_device(ct1), batch.to_device(ct2))
+    assert np.array_equal(batch.to_host(batch.relinearize(params, d3, rlk)), want2)
+    sk = E.SecretKey.from_ntt(s, params)
+    a, b = E.BfvCiphertext.from_array(ct1[0], params), E.BfvCiphertext.from_array(ct2[0], params)
+    prod3 = E.bfv_mul_no_relin(a, b)
+    t = P.plain_modulus
+    assert len(prod3.c) == 3 and E.decode_scalar(E.decrypt(prod3, sk)) == 21 % t
+    assert E.decode_scalar(E.decrypt(E.relinearize(prod3, rlk), sk)) == 21 % t
+    assert E.relinearize(a, rlk) is a                                                    # keyswitch.rs:63-65
+    with pytest.raises(E.ExactoError, match="relinearization only supports degree-2 ciphertexts"):
+        E.relinearize(E.BfvCiphertext(prod3.c + prod3.c[:1], params), rlk)
+    coeffs = rng.integers(0, q, n, dtype=np.uint64)
+    coeffs[:6] = [0, 1, q - 1, q // 2, q // 2 + 1, 42]
+    digs = E.gadget_decompose(E.CoeffPoly(coeffs, q), params)
+    assert np.array_equal(np.stack([dg.coeffs for dg in digs]), O.gadget_decompose(coeffs, q, P.gadget_base, P.gadget_digits))
+    if preset == "toy16_noaux":                                                          # keyswitch.rs:109-116 KAT
+        kat = to_params(O.OracleParams(n=16, q=65537, aux=(), plain_modulus=5, gadget_base=16))   # G = 5 for this q
+        c = np.zeros(16, np.uint64); c[0] = 42
+        assert [int(dg.coeffs[0]) for dg in E.gadget_decompose(E.CoeffPoly(c, 65537), kat)] == [65531, 3, 0, 0, 0]
