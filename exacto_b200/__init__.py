@@ -3,7 +3,7 @@
 Host mirror of the reference's public surface for that path (same names, argument meaning
 and error behaviour) over the C ABI of ``libexacto_b200.so`` (include/exacto_b200.h):
 
-    ring/      CoeffPoly, NttPoly, RnsPoly, RnsBasis, make_plan
+    ring/      CoeffPoly, NttPoly, RnsPoly, RnsBasis, make_plan; modular (scalar helpers of ring/modular.rs)
     params/    BfvParamsBuilder, BfvParams, DbfvParams, compact_bfv, compact_dbfv, u64_dbfv
     bfv/       BfvCiphertext, RelinKey, bfv_mul_and_relin, bfv_add, bfv_sub, bfv_neg,
                GaloisKey, bfv_apply_automorphism, bfv_trace, bfv_inner_product
@@ -19,6 +19,7 @@ There is no CPU fallback: every operation needs the CUDA library and a GPU.
 from .error import ExactoError
 from .params import (BfvParams, BfvParamsBuilder, DbfvParams, RnsBasis, cfg3_prime_dbfv, compact_bfv,
                      compact_dbfv, compute_gadget_digits, set_default_device, small_bfv, u64_dbfv)
+from . import modular
 from .ring import CoeffPoly, NttPoly, Plan, RnsPoly, make_plan
 from .bfv import (BfvCiphertext, GaloisKey, RelinKey, bfv_add, bfv_apply_automorphism, bfv_apply_automorphism_batch,
                   bfv_inner_product, bfv_mul_and_relin, bfv_mul_and_relin_batch, bfv_mul_no_relin, bfv_mul_no_relin_batch,

@@ -180,3 +180,25 @@ def test_cpp_host_mirror_builds_and_links(native_lib):
     exe = g.build_cpp_driver()
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 2 and "usage" in res.stderr
+
+
+def test_modular_helpers_reference_kats():
+    """ring/modular.rs:127-205 restated on exacto_b200.modular (host scalars), plus agreement with the oracle."""
+    from exacto_b200 import modular as M
+    from common import O
+    m = 65537
+    bk = M.barrett_constant(m)
+    assert [M.barrett_reduce(a, m, bk) for a in (0, 1, m, m + 1, 123456789)] == [0, 1, 0, 1, 123456789 % m]
+    assert M.mod_mul(1234, 5678, m, bk) == 1234 * 5678 % m and M.mod_mul(0, 5678, m, bk) == 0 and M.mod_mul(1, 5678, m, bk) == 5678
+    assert M.mod_add(100, 200, m) == 300 and M.mod_add(m - 1, 2, m) == 1
+    assert M.mod_sub(200, 100, m) == 100 and M.mod_sub(100, 200, m) == m - 100
+    assert M.mod_neg(0, m) == 0 and M.mod_neg(1, m) == m - 1 and M.mod_add(100, M.mod_neg(100, m), m) == 0
+    assert M.mod_pow(2, 10, m) == 1024 and M.mod_pow(2, 16, m) == 65536 and M.mod_pow(3, 0, m) == 1
+    assert M.mod_mul(12345, M.mod_inv(12345, m), m, bk) == 1 and M.mod_inv(2, 4) is None
+    mi = M.montgomery_inv_neg(m)
+    assert (m * mi + 1) % (1 << 64) == 0 and M.montgomery_reduce(12345 * m, m, mi) == 0
+    q = 1152921504606830593
+    for a, b in [(q - 1, q - 2), (12345678901234567, 98765432109876543), (0, 7)]:
+        assert M.mod_mul(a, b, q) == O.mod_mul(a, b, q) and M.mod_add(a, b, q) == O.mod_add(a, b, q)
+        assert M.mod_sub(a, b, q) == O.mod_sub(a, b, q)
+    assert M.montgomery_reduce((q - 5) * (q - 7), q, M.montgomery_inv_neg(q)) == (q - 5) * (q - 7) * pow(1 << 64, -1, q) % q
