@@ -145,3 +145,20 @@ def test_prop_public_key_roundtrip(value, seed):            # bfv/encrypt.rs tes
     assert E.decode_scalar(E.decrypt(E.encrypt_pk_with_sampler(E.encode_scalar(m, P), pk, P, smp), sk)) == m
     assert E.dbfv_decrypt(E.dbfv_encrypt_with_sampler(value, pk, dp, smp), sk) == value
     assert E.dbfv_decrypt(E.dbfv_encrypt_sk_with_sampler(value, sk, dp, smp), sk) == value
+
+
+def test_dbfv_div_by_base_and_change_base():
+    """dbfv/advanced.rs:195-221: 48 / 16 = 3 with the plaintext modulus divided by the base; values survive a
+    change of base 16 -> 4 (4 digits)."""
+    dp = E.compact_dbfv()                                   # base 16, p = 256
+    smp = NpSampler(43)
+    sk = E.gen_secret_key_with_sampler(dp.bfv_params, smp)
+    ct = E.dbfv_encrypt_sk_with_sampler(48, sk, dp, smp)
+    div = E.dbfv_div_by_base(ct)
+    assert E.dbfv_decrypt(div, sk) == 3 and div.params.plain_modulus == 16
+    for value in [0, 1, 15, 42, 127, 255]:
+        ct = E.dbfv_encrypt_sk_with_sampler(value, sk, dp, smp)
+        b4 = E.dbfv_change_base(ct, 4, 4)
+        assert E.dbfv_decrypt(b4, sk) == value and b4.params.base == 4 and b4.num_limbs() == 4
+    with pytest.raises(E.ExactoError, match="new base must be >= 2"):
+        E.dbfv_change_base(ct, 1, 4)
