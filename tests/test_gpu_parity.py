@@ -758,3 +758,32 @@ def test_mul_no_relin_relinearize_gadget_decompose(preset):
         kat = to_params(O.OracleParams(n=16, q=65537, aux=(), plain_modulus=5, gadget_base=16))   # G = 5 for this q
         c = np.zeros(16, np.uint64); c[0] = 42
         assert [int(dg.coeffs[0]) for dg in E.gadget_decompose(E.CoeffPoly(c, 65537), kat)] == [65531, 3, 0, 0, 0]
+
+
+@pytest.mark.parametrize("name,base,d,p,gb", [("d4_b2^16", 1 << 16, 4, 34_359_738_367, 256), ("d16_b2^4", 1 << 4, 16, 12_289, 16)])
+def test_paper_repro_other_profiles(name, base, d, p, gb):
+    """The other two profiles of src/bin/paper_repro.rs:41-65 (the u64 profile is cfg 4): d = 4 with a 35-bit BFV
+    plaintext modulus, d = 16 with gadget base 16 (G = 15) -- small batch (per-product kernels) and a batch large
+    enough for the per-limb kernel where the plan allows it, vs the oracle; decrypt KAT 13579 * 24680 where the profile has the noise budget."""
+    from exacto_b200 import batch
+    P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=p, gadget_base=gb)
+    S = H.DbfvSetup(P, base, d, 0)
+    dp = to_dbfv_params(P, base, d, 0)
+    rng = np.random.default_rng(1337 + d)
+    s = H.gen_secret_key(P, rng)
+    rlk_arr = H.gen_relin_key(P, s, rng)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    ca, cb = H.dbfv_encrypt_sk(S, 13_579, s, rng), H.dbfv_encrypt_sk(S, 24_680, s, rng)
+    want = O.dbfv_mul(P, base, d, 0, ca, cb, rlk_arr, threads=O.max_threads())
+    got = E.dbfv_mul(E.DbfvCiphertext.from_array(ca, dp), E.DbfvCiphertext.from_array(cb, dp), rlk)
+    assert np.array_equal(got.to_array(), want)
+    if d == 16:      # the d = 4 profile has no noise budget for one multiplication (reports/paper_reproduction.md: depth 0)
+        assert H.dbfv_decrypt(S, got.to_array(), s) == 13_579 * 24_680
+    B = 40 if d == 4 else 6
+    ct1 = rng.integers(0, P.q, (B, d, 2, P.n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (B, d, 2, P.n), dtype=np.uint64)
+    ct1[1] = ca; ct2[1] = cb
+    outs = batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk))
+    assert np.array_equal(outs[1], want)
+    for i in (0, B - 1):
+        assert np.array_equal(outs[i], O.dbfv_mul(P, base, d, 0, ct1[i], ct2[i], rlk_arr, threads=O.max_threads()))
