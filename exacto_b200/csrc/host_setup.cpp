@@ -334,12 +334,12 @@ static void build_small_basis(HostSetup *c) {
     s.rq = (u32)((((u128)1) << (32 + s.sh)) / q);
     s.plain32 = (p < ((u64)1 << 32) && c->P.sc.plain_s < ((u64)1 << 32)) ? 1u : 0u;
     // tensor01_kernel sums the products of one output limb before the small-prime inverse transforms:
-    // cnt terms are exact while cnt*|m|max still leaves the alpha margin (2^5), cnt*q/2 fits an i64 with room
-    // and the summed rounding terms stay below q in magnitude.
+    // cnt terms are exact while cnt*|m|max still leaves the alpha margin (2^5), the sum of cnt centred residues
+    // (|.| <= cnt*q/2) fits an i64, and the summed rounding terms stay below q in magnitude.
     u32 mt = 0;
-    for (u32 cnt = 1; cnt <= 15; cnt++) {
+    for (u32 cnt = 1; cnt <= 16; cnt++) {
         if (prod < (mmax * cnt) << 5) break;
-        if ((u128)cnt * q >= ((u128)1 << 63)) break;
+        if ((u128)cnt * q >= ((u128)1 << 64)) break;
         if ((u128)cnt * (p / 2 + 2) >= q) break;
         mt = cnt;
     }

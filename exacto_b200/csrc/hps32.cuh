@@ -77,7 +77,7 @@ EXB_HD i64 round_term32_signed(u64 a, const ScaleConsts &c) {
 }
 
 // Sum over the products of one output limb (tensor01_kernel):
-//   rsum = sum_ij round(p a_ij / q) as a signed integer (|rsum| < q),  ssum = sum_ij a_ij (centred, |ssum| < 2^62),
+//   rsum = sum_ij round(p a_ij / q) as a signed integer (|rsum| < q),  ssum = sum_ij a_ij (centred, |ssum| < 2^63),
 //   bk[i] = (T mod p_i) * Kp_i mod p_i with T = sum_ij t_ij.  M = (T - ssum) / q = sum_ij m_ij, so
 //   out = rsum + p * M  (mod q)  =  sum_ij [ round(p a_ij / q) + p m_ij ]  (mod q).
 EXB_HD u64 hps_scale32_sum(i64 rsum, i64 ssum, const u32 *bk, const ScaleConsts &c, const Scale32Consts &s) {

@@ -789,7 +789,7 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 // and sum_ij m_ij = (T_k - sum_ij a_ij) / q with T_k = sum_ij t_ij is LINEAR in the tensor, so the
 // small-prime point-wise products are summed in the NTT domain and inverse-transformed once per limb
 // instead of once per product; only the base-q transform and the rounding term stay per product
-// (the rounding is the non-linear part).  Exact while cnt * q < 2^63 and P' >= 2^5 * cnt * |m|max
+// (the rounding is the non-linear part).  Exact while cnt * q < 2^64 and P' >= 2^5 * cnt * |m|max
 // (checked on the host: SmallBasis::max_terms).  Component 2 keeps the per-product kernel: its gadget
 // digits are a non-linear function of each product.
 // One CTA per (pair, two computed limbs, component in {0, 1}); output r01s [pair][limb][2][n], coefficient domain.
@@ -886,7 +886,7 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             }
         }
 #pragma unroll
-        for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // < 16 * 2p -> [0, 2p)
+        for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // <= 16 * 2p < 2^32 -> [0, 2p)
         sts_u32x8(bs + (size_t)pi * n, e0, acc);
     }
     if (K == 3) inv32_smK<3>(bs, P.sb);

@@ -326,3 +326,23 @@ def test_mul_no_relin_relinearize_gadget_decompose(emu, preset):
     coeffs[0, :6] = [0, 1, q - 1, q // 2, q // 2 + 1, 42]
     want_d = np.stack([O.gadget_decompose(c, q, P.gadget_base, P.gadget_digits) for c in coeffs])
     assert np.array_equal(emu.gadget_decompose(h, coeffs, P.gadget_digits), want_d)
+
+
+def test_per_limb_tensor_path_sixteen_digits(emu):
+    """d = 16 (paper_repro's third profile): limbs sum up to 16 products -- the largest count the exactness
+    conditions allow for a 60-bit q -- on inputs where every centred residue and every |t_ij| sits at its bound."""
+    P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=12289,
+                       gadget_base=16)
+    h = emu.from_oracle(P)
+    d = 16
+    assert emu.tensor_per_limb(h, 16, d, 0) == 1
+    q, n = P.q, P.n
+    rng = np.random.default_rng(16)
+    rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    half = O.ntt_fwd(np.full(n, q // 2, np.uint64), q)
+    a = np.stack([np.stack([half, half])] * d)
+    b = a.copy()
+    b[1::2] = rng.integers(0, q, (d // 2, 2, n), dtype=np.uint64)
+    want = O.dbfv_mul(P, 16, d, 0, a, b, rlk, threads=8)
+    rc, got, err = emu.dbfv_mul(h, 16, d, 0, a[None], b[None], rlk)
+    assert rc == 0 and np.array_equal(got[0], want), err
