@@ -400,8 +400,9 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
 
 // Run the pipeline for `pairs` pairs whose inputs/outputs are on the device.
 static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1,
-                     const u64 *ct2, u64 *out, size_t pairs, cudaStream_t stream) {
+                     const u64 *ct2, u64 *out, size_t pairs, cudaStream_t stream, bool pipelined = false) {
     DeviceParams P = c->P;
+    P.pipelined = pipelined ? 1u : 0u;
     const u32 G = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;   // keyswitch.rs:86-89
     P.gadget_digits = G;
     size_t eb, rb, db, xb;
@@ -536,7 +537,7 @@ extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
-        if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream))) return rc;
+        if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream, true))) return rc;
         EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
         off += cnt;
     }

@@ -39,7 +39,7 @@ struct DeviceParams {
     u32 gadget_digits;           // G (number of relin keys actually used)
     u64 gadget_base;             // B
     u32 gadget_log2;             // w if B == 2^w, else 0
-    u32 pad_;
+    u32 pipelined;               // host hint: this call's kernels share the GPU with other chunks' (multi-stream pipeline)
     Modulus mod[kMaxBases];      // [0] = q, [1..A] = aux primes
     const Tw *twf[kMaxBases];    // forward twiddles (psi_rev) per base
     const Tw *twi[kMaxBases];    // inverse twiddles (psi_inv_rev) per base

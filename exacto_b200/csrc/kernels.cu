@@ -1315,7 +1315,9 @@ bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs)
     if (worst > P.sb.max_terms) return false;
     // It pays when limbs sum several products (fewer small-prime inverse transforms) and the per-limb CTAs
     // (1..d products each) still fill the GPU; small batches keep the finer-grained per-product kernel.
-    return M.num_products > M.num_limbs && pairs * M.num_duos * 2 >= 148;
+    // measured crossover when the kernel has the GPU to itself: 24-28 pairs at d = 8 (~200 CTAs); chunks of the
+    // host pipeline overlap with their neighbours' kernels, which fill the SMs a short grid leaves idle
+    return M.num_products > M.num_limbs && pairs * M.num_duos * 2 >= (P.pipelined ? 100u : 200u);
 }
 
 // Small batches at n = 4096: one CTA per transform instead of one per output limb (relin12_wide_kernel).

@@ -686,7 +686,7 @@ def test_per_limb_tensor_path_on_gpu():
     P = S.bfv
     dp = E.u64_dbfv()
     rng = np.random.default_rng(2024)
-    B = 20                                              # 20 pairs x 8 limbs x 2 components = 320 CTAs >= 2 x 148
+    B = 26                                              # 26 pairs x 4 limb duos x 2 components = 208 CTAs: per-limb kernel
     ct1 = rng.integers(0, P.q, (B, S.d, 2, P.n), dtype=np.uint64)
     ct2 = rng.integers(0, P.q, (B, S.d, 2, P.n), dtype=np.uint64)
     half = O.ntt_fwd(np.full(P.n, P.q // 2, np.uint64), P.q)
@@ -779,7 +779,7 @@ def test_paper_repro_other_profiles(name, base, d, p, gb):
     assert np.array_equal(got.to_array(), want)
     if d == 16:      # the d = 4 profile has no noise budget for one multiplication (reports/paper_reproduction.md: depth 0)
         assert H.dbfv_decrypt(S, got.to_array(), s) == 13_579 * 24_680
-    B = 40 if d == 4 else 6
+    B = 52 if d == 4 else 13        # 52 x 2 duos x 2 = 208, 13 x 8 duos x 2 = 208 CTAs: the per-limb kernel
     ct1 = rng.integers(0, P.q, (B, d, 2, P.n), dtype=np.uint64)
     ct2 = rng.integers(0, P.q, (B, d, 2, P.n), dtype=np.uint64)
     ct1[1] = ca; ct2[1] = cb
