@@ -291,6 +291,22 @@ inline BfvCiphertext relinearize(const BfvCiphertext &ct, const RelinKey &rlk) {
     return detail::unflatten(out.data(), 2, ct.params);
 }
 
+struct SecretKey {                                   // bfv/keygen.rs:13-17: s in RNS-NTT form
+    RnsPoly poly;
+    std::shared_ptr<BfvParams> params;
+};
+
+// bfv/encrypt.rs:111-178: m = round(p (c0 + c1 s + c2 s^2 + ...) / q) mod p, any ciphertext degree.
+inline CoeffPoly decrypt(const BfvCiphertext &ct, const SecretKey &sk) {
+    std::vector<uint64_t> a;
+    detail::flatten(ct, a);
+    const size_t n = ct.params->ring_degree;
+    std::vector<uint64_t> out(n);
+    check(exb_bfv_decrypt_host(ct.params->context(), a.data(), (uint32_t)ct.c.size(), sk.poly.components.at(0).evals.data(),
+                               out.data(), 1));
+    return CoeffPoly{std::move(out), ct.params->plain_modulus};
+}
+
 inline BfvCiphertext bfv_apply_automorphism(const BfvCiphertext &ct, const GaloisKey &gk) {   // bfv/eval.rs:512-561
     if (ct.c.size() != 2)                                                                     // :516-520
         throw ExactoError(ExactoError::InvalidParam, "automorphism requires degree-1 ciphertext");

@@ -3,7 +3,7 @@
 //   in.bin : ct1 [d][2][n] | ct2 [d][2][n] | rlk [G][2][n]   (u64, NTT domain)
 //   out.bin: dbfv_mul limbs [d][2][n] | bfv_mul_and_relin(limb0, limb0) [2][n] | dbfv_add [d][2][n]
 //            | NTT round trip of ct1 limb 0 comp 0 [n] | dbfv_apply_automorphism(ct1, sigma_3 with rlk as key) [d][2][n]
-//            | bfv_trace(ct1 limb 0, {3}) [2][n]
+//            | bfv_trace(ct1 limb 0, {3}) [2][n] | decrypt(ct1 limb 0, sk = rlk[0][1]) [n]
 // Prints "guards ok" after checking the reference's error behaviour (dbfv/eval.rs:90-102, bfv/eval.rs:93-97).
 #include <cstdio>
 #include <cstring>
@@ -94,6 +94,9 @@ int main(int argc, char **argv) {
         out.write(reinterpret_cast<const char *>(back.coeffs.data()), (std::streamsize)(n * 8));
         for (const auto &l : rot.limbs) dump(l);
         dump(tr);
+        const SecretKey sk{make_ct(pk + n, 1, bfv).c[0], bfv};            // any NTT-domain polynomial serves as s here
+        const CoeffPoly dec = decrypt(a.limbs[0], sk);
+        out.write(reinterpret_cast<const char *>(dec.coeffs.data()), (std::streamsize)(n * 8));
         return ok ? 0 : 4;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -326,7 +326,8 @@ def test_cpp_host_mirror(preset, tmp_path):
     assert np.array_equal(out[off:off + P.n], O.ntt_inv(ct1[0, 0], P.q))
     rot = O.bfv_apply_automorphism(P, ct1, rlk, 3, threads=O.max_threads())
     assert np.array_equal(out[off + P.n:off + P.n + lim].reshape(S.d, 2, P.n), rot)
-    assert np.array_equal(out[off + P.n + lim:].reshape(2, P.n), O.bfv_add(P, ct1[0], rot[0]))
+    assert np.array_equal(out[off + P.n + lim:off + P.n + lim + 2 * P.n].reshape(2, P.n), O.bfv_add(P, ct1[0], rot[0]))
+    assert np.array_equal(out[off + P.n + lim + 2 * P.n:], H.decrypt(P, ct1[0], rlk[0, 1]))
 
 
 def test_device_api_chunk_loop():
