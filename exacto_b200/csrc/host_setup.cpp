@@ -160,6 +160,20 @@ static bool schoolbook_overflow_risk(u64 p, u64 q, u32 n) {   // bfv/eval.rs:457
     return mt > i128_max || ms > i128_max;
 }
 
+// The reference's guard bounds n*(q/2)^2 (and times p), but the middle tensor component c0*d1 + c1*d0 reaches
+// twice that: for 2*n*(q/2)^2*p > i128::MAX >= n*(q/2)^2*p its schoolbook branch wraps (release) or panics
+// (debug) on worst-case inputs, so there is no well-defined result to reproduce.  Found by tests/test_gpu_fuzz.py.
+static bool schoolbook_middle_term_overflow(u64 p, u64 q, u32 n) {
+    auto sat = [](u128 a, u128 b) -> u128 {
+        if (a == 0 || b == 0) return 0;
+        if (a > (~(u128)0) / b) return ~(u128)0;
+        return a * b;
+    };
+    const u128 i128_max = (~(u128)0) >> 1;
+    const u128 mc = q / 2, mt = sat(sat(sat((u128)n, mc), mc), 2), ms = sat(mt, (u128)p);
+    return mt > i128_max || ms > i128_max;
+}
+
 // The dispatch of bfv_mul_no_relin (bfv/eval.rs:89-108), evaluated once per parameter set.
 static void decide_mul_support(HostSetup *c) {
     const u32 A = (u32)c->aux_moduli.size();
@@ -174,8 +188,12 @@ static void decide_mul_support(HostSetup *c) {
         c->mul_error = schoolbook_overflow_risk(c->plain, q, c->n)
                            ? "schoolbook BFV multiplication can overflow i128 for these parameters; use HPS "
                              "auxiliary basis"
-                           : "schoolbook BFV multiplication (no auxiliary basis) is not provided by the device "
-                             "library; use HPS auxiliary basis";
+                           : schoolbook_middle_term_overflow(c->plain, q, c->n)
+                                 ? "schoolbook BFV multiplication overflows i128 in its middle tensor term for these "
+                                   "parameters (2*n*(q/2)^2*p > i128::MAX: the reference result is undefined); use "
+                                   "HPS auxiliary basis"
+                                 : "schoolbook BFV multiplication (no auxiliary basis) is not provided by the device "
+                                   "library for these parameters; use HPS auxiliary basis";
     } else if (A == 1 && (u128)c->aux_moduli[0] <= ((u128)c->n * q) / 2) {   // bfv/eval.rs:170-178
         c->mul_status = EXB_INVALID_PARAM;
         c->mul_error = "single aux prime too small for HPS centering: P=" + std::to_string(c->aux_moduli[0]) +
@@ -382,7 +400,8 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
     // so the rounding never ties), so the device synthesises two 61-bit NTT primes (P ~ 2^122 >> n*q) and runs
     // its HPS pipeline; tests compare it with the literal O(n^2) restatement.
     if (c->user_aux == 0 && c->ct_moduli.size() == 1 && n >= 2 && c->plain < c->ct_moduli[0] &&
-        !schoolbook_overflow_risk(c->plain, c->ct_moduli[0], n)) {
+        !schoolbook_overflow_risk(c->plain, c->ct_moduli[0], n) &&
+        !schoolbook_middle_term_overflow(c->plain, c->ct_moduli[0], n)) {
         const u64 step = 2ull * n, top = (u64)1 << 61;
         for (u64 cand = (top - 1) / step * step + 1; cand > top / 2 && c->aux_moduli.size() < 2; cand -= step)
             if (cand != c->ct_moduli[0] && h_is_prime(cand)) c->aux_moduli.push_back(cand);

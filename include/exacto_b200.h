@@ -148,8 +148,11 @@ void exb_relin_key_destroy(exb_relin_key *key);
  *   single-aux P <= n*q/2      -> EXB_INVALID_PARAM  "single aux prime too small for HPS centering..."
  *   more than 2 aux primes     -> EXB_INVALID_PARAM  "HPS scaling supports 1 or 2 aux primes..."
  *   no aux basis, i128 overflow-> EXB_NOT_IMPLEMENTED "schoolbook BFV multiplication can overflow i128..."
- *   no aux basis otherwise, or more than one ciphertext prime -> EXB_NOT_IMPLEMENTED (the
- *   reference's O(n^2) schoolbook / BigInt branches are outside the device path). */
+ *   no aux basis, 2*n*(q/2)^2*p > i128::MAX (the reference's guard misses the middle tensor term and its
+ *     convolution wraps)        -> EXB_NOT_IMPLEMENTED "...overflows i128 in its middle tensor term..."
+ *   no aux basis otherwise: the exact schoolbook result, computed by the HPS pipeline on an internal
+ *     auxiliary basis;
+ *   more than one ciphertext prime -> EXB_NOT_IMPLEMENTED (the reference's BigInt branch is outside the device path). */
 int exb_bfv_mul_and_relin(exb_context *ctx, const uint64_t *ct1_dev, const uint64_t *ct2_dev,
                           const exb_relin_key *rlk, uint64_t *out_dev, size_t batch, void *stream);
 int exb_bfv_mul_and_relin_host(exb_context *ctx, const uint64_t *ct1_host, const uint64_t *ct2_host,

@@ -346,3 +346,16 @@ def test_per_limb_tensor_path_sixteen_digits(emu):
     want = O.dbfv_mul(P, 16, d, 0, a, b, rlk, threads=8)
     rc, got, err = emu.dbfv_mul(h, 16, d, 0, a[None], b[None], rlk)
     assert rc == 0 and np.array_equal(got[0], want), err
+
+
+def test_schoolbook_middle_term_band_refused(emu):
+    """The band the reference's overflow guard misses (bfv/eval.rs:457-464 bounds n (q/2)^2 p, the middle tensor
+    term reaches twice that): refused, while the literal oracle wraps and the big-int definition does not."""
+    P = O.OracleParams(n=64, q=1152921504606844417, aux=(), plain_modulus=8, gadget_base=10)
+    h = emu.from_oracle(P)
+    info = emu.info(h)
+    assert info[2] == 9
+    rc, _, err = emu.dbfv_mul(h, 2, 1, 0, np.zeros((1, 1, 2, 64), np.uint64), np.zeros((1, 1, 2, 64), np.uint64),
+                              np.zeros((P.gadget_digits, 2, 64), np.uint64))
+    assert rc == 9 and "overflows i128 in its middle tensor term" in err
+    assert emu.info(emu.from_oracle(O.OracleParams(n=64, q=1152921504606844417, aux=(), plain_modulus=4, gadget_base=10)))[2] == 0

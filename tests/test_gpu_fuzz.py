@@ -2,6 +2,8 @@
 64-bit transforms), 0 / 1 / 2 auxiliary primes, plaintext modulus, power-of-two and general gadget bases, dBFV
 digit counts -- against the literal oracle: dbfv_mul (host and device entry points), automorphism + key switch,
 decrypt.  Deterministic (seeded); the parameter sets are derived, not hand-picked."""
+import os
+
 import numpy as np
 import pytest
 
@@ -28,9 +30,12 @@ def ntt_prime(bits: int, n: int, skip=()):
     raise AssertionError("no prime")
 
 
-def overflow_risk(p, q, n):                      # bfv/eval.rs:457-464
+def overflow_risk(p, q, n):
+    """bfv/eval.rs:457-464 with the factor 2 of the middle tensor term c0*d1 + c1*d0 that the reference's guard
+    leaves out: in the band n*(q/2)^2*p <= i128::MAX < 2*n*(q/2)^2*p its schoolbook branch wraps on worst-case
+    inputs (this fuzz found it: case 201 at EXB_FUZZ_CASES=300), so the device refuses those sets too."""
     mc = q // 2
-    mt = n * mc * mc
+    mt = 2 * n * mc * mc
     return mt > (1 << 127) - 1 or mt * p > (1 << 127) - 1
 
 
@@ -38,7 +43,7 @@ def make_cases():
     rng = np.random.default_rng(20241018)
     cases = []
     qbits = [20, 31, 36, 40, 47, 52, 55, 57, 59, 60, 61, 62]
-    for idx in range(36):
+    for idx in range(int(os.environ.get("EXB_FUZZ_CASES", "36"))):      # EXB_FUZZ_CASES=300 for a longer soak
         logn = int(rng.integers(4, 14))
         if idx % 6 == 0:
             logn = 12                                    # the tuned path gets its share
@@ -98,3 +103,21 @@ def test_fuzz_parameter_sets(case):
     s = rng.integers(0, q, n, dtype=np.uint64)
     got = E.decrypt_batch(params, flat[:2], E.SecretKey.from_ntt(s, params))
     assert np.array_equal(got, np.stack([H.decrypt(P, c, s) for c in flat[:2]]))
+
+
+def test_schoolbook_middle_term_band_is_refused():
+    """n = 64, 60-bit q, p = 8, no aux: the reference's overflow guard passes (n*(q/2)^2*p < 2^127) but its middle
+    tensor term needs 128 bits; the literal oracle wraps there while the exact result is what the device would
+    compute -- no defined reference result, so the parameter set is refused like the overflow-risk ones."""
+    P = O.OracleParams(n=64, q=1152921504606844417, aux=(), plain_modulus=8, gadget_base=10)
+    params = to_params(P)
+    z = np.zeros((1, 2, 64), np.uint64)
+    with pytest.raises(E.ExactoError, match="overflows i128 in its middle tensor term"):
+        E.bfv_mul_and_relin_batch(params, z, z, E.RelinKey(np.zeros((P.gadget_digits, 2, 64), np.uint64), params))
+    aux = (ntt_prime(61, 64, skip=(P.q,)), ntt_prime(60, 64, skip=(P.q,)))
+    P2 = O.OracleParams(n=64, q=P.q, aux=aux, plain_modulus=8, gadget_base=10)       # with an aux basis it multiplies
+    rng = np.random.default_rng(0)
+    a, b = rng.integers(0, P.q, (1, 2, 64), dtype=np.uint64), rng.integers(0, P.q, (1, 2, 64), dtype=np.uint64)
+    k = rng.integers(0, P.q, (P2.gadget_digits, 2, 64), dtype=np.uint64)
+    p2 = to_params(P2)
+    assert np.array_equal(E.bfv_mul_and_relin_batch(p2, a, b, E.RelinKey(k, p2)), O.bfv_mul_and_relin(P2, a, b, k))
