@@ -216,7 +216,7 @@ NO_AUX = {
     "boot_scheme": dict(P=O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8), dbfv=None),
     "boot_dbfv": dict(P=O.OracleParams(n=16, q=65537, aux=(), plain_modulus=97, gadget_base=8), dbfv=(4, 2, 16)),
     "n256_q40": dict(P=O.OracleParams(n=256, q=1099509805057, aux=(), plain_modulus=257), dbfv=(16, 2, 256)),
-    "n4096_q50": dict(P=O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=65537, gadget_base=256), dbfv=None),
+    "n4096_q50": dict(P=O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=257, gadget_base=256), dbfv=None),
 }
 
 

@@ -507,7 +507,7 @@ NO_AUX_GPU = {
     "boot_scheme": (O.OracleParams(n=16, q=1125899906842817, aux=(), plain_modulus=29, gadget_base=8), None),
     "boot_dbfv": (O.OracleParams(n=16, q=65537, aux=(), plain_modulus=97, gadget_base=8), (4, 2, 16)),
     "n1024_q40": (O.OracleParams(n=1024, q=1099509805057, aux=(), plain_modulus=257), (16, 2, 256)),
-    "n4096_q50": (O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=65537, gadget_base=256), None),
+    "n4096_q50": (O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=257, gadget_base=256), None),
 }
 
 
