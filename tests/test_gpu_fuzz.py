@@ -95,6 +95,10 @@ def test_fuzz_parameter_sets(case):
     want = np.stack([O.dbfv_mul(P, b, d, pm, x, y, karr, threads=O.max_threads()) for x, y in zip(ct1, ct2)])
     assert np.array_equal(E.dbfv_mul_batch(dp, ct1, ct2, rlk), want)
     assert np.array_equal(batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk)), want)
+    # the two halves on their own (limb 0 of each pair)
+    want3 = np.stack([O.bfv_mul_no_relin(P, x, y) for x, y in zip(ct1[:, 0], ct2[:, 0])])
+    assert np.array_equal(E.bfv_mul_no_relin_batch(params, ct1[:, 0], ct2[:, 0]), want3)
+    assert np.array_equal(E.relinearize_batch(params, want3, rlk), O.relinearize(P, want3, karr))
     # automorphism + key switch on the limbs of the first operand, decrypt of products under a random "key"
     k = int(rng.integers(1, n)) * 2 + 1
     flat = ct1.reshape(B * d, 2, n)
