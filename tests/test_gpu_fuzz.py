@@ -125,3 +125,41 @@ def test_schoolbook_middle_term_band_is_refused():
     k = rng.integers(0, P.q, (P2.gadget_digits, 2, 64), dtype=np.uint64)
     p2 = to_params(P2)
     assert np.array_equal(E.bfv_mul_and_relin_batch(p2, a, b, E.RelinKey(k, p2)), O.bfv_mul_and_relin(P2, a, b, k))
+
+
+@pytest.mark.parametrize("qb", [31, 36, 37, 40, 47, 52, 55, 56, 57, 59, 60, 61, 62])
+@pytest.mark.parametrize("A", [0, 2])
+def test_fuzz_n4096_prime_sizes(qb, A):
+    """The tuned n = 4096 kernels across every size class of q: below 2^36 (generic 64-bit aux path), 2^36 .. 2^60
+    (internal 27-bit basis; lazy classes 2 and 1 of the 64-bit transforms), above (exact Harvey class), with two
+    auxiliary primes and with none (internal basis / refused when the schoolbook branch could overflow)."""
+    from exacto_b200 import batch
+    n = 4096
+    q = ntt_prime(qb, n)
+    rng = np.random.default_rng(qb * 3 + A)
+    p = int(rng.integers(2, 1 << 16))
+    if A == 0 and overflow_risk(p, q, n):
+        params = to_params(O.OracleParams(n=n, q=q, aux=(), plain_modulus=p, gadget_base=256))
+        z = np.zeros((1, 2, n), np.uint64)
+        with pytest.raises(E.ExactoError, match="schoolbook BFV multiplication"):
+            E.bfv_mul_and_relin_batch(params, z, z, E.RelinKey(np.zeros((params.gadget_digits, 2, n), np.uint64), params))
+        return
+    aux = ()
+    if A == 2:
+        a0 = ntt_prime(int(rng.integers(52, 62)), n, skip=(q,))
+        aux = (a0, ntt_prime(int(rng.integers(52, 62)), n, skip=(q, a0)))
+    P = O.OracleParams(n=n, q=q, aux=aux, plain_modulus=p, gadget_base=[256, 1 << 16, 1000][qb % 3])
+    d, b = 3, 16
+    dp = to_dbfv_params(P, b, d, b ** d)
+    B = 2
+    ct1 = rng.integers(0, q, (B, d, 2, n), dtype=np.uint64)
+    ct2 = rng.integers(0, q, (B, d, 2, n), dtype=np.uint64)
+    half = O.ntt_fwd(np.full(n, q // 2, np.uint64), q)
+    ct1[0] = half; ct2[0] = half
+    karr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    rlk = E.RelinKey(karr, dp.bfv_params)
+    want = np.stack([O.dbfv_mul(P, b, d, b ** d, x, y, karr, threads=O.max_threads()) for x, y in zip(ct1, ct2)])
+    assert np.array_equal(E.dbfv_mul_batch(dp, ct1, ct2, rlk), want)
+    big1, big2 = np.tile(ct1, (40, 1, 1, 1)), np.tile(ct2, (40, 1, 1, 1))             # 80 pairs: the per-limb kernel
+    got = batch.to_host(batch.dbfv_mul(dp, batch.to_device(big1), batch.to_device(big2), rlk))
+    assert np.array_equal(got[:2], want) and np.array_equal(got[-2:], want)
