@@ -359,3 +359,15 @@ def test_schoolbook_middle_term_band_refused(emu):
                               np.zeros((P.gadget_digits, 2, 64), np.uint64))
     assert rc == 9 and "overflows i128 in its middle tensor term" in err
     assert emu.info(emu.from_oracle(O.OracleParams(n=64, q=1152921504606844417, aux=(), plain_modulus=4, gadget_base=10)))[2] == 0
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("EXB_RUN_TSAN"), reason="set EXB_RUN_TSAN=1 (builds with -fsanitize=thread, ~2 min)")
+def test_kernels_race_free_under_thread_sanitizer():
+    """compute-sanitizer racecheck is closed on the GPU pool: the kernels run on the host emulator under
+    ThreadSanitizer instead (tools/tsan_kernels.cpp); the self-test proves a missing barrier would be reported."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([os.path.join(root, "tools", "run_tsan.sh")], capture_output=True, text=True)
+    assert res.returncode == 0 and "ThreadSanitizer" not in res.stdout + res.stderr, res.stdout + res.stderr
+    st = subprocess.run(["/tmp/exb_tsan_kernels", "--selftest"], capture_output=True, text=True)
+    assert "ThreadSanitizer: data race" in st.stdout + st.stderr
