@@ -1,8 +1,8 @@
 """bootstrap/: the multiplication entry points north_star names (bootstrap/bfv_host.rs:242-288) and the
 bootstrap body they call, as a sequence of GPU primitives of this package:
 
-    bfv_bootstrap                bootstrap/bfv_host.rs:134-209   modulus switch (host integers), re-encryption of
-                                 the phase (point-wise kernels), CoeffsToSlots (automorphism + key-switch kernel,
+    bfv_bootstrap                bootstrap/bfv_host.rs:134-209   modulus switch (the decrypt kernel on a context with
+                                 plaintext modulus q'), re-encryption of the phase (point-wise kernels), CoeffsToSlots (automorphism + key-switch kernel,
                                  batched over the n shifted copies), rounding polynomial (batched
                                  Paterson-Stockmeyer over all slots: bfv_mul_and_relin), SlotsToCoeffs
     dbfv_bootstrap               bootstrap/bfv_host.rs:212-236   all limbs in one batch; params swap, mul_depth = 0
@@ -221,9 +221,21 @@ def gen_bootstrap_key_with_sampler(sk, boot_params: BfvParams, q_prime: int, t_o
                         rounding_poly=compute_rounding_poly(t_orig, q_prime, tb), t_orig=t_orig, q_prime=q_prime)
 
 
+_MODSWITCH_PARAMS: Dict[tuple, BfvParams] = {}
+
+
+def _modswitch_params(n: int, q: int, q_prime: int) -> BfvParams:
+    """Context (n, q, plaintext modulus q') whose decrypt kernel performs the modulus switch q -> q'."""
+    key = (n, q, q_prime)
+    if key not in _MODSWITCH_PARAMS:
+        from .params import BfvParamsBuilder
+        _MODSWITCH_PARAMS[key] = BfvParamsBuilder().ring_degree(n).plain_modulus(q_prime).ct_moduli([q]).build()
+    return _MODSWITCH_PARAMS[key]
+
+
 def _bootstrap_batch(orig: BfvParams, cts: np.ndarray, bsk: BootstrapKey) -> np.ndarray:
     """bfv_bootstrap on a batch [B][2][n] of degree-1 ciphertexts under ``orig`` -> [B][2][n] under the boot
-    parameters.  Everything except the modulus switch (exact host integers, :151-160) stays in HBM."""
+    parameters; every step runs on the GPU."""
     import torch
     from . import batch
     boot = bsk.boot_params
@@ -231,15 +243,18 @@ def _bootstrap_batch(orig: BfvParams, cts: np.ndarray, bsk: BootstrapKey) -> np.
     qb, tb = boot.ct_basis.moduli[0], boot.plain_modulus
     B = cts.shape[0]
     dev = batch.to_device(cts)
-    coeffs = batch.to_host(batch.ntt_inverse(orig, 0, dev))                      # :147-148
-    sw = np.array([[[((qp * int(v) + q // 2) // q) % qp % tb for v in poly] for poly in ct] for ct in coeffs],
-                  dtype=object)                                                  # :151-171
-    trivial = [not coeffs[b, 1].any() for b in range(B)]                         # :179
+    # modulus switch q -> q' (:147-171): c' = floor((q' c + floor(q/2)) / q) mod q' on the coefficients of c0 and c1.
+    # That is exactly the scale-and-round step of decrypt with plaintext modulus q' on a one-component
+    # "ciphertext", so the decrypt kernel does it (INTT + Shoup scale) on a context (n, q, p = q').
+    ms = _modswitch_params(n, q, qp)
+    zero_key = torch.zeros(n, dtype=torch.int64, device=dev.device)
+    sw = batch.bfv_decrypt(ms, dev.reshape(B * 2, 1, n), zero_key).reshape(B, 2, n)      # values in [0, q')
+    if tb < qp:
+        sw = torch.remainder(sw, tb)                                                       # `% t_boot` :163-171
+    trivial = [not cts[b, 1].any() for b in range(B)]                            # :179 (c1 = 0 iff its NTT is 0)
     delta = qb // tb
-    c0_scaled = np.array((sw[:, 0] % qb) * delta % qb, dtype=np.uint64)          # scale_plaintext
-    c1_red = np.array(sw[:, 1] % qb, dtype=np.uint64)
-    c0n = batch.ntt_forward(boot, 0, batch.to_device(c0_scaled))                 # [B][n]
-    c1n = batch.ntt_forward(boot, 0, batch.to_device(c1_red))
+    c0n = batch.ntt_forward(boot, 0, batch.poly_scalar_mul(boot, 0, sw[:, 0].contiguous(), delta))   # scale_plaintext
+    c1n = batch.ntt_forward(boot, 0, sw[:, 1].contiguous())
     bsk_dev = batch.to_device(np.broadcast_to(bsk.bsk.to_array(), (B, 2, n)).copy())
     c1n2 = torch.stack([c1n, c1n], dim=1).contiguous()
     phase = batch.poly_mul(boot, 0, bsk_dev, c1n2)                               # bfv_plain_mul(bsk, c1')  :174

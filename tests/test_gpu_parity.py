@@ -788,3 +788,28 @@ def test_paper_repro_other_profiles(name, base, d, p, gb):
     assert np.array_equal(outs[1], want)
     for i in (0, B - 1):
         assert np.array_equal(outs[i], O.dbfv_mul(P, base, d, 0, ct1[i], ct2[i], rlk_arr, threads=O.max_threads()))
+
+
+def test_bootstrap_fast_path_at_full_ring_degree():
+    """The bootstrap pipeline beyond the reference's toy scale: n = 4096, original scheme without an auxiliary basis
+    (50-bit q, t = 5), boot scheme = the u64 profile's primes with t_boot = 29, q' = 25.  Trivial ciphertexts take the
+    fast path (modulus switch, re-encryption under bsk, degree-28 rounding polynomial): decode to m, and equal the
+    oracle pipeline word for word."""
+    from oracle import bootstrap_ref as B
+    orig = O.OracleParams(n=4096, q=1125899906826241, aux=(), plain_modulus=5, gadget_base=256)
+    boot = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=29,
+                          gadget_base=256)
+    op, bp = to_params(orig), to_params(boot)
+    rng = np.random.default_rng(4096)
+    s = H.gen_secret_key(orig, rng)
+    boot_s = B.create_boot_sk(orig, boot, s)
+    s_pt = B._center_to(O.ntt_inv(s, orig.q), orig.q, boot.plain_modulus)
+    bk = B.BootstrapKeyRef(H.encrypt_sk(boot, s_pt, boot_s, rng), boot, H.gen_relin_key(boot, boot_s, rng), {},
+                           B.compute_rounding_poly(5, 25, 29), 5, 25)
+    pk = _product_bootstrap_key(bk, bp)
+    boot_sk = E.SecretKey.from_ntt(boot_s, bp)
+    for m in (0, 3, 4):
+        out = E.bfv_bootstrap(E.trivial_encrypt(m, op), pk)
+        assert E.decode_scalar(E.decrypt(out, boot_sk)) % 5 == m
+        if m == 3:
+            assert np.array_equal(out.to_array(), B.bfv_bootstrap(orig, H.trivial_encrypt(orig, m), bk))
