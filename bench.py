@@ -34,7 +34,8 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-PUBLISHED_MS_PER_DBFV_MUL = 31.395      # reports/paper_reproduction.md:9 (hardware unstated) -- anchor only
+PUBLISHED_MS_PER_DBFV_MUL = 31.395      # reports/paper_reproduction.md:9 = BASELINE.md section 1, target profile row
+PUBLISHED_DBFV_MUL_PER_S = 1000.0 / PUBLISHED_MS_PER_DBFV_MUL   # 31.9 dbfv_mul/s: unstated CPU, all cores (rayon)
 WORKLOAD = ("paper_repro u64 profile: dbfv_mul, n=4096, q=1152921504606830593 (60 bit), aux "
             "18014398509998081 & 36028797018972161, BFV p=1040407, gadget B=256 G=8, dBFV p=2^64 b=256 d=8")
 N, D, A, G = 4096, 8, 2, 8
@@ -151,7 +152,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "dbfv_mul_per_s", "value": value, "unit": "dbfv_mul/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_DBFV_MUL_PER_S, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{sample} dbfv_mul per step on one synthetic pair"},
         "cpu_baseline": {"value": value, "unit": "dbfv_mul/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} dbfv_mul per step x {args.steps} steps, all 64 products (reference schedule)"},
@@ -321,7 +322,8 @@ def run_gpu(args):
         line = {
             "metric": "dbfv_mul_per_s", "value": value, "unit": "dbfv_mul/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "strong" if args.kshard else "weak", "vs_baseline": None, "dtype": "u64",
+            "higher_is_better": True, "scaling": "strong" if args.kshard else "weak",
+            "vs_baseline": value / PUBLISHED_DBFV_MUL_PER_S, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs,
                        "parallelism": (f"output limbs sharded x{world} (limb_masks), one NCCL all_gather per step, same {pairs} pairs on every rank"
