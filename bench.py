@@ -9,10 +9,13 @@ pairs of the paper_repro u64 profile (BASELINE.json configs[3]: n=4096, q=115292
 aux 18014398509998081 & 36028797018972161, BFV p=1040407, B=256 -> G=8; dBFV p=2^64, b=256, d=8).
 Rank r of an N-GPU run owns its own `--pairs` pairs (weak scaling, no data-path collective).
 
-`value`  : dbfv_mul/s with inputs resident in HBM (CUDA events, max over ranks).
-`e2e`    : the same metric through the host-buffer C-ABI call (exb_dbfv_mul_host): pinned host
-           inputs -> H2D -> kernels -> D2H inside the timed region.
-`roofline`: the dominant kernel of the step (tensor+scale), algorithmic bytes / measured duration.
+`value`  : dbfv_mul/s with inputs resident in HBM (CUDA events, max over ranks), >= 1 s timed region.
+`e2e`    : the same metric through the host-buffer C-ABI call with page-locked host buffers:
+           H2D -> kernels -> D2H inside the timed region, calls pipelined with exb_dbfv_mul_host_async
+           (sub-records: one synchronous 148-pair call at a time, pageable memory, the measured PCIe bound).
+`roofline`: the dominant kernel of the step, SURVEY 8(d) algorithmic bytes / measured duration, plus the
+           integer (IMAD) roofline of the whole step.
+`verified`: pairs of the timed outputs (device-resident and e2e) compared word for word with the oracle.
 `ntt`    : batched forward / inverse NTT throughput at n=4096 with its HBM roofline fraction.
 `cpu_baseline`: oracle/exacto_oracle.c (C restatement of the reference's CPU schedule, OpenMP over
            the d^2 products like rayon) timed on this box's host cores on a bounded sample.
@@ -21,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import glob
 import json
 import os
 import statistics
@@ -39,9 +43,13 @@ PUBLISHED_DBFV_MUL_PER_S = 1000.0 / PUBLISHED_MS_PER_DBFV_MUL   # 31.9 dbfv_mul/
 WORKLOAD = ("paper_repro u64 profile: dbfv_mul, n=4096, q=1152921504606830593 (60 bit), aux "
             "18014398509998081 & 36028797018972161, BFV p=1040407, gadget B=256 G=8, dBFV p=2^64 b=256 d=8")
 N, D, A, G = 4096, 8, 2, 8
-# dram__bytes_read.sum + dram__bytes_write.sum of one tensor01_kernel launch at the default workload (148 pairs),
-# from profiles/r01_ncu_fused_kernels_final.json (ncu --set full on tools/prof.py mul 148)
-TENSOR01_DRAM_BYTES = 398925568 + 72187648
+CT_BYTES = D * 2 * N * 8                         # one dBFV ciphertext: 512 KiB
+ALGO_BYTES_PER_DBFV_MUL = 3 * CT_BYTES           # 2 x 512 KiB in + 512 KiB out = 1 572 864 B
+# modular multiplications of the minimal bit-exact schedule per dbfv_mul
+MODMULS_LIVE, MODMULS_ALL = 17.0e6, 29.0e6       # 36 live products / all 64 products
+# 32-bit multiplier work of one 60-bit Shoup modmul: 5 full (2 units) + 4 low (1 unit) 32x32 products
+IMAD_UNITS_PER_MODMUL = 14
+SMALL_CALL_PAIRS = 148
 
 
 def measured_peaks():
@@ -54,6 +62,43 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def imad_peak(sm_mhz, n_sms=148):
+    """32-bit IMAD.LO-equivalents per second: measured 0.5 warp instruction / clk / SMSP on the fmaheavy pipe
+    (profiles/r01_pipe_costs.json: mad.lo.u32 at 97 % pipe-busy = 98.6 % of that rate)."""
+    return n_sms * 4 * 0.5 * 32 * sm_mhz * 1e6
+
+
+def static_profile(kernel_prefix):
+    """ncu --set full figures of a kernel from the newest profiles/*ncu_fused* JSON (static: captured on an earlier
+    run of the same workload; the kernel name is matched and the capture's duration is printed beside the live one)."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_fused_kernels*.json"))):
+        try:
+            doc = json.load(open(path))
+        except Exception:
+            continue
+        for k in doc.get("kernels", []):
+            if k.get("Kernel Name", "").startswith(kernel_prefix):
+                best = (path, doc, k)
+    if best is None:
+        return None
+    path, doc, k = best
+
+    def num(key):
+        try:
+            return float(str(k[key]).split()[0])
+        except Exception:
+            return None
+    rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
+    unit = 1e6 if "Mbyte" in str(k.get("dram__bytes_read.sum", "")) else (1e9 if "Gbyte" in str(k.get("dram__bytes_read.sum", "")) else 1.0)
+    pairs = doc.get("pairs_per_launch", 148)
+    return {"source": "static: " + os.path.relpath(path, ROOT), "pairs_per_launch": pairs,
+            "duration_ms": num("gpu__time_duration.sum"),
+            "dram_bytes_per_pair": (rd + wr) * unit / pairs if rd is not None and wr is not None else None,
+            "fmaheavy_busy_frac": (num("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed") or 0) / 100.0,
+            "issue_active_frac": (num("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0) / 100.0}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -64,14 +109,13 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "10", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -102,6 +146,19 @@ def host_threads() -> int:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def fill_uniform(rng, out: np.ndarray, q: int):
+    """Uniform residues in [0, q) written into `out` (uint64, any shape) in slabs: 60 random bits and one
+    conditional subtraction (q = 2^60 - 2^14 + 1, so the fold touches a 2^-46 fraction and stays uniform enough
+    for a throughput workload)."""
+    flat = out.reshape(-1)
+    bits = q.bit_length()
+    step = 1 << 24
+    for lo in range(0, flat.size, step):
+        x = rng.integers(0, 1 << bits, min(step, flat.size - lo), dtype=np.uint64)
+        np.subtract(x, np.uint64(q), out=x, where=x >= np.uint64(q))
+        flat[lo:lo + x.size] = x
 
 
 def synth(seed: int, pairs: int, q: int):
@@ -153,7 +210,8 @@ def run_reference(args):
         "impl": "reference", "metric": "dbfv_mul_per_s", "value": value, "unit": "dbfv_mul/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": value / PUBLISHED_DBFV_MUL_PER_S, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample} dbfv_mul per step on one synthetic pair"},
+        "config": {"workload": WORKLOAD, "sample": f"{sample} dbfv_mul per step on one synthetic pair",
+                   "products_per_dbfv_mul": 64},
         "cpu_baseline": {"value": value, "unit": "dbfv_mul/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} dbfv_mul per step x {args.steps} steps, all 64 products (reference schedule)"},
         "e2e": {"value": value, "unit": "dbfv_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,73 +221,44 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def bind_to_gpu_numa_node(gpu_index: int):
-    """Pin this rank to the CPUs NVML reports as local to its GPU, so the pinned staging buffers of the e2e leg are
-    first-touched on the GPU's NUMA node (matters when several ranks share the host).  Best effort."""
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-    except Exception:
-        pass
-
-
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     import exacto_b200 as E
-    from exacto_b200 import _native, batch
+    from exacto_b200 import _native, batch, hostmem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    bind_to_gpu_numa_node(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        # NCCL's own INFO lines (communicator / NVLS evidence) go to a file per rank, stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "exb_nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     params = E.u64_dbfv()
     P = params.bfv_params
     q = P.modulus(0)
     pairs = args.pairs
-    ct1_h, ct2_h = synth(0xE8AC70 + rank, pairs, q)
-    rlk_arr = np.random.default_rng(0x51AB).integers(0, q, (G, 2, N), dtype=np.uint64)
-    rlk = E.RelinKey(rlk_arr, P)
-    ct1, ct2 = batch.to_device(ct1_h, dev), batch.to_device(ct2_h, dev)
-    out = torch.empty_like(ct1)
     ctx = P.context(local)
     L = _native.lib()
+    rlk_arr = np.random.default_rng(0x51AB).integers(0, q, (G, 2, N), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, P)
 
-    if args.kshard and world > 1:
-        # strong-scaling mode: every rank holds the SAME pairs, computes only its output limbs (products with
-        # equal i+j stay on one rank), then one NCCL all-gather of the limbs -- the path's only exchange step
-        from exacto_b200.sharding import limb_masks
-        ct1_h, ct2_h = synth(0xE8AC70, pairs, q)
-        ct1, ct2 = batch.to_device(ct1_h, dev), batch.to_device(ct2_h, dev)
-        out = torch.zeros_like(ct1)
-        masks = limb_masks(D, world)
-        my_limbs = [k for k in range(D) if (masks[rank] >> k) & 1]
-        owner = [next(r for r in range(world) if (masks[r] >> k) & 1) for k in range(D)]
-        gathered = [torch.empty_like(out) for _ in range(world)]
+    # Inputs live in page-locked host memory (exb_host_alloc); the device-resident leg uploads them once.
+    shape = (pairs, D, 2, N)
+    h1, h2 = hostmem.PinnedArray(ctx, shape), hostmem.PinnedArray(ctx, shape)
+    rng = np.random.default_rng(0xE8AC70 + rank)
+    fill_uniform(rng, h1.array, q)
+    fill_uniform(rng, h2.array, q)
+    ct1 = torch.from_numpy(h1.array.view(np.int64)).to(dev)
+    ct2 = torch.from_numpy(h2.array.view(np.int64)).to(dev)
+    out = torch.empty_like(ct1)
 
-        def step():
-            if masks[rank]:
-                batch.dbfv_mul(params, ct1, ct2, rlk, out=out, limb_mask=masks[rank])
-            dist.all_gather(gathered, out)
-            for k in range(D):
-                if owner[k] != rank:
-                    out[:, k].copy_(gathered[owner[k]][:, k])
-    else:
-        args.kshard = False
-
-        def step():
-            batch.dbfv_mul(params, ct1, ct2, rlk, out=out, all_products=args.all_products)
+    def step(all_products=False):
+        batch.dbfv_mul(params, ct1, ct2, rlk, out=out, all_products=all_products)
 
     def barrier():
         torch.cuda.synchronize()
@@ -237,120 +266,227 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_device(steps, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(**kw)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- device-resident leg ---------------------------------------------------------------------------
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     _native.check(L.exb_profile_enable(ctx.handle, 1))
     launches0 = batch.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = timed_device(args.steps)
     launches = batch.launch_count() - launches0
     stage_ms = (ctypes.c_double * 5)()
     stage_n = (ctypes.c_ulonglong * 5)()
     _native.check(L.exb_profile_read(ctx.handle, stage_ms, stage_n))
     _native.check(L.exb_profile_enable(ctx.handle, 0))
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = pairs * (1 if args.kshard else world) * args.steps / (elapsed_ms * 1e-3)
-    if args.kshard:       # verify the gathered result against a full local computation (outside the timed region)
-        full = batch.dbfv_mul(params, ct1, ct2, rlk)
-        torch.cuda.synchronize()
-        assert torch.equal(full, out), "k-sharded + all-gather result differs from the local dbfv_mul"
+    value = pairs * world * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H per step) -----------------------
-    e2e_pairs = min(pairs, args.e2e_pairs)
-    h1 = torch.from_numpy(ct1_h[:e2e_pairs].view(np.int64)).pin_memory()
-    h2 = torch.from_numpy(ct2_h[:e2e_pairs].view(np.int64)).pin_memory()
-    ho = torch.empty_like(h1).pin_memory()
-    flags = _native.EXB_DBFV_ALL_PRODUCTS if args.all_products else 0
+    # ---- verification of the timed output against the oracle (first / middle / last pair) -----------------
+    verify_idx = sorted({0, pairs // 2, pairs - 1})
+    want = {}
+    verified = {"pairs_checked": verify_idx, "device": None, "e2e": None}
+    if rank == 0 and not args.no_verify:
+        import oracle as O
+        from oracle import harness as H
+        S = H.u64_dbfv()
+        for i in verify_idx:
+            want[i] = O.dbfv_mul(S.bfv, S.base, S.d, S.plain_modulus, h1.array[i], h2.array[i], rlk_arr,
+                                 threads=host_threads())
+        got = out[verify_idx].cpu().numpy().view(np.uint64)
+        verified["device"] = all(np.array_equal(got[j], want[i]) for j, i in enumerate(verify_idx))
 
-    def e2e_step():
-        _native.check(L.exb_dbfv_mul_host(ctx.handle, params.base, D, params.plain_modulus, h1.data_ptr(),
-                                          h2.data_ptr(), rlk.native(ctx), ho.data_ptr(), e2e_pairs, flags))
+    # ---- like-for-like with the reference schedule: all 64 products ---------------------------------------
+    ap_steps = max(2, args.steps // 4)
+    step(all_products=True)
+    barrier()
+    ap_ms = timed_device(ap_steps, all_products=True)
+    ap_value = pairs * world * ap_steps / (ap_ms * 1e-3)
+    ap_ok = None
+    if rank == 0 and want:
+        got = out[verify_idx].cpu().numpy().view(np.uint64)
+        ap_ok = all(np.array_equal(got[j], want[i]) for j, i in enumerate(verify_idx))
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
+    # ---- e2e: host buffers through the C ABI, calls pipelined (H2D + kernels + D2H per step) ---------------
+    outs = [hostmem.PinnedArray(ctx, shape), hostmem.PinnedArray(ctx, shape)]
+
+    def e2e_run(steps, a1, a2, npairs, all_products=False):
+        """`steps` calls over the first `npairs` pairs, at most two in flight; returns (seconds, checksum)."""
+        check = 0
+        pend = None
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            nxt = hostmem.dbfv_mul_batch_async(params, a1[:npairs], a2[:npairs], rlk, outs[s & 1].array[:npairs],
+                                               all_products=all_products)
+            if pend is not None:
+                check ^= int(pend.wait()[0, 0, 0, 0])        # the D2H result is read on the host
+            pend = nxt
+        check ^= int(pend.wait()[0, 0, 0, 0])
+        return max_over_ranks(time.perf_counter() - t0), check
+
+    e2e_run(2, h1.array, h2.array, pairs)
+    e2e_s, checksum = e2e_run(args.steps, h1.array, h2.array, pairs)
+    e2e_value = pairs * world * args.steps / e2e_s
+    last_out = outs[(args.steps - 1) & 1].array
+    if rank == 0 and want:
+        verified["e2e"] = all(np.array_equal(last_out[i], want[i]) for i in verify_idx)
+    e2e_ap_s, _ = e2e_run(ap_steps, h1.array, h2.array, pairs, all_products=True)
+    e2e_ap_value = pairs * world * ap_steps / e2e_ap_s
+
+    small = min(SMALL_CALL_PAIRS, pairs)
+    small_steps = args.steps * 4
+    e2e_run(2, h1.array, h2.array, small)
+    s_async, _ = e2e_run(small_steps, h1.array, h2.array, small)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = e2e_pairs * world * args.steps / e2e_s
-    checksum = int(ho[0, 0, 0, :4].sum().item())          # D2H result actually read on the host
-    ct_bytes = D * 2 * N * 8
+    for _ in range(small_steps):                          # one synchronous call at a time (round 1's e2e configuration)
+        _native.check(L.exb_dbfv_mul_host(ctx.handle, params.base, D, params.plain_modulus, h1.array.ctypes.data,
+                                          h2.array.ctypes.data, rlk.native(ctx), outs[0].array.ctypes.data, small, 0))
+    s_sync = max_over_ranks(time.perf_counter() - t0)
+
+    # pageable memory (what a plain Vec<u64> is): bounded sample
+    pg_pairs = min(pairs, 592)
+    pg1, pg2 = np.array(h1.array[:pg_pairs]), np.array(h2.array[:pg_pairs])
+    pgo = np.empty_like(pg1)
+    for _ in range(2):
+        _native.check(L.exb_dbfv_mul_host(ctx.handle, params.base, D, params.plain_modulus, pg1.ctypes.data,
+                                          pg2.ctypes.data, rlk.native(ctx), pgo.ctypes.data, pg_pairs, 0))
+    barrier()
+    t0 = time.perf_counter()
+    pg_steps = 4
+    for _ in range(pg_steps):
+        _native.check(L.exb_dbfv_mul_host(ctx.handle, params.base, D, params.plain_modulus, pg1.ctypes.data,
+                                          pg2.ctypes.data, rlk.native(ctx), pgo.ctypes.data, pg_pairs, 0))
+    s_page = max_over_ranks(time.perf_counter() - t0)
+    pageable_ok = bool(np.array_equal(pgo[0], want[0])) if (rank == 0 and want) else None
+    del pg1, pg2, pgo
+
+    # PCIe / host-fabric bound of this box: the same bytes per step, copies only, all ranks at once
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    t_h1, t_h2 = torch.from_numpy(h1.array.view(np.int64)), torch.from_numpy(h2.array.view(np.int64))
+    t_ho = torch.from_numpy(outs[0].array.view(np.int64))
+
+    def copies(steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            with torch.cuda.stream(s_up):
+                ct1.copy_(t_h1, non_blocking=True); ct2.copy_(t_h2, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                t_ho.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    copies(1)
+    pcie_steps = max(2, args.steps // 2)
+    pcie_s = copies(pcie_steps)
+    pcie_bound = pairs * world * pcie_steps / pcie_s
+    h2d_gbs = 2 * pairs * CT_BYTES * world * pcie_steps / pcie_s / 1e9
+
+    # ---- k-sharded dbfv_mul (N > 1): one SMALL batch split by output limb across the ranks ---------------
+    kshard = None
+    if world > 1 and not args.no_kshard:
+        kshard = bench_kshard(torch, dist, E, batch, params, rlk, rlk_arr, q, dev, rank, world, args, value / world)
 
     line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
-        n_products = 64 if args.all_products else 36
-        n_limbs = 15 if args.all_products else 8
-        small = os.environ.get("EXB_AUX_BASIS") != "reference"
-        per_limb = small and stage_n[2] > 0          # tensor01_kernel (comps 0/1 per output limb) + per-product comp 2
-        # algorithmic bytes per pair of the dominant kernel: unique inputs (both operands in
-        # every base it reads) + its outputs
-        if not small:
-            in_bytes = 2 * D * 2 * (1 + A) * N * 8                      # q + two 64-bit aux bases
-        else:
-            in_bytes = 2 * D * 2 * N * 8 + 2 * D * 2 * 3 * N * 4        # q (u64) + three 27-bit internal primes (u32)
-        if per_limb:
-            kernel_name = ("tensor01_kernel (components 0/1 per output limb: per product point-wise tensor mod q + INTT + "
-                           "rounding term; per limb the summed 27-bit point-wise tensors, 3 INTT32 and the exact m recombination)")
-            tensor_bytes = in_bytes + n_limbs * 2 * N * 8
-        else:
-            kernel_name = ("tensor32_kernel" if small else "tensor_kernel") + " (per product and component: point-wise tensor, INTTs, hps_scale, gadget digits)"
-            tensor_bytes = in_bytes + n_products * (2 * N * 8 + G * N * 2)
-        t_ms = stage_ms[1] / max(stage_n[1], 1)
-        achieved = tensor_bytes * pairs / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
-        stages = {nm: {"ms_per_launch": stage_ms[i] / max(stage_n[i], 1), "launches": int(stage_n[i])}
-                  for i, nm in enumerate(["lift", "tensor01_per_limb" if per_limb else "tensor_scale", "tensor_c2_per_product",
-                                          "relin", "reduce"]) if stage_n[i]}
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        ipeak = imad_peak(sm_mhz)
+        per_limb = stage_n[2] > 0          # tensor01_kernel (comps 0/1 per output limb) + per-product comp 2
+        names = ["lift", "tensor01_per_limb" if per_limb else "tensor_scale", "tensor_c2_per_product", "relin", "reduce"]
+        stages = {nm: {"ms_per_step": stage_ms[i] / max(args.steps, 1), "launches": int(stage_n[i])}
+                  for i, nm in enumerate(names) if stage_n[i]}
         total_stage = sum(stage_ms[i] for i in range(5)) or 1.0
+        dom = max(range(5), key=lambda i: stage_ms[i])
+        dom_kernel = {"lift": "lift32_kernel", "tensor01_per_limb": "tensor01_kernel", "tensor_scale": "tensor32_kernel",
+                      "tensor_c2_per_product": "tensor32_kernel", "relin": "relin12_kernel", "reduce": "reduce_mac_kernel"}[names[dom]]
+        dom_ms_per_step = stage_ms[dom] / max(args.steps, 1)
+        pairs_per_launch = pairs * args.steps / max(stage_n[dom], 1)
+        achieved = ALGO_BYTES_PER_DBFV_MUL * pairs / (dom_ms_per_step * 1e-3) / 1e9 if dom_ms_per_step > 0 else 0.0
+        prof = static_profile(dom_kernel)
+        traffic = None
+        if prof and prof["dram_bytes_per_pair"]:
+            traffic = prof["dram_bytes_per_pair"] * pairs_per_launch
+        int_units = MODMULS_LIVE * IMAD_UNITS_PER_MODMUL
         line = {
             "metric": "dbfv_mul_per_s", "value": value, "unit": "dbfv_mul/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "strong" if args.kshard else "weak",
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / PUBLISHED_DBFV_MUL_PER_S, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs,
-                       "parallelism": (f"output limbs sharded x{world} (limb_masks), one NCCL all_gather per step, same {pairs} pairs on every rank"
-                                       if args.kshard else f"pairs sharded x{world}, no collective"),
-                       "products_per_dbfv_mul": n_products,
-                       "dead_products": "computed (reference schedule)" if args.all_products else
-                       "skipped (28 of 64 products feed limbs k>=d that reduce() discards; output bit-identical)",
-                       "l2": f"inputs+outputs {3 * pairs * ct_bytes / 2**20:.0f} MiB + workspace > 126 MB L2 per step"},
+                       "parallelism": f"pairs sharded x{world}, no collective",
+                       "products_per_dbfv_mul": 36,
+                       "dead_products": "skipped (28 of 64 products feed limbs k>=d that reduce() discards; output "
+                                        "bit-identical); the `all_products` record runs the reference's 64",
+                       "timed_region_s": elapsed_ms * 1e-3,
+                       "l2": f"inputs+outputs {3 * pairs * CT_BYTES / 2**20:.0f} MiB + workspace per step: larger than the 126 MB L2"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "dbfv_mul/s", "h2d_bytes_per_step": 2 * e2e_pairs * ct_bytes,
-                    "d2h_bytes_per_step": e2e_pairs * ct_bytes, "pairs_per_step": e2e_pairs, "result_checksum": checksum},
+            "verified": bool(verified["device"]) and bool(verified["e2e"]) if not args.no_verify else None,
+            "verification": dict(verified, all_products=ap_ok, pageable=pageable_ok,
+                                 against="oracle/exacto_oracle.c dbfv_mul, word for word"),
+            "e2e": {"value": e2e_value, "unit": "dbfv_mul/s", "h2d_bytes_per_step": 2 * pairs * CT_BYTES,
+                    "d2h_bytes_per_step": pairs * CT_BYTES, "pairs_per_step": pairs, "result_checksum": checksum,
+                    "api": "exb_dbfv_mul_host_async + exb_wait, page-locked buffers from exb_host_alloc, two calls in flight",
+                    "pcie_bound": pcie_bound, "pcie_h2d_gbs": h2d_gbs,
+                    "frac_of_bound": e2e_value / min(value, pcie_bound),
+                    "bound_note": "pcie_bound = the same H2D + D2H bytes per step with no kernels, all ranks at once",
+                    "all_products": e2e_ap_value,
+                    "calls_of_148_pairs_async": small * world * small_steps / s_async,
+                    "calls_of_148_pairs_sync": small * world * small_steps / s_sync,
+                    "pageable": pg_pairs * world * pg_steps / s_page},
+            "all_products": {"value": ap_value, "products_per_dbfv_mul": 64, "steps": ap_steps, "same_output": ap_ok,
+                             "e2e": e2e_ap_value},
             "gpu_launches": int(launches),
             "bfv_mul_and_relin_equiv_per_s": value * 64,
-            "roofline": {"kernel": kernel_name,
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": dom_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None,
-                         "traffic": (TENSOR01_DRAM_BYTES if (pairs == 148 and per_limb and not args.all_products) else None),
-                         "algorithmic_bytes": tensor_bytes * pairs,
-                         "peak_source": peak_src, "share_of_step": stage_ms[1] / total_stage,
-                         "note": "integer-pipe bound kernel: see DESIGN.md; HBM fraction is reported, not the target",
-                         # what actually bounds it (ncu --set full of this kernel at this workload,
-                         # profiles/r01_ncu_fused_kernels_final.json): the integer-multiply pipe
-                         "binding_pipe": ({"metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
-                                           "busy_frac": 0.523, "issue_active_frac": 0.502} if per_limb else None)},
+                         "traffic": traffic,
+                         "traffic_source": (prof["source"] + f" ({prof['pairs_per_launch']} pairs/launch, {prof['duration_ms']} ms) scaled to "
+                                            f"{pairs_per_launch:.0f} pairs/launch") if prof else None,
+                         "algorithmic_bytes": ALGO_BYTES_PER_DBFV_MUL * pairs_per_launch,
+                         "algorithmic_bytes_per_unit": ALGO_BYTES_PER_DBFV_MUL,
+                         "peak_source": peak_src, "share_of_step": stage_ms[dom] / total_stage,
+                         "ms_per_step": dom_ms_per_step,
+                         "note": "SURVEY 8(d) bytes (2 x 512 KiB in + 512 KiB out per dbfv_mul) over the dominant kernel's time; "
+                                 "the kernel is integer-pipe bound (see `integer`), the HBM fraction is reported, not the target",
+                         "whole_step_frac": ALGO_BYTES_PER_DBFV_MUL * value / world / 1e9 / peak,
+                         "integer": {"bound": "imad", "unit": "32-bit IMAD.LO-equivalents/s",
+                                     "peak": ipeak, "peak_source": f"148 SMs x 4 SMSP x 0.5 warp-instr/clk x 32 lanes x {sm_mhz:.0f} MHz "
+                                                                   "(profiles/r01_pipe_costs.json: mad.lo.u32 reaches 98.6 % of it)",
+                                     "modmuls_per_dbfv_mul": MODMULS_LIVE, "imad_units_per_modmul": IMAD_UNITS_PER_MODMUL,
+                                     "achieved": int_units * value / world,
+                                     "frac": int_units * value / world / ipeak,
+                                     "all_products_frac": MODMULS_ALL * IMAD_UNITS_PER_MODMUL * ap_value / world / ipeak,
+                                     "note": "SURVEY 8(d): modmuls of the minimal bit-exact schedule (17 M with dead products skipped, "
+                                             "29 M with all 64) x dbfv_mul/s x 14 multiplier units of a 60-bit Shoup modmul / IMAD peak; the "
+                                             "27-bit internal basis does part of that work with cheaper multiplies",
+                                     "pipe_busy": ({"metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                                                    "busy_frac": prof["fmaheavy_busy_frac"], "issue_active_frac": prof["issue_active_frac"],
+                                                    "source": prof["source"]} if prof else None)}},
             "stages": stages,
             "published_anchor_ms_per_dbfv_mul": PUBLISHED_MS_PER_DBFV_MUL,
         }
+        if kshard is not None:
+            line["kshard"] = kshard
         if not args.no_ntt:
             line["ntt"] = bench_ntt(torch, batch, P, peak, peak_src, args)
             line["widened"] = bench_widened(torch, batch, P, peak, args)
@@ -378,6 +514,42 @@ def run_gpu(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def bench_kshard(torch, dist, E, batch, params, rlk, rlk_arr, q, dev, rank, world, args, single_gpu_value):
+    """Strong scaling of ONE 148-pair batch: every rank holds the same pairs, owns disjoint output limbs k
+    (products with equal i+j stay on one rank, dbfv/eval.rs:109-136) and the relinearisation epilogue stores
+    each finished limb straight into every peer's output over NVLink (exacto_b200.sharding.KShard)."""
+    from exacto_b200.sharding import KShard
+    kp = SMALL_CALL_PAIRS
+    ct1_h, ct2_h = synth(0xE8AC70, kp, q)
+    a, b = batch.to_device(ct1_h, dev), batch.to_device(ct2_h, dev)
+    ks = KShard(params, kp, dev)
+    for _ in range(3):
+        res = ks.mul(a, b, rlk)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    steps = max(args.steps * 4, 20)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        res = ks.mul(a, b, rlk)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    full = batch.dbfv_mul(params, a, b, rlk)
+    torch.cuda.synchronize()
+    ok = torch.tensor([1 if torch.equal(full, res) else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    value = kp * steps / (ms * 1e-3)
+    rec = {"value": value, "unit": "dbfv_mul/s", "scaling": "strong", "pairs": kp, "steps": steps, "ms_per_step": ms / steps,
+           "transport": ks.transport, "limb_masks": ks.masks,
+           "bytes_on_wire_per_dbfv_mul_per_rank": ks.wire_bytes_per_pair_per_rank(),
+           "ideal_bytes_per_rank": CT_BYTES * (world - 1) / world,
+           "verified": bool(int(ok.item())), "single_gpu_same_batch_value": None}
+    ks.close()
+    return rec
 
 
 def bench_ntt(torch, batch, P, peak, peak_src, args):
@@ -442,19 +614,18 @@ def bench_widened(torch, batch, P, peak, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="exacto_b200", choices=["exacto_b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=148, help="ciphertext pairs per GPU per step")
-    ap.add_argument("--e2e-pairs", type=int, default=148)
-    ap.add_argument("--all-products", action="store_true", help="compute all 64 products like the reference")
+    ap.add_argument("--pairs", type=int, default=20 * 148,
+                    help="ciphertext pairs per GPU per step (20 x 148: a 20-step timed region lasts > 1 s)")
     ap.add_argument("--ntt-count", type=int, default=16384)
     ap.add_argument("--ntt-reps", type=int, default=10)
     ap.add_argument("--cpu-trials", type=int, default=20)
-    ap.add_argument("--kshard", action="store_true",
-                    help="N>1: shard ONE batch by output limb + NCCL all-gather (strong scaling) instead of sharding pairs")
+    ap.add_argument("--no-kshard", action="store_true", help="N>1: skip the k-sharded strong-scaling record")
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

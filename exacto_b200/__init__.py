@@ -33,6 +33,7 @@ from .encrypt import (SecretKey, decode_scalar, decrypt, decrypt_batch, dbfv_dec
 from .keygen import (PublicKey, apply_automorphism, gen_galois_key_with_sampler, gen_public_key_with_sampler,
                      gen_relin_key_with_sampler, gen_secret_key_with_sampler)
 from .advanced import dbfv_change_base, dbfv_div_by_base
+from .hostmem import PendingMul, PinnedArray, dbfv_mul_batch_async, pinned_empty
 from .bootstrap import (BootstrapKey, bfv_bootstrap, bfv_monomial_mul, coeffs_to_slots, compute_rounding_poly,
                         create_boot_sk, dbfv_bootstrap, dbfv_mul_chain_then_bootstrap, dbfv_mul_then_bootstrap,
                         eval_poly_homomorphic, eval_poly_homomorphic_batch, extract_coefficient,

@@ -34,7 +34,14 @@ SYMBOLS = {
     "exb_last_error": (ctypes.c_char_p, []),
     "exb_version": (ctypes.c_char_p, []),
     "exb_context_create": (ctypes.c_int, [ctypes.POINTER(BfvParamsC), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "exb_context_create_ex": (ctypes.c_int, [ctypes.POINTER(BfvParamsC), ctypes.c_int, c_u32, ctypes.POINTER(c_vp)]),
     "exb_context_destroy": (None, [c_vp]),
+    "exb_context_set_option": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int64]),
+    "exb_ntt_format_id": (ctypes.c_int, [c_vp, c_u32, ctypes.POINTER(c_u64)]),
+    "exb_host_alloc": (ctypes.c_int, [c_vp, c_sz, ctypes.POINTER(c_vp)]),
+    "exb_host_free": (ctypes.c_int, [c_vp, c_vp]),
+    "exb_host_register": (ctypes.c_int, [c_vp, c_vp, c_sz]),
+    "exb_host_unregister": (ctypes.c_int, [c_vp, c_vp]),
     "exb_context_gadget": (ctypes.c_int, [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u32)]),
     "exb_context_psi": (ctypes.c_int, [c_vp, c_u32, ctypes.POINTER(c_u64)]),
     "exb_launch_count": (ctypes.c_ulonglong, []),
@@ -69,10 +76,14 @@ SYMBOLS = {
     "exb_bfv_apply_automorphism_host": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint64, c_vp, c_vp, c_sz]),
     "exb_dbfv_mul": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, c_sz, c_u32, c_u32, c_vp]),
     "exb_dbfv_mul_host": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, c_sz, c_u32]),
+    "exb_dbfv_mul_host_async": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, c_sz, c_u32, ctypes.POINTER(c_u64)]),
+    "exb_bfv_mul_and_relin_host_async": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, ctypes.POINTER(c_u64)]),
+    "exb_wait": (ctypes.c_int, [c_vp, c_u64]),
     "exb_dbfv_small_reps": (ctypes.c_int, [c_u64, c_u32, c_u64, c_vp]),
 }
 
 EXB_DBFV_ALL_PRODUCTS = 1
+EXB_CTX_REFERENCE_AUX_BASIS = 1
 
 _lib = None
 

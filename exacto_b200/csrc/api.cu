@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/exacto_b200.h"
@@ -40,17 +41,23 @@ static int fail(int code, const std::string &msg) {
 // ---------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------
-static const int kSlots = 3;
+// Workspace slots.  Device-resident entry points take a slot of the `ws` pool for the duration of their
+// enqueue (two host threads on two streams get two slots and overlap on the host and on the GPU); the
+// host-buffer pipeline owns the `hs` slots, each with its own stream and staging buffers.
+static const int kSlots = 4;
+static const int kHostSlots = 4;
 
 struct Workspace {
-    cudaStream_t stream = nullptr;
+    std::mutex mu;                                        // held while a call enqueues work that uses the slot
+    cudaStream_t stream = nullptr;                        // host pipeline slots only (owned)
+    cudaEvent_t done = nullptr;                           // recorded after the last launch that used the slot
+    const void *last_tag = nullptr;                       // stream handle of that work: compared, never dereferenced
+    bool used = false;
     u64 *ext = nullptr, *r01 = nullptr, *excess = nullptr, *wide = nullptr;
     void *digits = nullptr;
     size_t ext_b = 0, r01_b = 0, excess_b = 0, digits_b = 0, wide_b = 0;
     u64 *in1 = nullptr, *in2 = nullptr, *out = nullptr;   // staging for the *_host entry points
     size_t in_b = 0, out_b = 0;
-    cudaStream_t last = nullptr;                          // stream of the work that used this slot last
-    bool used = false;
 };
 
 struct StageEvents {
@@ -58,22 +65,59 @@ struct StageEvents {
     bool has_reduce, has_c2;
 };
 
+// One asynchronous host-buffer call in flight: the events that mark its last chunk on every slot it used.
+struct Ticket {
+    std::vector<cudaEvent_t> events;
+};
+
+struct Tuning {                                           // exb_context_set_option
+    size_t device_chunk_bytes = (size_t)4 << 30;          // workspace budget of one device-resident chunk
+    size_t host_chunk_products = 1024;                    // products per chunk of the host-buffer pipeline
+};
+
 struct exb_context : HostSetup {
     int device = 0;
     bool profiling = false;
-    std::vector<StageEvents> events;
+    Tuning tune;
     std::vector<Tw *> d_tables;       // owned device twiddle tables
-    Workspace ws[kSlots];
-    // Entry points that touch the workspaces are serialised per context (the reference's functions are
-    // re-entrant; callers may share one context between host threads).
-    std::recursive_mutex mu;
+    Workspace ws[kSlots];             // device-resident calls
+    Workspace hs[kHostSlots];         // host-buffer pipeline
+    std::mutex mu;                    // slot selection, profiling record, tickets
+    std::mutex host_mu;               // one host-buffer call enqueues at a time (its chunks stay in order)
+    std::vector<StageEvents> events;
+    unsigned rr = 0, host_rr = 0;
+    uint64_t next_ticket = 1;
+    std::unordered_map<uint64_t, Ticket> tickets;
 };
 
-// A workspace slot is reused by work on another stream only after the earlier work has finished.
-static int claim(Workspace &w, cudaStream_t stream) {
-    if (w.used && w.last != stream) EXB_CUDA(cudaStreamSynchronize(w.last));
-    w.last = stream;
-    w.used = true;
+// Take a workspace slot for work that is about to be enqueued on `stream`: the slot this stream used last if it
+// is free, else any free slot, else wait for one.  Work left in the slot by ANOTHER stream is ordered before the
+// new work with the slot's own event (cudaStreamWaitEvent): no host blocking, and a user stream that has since
+// been destroyed is never touched.
+static int acquire(exb_context *c, cudaStream_t stream, std::unique_lock<std::mutex> *held, Workspace **out) {
+    Workspace *w = nullptr;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (int pass = 0; pass < 2 && !w; pass++)
+            for (int i = 0; i < kSlots && !w; i++) {
+                Workspace &cand = c->ws[(c->rr + i) % kSlots];
+                if (pass == 0 && !(cand.used && cand.last_tag == (const void *)stream)) continue;
+                std::unique_lock<std::mutex> l(cand.mu, std::try_to_lock);
+                if (l.owns_lock()) { *held = std::move(l); w = &cand; }
+            }
+        if (!w) w = &c->ws[c->rr++ % kSlots];
+    }
+    if (!held->owns_lock()) *held = std::unique_lock<std::mutex>(w->mu);
+    if (w->used && w->last_tag != (const void *)stream) EXB_CUDA(cudaStreamWaitEvent(stream, w->done, 0));
+    *out = w;
+    return EXB_OK;
+}
+
+// The slot's work has been enqueued on `stream`.
+static int release(Workspace *w, cudaStream_t stream) {
+    EXB_CUDA(cudaEventRecord(w->done, stream));
+    w->last_tag = (const void *)stream;
+    w->used = true;
     return EXB_OK;
 }
 
@@ -106,28 +150,35 @@ static int grow_in2_out(Workspace &w, size_t want) {
 
 extern "C" const char *exb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *exb_version(void) { return "exacto_b200 0.1 (sm_100a)"; }
-extern "C" unsigned long long exb_launch_count(void) { return exb::g_launch_count; }
+extern "C" unsigned long long exb_launch_count(void) { return exb::g_launch_count.load(std::memory_order_relaxed); }
+
+static void free_workspace(Workspace &w) {
+    cudaFree(w.ext); cudaFree(w.r01); cudaFree(w.excess); cudaFree(w.digits); cudaFree(w.wide);
+    cudaFree(w.in1); cudaFree(w.in2); cudaFree(w.out);
+    if (w.done) cudaEventDestroy(w.done);
+    if (w.stream) cudaStreamDestroy(w.stream);
+}
 
 extern "C" void exb_context_destroy(exb_context *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
     for (StageEvents &se : c->events) for (auto &e : se.ev) cudaEventDestroy(e);
+    for (auto &kv : c->tickets) for (cudaEvent_t e : kv.second.events) cudaEventDestroy(e);
     for (Tw *t : c->d_tables) cudaFree(t);
-    for (Workspace &w : c->ws) {
-        cudaFree(w.ext); cudaFree(w.r01); cudaFree(w.excess); cudaFree(w.digits); cudaFree(w.wide);
-        cudaFree(w.in1); cudaFree(w.in2); cudaFree(w.out);
-        if (w.stream) cudaStreamDestroy(w.stream);
-    }
+    for (Workspace &w : c->ws) free_workspace(w);
+    for (Workspace &w : c->hs) free_workspace(w);
     delete c;
 }
 
-extern "C" int exb_context_create(const exb_bfv_params *p, int device, exb_context **out) {
+extern "C" int exb_context_create_ex(const exb_bfv_params *p, int device, uint32_t flags, exb_context **out) {
     if (!p || !out) return fail(EXB_INVALID_PARAM, "null argument");
     *out = nullptr;
+    if (flags & ~(uint32_t)EXB_CTX_REFERENCE_AUX_BASIS) return fail(EXB_INVALID_PARAM, "unknown context flag");
     exb_context *c = new exb_context();
     c->device = device;
     std::string err;
-    int rc = host_setup_build(p, c, &err);
+    int rc = host_setup_build(p, c, &err, flags);
     if (rc != EXB_OK) { delete c; return fail(rc, err); }
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) {
@@ -162,11 +213,35 @@ extern "C" int exb_context_create(const exb_bfv_params *p, int device, exb_conte
         c->P.sb.twf[i] = df; c->P.sb.twi[i] = di;
     }
     for (Workspace &w : c->ws)
-        if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) != cudaSuccess) {
+            exb_context_destroy(c);
+            return fail(EXB_CUDA_ERROR, "cudaEventCreate failed");
+        }
+    for (Workspace &w : c->hs)
+        if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) != cudaSuccess) {
             exb_context_destroy(c);
             return fail(EXB_CUDA_ERROR, "cudaStreamCreate failed");
         }
+    launch_prepare(device);
     *out = c;
+    return EXB_OK;
+}
+
+extern "C" int exb_context_create(const exb_bfv_params *p, int device, exb_context **out) {
+    return exb_context_create_ex(p, device, 0, out);
+}
+
+// Tuning knobs (tests and lab sweeps use them; the defaults are the measured optimum).
+extern "C" int exb_context_set_option(exb_context *c, const char *name, int64_t value) {
+    if (!c || !name) return fail(EXB_INVALID_PARAM, "null argument");
+    std::lock_guard<std::mutex> g(c->mu);
+    const std::string k(name);
+    if (k == "device_chunk_bytes" && value > 0) c->tune.device_chunk_bytes = (size_t)value;
+    else if (k == "host_chunk_products" && value > 0) c->tune.host_chunk_products = (size_t)value;
+    else if (k == "tensor_per_product") c->P.tensor_per_product = value ? 1u : 0u;
+    else if (k == "relin_narrow") c->P.relin_narrow = value ? 1u : 0u;
+    else return fail(EXB_INVALID_PARAM, "unknown option or value out of range: " + k);
     return EXB_OK;
 }
 
@@ -178,9 +253,13 @@ extern "C" int exb_profile_enable(exb_context *c, int on) {
 
 extern "C" int exb_profile_read(exb_context *c, double *ms, unsigned long long *launches) {
     if (!c || !ms || !launches) return fail(EXB_INVALID_PARAM, "null argument");
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::vector<StageEvents> evs;
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        evs.swap(c->events);
+    }
     EXB_CUDA(cudaSetDevice(c->device));
-    for (StageEvents &se : c->events) {
+    for (StageEvents &se : evs) {
         EXB_CUDA(cudaEventSynchronize(se.ev[5]));
         for (int k = 0; k < 5; k++) {
             float t = 0.f;
@@ -189,7 +268,6 @@ extern "C" int exb_profile_read(exb_context *c, double *ms, unsigned long long *
         }
         for (auto &e : se.ev) cudaEventDestroy(e);
     }
-    c->events.clear();
     return EXB_OK;
 }
 
@@ -204,6 +282,20 @@ extern "C" int exb_context_psi(const exb_context *c, uint32_t idx, uint64_t *psi
     if (!c || !psi) return fail(EXB_INVALID_PARAM, "null argument");
     if (idx >= c->psi.size()) return fail(EXB_INVALID_PARAM, "modulus index out of range");
     *psi = c->psi[idx];
+    return EXB_OK;
+}
+
+extern "C" int exb_ntt_format_id(const exb_context *c, uint32_t idx, uint64_t *id) {
+    if (!c || !id) return fail(EXB_INVALID_PARAM, "null argument");
+    if (idx >= c->psi.size()) return fail(EXB_INVALID_PARAM, "modulus index out of range");
+    std::vector<u64> all;
+    all.push_back(c->ct_moduli[0]);
+    for (u64 a : c->aux_moduli) all.push_back(a);
+    for (size_t i = 1; i < c->ct_moduli.size(); i++) all.push_back(c->ct_moduli[i]);
+    u64 h = 0xcbf29ce484222325ull;                          // FNV-1a over (n, q, psi, ordering tag)
+    const u64 words[4] = {c->n, all[idx], c->psi[idx], 0x4354626974726576ull /* "CTbitrev" */};
+    for (u64 w : words) for (int b = 0; b < 8; b++) { h ^= (w >> (8 * b)) & 0xff; h *= 0x100000001b3ull; }
+    *id = ((u64)EXB_NTT_FORMAT_VERSION << 56) ^ (h & 0x00ffffffffffffffull);
     return EXB_OK;
 }
 
@@ -278,11 +370,10 @@ extern "C" int exb_ntt_inverse(exb_context *c, uint32_t idx, const uint64_t *in,
 static int ntt_host(exb_context *c, u32 idx, const u64 *in, u64 *out, size_t count, bool fwd) {
     int rc = check_base(c, idx);
     if (rc) return rc;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::lock_guard<std::mutex> lock(c->host_mu);
     if (count == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
-    Workspace &w = c->ws[0];
-    if ((rc = claim(w, w.stream))) return rc;
+    Workspace &w = c->hs[0];
     const size_t bytes = count * c->n * sizeof(u64);
     rc = grow((void **)&w.in1, &w.in_b, bytes);
     if (rc) return rc;
@@ -365,7 +456,7 @@ static int relin_key_make(exb_context *c, const u64 *src, bool src_is_host, u32 
     return EXB_OK;
 }
 extern "C" int exb_relin_key_load(exb_context *c, const uint64_t *rlk_host, uint32_t num_keys, exb_relin_key **out) {
-    return relin_key_make(c, rlk_host, true, num_keys, c ? c->ws[0].stream : nullptr, out);
+    return relin_key_make(c, rlk_host, true, num_keys, nullptr, out);
 }
 extern "C" int exb_relin_key_load_device(exb_context *c, const uint64_t *rlk_dev, uint32_t num_keys, void *stream,
                                          exb_relin_key **out) {
@@ -398,7 +489,7 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
     return *ext_b + *r01_b + *dig_b + *exc_b;
 }
 
-// Run the pipeline for `pairs` pairs whose inputs/outputs are on the device.
+// Run the pipeline for `pairs` pairs whose inputs/outputs are on the device.  The caller holds the slot.
 static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1,
                      const u64 *ct2, u64 *out, size_t pairs, cudaStream_t stream, bool pipelined = false) {
     DeviceParams P = c->P;
@@ -408,7 +499,6 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     size_t eb, rb, db, xb;
     ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
     int rc;
-    if ((rc = claim(w, stream))) return rc;
     if ((rc = grow((void **)&w.ext, &w.ext_b, eb * pairs))) return rc;
     if ((rc = grow((void **)&w.r01, &w.r01_b, rb * pairs))) return rc;
     if ((rc = grow(&w.digits, &w.digits_b, db * pairs))) return rc;
@@ -452,6 +542,7 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     }
     if (prof) {
         EXB_CUDA(cudaEventRecord(se.ev[5], stream));
+        std::lock_guard<std::mutex> g(c->mu);
         c->events.push_back(se);
     }
     return check_launch("ct-mul pipeline");
@@ -467,9 +558,7 @@ static int mul_precheck(exb_context *c, const exb_relin_key *rlk) {
 static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G) {
     size_t eb, rb, db, xb;
     const size_t per = ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
-    // EXB_DEVICE_CHUNK_BYTES (tests only) forces small chunks so the chunk loop is exercised
-    static const size_t budget = getenv("EXB_DEVICE_CHUNK_BYTES") ? (size_t)atoll(getenv("EXB_DEVICE_CHUNK_BYTES")) : ((size_t)4 << 30);
-    size_t chunk = budget / (per ? per : 1);
+    size_t chunk = c->tune.device_chunk_bytes / (per ? per : 1);
     return chunk ? chunk : 1;
 }
 
@@ -478,21 +567,23 @@ extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t 
                             uint32_t flags, uint32_t limb_mask, void *stream) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, limb_mask, &hp))) return rc;
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::unique_lock<std::mutex> held;
+    Workspace *w = nullptr;
+    if ((rc = acquire(c, st, &held, &w))) return rc;
     const size_t stride = (size_t)d * 2 * c->n;
     const size_t chunk = device_chunk_pairs(c, hp, c->gadget_digits);
-    for (size_t off = 0; off < batch; off += chunk) {
+    for (size_t off = 0; off < batch && !rc; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
-        rc = run_pairs(c, c->ws[0], hp, rlk, ct1 + off * stride, ct2 + off * stride, out + off * stride, cnt,
-                       (cudaStream_t)stream);
-        if (rc) return rc;
+        rc = run_pairs(c, *w, hp, rlk, ct1 + off * stride, ct2 + off * stride, out + off * stride, cnt, st);
     }
-    return EXB_OK;
+    const int rc2 = release(w, st);
+    return rc ? rc : rc2;
 }
 
 extern "C" int exb_bfv_mul_and_relin(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
@@ -501,53 +592,153 @@ extern "C" int exb_bfv_mul_and_relin(exb_context *c, const uint64_t *ct1, const 
     return exb_dbfv_mul(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0, 0, stream);
 }
 
-// Host-buffer entry: chunks pipelined over kSlots streams (H2D, kernels, D2H overlap).
-extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
-                                 const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
-                                 uint32_t flags) {
+// ---- host memory for the *_host entry points --------------------------------------------------------
+// The reference owns plain Vec<u64> (bfv/mod.rs:19-24).  Page-locked memory is what lets the copies of the
+// host-buffer pipeline run asynchronously at PCIe speed: allocate ciphertext storage with exb_host_alloc, or
+// pin an existing allocation in place with exb_host_register.
+extern "C" int exb_host_alloc(exb_context *c, size_t bytes, void **p) {
+    if (!c || !p) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaHostAlloc(p, bytes ? bytes : 8, cudaHostAllocPortable));
+    return EXB_OK;
+}
+extern "C" int exb_host_free(exb_context *c, void *p) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaFreeHost(p));
+    return EXB_OK;
+}
+extern "C" int exb_host_register(exb_context *c, void *p, size_t bytes) {
+    if (!c || !p) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return EXB_OK;
+}
+extern "C" int exb_host_unregister(exb_context *c, void *p) {
+    if (!c || !p) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaHostUnregister(p));
+    return EXB_OK;
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------------------------------
+// A call is cut into chunks; chunk i goes to host slot (host_rr + i) % kHostSlots, whose stream runs
+// H2D(ct1, ct2) -> kernels -> D2H(out).  Slots keep rotating ACROSS calls, so with the asynchronous entry the
+// next call's first H2D overlaps this call's last kernels and D2H: the copy engines and the SMs stay busy and
+// only the very first fill and the very last drain of a sequence of calls are exposed.
+static int host_pipeline(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                         const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch, uint32_t flags,
+                         bool taper, Ticket *tk) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    if (c->ct_moduli.size() > 1)
+        return fail(EXB_NOT_IMPLEMENTED, "host-buffer entry points need a single ciphertext prime (use the device-resident call)");
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, 0, &hp))) return rc;
     if (batch == 0) return EXB_OK;
+    std::lock_guard<std::mutex> lock(c->host_mu);
     EXB_CUDA(cudaSetDevice(c->device));
     const size_t stride = (size_t)d * 2 * c->n;
-    // chunk size: enough CTAs to fill the GPU a few times, small enough that H2D / kernels / D2H of
-    // consecutive chunks overlap on the three streams (EXB_HOST_CHUNK_PRODUCTS overrides, lab only)
-    static const size_t chunk_products = getenv("EXB_HOST_CHUNK_PRODUCTS") ? (size_t)atol(getenv("EXB_HOST_CHUNK_PRODUCTS")) : 1024;
-    size_t chunk = chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
+    // chunk size: enough CTAs to fill the GPU, small enough that H2D / kernels / D2H of consecutive chunks overlap
+    size_t chunk = c->tune.host_chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
     if (chunk < 1) chunk = 1;
-    if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
-    // the call is synchronous, so the first chunk's H2D and the last chunk's kernels + D2H are exposed:
-    // taper both ends (half-size first chunk, remainder split over the last two)
+    if (batch < chunk * (kHostSlots - 1)) chunk = (batch + kHostSlots - 2) / (kHostSlots - 1);
+    bool used[kHostSlots] = {};
     size_t ci = 0;
     for (size_t off = 0; off < batch; ci++) {
-        Workspace &w = c->ws[ci % kSlots];
+        const int si = (int)(c->host_rr++ % kHostSlots);
+        Workspace &w = c->hs[si];
         const size_t left = batch - off;
         size_t cnt = chunk;
-        if (ci == 0 && batch > 2 * chunk) cnt = (chunk + 1) / 2;
-        else if (left <= chunk) cnt = left;
-        else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
+        if (taper) {
+            // a synchronous call exposes the first chunk's H2D and the last chunk's kernels + D2H: taper both
+            // ends (half-size first chunk, remainder split over the last two)
+            if (ci == 0 && batch > 2 * chunk) cnt = (chunk + 1) / 2;
+            else if (left <= chunk) cnt = left;
+            else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
+        }
+        if (cnt > left) cnt = left;
         if (cnt > chunk) cnt = chunk;
         const size_t bytes = cnt * stride * 8;
-        if ((rc = claim(w, w.stream))) return rc;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
         if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream, true))) return rc;
         EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
+        used[si] = true;
         off += cnt;
     }
-    for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
+    for (int si = 0; si < kHostSlots; si++) {
+        if (!used[si]) continue;
+        cudaEvent_t e;
+        EXB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        tk->events.push_back(e);
+        EXB_CUDA(cudaEventRecord(e, c->hs[si].stream));
+    }
+    return EXB_OK;
+}
+
+static int wait_ticket(Ticket &tk) {
+    cudaError_t first = cudaSuccess;
+    for (cudaEvent_t e : tk.events) {
+        const cudaError_t r = cudaEventSynchronize(e);
+        if (r != cudaSuccess && first == cudaSuccess) first = r;
+        cudaEventDestroy(e);
+    }
+    tk.events.clear();
+    if (first != cudaSuccess) return fail(EXB_CUDA_ERROR, std::string("host pipeline: ") + cudaGetErrorString(first));
+    return EXB_OK;
+}
+
+extern "C" int exb_dbfv_mul_host(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                                 const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                                 uint32_t flags) {
+    Ticket tk;
+    const int rc = host_pipeline(c, base, d, pm, ct1, ct2, rlk, out, batch, flags, true, &tk);
+    const int rc2 = wait_ticket(tk);
+    return rc ? rc : rc2;
+}
+
+extern "C" int exb_dbfv_mul_host_async(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                                       const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                                       uint32_t flags, exb_ticket *ticket) {
+    if (!ticket) return fail(EXB_INVALID_PARAM, "null ticket");
+    *ticket = 0;
+    Ticket tk;
+    const int rc = host_pipeline(c, base, d, pm, ct1, ct2, rlk, out, batch, flags, false, &tk);
+    if (rc) { wait_ticket(tk); return rc; }
+    std::lock_guard<std::mutex> g(c->mu);
+    *ticket = c->next_ticket++;
+    c->tickets.emplace(*ticket, std::move(tk));
     return EXB_OK;
 }
 
 extern "C" int exb_bfv_mul_and_relin_host(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
                                           const exb_relin_key *rlk, uint64_t *out, size_t batch) {
     return exb_dbfv_mul_host(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0);
+}
+
+extern "C" int exb_bfv_mul_and_relin_host_async(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,
+                                                const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                                                exb_ticket *ticket) {
+    return exb_dbfv_mul_host_async(c, 2, 1, 0, ct1, ct2, rlk, out, batch, 0, ticket);
+}
+
+// Block until the call behind `ticket` has delivered its output to host memory.  A ticket is waited once.
+extern "C" int exb_wait(exb_context *c, exb_ticket ticket) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    if (ticket == 0) return EXB_OK;                      // a call that had nothing to do
+    Ticket tk;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        auto it = c->tickets.find(ticket);
+        if (it == c->tickets.end()) return fail(EXB_INVALID_PARAM, "unknown or already waited ticket");
+        tk = std::move(it->second);
+        c->tickets.erase(it);
+    }
+    return wait_ticket(tk);
 }
 
 // ---- Galois automorphism + key switch (bfv/eval.rs:512-561) -------------------------------------
@@ -578,17 +769,16 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
                                                const exb_relin_key *gk, uint64_t *out, size_t batch) {
     int rc = galois_precheck(c, gk, element);
     if (rc) return rc;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::lock_guard<std::mutex> lock(c->host_mu);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     const size_t stride = 2 * (size_t)c->n;
     size_t chunk = 1024;                                   // 64 MiB of ciphertexts at n = 4096
-    if (batch < chunk * kSlots) chunk = (batch + kSlots - 1) / kSlots;
+    if (batch < chunk * kHostSlots) chunk = (batch + kHostSlots - 1) / kHostSlots;
     size_t ci = 0;
     for (size_t off = 0; off < batch; off += chunk, ci++) {
-        Workspace &w = c->ws[ci % kSlots];
+        Workspace &w = c->hs[ci % kHostSlots];
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
-        if ((rc = claim(w, w.stream))) return rc;
         if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
         if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
         EXB_CUDA(cudaMemcpyAsync(w.in1, ct + off * stride, cnt * stride * 8, cudaMemcpyHostToDevice, w.stream));
@@ -596,7 +786,7 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
         if ((rc = check_launch("galois"))) return rc;
         EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, cnt * stride * 8, cudaMemcpyDeviceToHost, w.stream));
     }
-    for (Workspace &w : c->ws) EXB_CUDA(cudaStreamSynchronize(w.stream));
+    for (Workspace &w : c->hs) EXB_CUDA(cudaStreamSynchronize(w.stream));
     return EXB_OK;
 }
 
@@ -623,11 +813,10 @@ extern "C" int exb_bfv_decrypt_host(exb_context *c, const uint64_t *ct, uint32_t
                                     uint64_t *out, size_t batch) {
     int rc = decrypt_precheck(c, ncomp);
     if (rc) return rc;
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    std::lock_guard<std::mutex> lock(c->host_mu);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
-    Workspace &w = c->ws[0];
-    if ((rc = claim(w, w.stream))) return rc;
+    Workspace &w = c->hs[0];
     const size_t n = c->n, in_bytes = batch * ncomp * n * 8, out_bytes = batch * n * 8;
     if ((rc = grow((void **)&w.in1, &w.in_b, in_bytes))) return rc;
     if ((rc = grow_in2_out(w, out_bytes > n * 8 ? out_bytes : n * 8))) return rc;
@@ -646,14 +835,16 @@ extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const u
                                     size_t batch, void *stream) {
     if (!c) return fail(EXB_INVALID_PARAM, "null argument");
     if (c->mul_status != EXB_OK) return fail(c->mul_status, c->mul_error);
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
     HostPlan hp;
     int rc = build_plan(1, 2, 0, 0, 0, &hp);
     if (rc) return rc;
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    Workspace &w = c->ws[0];
+    std::unique_lock<std::mutex> held;
+    Workspace *wp = nullptr;
+    if ((rc = acquire(c, st, &held, &wp))) return rc;
+    Workspace &w = *wp;
     const size_t n = c->n;
     size_t eb, rb, db, xb;
     ws_bytes_per_pair(c, hp, c->gadget_digits, &eb, &rb, &db, &xb);
@@ -662,13 +853,13 @@ extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const u
     if (chunk < 1) chunk = 1;
     for (size_t off = 0; off < batch; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
-        if ((rc = claim(w, st))) return rc;
         if ((rc = grow((void **)&w.ext, &w.ext_b, eb * cnt))) return rc;
         if ((rc = grow((void **)&w.r01, &w.r01_b, 3 * n * 8 * cnt))) return rc;
         launch_lift(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, cnt, st);
         launch_tensor(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, w.r01, nullptr, c->digits32, cnt, st, nullptr, true);
         launch_ntt_fwd(c->P, 0, w.r01, out3 + off * 3 * n, 3 * cnt, st);      // hps_scale ends with from_coeff_poly (:412)
     }
+    if ((rc = release(&w, st))) return rc;
     return check_launch("bfv_mul_no_relin");
 }
 
@@ -678,7 +869,6 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
     if (rlk->ctx != c) return fail(EXB_INVALID_PARAM, "relinearisation key belongs to another context");
     if (ncomp > 3) return fail(EXB_INVALID_PARAM, "relinearization only supports degree-2 ciphertexts");   // :66-70
     if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "relinearize on the device path needs a single ciphertext prime");
-    std::lock_guard<std::recursive_mutex> lock(c->mu);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -695,14 +885,16 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
     DeviceParams P = c->P;
     const u32 G = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;                    // :86-89
     P.gadget_digits = G;
-    Workspace &w = c->ws[0];
+    std::unique_lock<std::mutex> held;
+    Workspace *wp = nullptr;
+    if ((rc = acquire(c, st, &held, &wp))) return rc;
+    Workspace &w = *wp;
     const size_t dig_b = (size_t)(G ? G : 1) * n * (c->digits32 ? 4 : 2);
     const size_t per = n * 8 + 2 * n * 8 + dig_b + (size_t)(G + 1) * 2 * n * 8;
     size_t chunk = ((size_t)4 << 30) / per;
     if (chunk < 1) chunk = 1;
     for (size_t off = 0; off < batch; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
-        if ((rc = claim(w, st))) return rc;
         if ((rc = grow((void **)&w.ext, &w.ext_b, cnt * n * 8))) return rc;    // c2 in the coefficient domain
         if ((rc = grow((void **)&w.r01, &w.r01_b, cnt * 2 * n * 8))) return rc;
         if ((rc = grow(&w.digits, &w.digits_b, cnt * dig_b))) return rc;
@@ -718,6 +910,7 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
         }
         launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out + off * 2 * n, nullptr, cnt, st, wide, true);
     }
+    if ((rc = release(&w, st))) return rc;
     return check_launch("relinearize");
 }
 

@@ -290,11 +290,10 @@ static int build_mod32(u32 n, u32 logn, u32 p, Mod32 *m, std::vector<Tw32> *twf,
 //   |m| <= Mmax = n*q/2 + 2 for every input (|t| <= 2 n (q/2)^2 for the middle tensor term);
 //   the reference's centred CRT of m (bfv/eval.rs:316-321, :385-388) cannot wrap: P_ref/2 > Mmax;
 //   ours cannot either and alpha is exact: P' >= 2^8 * Mmax (fixed-point error < 2^-28).
-static void build_small_basis(HostSetup *c) {
+static void build_small_basis(HostSetup *c, uint32_t flags) {
     SmallBasis &sb = c->P.sb;
     memset(&sb, 0, sizeof sb);
-    const char *env = getenv("EXB_AUX_BASIS");
-    if (env && strcmp(env, "reference") == 0) return;
+    if (flags & EXB_CTX_REFERENCE_AUX_BASIS) return;
     const u32 A = (u32)c->aux_moduli.size(), n = c->n;
     if (c->logn != 12 || c->mul_status != EXB_OK || A < 1 || A > (u32)kMaxAux) return;
     const u64 q = c->ct_moduli[0];
@@ -373,7 +372,7 @@ static void build_small_basis(HostSetup *c) {
     sb.enabled = 1;
 }
 
-int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
+int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err, uint32_t flags) {
     if (!p || !c) return fail(err, EXB_INVALID_PARAM, "null argument");
     const u32 n = p->ring_degree;
     if (n < 2 || (n & (n - 1)))                                           // params/mod.rs:82-84
@@ -455,7 +454,7 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err) {
     int rc = fill_scale_consts(c, err);
     if (rc != EXB_OK) return rc;
     decide_mul_support(c);
-    build_small_basis(c);
+    build_small_basis(c, flags);
     return EXB_OK;
 }
 

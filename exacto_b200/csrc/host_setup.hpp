@@ -40,6 +40,8 @@ struct DeviceParams {
     u64 gadget_base;             // B
     u32 gadget_log2;             // w if B == 2^w, else 0
     u32 pipelined;               // host hint: this call's kernels share the GPU with other chunks' (multi-stream pipeline)
+    u32 tensor_per_product;      // option: never use tensor01_kernel (per-product tensor kernel only)
+    u32 relin_narrow;            // option: never use relin12_wide_kernel
     Modulus mod[kMaxBases];      // [0] = q, [1..A] = aux primes
     const Tw *twf[kMaxBases];    // forward twiddles (psi_rev) per base
     const Tw *twi[kMaxBases];    // inverse twiddles (psi_inv_rev) per base
@@ -86,7 +88,7 @@ struct HostSetup {
 };
 
 // BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new (ring/rns.rs:35-63).
-int host_setup_build(const exb_bfv_params *p, HostSetup *hs, std::string *err);
+int host_setup_build(const exb_bfv_params *p, HostSetup *hs, std::string *err, uint32_t flags = 0);
 
 struct HostPlan {
     MulPlan M;

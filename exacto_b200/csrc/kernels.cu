@@ -15,6 +15,7 @@
 // basis, 32-bit) modular arithmetic on the integer pipes, staged through shared memory.
 #include "kernels.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -26,7 +27,7 @@
 
 namespace exb {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // Streaming 64-bit load that does not allocate in L1 (keeps L1 for the twiddle tables).
 __device__ __forceinline__ u64 ld_stream(const u64 *p) {
@@ -1300,12 +1301,29 @@ __global__ void reduce_mac_kernel(Modulus mod, u64 *__restrict__ out_limb, const
     }
 }
 
+// SM count of the current device (grid sizing of the persistent / small-batch paths).
+#ifndef EXB_HOST_EMUL
+int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+#else
+int num_sms() { return 148; }
+#endif
+
 // Components 0/1 can be produced per output limb (tensor01_kernel) when the internal basis is on and
 // every limb sums at most SmallBasis::max_terms products.
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs) {
     if (!P.sb.enabled || P.logn != 12) return false;
-    static const bool off = getenv("EXB_TENSOR_PER_PRODUCT") != nullptr;   // lab switch: the per-product kernel only
-    if (off) return false;
+    if (P.tensor_per_product) return false;                 // exb_context_set_option: the per-product kernel only
     u32 worst = 0;
     for (u32 l = 0; l < M.num_limbs; l++) {
         const u32 k = M.limb_k[l];
@@ -1322,8 +1340,7 @@ bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs)
 
 // Small batches at n = 4096: one CTA per transform instead of one per output limb (relin12_wide_kernel).
 bool relin_goes_wide(const DeviceParams &P, const MulPlan &M, size_t pairs) {
-    static const bool off = getenv("EXB_RELIN_NARROW") != nullptr;         // lab switch
-    return !off && P.logn == 12 && P.gadget_digits > 0 && pairs * M.num_limbs < 148;
+    return !P.relin_narrow && P.logn == 12 && P.gadget_digits > 0 && pairs * M.num_limbs < (size_t)num_sms();
 }
 size_t relin_wide_scratch_bytes(const DeviceParams &P, const MulPlan &M, size_t pairs) {
     return pairs * M.num_limbs * (size_t)(P.gadget_digits + 1) * 2 * P.n * sizeof(u64);
@@ -1333,7 +1350,6 @@ size_t relin_wide_scratch_bytes(const DeviceParams &P, const MulPlan &M, size_t 
 // ---------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------
-constexpr int kNumSMs = 148;   // B200
 
 static inline u32 block_threads(const DeviceParams &P) {
     if (P.logn == 12) return kThreads12;
@@ -1343,31 +1359,30 @@ static inline u32 block_threads(const DeviceParams &P) {
     return t;
 }
 
-template <typename K>
-static void set_smem(K kernel, size_t bytes) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
 
 template <bool FWD, int LAZY, int NB>
 static void launch_ntt12_nb(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
     const size_t sm = 2 * 4096 * 8;
-    const unsigned grid = (unsigned)(count < (size_t)kNumSMs * 2 ? count : (size_t)kNumSMs * 2);
-    static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;
+    const size_t slots = (size_t)num_sms() * 2;               // persistent: 2 CTAs per SM
+    const unsigned grid = (unsigned)(count < slots ? count : slots);
     const Tw *tw = FWD ? P.twf[base] : P.twi[base];
     const TwHead &head = FWD ? P.headf[base] : P.headi[base];
+#ifdef EXB_LAB
+    static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;   // lab build: copy only
     if (dbg == 1) {
-        set_smem(ntt12_persist_kernel<FWD, LAZY, NB, 1>, sm);
         ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
         return;
     }
-    set_smem(ntt12_persist_kernel<FWD, LAZY, NB>, sm);
+#endif
     ntt12_persist_kernel<FWD, LAZY, NB><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
 }
 template <bool FWD, int LAZY>
 static void launch_ntt12_l(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
-    static const int nb = getenv("EXB_NTT_NB") ? atoi(getenv("EXB_NTT_NB")) : kNB;   // lab switch
-    if (nb == 4) launch_ntt12_nb<FWD, LAZY, 4>(P, base, in, out, count, s);
-    else launch_ntt12_nb<FWD, LAZY, 3>(P, base, in, out, count, s);
+#ifdef EXB_LAB
+    static const int nb = getenv("EXB_NTT_NB") ? atoi(getenv("EXB_NTT_NB")) : kNB;   // lab build: 16 values per thread
+    if (nb == 4) { launch_ntt12_nb<FWD, LAZY, 4>(P, base, in, out, count, s); return; }
+#endif
+    launch_ntt12_nb<FWD, LAZY, 3>(P, base, in, out, count, s);
 }
 template <bool FWD>
 static void launch_ntt12(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
@@ -1383,7 +1398,6 @@ void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, si
     if (P.logn == 12) {
         launch_ntt12<true>(P, base, in, out, count, s);
     } else {
-        set_smem(ntt_fwd_kernel<0>, sm);
         ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.headf[base], P.mod[base], P.logn);
     }
     g_launch_count++;
@@ -1395,7 +1409,6 @@ void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, si
     if (P.logn == 12) {
         launch_ntt12<false>(P, base, in, out, count, s);
     } else {
-        set_smem(ntt_inv_kernel<0>, sm);
         ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.headi[base], P.mod[base], P.logn);
     }
     g_launch_count++;
@@ -1405,7 +1418,7 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
                     size_t words, cudaStream_t s) {
     if (words == 0) return;
     size_t blocks = (words + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     poly_op_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, (int)op, a, b, scalar, out, words);
     g_launch_count++;
 }
@@ -1418,7 +1431,6 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
     if (pairs == 0) return;
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
-        set_smem(lift32_kernel, sm32);
         lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext_small_part(ext));
         g_launch_count++;
         return;
@@ -1426,10 +1438,8 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
     const size_t sm = (size_t)P.n * 8 * 2;
     const unsigned grid = (unsigned)(pairs * 4 * M.d);
     if (P.logn == 12) {
-        set_smem(lift_kernel<12>, sm);
         lift_kernel<12><<<grid, kThreads12, sm, s>>>(P, M.d, ct1, ct2, ext);
     } else {
-        set_smem(lift_kernel<0>, sm);
         lift_kernel<0><<<grid, block_threads(P), sm, s>>>(P, M.d, ct1, ct2, ext);
     }
     g_launch_count++;
@@ -1443,11 +1453,9 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
         const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
-        set_smem(tensor32_kernel<DigT>, sm32);
         if (!raw3 && tensor_sums_per_limb(P, M, pairs)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
             const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
-            set_smem(tensor01_kernel, sm01);
             tensor01_kernel<<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
             if (mid) cudaEventRecord(mid, s);
             tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01,
@@ -1461,10 +1469,8 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
         return;
     }
     if (P.logn == 12) {
-        set_smem(tensor_kernel<12, DigT>, sm);
         tensor_kernel<12, DigT><<<grid, kThreads12, sm, s>>>(P, M, ct1, ext, r01, digits, raw3 ? 1u : 0u);
     } else {
-        set_smem(tensor_kernel<0, DigT>, sm);
         tensor_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, ct1, ext, r01, digits, raw3 ? 1u : 0u);
     }
     if (mid) cudaEventRecord(mid, s);
@@ -1481,7 +1487,7 @@ void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, cons
 void launch_gadget_digits(const DeviceParams &P, const u64 *coeffs, void *out, int out_kind, size_t count, cudaStream_t s) {
     if (count == 0) return;
     size_t blocks = (count * P.n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     if (out_kind == 0) gadget_digits_kernel<int16_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int16_t *)out, count);
     else if (out_kind == 1) gadget_digits_kernel<int32_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int32_t *)out, count);
     else gadget_digits_kernel<u64, true><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (u64 *)out, count);
@@ -1498,20 +1504,17 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     const u32 flags12 = r01_ntt ? 3u : (tensor_sums_per_limb(P, M, pairs) ? 1u : 0u);
     if (wide_scratch && relin_goes_wide(P, M, pairs)) {
         const u32 summed = flags12;
-        set_smem(relin12_wide_kernel<DigT>, (size_t)P.n * 8);
         relin12_wide_kernel<DigT><<<grid * (P.gadget_digits + 1), kThreads12, (size_t)P.n * 8, s>>>(
             P, M, r01, digits, rlk_mont, wide_scratch, summed);
         size_t blocks = (pairs * M.num_limbs * 2 * (size_t)P.n + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
         relin_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(P, M, wide_scratch, out, excess, pairs);
         g_launch_count += 2;
         return;
     }
     if (P.logn == 12) {
-        set_smem(relin12_kernel<DigT>, sm);
         relin12_kernel<DigT><<<grid, kThreads12, sm, s>>>(P, M, r01, digits, rlk_mont, out, excess, flags12);
     } else {
-        set_smem(relin_kernel<0, DigT>, sm);
         relin_kernel<0, DigT><<<grid, block_threads(P), sm, s>>>(P, M, r01, digits, rlk_mont, out, excess, r01_ntt ? 1u : 0u);
     }
     g_launch_count++;
@@ -1531,10 +1534,8 @@ void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32
     const size_t sm = (size_t)P.n * 8 * 3;
     const u32 k = element & (2 * P.n - 1);
     if (P.logn == 12) {
-        set_smem(galois_kernel<12>, sm);
         galois_kernel<12><<<(unsigned)count, kThreads12, sm, s>>>(P, ct, gk_mont, k, out);
     } else {
-        set_smem(galois_kernel<0>, sm);
         galois_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(P, ct, gk_mont, k, out);
     }
     g_launch_count++;
@@ -1545,10 +1546,8 @@ void launch_decrypt(const DeviceParams &P, const u64 *ct, u32 ncomp, const u64 *
     if (count == 0) return;
     const size_t sm = (size_t)P.n * 8;
     if (P.logn == 12) {
-        set_smem(decrypt_kernel<12>, sm);
         decrypt_kernel<12><<<(unsigned)count, kThreads12, sm, s>>>(P, ct, ncomp, sk_ntt, out);
     } else {
-        set_smem(decrypt_kernel<0>, sm);
         decrypt_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(P, ct, ncomp, sk_ntt, out);
     }
     g_launch_count++;
@@ -1562,10 +1561,42 @@ void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_l
     const u64 s_mont = (u64)(((unsigned __int128)abs_scalar_mod_q << 64) % m.m);
     const u32 words = 2 * P.n;
     size_t blocks = (pairs * words + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     reduce_mac_kernel<<<(unsigned)blocks, 256, 0, s>>>(m, out_limb, excess_limb, s_mont, negative ? 1 : 0,
                                                       out_stride, excess_stride, words, pairs);
     g_launch_count++;
+}
+
+// Opt every kernel that uses dynamic shared memory into the device's full budget, once per device (called from
+// exb_context_create) instead of on every launch.
+template <typename K>
+static void opt_in(K kernel, int bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
+void launch_prepare(int device) {
+    static std::atomic<unsigned long long> done{0};
+    if (device >= 0 && device < 64 && ((done.load() >> device) & 1ull)) return;
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess || optin <= 0) optin = 227 * 1024;
+    opt_in(ntt_fwd_kernel<0>, optin); opt_in(ntt_inv_kernel<0>, optin);
+#define EXB_OPT_NTT(F, L) opt_in(ntt12_persist_kernel<F, L, 3>, optin);
+    EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
+#undef EXB_OPT_NTT
+#ifdef EXB_LAB
+#define EXB_OPT_NTT(F, L) opt_in(ntt12_persist_kernel<F, L, 4>, optin); opt_in(ntt12_persist_kernel<F, L, 3, 1>, optin); opt_in(ntt12_persist_kernel<F, L, 4, 1>, optin);
+    EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
+#undef EXB_OPT_NTT
+#endif
+    opt_in(lift32_kernel, optin); opt_in(lift_kernel<12>, optin); opt_in(lift_kernel<0>, optin);
+    opt_in(tensor01_kernel, optin);
+    opt_in(tensor32_kernel<int16_t>, optin); opt_in(tensor32_kernel<int32_t>, optin);
+    opt_in(tensor_kernel<12, int16_t>, optin); opt_in(tensor_kernel<12, int32_t>, optin);
+    opt_in(tensor_kernel<0, int16_t>, optin); opt_in(tensor_kernel<0, int32_t>, optin);
+    opt_in(relin12_kernel<int16_t>, optin); opt_in(relin12_kernel<int32_t>, optin);
+    opt_in(relin12_wide_kernel<int16_t>, optin); opt_in(relin12_wide_kernel<int32_t>, optin);
+    opt_in(relin_kernel<0, int16_t>, optin); opt_in(relin_kernel<0, int32_t>, optin);
+    opt_in(galois_kernel<12>, optin); opt_in(galois_kernel<0>, optin);
+    opt_in(decrypt_kernel<12>, optin); opt_in(decrypt_kernel<0>, optin);
+    if (device >= 0 && device < 64) done.fetch_or(1ull << device);
 }
 
 #endif  // EXB_HOST_EMUL

@@ -5,6 +5,8 @@
 #endif
 #include <stdint.h>
 
+#include <atomic>
+
 #include "host_setup.hpp"
 
 namespace exb {
@@ -58,9 +60,13 @@ void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32
 void launch_decrypt(const DeviceParams &P, const u64 *ct, u32 ncomp, const u64 *sk_ntt, u64 *out, size_t count,
                     cudaStream_t s);
 
-#endif  // EXB_HOST_EMUL
+// Once per device: opt the kernels into their dynamic shared-memory sizes.
+void launch_prepare(int device);
+#endif
+
+int num_sms();                                           // SM count of the current device (148 on B200)
 
 // Count of kernels launched by this library (bench.py's gpu_launches).
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 }  // namespace exb

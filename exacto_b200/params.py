@@ -101,8 +101,19 @@ class _NativeContext:
         c.num_aux_moduli, c.aux_moduli = len(aux_list), aux
         c.plain_modulus, c.gadget_base, c.gadget_digits = params.plain_modulus, params.gadget_base, params.gadget_digits
         h = ctypes.c_void_p()
-        _native.check(L.exb_context_create(ctypes.byref(c), device, ctypes.byref(h)))
+        _native.check(L.exb_context_create_ex(ctypes.byref(c), device, params.context_flags, ctypes.byref(h)))
         self.handle, self.device, self._L = h, device, L
+
+    def set_option(self, name: str, value: int) -> None:
+        """exb_context_set_option: tuning knobs (device_chunk_bytes, host_chunk_products, tensor_per_product,
+        relin_narrow)."""
+        _native.check(self._L.exb_context_set_option(self.handle, name.encode(), int(value)))
+
+    def ntt_format_id(self, index: int = 0) -> int:
+        """Identifier of the NTT-domain word format this context produces (exb_ntt_format_id)."""
+        out = ctypes.c_uint64()
+        _native.check(self._L.exb_ntt_format_id(self.handle, index, ctypes.byref(out)))
+        return out.value
 
     def __del__(self):
         try:
@@ -123,6 +134,7 @@ class BfvParams:
     sigma: float
     gadget_base: int
     gadget_digits: int
+    context_flags: int = field(default=0, repr=False, compare=False)   # exb_context_create_ex flags (set before first use)
     _ctx: Dict[int, _NativeContext] = field(default_factory=dict, repr=False, compare=False)
     _lock: threading.Lock = field(default_factory=threading.Lock, repr=False, compare=False)
 

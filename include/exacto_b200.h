@@ -25,10 +25,14 @@
  *     exb_last_error() gives the message of the calling thread's last failure.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
  *     are stream-ordered and asynchronous unless they take host pointers.
- *   - One hot-path call may be in flight per context (it owns the workspace);
- *     use one context per stream for concurrency.  There is no CPU fallback:
- *     every entry point fails with EXB_NOT_IMPLEMENTED / a CUDA error rather
- *     than computing on the host.
+ *   - A context owns a small pool of workspaces: device-resident calls on different
+ *     streams (from one or several host threads) take different workspaces and overlap
+ *     on the GPU; host-buffer calls are pipelined over the context's own streams.
+ *     There is no CPU fallback: every entry point fails with EXB_NOT_IMPLEMENTED / a
+ *     CUDA error rather than computing on the host.
+ *   - NTT-domain words are a PRIVATE interchange format (see "Interchange format"
+ *     below): data written by the upstream crate's concrete-ntt plan must cross the
+ *     boundary in the coefficient domain.
  */
 #ifndef EXACTO_B200_H
 #define EXACTO_B200_H
@@ -66,10 +70,12 @@ typedef struct exb_bfv_params {
     uint32_t gadget_digits;        /* 0 = compute_gadget_digits (params/mod.rs:126) */
 } exb_bfv_params;
 
-/* Threading: the reference's functions are re-entrant; here a context may be shared by host threads --
- * entry points that use its workspaces serialise on a per-context lock, and a workspace slot waits for the
- * stream that used it last, so device-resident calls on different streams stay correct (they do not overlap;
- * use one context per stream for concurrency).  exb_last_error() is thread-local. */
+/* Threading: the reference's functions are re-entrant (and dbfv_mul fans out on rayon, dbfv/eval.rs:117); here a
+ * context may be shared by host threads.  Every device-resident entry point takes one of the context's workspace
+ * slots while it enqueues; calls on different streams use different slots and run concurrently, and a slot that
+ * is reused by another stream is ordered behind its previous work with a CUDA event (no host blocking, no stored
+ * user stream is ever dereferenced).  Host-buffer entry points serialise their enqueue on a second lock and run
+ * on the context's own streams.  exb_last_error() is thread-local. */
 typedef struct exb_context exb_context;       /* BfvParams + plans + workspace on one GPU */
 typedef struct exb_relin_key exb_relin_key;   /* device-resident RelinKey                 */
 
@@ -81,13 +87,30 @@ enum {
     EXB_DBFV_ALL_PRODUCTS = 1u
 };
 
+/* Flags of exb_context_create_ex. */
+enum {
+    /* Keep the parameter set's own auxiliary primes inside the lift / tensor kernels instead of the internal
+     * 27-bit basis (both are bit-identical to the reference; tests compare the two). */
+    EXB_CTX_REFERENCE_AUX_BASIS = 1u
+};
+
+/* Handle of one asynchronous host-buffer call (exb_*_host_async); 0 = nothing to wait for. */
+typedef uint64_t exb_ticket;
+
 const char *exb_last_error(void);
 const char *exb_version(void);
 
 /* ---- context: BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new
  * (ring/rns.rs:35-63) + make_plan (ring/ntt.rs:19-29) -------------------------- */
 int exb_context_create(const exb_bfv_params *params, int device, exb_context **out);
+int exb_context_create_ex(const exb_bfv_params *params, int device, uint32_t flags, exb_context **out);
 void exb_context_destroy(exb_context *ctx);
+/* Tuning knobs (the defaults are the measured optimum; tests use them to force every code path):
+ *   "device_chunk_bytes"  workspace budget of one chunk of a device-resident call (default 4 GiB)
+ *   "host_chunk_products" per-digit products per chunk of the host-buffer pipeline (default 1024)
+ *   "tensor_per_product"  1 = never sum components 0/1 per output limb (tensor01_kernel off)
+ *   "relin_narrow"        1 = never give each relinearisation transform its own CTA */
+int exb_context_set_option(exb_context *ctx, const char *name, int64_t value);
 /* Effective values after defaults were applied. */
 int exb_context_gadget(const exb_context *ctx, uint64_t *gadget_base, uint32_t *gadget_digits);
 /* psi of modulus `modulus_index` (0 = q, 1.. = aux primes). */
@@ -111,6 +134,29 @@ int exb_device_free(exb_context *ctx, void *dev_ptr);
 int exb_copy_to_device(exb_context *ctx, void *dst_dev, const void *src_host, size_t bytes, void *stream);
 int exb_copy_to_host(exb_context *ctx, void *dst_host, const void *src_dev, size_t bytes, void *stream);
 int exb_synchronize(exb_context *ctx, void *stream);
+
+/* Page-locked host memory for the *_host entry points.  The reference owns plain Vec<u64> (bfv/mod.rs:19-24);
+ * pageable memory works but the copies then run synchronously at a fraction of PCIe speed.  Either allocate
+ * ciphertext storage here (exb_host_alloc / exb_host_free) or pin an existing allocation in place
+ * (exb_host_register / exb_host_unregister, e.g. a long-lived Vec<u64>). */
+int exb_host_alloc(exb_context *ctx, size_t bytes, void **host_ptr);
+int exb_host_free(exb_context *ctx, void *host_ptr);
+int exb_host_register(exb_context *ctx, void *host_ptr, size_t bytes);
+int exb_host_unregister(exb_context *ctx, void *host_ptr);
+
+/* ---- Interchange format.  NTT-domain polynomials are in THIS library's evaluation order: forward =
+ * Cooley-Tukey, natural -> bit-reversed, psi = x^((q-1)/2n) for the first x >= 2 whose psi has order 2n
+ * (exb_context_psi).  The upstream crate's NttPoly words come from concrete-ntt 0.2.0's own root and order,
+ * which no reference test pins and which cannot be reproduced here: NTT-domain buffers written by the
+ * upstream crate (ciphertexts, relin / Galois keys, secret keys) are NOT interchangeable with this library's
+ * and nothing in the words themselves can reveal the difference.  This is a breaking format difference:
+ * cross the boundary in the coefficient domain (unique, canonical residues) -- exb_ntt_forward[_host]
+ * imports CoeffPoly data, exb_ntt_inverse[_host] exports it -- or keep every from_coeff_poly / to_coeff_poly
+ * on this library (INTEGRATION.md replaces ring/ntt.rs wholesale, which does exactly that).
+ * exb_ntt_format_id() identifies the format of the words a context produces: (version << 56) ^ a hash of
+ * (n, q, psi, ordering); store it beside any serialised NTT-domain buffer and compare on load. */
+#define EXB_NTT_FORMAT_VERSION 1u
+int exb_ntt_format_id(const exb_context *ctx, uint32_t modulus_index, uint64_t *format_id);
 
 /* ---- ring/: NttPoly::from_coeff_poly (ring/ntt.rs:42-55) and NttPoly::to_coeff_poly
  * (ring/ntt.rs:58-67), batched over `count` polynomials; in == out allowed. -------- */
@@ -207,6 +253,19 @@ int exb_dbfv_mul(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t 
 int exb_dbfv_mul_host(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
                       const uint64_t *ct1_host, const uint64_t *ct2_host, const exb_relin_key *rlk,
                       uint64_t *out_host, size_t batch, uint32_t flags);
+/* Asynchronous forms of the host-buffer calls: the work is enqueued on the context's pipeline and the call
+ * returns; exb_wait(ticket) blocks until the output has landed in out_host.  Inputs must stay valid and
+ * unmodified, and out_host unread, until then.  Calls are pipelined across each other: the next call's
+ * uploads overlap this call's kernels and downloads, so a stream of calls runs at max(PCIe, kernel) speed
+ * instead of their sum.  Host memory should be page-locked (exb_host_alloc / exb_host_register).
+ * The synchronous forms above are async + wait.  The reference has no counterpart (its calls are CPU-synchronous,
+ * bfv/eval.rs:73-82, dbfv/eval.rs:82-149); ownership is unchanged: inputs borrowed, output caller-owned. */
+int exb_dbfv_mul_host_async(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
+                            const uint64_t *ct1_host, const uint64_t *ct2_host, const exb_relin_key *rlk,
+                            uint64_t *out_host, size_t batch, uint32_t flags, exb_ticket *ticket);
+int exb_bfv_mul_and_relin_host_async(exb_context *ctx, const uint64_t *ct1_host, const uint64_t *ct2_host,
+                                     const exb_relin_key *rlk, uint64_t *out_host, size_t batch, exb_ticket *ticket);
+int exb_wait(exb_context *ctx, exb_ticket ticket);
 /* SmallReps::compute_simple (dbfv/lattice.rs:104-122): reps[(d-1)][d]. */
 int exb_dbfv_small_reps(uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus, int64_t *reps);
 

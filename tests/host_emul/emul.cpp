@@ -91,7 +91,11 @@ int emu_create(uint32_t n, const uint64_t *ct_moduli, uint32_t num_ct, const uin
     p.num_aux_moduli = num_aux; p.aux_moduli = aux; p.plain_modulus = plain;
     p.gadget_base = gadget_base; p.gadget_digits = gadget_digits;
     emu_ctx *c = new emu_ctx();
-    int rc = host_setup_build(&p, &c->hs, &g_emu_err);
+    // test infrastructure: the aux-basis choice is a context flag in the product (EXB_CTX_REFERENCE_AUX_BASIS);
+    // the emulator takes it from the environment so one fixture covers both
+    const char *env = getenv("EXB_AUX_BASIS");
+    const uint32_t cflags = (env && strcmp(env, "reference") == 0) ? (uint32_t)EXB_CTX_REFERENCE_AUX_BASIS : 0u;
+    int rc = host_setup_build(&p, &c->hs, &g_emu_err, cflags);
     if (rc) { delete c; return rc; }
     for (int b = 0; b < kMaxBases; b++)
         if (c->hs.has_plan[b]) { c->hs.P.twf[b] = c->hs.twf[b].data(); c->hs.P.twi[b] = c->hs.twi[b].data(); }

@@ -256,16 +256,16 @@ def test_smoke_entry():
     g.smoke()
 
 
-def test_both_aux_basis_paths(monkeypatch):
+def test_both_aux_basis_paths():
     """cfg 3' and cfg 4 through both tensor paths: the internal 27-bit auxiliary basis (default when it is
-    provably result-identical) and the reference's own aux primes (EXB_AUX_BASIS=reference)."""
+    provably result-identical) and the reference's own aux primes (EXB_CTX_REFERENCE_AUX_BASIS)."""
     g = golden()
     for name in ("cfg3p_dbfv", "u64_dbfv"):
         P, base, d, pm, seed, _ = CASES[name]
         ct1, ct2, rlk_arr = golden_inputs(P, d, seed)
         for mode in ("reference", "internal"):
-            monkeypatch.setenv("EXB_AUX_BASIS", mode)
             params = to_dbfv_params(P, base, d, pm)            # fresh params -> fresh native context
+            params.bfv_params.context_flags = 1 if mode == "reference" else 0
             rlk = E.RelinKey(rlk_arr, params.bfv_params)
             out = E.dbfv_mul_batch(params, ct1[None], ct2[None], rlk)
             assert digest(out[0]) == str(g[f"{name}/dbfv_sha256"]), (name, mode)
@@ -331,27 +331,24 @@ def test_cpp_host_mirror(preset, tmp_path):
 
 
 def test_device_api_chunk_loop():
-    """exb_dbfv_mul splits large batches into workspace-bounded chunks; force tiny chunks (env is read once
-    per process, so this runs in a subprocess) and compare with the oracle."""
-    import subprocess, sys, textwrap
-    code = textwrap.dedent("""
-        import sys, numpy as np
-        sys.path.insert(0, %r); sys.path.insert(0, %r)
-        import exacto_b200 as E, oracle as O
-        from exacto_b200 import batch
-        from common import CASES, to_dbfv_params
-        P, base, d, pm, seed, _ = CASES["n64_a2_rep"]
-        rng = np.random.default_rng(3)
-        ct1 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64); ct2 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64)
-        rk = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
-        params = to_dbfv_params(P, base, d, pm)
-        got = batch.to_host(batch.dbfv_mul(params, batch.to_device(ct1), batch.to_device(ct2), E.RelinKey(rk, params.bfv_params)))
-        want = np.stack([O.dbfv_mul(P, base, d, pm, a, b, rk) for a, b in zip(ct1, ct2)])
-        assert np.array_equal(got, want); print("chunk loop ok")
-    """) % (ROOT_DIR, TESTS_DIR)
-    env = dict(__import__("os").environ, EXB_DEVICE_CHUNK_BYTES=str(2 * 40000))   # ~2 pairs per chunk at n=64
-    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
-    assert res.returncode == 0 and "chunk loop ok" in res.stdout, res.stdout + res.stderr
+    """exb_dbfv_mul splits large batches into workspace-bounded chunks; force tiny chunks
+    (exb_context_set_option "device_chunk_bytes") and compare with the oracle; same for the host pipeline."""
+    from exacto_b200 import batch
+    P, base, d, pm, seed, _ = CASES["n64_a2_rep"]
+    rng = np.random.default_rng(3)
+    ct1 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64); ct2 = rng.integers(0, P.q, (7, d, 2, P.n), dtype=np.uint64)
+    rk = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    params = to_dbfv_params(P, base, d, pm)
+    ctx = params.bfv_params.context()
+    ctx.set_option("device_chunk_bytes", 2 * 40000)                 # ~2 pairs per chunk at n=64
+    ctx.set_option("host_chunk_products", 2 * d * d)                # 2 pairs per host chunk
+    rlk = E.RelinKey(rk, params.bfv_params)
+    want = np.stack([O.dbfv_mul(P, base, d, pm, a, b, rk) for a, b in zip(ct1, ct2)])
+    got = batch.to_host(batch.dbfv_mul(params, batch.to_device(ct1), batch.to_device(ct2), rlk))
+    assert np.array_equal(got, want)
+    assert np.array_equal(E.dbfv_mul_batch(params, ct1, ct2, rlk), want)
+    with pytest.raises(E.ExactoError):
+        ctx.set_option("no_such_option", 1)
 
 
 @pytest.mark.parametrize("n", [16, 2048, 8192])
@@ -677,11 +674,76 @@ def test_shared_context_from_host_threads_and_streams():
     assert all(np.array_equal(batch.to_host(o), w) for o, w in zip(outs, want))
 
 
+def test_async_host_api_pinned_memory_and_slot_pool():
+    """exb_*_host_async / exb_wait: several calls in flight on page-locked buffers (exb_host_alloc), waited out of
+    order; a ticket is waited once.  Device-resident calls from more host threads and streams than the context has
+    workspace slots (slot reuse is ordered by the slot's own event).  exb_host_register pins a numpy array in place."""
+    import ctypes, threading
+    from exacto_b200 import _native, batch, hostmem
+    S = H.cfg3_prime()
+    P = S.bfv
+    dp = to_dbfv_params(P, S.base, S.d, S.plain_modulus)
+    ctx = dp.bfv_params.context()
+    rng = np.random.default_rng(7)
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    shape = (5, S.d, 2, P.n)
+    calls = []
+    for i in range(6):
+        a, b, o = (hostmem.pinned_empty(dp, shape) for _ in range(3))
+        a.array[:] = rng.integers(0, P.q, shape, dtype=np.uint64)
+        b.array[:] = rng.integers(0, P.q, shape, dtype=np.uint64)
+        calls.append((a, b, o))
+    want = [np.stack([O.dbfv_mul(P, S.base, S.d, S.plain_modulus, x, y, rlk_arr, threads=O.max_threads())
+                      for x, y in zip(a.array, b.array)]) for a, b, _ in calls]
+    ctx.set_option("host_chunk_products", 2 * S.d * S.d)             # several chunks per call
+    pend = [hostmem.dbfv_mul_batch_async(dp, a.array, b.array, rlk, o.array) for a, b, o in calls]
+    for i in reversed(range(6)):
+        assert np.array_equal(pend[i].wait(), want[i]), i
+    L = _native.lib()
+    t = ctypes.c_uint64()
+    a, b, o = calls[0]
+    _native.check(L.exb_dbfv_mul_host_async(ctx.handle, dp.base, S.d, dp.plain_modulus, a.array.ctypes.data,
+                                            b.array.ctypes.data, rlk.native(ctx), o.array.ctypes.data, 5, 0, ctypes.byref(t)))
+    assert t.value != 0
+    _native.check(L.exb_wait(ctx.handle, t.value))
+    assert L.exb_wait(ctx.handle, t.value) == 1                      # EXB_INVALID_PARAM: already waited
+    assert b"ticket" in L.exb_last_error()
+    # pin an ordinary numpy array in place
+    x = np.ascontiguousarray(rng.integers(0, P.q, shape, dtype=np.uint64))
+    _native.check(L.exb_host_register(ctx.handle, x.ctypes.data, x.nbytes))
+    got = E.dbfv_mul_batch(dp, x, calls[1][1].array, rlk)
+    _native.check(L.exb_host_unregister(ctx.handle, x.ctypes.data))
+    assert np.array_equal(got[0], O.dbfv_mul(P, S.base, S.d, S.plain_modulus, x[0], calls[1][1].array[0], rlk_arr))
+    # 6 host threads x own stream x 3 calls each on one context (4 workspace slots)
+    dev_in = [(batch.to_device(a.array), batch.to_device(b.array)) for a, b, _ in calls]
+    torch.cuda.synchronize()
+    res, errs = [None] * 6, []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    res[i] = batch.dbfv_mul(dp, dev_in[i][0], dev_in[i][1], rlk)
+            st.synchronize()
+        except Exception as exc:                           # pragma: no cover
+            errs.append(exc)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    [t_.start() for t_ in ts]; [t_.join() for t_ in ts]
+    assert not errs, errs
+    torch.cuda.synchronize()
+    assert all(np.array_equal(batch.to_host(r), w) for r, w in zip(res, want))
+    # the NTT-domain format id is a function of (n, q, psi, ordering)
+    assert ctx.ntt_format_id(0) == to_dbfv_params(P, S.base, S.d, S.plain_modulus).bfv_params.context().ntt_format_id(0)
+    assert ctx.ntt_format_id(0) != ctx.ntt_format_id(1)
+    assert ctx.ntt_format_id(0) >> 56 == 1
+
+
 def test_per_limb_tensor_path_on_gpu():
     """Batches large enough for tensor01_kernel (components 0/1 summed per output limb) vs the oracle, device and
-    host entry points, and the same batch through the per-product kernel only (EXB_TENSOR_PER_PRODUCT, read once per
-    process: subprocess)."""
-    import subprocess, sys, tempfile
+    host entry points, and the same batch through the per-product kernel only (option "tensor_per_product")."""
     from exacto_b200 import batch
     S = H.u64_dbfv()
     P = S.bfv
@@ -697,20 +759,13 @@ def test_per_limb_tensor_path_on_gpu():
     want = np.stack([O.dbfv_mul(P, S.base, S.d, S.plain_modulus, a, b, rlk_arr, threads=O.max_threads()) for a, b in zip(ct1, ct2)])
     got = batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk))
     assert np.array_equal(got, want)
-    with tempfile.TemporaryDirectory() as tmp:
-        np.savez(f"{tmp}/in.npz", ct1=ct1, ct2=ct2, rlk=rlk_arr)
-        code = "\n".join([
-            f"import sys; sys.path.insert(0, {ROOT_DIR!r})",
-            "import numpy as np, exacto_b200 as E",
-            "from exacto_b200 import batch",
-            f"d = np.load({tmp!r} + '/in.npz'); dp = E.u64_dbfv()",
-            "rlk = E.RelinKey(d['rlk'], dp.bfv_params)",
-            "out = batch.to_host(batch.dbfv_mul(dp, batch.to_device(d['ct1']), batch.to_device(d['ct2']), rlk))",
-            f"np.save({tmp!r} + '/out.npy', out)"])
-        env = dict(_os.environ, EXB_TENSOR_PER_PRODUCT="1")
-        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-        assert res.returncode == 0, res.stderr
-        assert np.array_equal(np.load(f"{tmp}/out.npy"), want)
+    ctx = dp.bfv_params.context()
+    ctx.set_option("tensor_per_product", 1)
+    try:
+        got = batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk))
+    finally:
+        ctx.set_option("tensor_per_product", 0)
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("preset", ["compact", "u64", "cfg3", "toy16_noaux", "n64_base10"])
