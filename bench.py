@@ -100,20 +100,63 @@ def static_profile(kernel_prefix):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region: NVML polled every ~4 ms from a thread (the
+    B200_PROFILING.md clocks line at a finer period), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.rows, self.reasons, self.p, self.f = [], set(), None, None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "10", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((float(mhz), pw))
+                        for bit, nm in self.BITS.items():
+                            if mask & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.mode = "nvml"
         except Exception:
-            self.p = None
+            self.mode = "nvidia-smi"
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                           "-lms", "10", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
 
     def stop(self):
+        if self.mode == "nvml":
+            self._stop.set()
+            self.t.join(timeout=2)
+            if not self.rows:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            sm = [r[0] for r in self.rows]
+            return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": self.max_mhz,
+                    "power_w_max": max(r[1] for r in self.rows), "samples": len(sm), "reasons": sorted(self.reasons),
+                    "source": "nvml polled every ~4 ms during the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -137,7 +180,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 10"}
 
 
 def host_threads() -> int:
@@ -336,9 +379,9 @@ def run_gpu(args):
             nxt = hostmem.dbfv_mul_batch_async(params, a1[:npairs], a2[:npairs], rlk, outs[s & 1].array[:npairs],
                                                all_products=all_products)
             if pend is not None:
-                check ^= int(pend.wait()[0, 0, 0, 0])        # the D2H result is read on the host
+                check = (check + int(pend.wait()[0, 0, 0, 0])) & 0xFFFFFFFFFFFFFFFF   # the D2H result is read on the host
             pend = nxt
-        check ^= int(pend.wait()[0, 0, 0, 0])
+        check = (check + int(pend.wait()[0, 0, 0, 0])) & 0xFFFFFFFFFFFFFFFF
         return max_over_ranks(time.perf_counter() - t0), check
 
     e2e_run(2, h1.array, h2.array, pairs)
@@ -540,6 +583,12 @@ def bench_kshard(torch, dist, E, batch, params, rlk, rlk_arr, q, dev, rank, worl
     ms = float(t.item())
     full = batch.dbfv_mul(params, a, b, rlk)
     torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        batch.dbfv_mul(params, a, b, rlk, out=full)
+    e1.record()
+    torch.cuda.synchronize()
+    single = kp * steps / (e0.elapsed_time(e1) * 1e-3)
     ok = torch.tensor([1 if torch.equal(full, res) else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     value = kp * steps / (ms * 1e-3)
@@ -547,7 +596,7 @@ def bench_kshard(torch, dist, E, batch, params, rlk, rlk_arr, q, dev, rank, worl
            "transport": ks.transport, "limb_masks": ks.masks,
            "bytes_on_wire_per_dbfv_mul_per_rank": ks.wire_bytes_per_pair_per_rank(),
            "ideal_bytes_per_rank": CT_BYTES * (world - 1) / world,
-           "verified": bool(int(ok.item())), "single_gpu_same_batch_value": None}
+           "verified": bool(int(ok.item())), "single_gpu_same_batch_value": single}
     ks.close()
     return rec
 

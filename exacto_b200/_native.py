@@ -79,6 +79,11 @@ SYMBOLS = {
     "exb_dbfv_mul_host_async": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, c_sz, c_u32, ctypes.POINTER(c_u64)]),
     "exb_bfv_mul_and_relin_host_async": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, ctypes.POINTER(c_u64)]),
     "exb_wait": (ctypes.c_int, [c_vp, c_u64]),
+    "exb_dbfv_mul_scatter": (ctypes.c_int, [c_vp, c_u64, c_u32, c_u64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp), c_u32,
+                                            c_sz, c_u32, c_u32, c_vp]),
+    "exb_ipc_export": (ctypes.c_int, [c_vp, c_vp, ctypes.c_char_p]),
+    "exb_ipc_open": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "exb_ipc_close": (ctypes.c_int, [c_vp, c_vp]),
     "exb_dbfv_small_reps": (ctypes.c_int, [c_u64, c_u32, c_u64, c_vp]),
 }
 

@@ -88,6 +88,16 @@ struct exb_context : HostSetup {
     unsigned rr = 0, host_rr = 0;
     uint64_t next_ticket = 1;
     std::unordered_map<uint64_t, Ticket> tickets;
+
+    // true when reduce() (dbfv/reduction.rs:28-52) has nothing to add: every small representative is zero
+    bool excess_free(uint32_t d, uint64_t base, uint64_t pm) const {
+        if (d < 2 || d > (uint32_t)kMaxDigits || base < 2) return true;
+        std::vector<int64_t> reps((size_t)(d - 1) * d, 0);
+        std::string err;
+        if (host_small_reps(base, d, pm, reps.data(), &err) != EXB_OK) return true;   // the plan reports the error
+        for (int64_t r : reps) if (r != 0) return false;
+        return true;
+    }
 };
 
 // Take a workspace slot for work that is about to be enqueued on `stream`: the slot this stream used last if it
@@ -562,12 +572,14 @@ static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G
     return chunk ? chunk : 1;
 }
 
-extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
-                            const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
-                            uint32_t flags, uint32_t limb_mask, void *stream) {
+static int dbfv_mul_device(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                           const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, uint64_t *const *peers,
+                           uint32_t num_peers, size_t batch, uint32_t flags, uint32_t limb_mask, void *stream) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
+    if (num_peers > (uint32_t)kMaxPeers) return fail(EXB_INVALID_PARAM, "at most 7 peer output buffers");
+    if (num_peers && !peers) return fail(EXB_INVALID_PARAM, "null peer list");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, limb_mask, &hp))) return rc;
     if (batch == 0) return EXB_OK;
@@ -578,12 +590,59 @@ extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t 
     if ((rc = acquire(c, st, &held, &w))) return rc;
     const size_t stride = (size_t)d * 2 * c->n;
     const size_t chunk = device_chunk_pairs(c, hp, c->gadget_digits);
+    hp.M.num_peers = num_peers;
     for (size_t off = 0; off < batch && !rc; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        for (uint32_t p = 0; p < num_peers; p++) hp.M.peer_out[p] = peers[p] + off * stride;
         rc = run_pairs(c, *w, hp, rlk, ct1 + off * stride, ct2 + off * stride, out + off * stride, cnt, st);
     }
     const int rc2 = release(w, st);
     return rc ? rc : rc2;
+}
+
+extern "C" int exb_dbfv_mul(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                            const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, size_t batch,
+                            uint32_t flags, uint32_t limb_mask, void *stream) {
+    return dbfv_mul_device(c, base, d, pm, ct1, ct2, rlk, out, nullptr, 0, batch, flags, limb_mask, stream);
+}
+
+// k-sharded dbfv_mul: this rank computes the output limbs of `limb_mask` and stores each finished limb into its
+// own `out` AND into the `num_peers` peer buffers (other GPUs' outputs, mapped with exb_ipc_open) from the
+// relinearisation kernel's epilogue -- the gather of dbfv/eval.rs:125-136's per-k sums rides on the compute.
+extern "C" int exb_dbfv_mul_scatter(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
+                                    const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out,
+                                    uint64_t *const *peer_outs, uint32_t num_peers, size_t batch, uint32_t flags,
+                                    uint32_t limb_mask, void *stream) {
+    if (c && !c->excess_free(d, base, pm))
+        return fail(EXB_NOT_IMPLEMENTED, "k-sharded dbfv_mul needs all-zero small representatives (p = b^d): the general "
+                                         "reduction adds excess limbs held by other ranks");
+    return dbfv_mul_device(c, base, d, pm, ct1, ct2, rlk, out, peer_outs, num_peers, batch, flags, limb_mask, stream);
+}
+
+// CUDA IPC plumbing for the peer buffers (one process per GPU): export the handle of an exb_device_alloc
+// allocation, open a peer's handle (peer access is enabled lazily), close it.
+extern "C" int exb_ipc_export(exb_context *c, void *dev_ptr, uint8_t handle[64]) {
+    if (!c || !dev_ptr || !handle) return fail(EXB_INVALID_PARAM, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    EXB_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    EXB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return EXB_OK;
+}
+extern "C" int exb_ipc_open(exb_context *c, const uint8_t handle[64], void **dev_ptr) {
+    if (!c || !dev_ptr || !handle) return fail(EXB_INVALID_PARAM, "null argument");
+    EXB_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    EXB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EXB_OK;
+}
+extern "C" int exb_ipc_close(exb_context *c, void *dev_ptr) {
+    if (!c) return fail(EXB_INVALID_PARAM, "null context");
+    EXB_CUDA(cudaSetDevice(c->device));
+    EXB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return EXB_OK;
 }
 
 extern "C" int exb_bfv_mul_and_relin(exb_context *c, const uint64_t *ct1, const uint64_t *ct2,

@@ -514,6 +514,7 @@ int host_build_plan(u32 d, u64 base, u64 pm, u32 flags, u32 limb_mask, HostPlan 
         for (u32 j = 0; j < d; j++) {
             if (need[i + j]) {
                 M.prod_i[np] = (uint8_t)i; M.prod_j[np] = (uint8_t)j; M.prod_of[i][j] = (int16_t)np; np++;
+                M.need_lhs |= 1u << i; M.need_rhs |= 1u << j;
             } else {
                 M.prod_of[i][j] = -1;
             }

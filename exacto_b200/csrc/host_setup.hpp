@@ -19,6 +19,7 @@ constexpr int kMaxBases = 1 + kMaxAux;
 constexpr int kMaxDigits = 16;                 // dBFV digits d
 constexpr int kMaxProducts = kMaxDigits * kMaxDigits;
 constexpr int kMaxLimbs = 2 * kMaxDigits - 1;
+constexpr int kMaxPeers = 7;                   // other GPUs of one 8-GPU box (k-sharded dbfv_mul)
 
 // Internal 27-bit auxiliary basis (see ntt32_core.cuh / hps32.cuh): replaces the reference's aux
 // primes inside the lift / tensor kernels when that is provably result-identical.
@@ -67,6 +68,12 @@ struct MulPlan {
     uint8_t pad3_[2];
     u32 num_duos;
     int16_t prod_of[kMaxDigits][kMaxDigits]; // (i, j) -> product index or -1
+    // Input limbs that feed a live product (bit i): the lift skips the others (k-sharded ranks need few of them).
+    u32 need_lhs, need_rhs;
+    // k-sharded dbfv_mul: every finished output limb k < d is also stored into the peers' output buffers
+    // (same [pair][d][2][n] layout) over NVLink peer memory, so no separate gather pass is needed.
+    u32 num_peers, pad4_;
+    u64 *peer_out[kMaxPeers];
 };
 
 struct HostSetup {

@@ -40,6 +40,13 @@ __device__ __forceinline__ u64 ld_stream(const u64 *p) {
 #endif
 }
 
+// Stores into peer GPUs' memory (k-sharded dbfv_mul) are made visible system-wide before the kernel ends.
+__device__ __forceinline__ void peer_fence() {
+#ifndef EXB_HOST_EMUL
+    __threadfence_system();
+#endif
+}
+
 // ---------------------------------------------------------------------------------
 // Shared-memory transforms.  LOGN == 12: 256 threads, radix-16 register passes on a
 // swizzled image.  LOGN == 0: any n = 2^logn, radix-2 stages on a linear image.
@@ -461,7 +468,7 @@ __global__ void poly_op_kernel(Modulus mod, int op, const u64 *__restrict__ a, c
 // ---------------------------------------------------------------------------------
 template <int LOGN>
 __global__ void __launch_bounds__(LOGN == 12 ? kThreads12 : 256, LOGN == 12 ? 2 : 1)
-lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
+lift_kernel(const __grid_constant__ DeviceParams P, u32 d, u32 need_lhs, u32 need_rhs, const u64 *__restrict__ ct1,
             const u64 *__restrict__ ct2, u64 *__restrict__ ext) {
     EXB_DYN_SMEM(smem);
     const u32 n = P.n, A = P.num_aux;
@@ -471,6 +478,7 @@ lift_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict
     const u32 limb = (idx >> 1) % d;
     const u32 side = (idx / (2 * d)) & 1u;
     const size_t pair = idx / (4 * d);
+    if (!(((side ? need_rhs : need_lhs) >> limb) & 1u)) return;      // no live product reads this limb
     const u64 *src = (side ? ct2 : ct1) + ((pair * d + limb) * 2 + comp) * (size_t)n;
     u64 *dst = ext + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)(1 + A)) * n;
     const Modulus &mq = P.mod[0];
@@ -654,7 +662,7 @@ __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
 // n^-1 constants of the inverse transforms that follow (SmallBasis::mq_r for q, Mod32::ninv for the small primes).
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads12, 2)
-lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restrict__ ct1,
+lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, u32 need_lhs, u32 need_rhs, const u64 *__restrict__ ct1,
               const u64 *__restrict__ ct2, u32 *__restrict__ ext_s) {
     EXB_DYN_SMEM(smem);
     constexpr u32 n = 4096;
@@ -666,6 +674,7 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, const u64 *__restri
     const u32 limb = (idx >> 1) % d;
     const u32 side = (idx / (2 * d)) & 1u;
     const size_t pair = idx / (4 * d);
+    if (!(((side ? need_rhs : need_lhs) >> limb) & 1u)) return;      // no live product reads this limb
     const u64 *src = (side ? ct2 : ct1) + ((pair * d + limb) * 2 + comp) * (size_t)n;
     u32 *ds = ext_s + ((((pair * 2 + side) * d + limb) * 2 + comp) * (size_t)K) * n;
     const Modulus &mq = P.mod[0];
@@ -1000,6 +1009,14 @@ relin_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mul
         dst[e] = acc0[e];
         dst[n + e] = acc1[e];
     }
+    if (k < d && M.num_peers) {            // k-sharded: the finished limb goes straight into every peer's output
+        const size_t off = ((pair * d + k) * 2) * (size_t)n;
+        for (u32 p = 0; p < M.num_peers; p++) {
+            u64 *pd = M.peer_out[p] + off;
+            for (u32 e = threadIdx.x; e < n; e += blockDim.x) { pd[e] = acc0[e]; pd[n + e] = acc1[e]; }
+        }
+        peer_fence();
+    }
 }
 
 // n = 4096 specialisation of relin_kernel: 8 consecutive coefficients per thread, 128-bit accesses.
@@ -1077,11 +1094,16 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
     }
     u64 *dst = k < d ? out + ((pair * d + k) * 2) * (size_t)n
                      : excess + ((pair * (NL - M.num_low) + (limb - M.num_low)) * 2) * (size_t)n;
+    const u32 np = k < d ? M.num_peers : 0u;   // k-sharded: the finished limb also goes into every peer's output
+    const size_t off = ((pair * d + k) * 2) * (size_t)n;
     u64 v[8];
     lds_u64x4(acc0, e0, v); lds_u64x4(acc0, e0 + 4, v + 4);
     stg_u64x4(dst + e0, v); stg_u64x4(dst + e0 + 4, v + 4);
+    for (u32 p = 0; p < np; p++) { u64 *pd = M.peer_out[p] + off + e0; stg_u64x4(pd, v); stg_u64x4(pd + 4, v + 4); }
     lds_u64x4(acc1, e0, v); lds_u64x4(acc1, e0 + 4, v + 4);
     stg_u64x4(dst + n + e0, v); stg_u64x4(dst + n + e0 + 4, v + 4);
+    for (u32 p = 0; p < np; p++) { u64 *pd = M.peer_out[p] + off + n + e0; stg_u64x4(pd, v); stg_u64x4(pd + 4, v + 4); }
+    if (np) peer_fence();
 }
 
 // ---------------------------------------------------------------------------------
@@ -1186,7 +1208,10 @@ __global__ void relin_reduce_kernel(const __grid_constant__ DeviceParams P, cons
         u64 *dst = k < d ? out + ((pair * d + k) * 2) * (size_t)n
                          : excess + ((pair * (NL - M.num_low) + (limb - M.num_low)) * 2) * (size_t)n;
         dst[e] = acc;
+        if (k < d)
+            for (u32 p = 0; p < M.num_peers; p++) M.peer_out[p][((pair * d + k) * 2) * (size_t)n + e] = acc;
     }
+    if (M.num_peers) peer_fence();
 }
 
 // ---------------------------------------------------------------------------------
@@ -1431,16 +1456,16 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
     if (pairs == 0) return;
     if (P.sb.enabled && P.logn == 12) {
         const size_t sm32 = 4096 * 8 + (size_t)P.sb.K * 4096 * 4;
-        lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, ct1, ct2, ext_small_part(ext));
+        lift32_kernel<<<(unsigned)(pairs * 4 * M.d), kThreads12, sm32, s>>>(P, M.d, M.need_lhs, M.need_rhs, ct1, ct2, ext_small_part(ext));
         g_launch_count++;
         return;
     }
     const size_t sm = (size_t)P.n * 8 * 2;
     const unsigned grid = (unsigned)(pairs * 4 * M.d);
     if (P.logn == 12) {
-        lift_kernel<12><<<grid, kThreads12, sm, s>>>(P, M.d, ct1, ct2, ext);
+        lift_kernel<12><<<grid, kThreads12, sm, s>>>(P, M.d, M.need_lhs, M.need_rhs, ct1, ct2, ext);
     } else {
-        lift_kernel<0><<<grid, block_threads(P), sm, s>>>(P, M.d, ct1, ct2, ext);
+        lift_kernel<0><<<grid, block_threads(P), sm, s>>>(P, M.d, M.need_lhs, M.need_rhs, ct1, ct2, ext);
     }
     g_launch_count++;
 }

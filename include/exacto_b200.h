@@ -253,6 +253,23 @@ int exb_dbfv_mul(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t 
 int exb_dbfv_mul_host(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
                       const uint64_t *ct1_host, const uint64_t *ct2_host, const exb_relin_key *rlk,
                       uint64_t *out_host, size_t batch, uint32_t flags);
+/* ---- k-sharded dbfv_mul across the GPUs of one box (one process per GPU).  Every rank holds the same
+ * ciphertext pairs and owns the output limbs of its `limb_mask` (products with equal i + j stay on one rank, so
+ * the per-k accumulation of dbfv/eval.rs:125-136 is local).  The relinearisation kernel stores each finished
+ * limb into this rank's `out_dev` and into `peer_outs_dev[0..num_peers)` -- the other ranks' output buffers,
+ * same [batch][d][2][n] layout, mapped over NVLink with exb_ipc_open -- so the path's only exchange step
+ * overlaps the compute and moves exactly 512 KiB * (N-1)/N per dbfv_mul into each rank.  The caller
+ * synchronises the ranks (any barrier after the stream work) before reading.  Needs p = b^d (all-zero small
+ * representatives, every BASELINE config): EXB_NOT_IMPLEMENTED otherwise. */
+int exb_dbfv_mul_scatter(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
+                         const uint64_t *ct1_dev, const uint64_t *ct2_dev, const exb_relin_key *rlk,
+                         uint64_t *out_dev, uint64_t *const *peer_outs_dev, uint32_t num_peers, size_t batch,
+                         uint32_t flags, uint32_t limb_mask, void *stream);
+/* CUDA IPC for those buffers: `dev_ptr` must be the base of an exb_device_alloc allocation. */
+int exb_ipc_export(exb_context *ctx, void *dev_ptr, uint8_t handle[64]);
+int exb_ipc_open(exb_context *ctx, const uint8_t handle[64], void **peer_dev_ptr);
+int exb_ipc_close(exb_context *ctx, void *peer_dev_ptr);
+
 /* Asynchronous forms of the host-buffer calls: the work is enqueued on the context's pipeline and the call
  * returns; exb_wait(ticket) blocks until the output has landed in out_host.  Inputs must stay valid and
  * unmodified, and out_host unread, until then.  Calls are pipelined across each other: the next call's

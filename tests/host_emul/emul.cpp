@@ -190,7 +190,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
     const u64 *rk = rlk_mont.data();
     if (small) {
         u32 *exts = reinterpret_cast<u32 *>(extp);
-        emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, ct1, ct2, exts); });
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, d, M.need_lhs, M.need_rhs, ct1, ct2, exts); });
         const size_t sm32 = n * 8 + (size_t)P.sb.K * n * 4;
         // the emulator always takes the per-limb kernel when it is legal (large-batch decision), so the CPU tier
         // covers it on small inputs; `per_product` forces the other kernel
@@ -217,7 +217,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         }
         if (wide_relin) emu_launch(4, 256, 0, [&]() { relin_reduce_kernel(P, M, wp, out, xp, pairs); });
     } else if (P.logn == 12) {
-        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, M.need_lhs, M.need_rhs, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
@@ -228,7 +228,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
             emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
         }
     } else {
-        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, M.need_lhs, M.need_rhs, ct1, ct2, extp); });
         if (hs.digits32) {
             int32_t *dg = dig32.data();
             emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
@@ -277,13 +277,13 @@ int emu_bfv_mul_no_relin(emu_ctx *c, const uint64_t *ct1, const uint64_t *ct2, u
     int16_t *nodig = nullptr;
     if (small) {
         u32 *exts = reinterpret_cast<u32 *>(extp);
-        emu_launch((unsigned)(pairs * 4), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, 1, ct1, ct2, exts); });
+        emu_launch((unsigned)(pairs * 4), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { lift32_kernel(P, 1, 1u, 1u, ct1, ct2, exts); });
         emu_launch((unsigned)(pairs * 3), thr, n * 8 + (size_t)P.sb.K * n * 4, [&]() { tensor32_kernel<int16_t>(P, M, ct1, ct2, exts, r01p, nodig, 2u); });
     } else if (P.logn == 12) {
-        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<12>(P, 1, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<12>(P, 1, 1u, 1u, ct1, ct2, extp); });
         emu_launch((unsigned)(pairs * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, nodig, 1u); });
     } else {
-        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<0>(P, 1, ct1, ct2, extp); });
+        emu_launch((unsigned)(pairs * 4), thr, n * 16, [&]() { lift_kernel<0>(P, 1, 1u, 1u, ct1, ct2, extp); });
         emu_launch((unsigned)(pairs * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, nodig, 1u); });
     }
     return emu_ntt(c, 0, 1, r01p, out3, pairs * 3);

@@ -741,6 +741,55 @@ def test_async_host_api_pinned_memory_and_slot_pool():
     assert ctx.ntt_format_id(0) >> 56 == 1
 
 
+@pytest.mark.parametrize("pairs", [2, 30])
+def test_dbfv_mul_scatter_peer_stores(pairs):
+    """exb_dbfv_mul_scatter (k-sharded dbfv_mul): two 'ranks' on one GPU own disjoint output limbs and store their
+    finished limbs into both output buffers from the relin epilogue (narrow and wide relin paths); the union is the
+    oracle's dbfv_mul, and limbs a rank does not own stay untouched in its peers' buffers until their owner writes."""
+    import ctypes
+    from exacto_b200 import _native, batch
+    from exacto_b200.sharding import limb_masks
+    S = H.u64_dbfv()
+    P = S.bfv
+    dp = E.u64_dbfv()
+    ctx = dp.bfv_params.context()
+    L = _native.lib()
+    rng = np.random.default_rng(77 + pairs)
+    ct1 = rng.integers(0, P.q, (pairs, S.d, 2, P.n), dtype=np.uint64)
+    ct2 = rng.integers(0, P.q, (pairs, S.d, 2, P.n), dtype=np.uint64)
+    rlk_arr = rng.integers(0, P.q, (P.gadget_digits, 2, P.n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    want = np.stack([O.dbfv_mul(P, S.base, S.d, S.plain_modulus, a, b, rlk_arr, threads=O.max_threads())
+                     for a, b in zip(ct1[:3], ct2[:3])])
+    a, b = batch.to_device(ct1), batch.to_device(ct2)
+    masks = limb_masks(S.d, 2)
+    outs = [torch.full_like(a, -1), torch.full_like(a, -1)]
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(2):
+        peer = (ctypes.c_void_p * 1)(outs[1 - r].data_ptr())
+        _native.check(L.exb_dbfv_mul_scatter(ctx.handle, dp.base, S.d, dp.plain_modulus, a.data_ptr(), b.data_ptr(),
+                                             rlk.native(ctx), outs[r].data_ptr(), peer, 1, pairs, 0, masks[r], st))
+        if r == 0:
+            torch.cuda.synchronize()
+            h0 = batch.to_host(outs[1])
+            for k in range(S.d):
+                if (masks[0] >> k) & 1:
+                    assert np.array_equal(h0[:3, k], want[:, k])
+                else:
+                    assert np.all(h0[:, k] == np.uint64(0xFFFFFFFFFFFFFFFF))
+    torch.cuda.synchronize()
+    assert np.array_equal(batch.to_host(outs[0])[:3], want) and torch.equal(outs[0], outs[1])
+    # p != b^d (non-zero small representatives) is refused: the general reduction needs limbs of other ranks
+    C = CASES["n64_a2_rep"]
+    pr = to_dbfv_params(C[0], C[1], C[2], C[3])
+    z = torch.zeros((1, C[2], 2, C[0].n), dtype=torch.int64, device="cuda")
+    rk = E.RelinKey(np.zeros((C[0].gadget_digits, 2, C[0].n), np.uint64), pr.bfv_params)
+    c2 = pr.bfv_params.context()
+    rc = L.exb_dbfv_mul_scatter(c2.handle, pr.base, C[2], pr.plain_modulus, z.data_ptr(), z.data_ptr(), rk.native(c2),
+                                z.data_ptr(), None, 0, 1, 0, 1, st)
+    assert rc == 9 and b"small representatives" in L.exb_last_error()
+
+
 def test_per_limb_tensor_path_on_gpu():
     """Batches large enough for tensor01_kernel (components 0/1 summed per output limb) vs the oracle, device and
     host entry points, and the same batch through the per-product kernel only (option "tensor_per_product")."""

@@ -141,7 +141,7 @@ def test_pair_range_and_limb_masks():
 def _gloo_worker(rank, world, port, tmp):
     import torch
     import torch.distributed as dist
-    from exacto_b200.sharding import gather_limbs, limb_masks, pair_range
+    from exacto_b200.sharding import gather_limbs, gather_wire_bytes_per_rank, limb_masks, limb_owner, pair_range
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     P, base, d, pm = H.toy(16), 16, 2, 256
     rng = np.random.default_rng(99)
@@ -161,6 +161,18 @@ def _gloo_worker(rank, world, port, tmp):
             part[:, k] = full[:, k]
     got = gather_limbs(torch.from_numpy(part.view(np.int64)), masks).numpy().view(np.uint64)
     assert np.array_equal(got, full)
+    # only owned limbs travel: each rank receives exactly the limbs it does not own
+    limb_bytes = 2 * P.n * 8
+    assert sum(gather_wire_bytes_per_rank(masks, d, r, limb_bytes) for r in range(world)) == d * limb_bytes * (world - 1)
+    assert sorted(limb_owner(masks, d)) == sorted(r for r in range(world) for k in range(d) if (masks[r] >> k) & 1)
+    # u64 profile (d = 8) split over 3 ranks with uneven limb counts
+    m3 = limb_masks(8, world)
+    t8 = torch.arange(3 * 8 * 2 * 4, dtype=torch.int64).reshape(3, 8, 2, 4)
+    mine8 = torch.zeros_like(t8)
+    for k in range(8):
+        if (m3[rank] >> k) & 1:
+            mine8[:, k] = t8[:, k]
+    assert torch.equal(gather_limbs(mine8, m3), t8)
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
