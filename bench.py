@@ -276,10 +276,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own INFO lines (communicator / NVLS evidence) go to a file per rank, stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "exb_nccl_%h_%p.log"))
+        os.environ.setdefault("NCCL_DEBUG", "WARN")    # a caller's own NCCL_DEBUG (e.g. INFO for communicator evidence) wins
         dist.init_process_group("nccl", device_id=dev)
     params = E.u64_dbfv()
     P = params.bfv_params

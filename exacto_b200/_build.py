@@ -8,8 +8,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libexacto_b200.so")
-SOURCES = ["kernels.cu", "api.cu", "host_setup.cpp"]
-HEADERS = ["kernels.cuh", "host_setup.hpp", "modarith.cuh", "ntt_core.cuh", "ntt32_core.cuh", "hps.cuh", "hps32.cuh",
+SOURCES = ["kernels.cu", "rns_kernels.cu", "api.cu", "host_setup.cpp"]
+HEADERS = ["kernels.cuh", "host_setup.hpp", "modarith.cuh", "ntt_core.cuh", "ntt32_core.cuh", "hps.cuh", "hps32.cuh", "rns.cuh",
            os.path.join("..", "..", "include", "exacto_b200.h")]
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
               "-lineinfo", "-O3", "-std=c++17"]

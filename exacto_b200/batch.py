@@ -34,6 +34,12 @@ def _check(t: torch.Tensor, shape_tail, what: str):
         raise InvalidParam(f"{what}: trailing shape {tuple(t.shape)} != (..., {shape_tail})")
 
 
+def _ct_tail(params: BfvParams):
+    """Trailing shape of one ciphertext component: (n,) for a single ciphertext prime, (L, n) otherwise."""
+    L = params.ct_basis.num_moduli()
+    return (params.ring_degree,) if L == 1 else (L, params.ring_degree)
+
+
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -63,22 +69,23 @@ def ntt_inverse(params: BfvParams, index: int, polys: torch.Tensor, out: Optiona
 def bfv_mul_and_relin(params: BfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: RelinKey,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bfv/eval.rs:73-82 over [B, 2, n]."""
-    n = params.ring_degree
-    _check(ct1, (2, n), "ct1"); _check(ct2, (2, n), "ct2")
+    tail = (2,) + _ct_tail(params)
+    _check(ct1, tail, "ct1"); _check(ct2, tail, "ct2")
     if ct1.shape != ct2.shape:
         raise InvalidParam("ct1/ct2 shape mismatch")
     out = torch.empty_like(ct1) if out is None else out
     ctx = params.context(ct1.device.index)
     _native.check(_native.lib().exb_bfv_mul_and_relin(ctx.handle, ct1.data_ptr(), ct2.data_ptr(), rlk.native(ctx),
-                                                      out.data_ptr(), ct1.numel() // (2 * n), _stream(ct1)))
+                                                      out.data_ptr(), ct1.numel() // int(np.prod(tail)), _stream(ct1)))
     return out
 
 
 def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: RelinKey,
              out: Optional[torch.Tensor] = None, *, all_products: bool = False, limb_mask: int = 0) -> torch.Tensor:
     """dbfv/eval.rs:82-149 over [B, d, 2, n].  ``limb_mask`` selects output limbs (multi-GPU k-sharding)."""
-    n, d = params.bfv_params.ring_degree, params.num_digits
-    _check(ct1, (d, 2, n), "ct1"); _check(ct2, (d, 2, n), "ct2")
+    d = params.num_digits
+    tail = (d, 2) + _ct_tail(params.bfv_params)
+    _check(ct1, tail, "ct1"); _check(ct2, tail, "ct2")
     if ct1.shape != ct2.shape:
         raise InvalidParam("ct1/ct2 shape mismatch")
     out = torch.empty_like(ct1) if out is None else out
@@ -86,17 +93,17 @@ def dbfv_mul(params: DbfvParams, ct1: torch.Tensor, ct2: torch.Tensor, rlk: Reli
     flags = _native.EXB_DBFV_ALL_PRODUCTS if all_products else 0
     _native.check(_native.lib().exb_dbfv_mul(ctx.handle, params.base, d, params.plain_modulus, ct1.data_ptr(),
                                              ct2.data_ptr(), rlk.native(ctx), out.data_ptr(),
-                                             ct1.numel() // (d * 2 * n), flags, limb_mask, _stream(ct1)))
+                                             ct1.numel() // int(np.prod(tail)), flags, limb_mask, _stream(ct1)))
     return out
 
 
 def bfv_mul_no_relin(params: BfvParams, ct1: torch.Tensor, ct2: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bfv/eval.rs:89-108 over [B, 2, n] -> [B, 3, n]."""
-    n = params.ring_degree
-    _check(ct1, (2, n), "ct1"); _check(ct2, (2, n), "ct2")
-    if ct1.shape != ct2.shape or ct1.dim() != 3:
+    tail = _ct_tail(params)
+    _check(ct1, (2,) + tail, "ct1"); _check(ct2, (2,) + tail, "ct2")
+    if ct1.shape != ct2.shape or ct1.dim() != 2 + len(tail):
         raise InvalidParam("ct1/ct2: need matching [batch, 2, n]")
-    out = torch.empty((ct1.shape[0], 3, n), dtype=torch.int64, device=ct1.device) if out is None else out
+    out = torch.empty((ct1.shape[0], 3) + tail, dtype=torch.int64, device=ct1.device) if out is None else out
     ctx = params.context(ct1.device.index)
     _native.check(_native.lib().exb_bfv_mul_no_relin(ctx.handle, ct1.data_ptr(), ct2.data_ptr(), out.data_ptr(), ct1.shape[0],
                                                      _stream(ct1)))
@@ -105,11 +112,11 @@ def bfv_mul_no_relin(params: BfvParams, ct1: torch.Tensor, ct2: torch.Tensor, ou
 
 def relinearize(params: BfvParams, ct3: torch.Tensor, rlk: RelinKey, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bfv/keyswitch.rs:59-101 over [B, 3, n] -> [B, 2, n]."""
-    n = params.ring_degree
-    _check(ct3, (3, n), "ct3")
-    if ct3.dim() != 3:
+    tail = _ct_tail(params)
+    _check(ct3, (3,) + tail, "ct3")
+    if ct3.dim() != 2 + len(tail):
         raise InvalidParam("ct3: need [batch, 3, n]")
-    out = torch.empty((ct3.shape[0], 2, n), dtype=torch.int64, device=ct3.device) if out is None else out
+    out = torch.empty((ct3.shape[0], 2) + tail, dtype=torch.int64, device=ct3.device) if out is None else out
     ctx = params.context(ct3.device.index)
     _native.check(_native.lib().exb_bfv_relinearize(ctx.handle, ct3.data_ptr(), 3, rlk.native(ctx), out.data_ptr(), ct3.shape[0],
                                                     _stream(ct3)))

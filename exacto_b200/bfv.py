@@ -37,15 +37,20 @@ class BfvCiphertext:
     # -- array views used by the batched entry points --------------------------------
     @staticmethod
     def from_array(arr, params: BfvParams) -> "BfvCiphertext":
-        """arr: [k][n] NTT-domain residues mod q_0 (single ciphertext prime)."""
+        """arr: [k][n] NTT-domain residues mod q_0, or [k][L][n] for a multi-prime ciphertext modulus."""
         arr = _u64(arr)
-        plan = Plan(params, 0)
-        q = plan.modulus()
-        return BfvCiphertext([RnsPoly([NttPoly(arr[i].copy(), q, plan)], params.ring_degree)
-                              for i in range(arr.shape[0])], params)
+        L = params.ct_basis.num_moduli()
+        if L == 1 and arr.ndim == 2:
+            arr = arr[:, None, :]
+        plans = [Plan(params, params.ct_index(l)) for l in range(L)]
+        return BfvCiphertext([RnsPoly([NttPoly(arr[i, l].copy(), plans[l].modulus(), plans[l]) for l in range(L)],
+                                      params.ring_degree) for i in range(arr.shape[0])], params)
 
     def to_array(self) -> np.ndarray:
-        return np.stack([ci.components[0].evals for ci in self.c])
+        """[k][n] for a single ciphertext prime, [k][L][n] otherwise."""
+        if len(self.c[0].components) == 1:
+            return np.stack([ci.components[0].evals for ci in self.c])
+        return np.stack([np.stack([comp.evals for comp in ci.components]) for ci in self.c])
 
 
 class RelinKey:
@@ -53,20 +58,25 @@ class RelinKey:
     (Montgomery form) is created on first use and cached per device."""
 
     def __init__(self, keys, params: BfvParams):
+        L = params.ct_basis.num_moduli()
         if isinstance(keys, np.ndarray):
-            self.array = _u64(keys)                                    # [G][2][n]
-        else:
+            self.array = _u64(keys)                                    # [G][2][n]  ([G][2][L][n] for L > 1 primes)
+        elif L == 1:
             self.array = np.stack([np.stack([k0.components[0].evals, k1.components[0].evals])
                                    for (k0, k1) in keys]) if len(keys) else np.zeros((0, 2, params.ring_degree), np.uint64)
+        else:
+            self.array = np.stack([np.stack([np.stack([c.evals for c in k.components]) for k in pair]) for pair in keys]) \
+                if len(keys) else np.zeros((0, 2, L, params.ring_degree), np.uint64)
         self.params = params
         self._native = {}
 
     @property
     def keys(self):
-        plan = Plan(self.params, 0)
-        q, n = plan.modulus(), self.params.ring_degree
-        return [(RnsPoly([NttPoly(self.array[g, 0], q, plan)], n), RnsPoly([NttPoly(self.array[g, 1], q, plan)], n))
-                for g in range(self.array.shape[0])]
+        n, L = self.params.ring_degree, self.params.ct_basis.num_moduli()
+        plans = [Plan(self.params, self.params.ct_index(l)) for l in range(L)]
+        arr = self.array if self.array.ndim == 4 else self.array[:, :, None, :]
+        return [tuple(RnsPoly([NttPoly(arr[g, c, l], plans[l].modulus(), plans[l]) for l in range(L)], n) for c in range(2))
+                for g in range(arr.shape[0])]
 
     def native(self, ctx) -> ctypes.c_void_p:
         key = id(ctx)
@@ -140,8 +150,8 @@ def bfv_mul_and_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray,
                             device: Optional[int] = None) -> np.ndarray:
     """Batched host-buffer form: ct [B][2][n] -> [B][2][n] (exb_bfv_mul_and_relin_host)."""
     ct1, ct2 = _u64(ct1), _u64(ct2)
-    n = params.ring_degree
-    if ct1.shape != ct2.shape or ct1.shape[1:] != (2, n):
+    n, L = params.ring_degree, params.ct_basis.num_moduli()
+    if ct1.shape != ct2.shape or ct1.shape[1:] != ((2, n) if L == 1 else (2, L, n)):
         raise InvalidParam("multiplication requires degree-1 ciphertexts")
     ctx = params.context(device)
     out = np.empty_like(ct1)
@@ -172,13 +182,14 @@ def bfv_mul_no_relin(ct1: BfvCiphertext, ct2: BfvCiphertext) -> BfvCiphertext:
 def bfv_mul_no_relin_batch(params: BfvParams, ct1: np.ndarray, ct2: np.ndarray) -> np.ndarray:
     """ct [B][2][n] x2 -> [B][3][n] (exb_bfv_mul_no_relin)."""
     ct1, ct2 = _u64(ct1), _u64(ct2)
-    n = params.ring_degree
-    if ct1.shape != ct2.shape or ct1.shape[1:] != (2, n):
+    n, Lq = params.ring_degree, params.ct_basis.num_moduli()
+    tail = (n,) if Lq == 1 else (Lq, n)                   # multi-prime ciphertexts are [B][k][L][n]
+    if ct1.shape != ct2.shape or ct1.shape[1:] != (2,) + tail:
         raise InvalidParam("multiplication requires degree-1 ciphertexts")
     L = _native.lib()
     return _dev_call(params, lambda ctx, d, o: L.exb_bfv_mul_no_relin(ctx.handle, d[0].data_ptr(), d[1].data_ptr(), o.data_ptr(),
                                                                       ct1.shape[0], None),
-                     ct1, ct2, out_shape=(ct1.shape[0], 3, n))
+                     ct1, ct2, out_shape=(ct1.shape[0], 3) + tail)
 
 
 def relinearize(ct: BfvCiphertext, rlk: RelinKey) -> BfvCiphertext:
@@ -195,13 +206,14 @@ def relinearize(ct: BfvCiphertext, rlk: RelinKey) -> BfvCiphertext:
 def relinearize_batch(params: BfvParams, ct3: np.ndarray, rlk: RelinKey) -> np.ndarray:
     """ct [B][3][n] -> [B][2][n] (exb_bfv_relinearize)."""
     ct3 = _u64(ct3)
-    n = params.ring_degree
-    if ct3.ndim != 3 or ct3.shape[1:] != (3, n):
+    n, Lq = params.ring_degree, params.ct_basis.num_moduli()
+    tail = (n,) if Lq == 1 else (Lq, n)
+    if ct3.shape[1:] != (3,) + tail:
         raise InvalidParam("relinearization only supports degree-2 ciphertexts")
     L = _native.lib()
     return _dev_call(params, lambda ctx, d, o: L.exb_bfv_relinearize(ctx.handle, d[0].data_ptr(), 3, rlk.native(ctx), o.data_ptr(),
                                                                      ct3.shape[0], None),
-                     ct3, out_shape=(ct3.shape[0], 2, n))
+                     ct3, out_shape=(ct3.shape[0], 2) + tail)
 
 
 def gadget_decompose(poly, params: BfvParams) -> list:

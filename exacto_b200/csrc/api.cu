@@ -222,6 +222,23 @@ extern "C" int exb_context_create_ex(const exb_bfv_params *p, int device, uint32
         c->d_tables.push_back(reinterpret_cast<Tw *>(df)); c->d_tables.push_back(reinterpret_cast<Tw *>(di));
         c->P.sb.twf[i] = df; c->P.sb.twi[i] = di;
     }
+    if (c->rns_enabled) {
+        auto up = [&](const std::vector<Tw> &h, const Tw **dst) {
+            Tw *d = nullptr;
+            if (cudaMalloc(&d, sizeof(Tw) * n) != cudaSuccess ||
+                cudaMemcpy(d, h.data(), sizeof(Tw) * n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return false; }
+            c->d_tables.push_back(d);
+            *dst = d;
+            return true;
+        };
+        bool ok = true;
+        for (u32 l = 0; ok && l < c->R.L; l++) ok = up(c->rns_twf_q[l], &c->T.twf_q[l]) && up(c->rns_twi_q[l], &c->T.twi_q[l]);
+        for (u32 k = 0; ok && k < c->R.K; k++) ok = up(c->rns_twf_e[k], &c->T.twf_e[k]) && up(c->rns_twi_e[k], &c->T.twi_e[k]);
+        if (!ok) {
+            exb_context_destroy(c);
+            return fail(EXB_CUDA_ERROR, "multi-prime twiddle upload failed");
+        }
+    }
     for (Workspace &w : c->ws)
         if (cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) != cudaSuccess) {
             exb_context_destroy(c);
@@ -349,12 +366,31 @@ static int check_launch(const char *what) {
     return EXB_OK;
 }
 
+// Modulus indices: 0 = q_0, 1..A = aux primes, then the remaining ciphertext primes q_1.. (multi-prime sets).
+static int rns_prime_of(const exb_context *c, u32 idx) {          // ciphertext prime l >= 1 behind `idx`, or -1
+    const u32 A = c->user_aux;
+    if (!c->rns_enabled || idx <= A) return -1;
+    const u32 l = idx - A;
+    return l < c->R.L ? (int)l : -1;
+}
 static int check_base(const exb_context *c, u32 idx) {
     if (!c) return fail(EXB_INVALID_PARAM, "null context");
     const u32 A = c->user_aux;                       // an internal auxiliary pair is not addressable
+    if (rns_prime_of(c, idx) >= 0) return EXB_OK;
     if (idx != 0 && (A > (u32)kMaxAux || idx > A))
         return fail(EXB_MODULUS_MISMATCH, "modulus index " + std::to_string(idx) + " has no device plan");
     return EXB_OK;
+}
+static const Modulus &modulus_of(const exb_context *c, u32 idx) {
+    const int l = rns_prime_of(c, idx);
+    return l >= 0 ? c->R.q[l] : c->P.mod[idx];
+}
+static void ntt_any(exb_context *c, u32 idx, bool fwd, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+    const int l = rns_prime_of(c, idx);
+    if (l >= 0) launch_ntt_plan(c->R.q[l], fwd ? c->T.twf_q[l] : c->T.twi_q[l], fwd ? c->T.headf_q[l] : c->T.headi_q[l],
+                                c->logn, fwd, in, out, count, s);
+    else if (fwd) launch_ntt_fwd(c->P, (int)idx, in, out, count, s);
+    else launch_ntt_inv(c->P, (int)idx, in, out, count, s);
 }
 
 // ---------------------------------------------------------------------------------
@@ -365,7 +401,7 @@ extern "C" int exb_ntt_forward(exb_context *c, uint32_t idx, const uint64_t *in,
     int rc = check_base(c, idx);
     if (rc) return rc;
     EXB_CUDA(cudaSetDevice(c->device));
-    launch_ntt_fwd(c->P, (int)idx, in, out, count, (cudaStream_t)stream);
+    ntt_any(c, idx, true, in, out, count, (cudaStream_t)stream);
     return check_launch("ntt_fwd");
 }
 extern "C" int exb_ntt_inverse(exb_context *c, uint32_t idx, const uint64_t *in, uint64_t *out, size_t count,
@@ -373,7 +409,7 @@ extern "C" int exb_ntt_inverse(exb_context *c, uint32_t idx, const uint64_t *in,
     int rc = check_base(c, idx);
     if (rc) return rc;
     EXB_CUDA(cudaSetDevice(c->device));
-    launch_ntt_inv(c->P, (int)idx, in, out, count, (cudaStream_t)stream);
+    ntt_any(c, idx, false, in, out, count, (cudaStream_t)stream);
     return check_launch("ntt_inv");
 }
 
@@ -388,8 +424,7 @@ static int ntt_host(exb_context *c, u32 idx, const u64 *in, u64 *out, size_t cou
     rc = grow((void **)&w.in1, &w.in_b, bytes);
     if (rc) return rc;
     EXB_CUDA(cudaMemcpyAsync(w.in1, in, bytes, cudaMemcpyHostToDevice, w.stream));
-    if (fwd) launch_ntt_fwd(c->P, (int)idx, w.in1, w.in1, count, w.stream);
-    else launch_ntt_inv(c->P, (int)idx, w.in1, w.in1, count, w.stream);
+    ntt_any(c, idx, fwd, w.in1, w.in1, count, w.stream);
     rc = check_launch("ntt_host");
     if (rc) return rc;
     EXB_CUDA(cudaMemcpyAsync(out, w.in1, bytes, cudaMemcpyDeviceToHost, w.stream));
@@ -408,7 +443,7 @@ static int poly_op(exb_context *c, u32 idx, PolyOp op, const u64 *a, const u64 *
     int rc = check_base(c, idx);
     if (rc) return rc;
     EXB_CUDA(cudaSetDevice(c->device));
-    launch_poly_op(c->P.mod[idx], op, a, b, scalar, out, words, (cudaStream_t)stream);
+    launch_poly_op(modulus_of(c, idx), op, a, b, scalar, out, words, (cudaStream_t)stream);
     return check_launch("poly_op");
 }
 extern "C" int exb_poly_add(exb_context *c, uint32_t i, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t w, void *s) {
@@ -426,7 +461,7 @@ extern "C" int exb_poly_mul(exb_context *c, uint32_t i, const uint64_t *a, const
 extern "C" int exb_poly_scalar_mul(exb_context *c, uint32_t i, const uint64_t *a, uint64_t scalar, uint64_t *o, size_t w, void *s) {
     int rc = check_base(c, i);
     if (rc) return rc;
-    return poly_op(c, i, OP_SCALAR_MUL, a, nullptr, scalar % c->P.mod[i].m, o, w, s);   // ring/ntt.rs:133
+    return poly_op(c, i, OP_SCALAR_MUL, a, nullptr, scalar % modulus_of(c, i).m, o, w, s);   // ring/ntt.rs:133
 }
 extern "C" int exb_bfv_add(exb_context *c, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t batch, void *s) {
     if (!c) return fail(EXB_INVALID_PARAM, "null context");
@@ -451,12 +486,15 @@ static int relin_key_make(exb_context *c, const u64 *src, bool src_is_host, u32 
     EXB_CUDA(cudaSetDevice(c->device));
     exb_relin_key *k = new exb_relin_key();
     k->ctx = c; k->num_keys = num_keys;
-    const size_t words = (size_t)num_keys * 2 * c->n;
+    const size_t L = c->ct_moduli.size();
+    const size_t words = (size_t)num_keys * 2 * L * c->n;             // multi-prime keys are [G][2][L][n]
+    if (L > 1 && !c->rns_enabled) { delete k; return fail(c->mul_status ? c->mul_status : EXB_NOT_IMPLEMENTED, c->mul_error); }
     if (cudaMalloc(&k->d_mont, words ? words * 8 : 8) != cudaSuccess) { delete k; return fail(EXB_CUDA_ERROR, "cudaMalloc relin key"); }
     if (words) {
         cudaError_t e = cudaMemcpyAsync(k->d_mont, src, words * 8, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream);
         if (e != cudaSuccess) { exb_relin_key_destroy(k); return fail(EXB_CUDA_ERROR, cudaGetErrorString(e)); }
-        launch_poly_op(c->P.mod[0], OP_TO_MONT, k->d_mont, nullptr, 0, k->d_mont, words, stream);
+        if (L > 1) launch_rns_to_mont(c->R, k->d_mont, (size_t)num_keys * 2 * L, stream);
+        else launch_poly_op(c->P.mod[0], OP_TO_MONT, k->d_mont, nullptr, 0, k->d_mont, words, stream);
         rc = check_launch("relin key to Montgomery");
         if (rc) { exb_relin_key_destroy(k); return rc; }
         e = cudaStreamSynchronize(stream);
@@ -572,6 +610,51 @@ static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G
     return chunk ? chunk : 1;
 }
 
+// Multi-prime ciphertext modulus (bfv_mul_generic_rns, bfv/eval.rs:113-147, and the L > 1 relinearize):
+// ct [batch][d][2][L][n].  mode 0: multiply + relinearise + per-k sums; mode 1: bfv_mul_no_relin -> [batch][3][L][n].
+static int rns_check_plan(const HostPlan &hp) {
+    for (int64_t r : hp.reps)
+        if (r != 0)
+            return fail(EXB_NOT_IMPLEMENTED, "multi-prime dbfv_mul on the device path needs all-zero small representatives (p = b^d)");
+    if (hp.M.num_limbs != hp.num_low)
+        return fail(EXB_NOT_IMPLEMENTED, "multi-prime dbfv_mul on the device path computes the limbs k < d only");
+    return EXB_OK;
+}
+
+// The caller holds workspace `w`; inputs / outputs are on the device.
+static int rns_mul_on(exb_context *c, Workspace *w, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1,
+                      const u64 *ct2, u64 *out, size_t batch, int mode, cudaStream_t st) {
+    const u32 G = rlk ? (rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits) : 0;
+    const size_t per = rns_workspace_words(c->R, hp.M, 1) * 8;
+    size_t chunk = c->tune.device_chunk_bytes / (per ? per : 1);
+    if (chunk < 1) chunk = 1;
+    const size_t in_stride = (size_t)hp.M.d * 2 * c->R.L * c->n;
+    const size_t out_stride = mode == 1 ? (size_t)3 * c->R.L * c->n : in_stride;
+    int rc = EXB_OK;
+    for (size_t off = 0; off < batch && !rc; off += chunk) {
+        const size_t cnt = batch - off < chunk ? batch - off : chunk;
+        if ((rc = grow((void **)&w->ext, &w->ext_b, per * cnt))) break;
+        launch_rns_mul(c->R, c->T, hp.M, ct1 + off * in_stride, ct2 + off * in_stride, rlk ? rlk->d_mont : nullptr, G,
+                       w->ext, out + off * out_stride, cnt, mode, st);
+        rc = check_launch("multi-prime ct-mul pipeline");
+    }
+    return rc;
+}
+
+static int rns_mul(exb_context *c, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1, const u64 *ct2,
+                   u64 *out, size_t batch, int mode, cudaStream_t st) {
+    int rc = rns_check_plan(hp);
+    if (rc) return rc;
+    if (batch == 0) return EXB_OK;
+    EXB_CUDA(cudaSetDevice(c->device));
+    std::unique_lock<std::mutex> held;
+    Workspace *w = nullptr;
+    if ((rc = acquire(c, st, &held, &w))) return rc;
+    rc = rns_mul_on(c, w, hp, rlk, ct1, ct2, out, batch, mode, st);
+    const int rc2 = release(w, st);
+    return rc ? rc : rc2;
+}
+
 static int dbfv_mul_device(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
                            const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, uint64_t *const *peers,
                            uint32_t num_peers, size_t batch, uint32_t flags, uint32_t limb_mask, void *stream) {
@@ -582,6 +665,10 @@ static int dbfv_mul_device(exb_context *c, uint64_t base, uint32_t d, uint64_t p
     if (num_peers && !peers) return fail(EXB_INVALID_PARAM, "null peer list");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, limb_mask, &hp))) return rc;
+    if (c->rns_enabled) {
+        if (num_peers) return fail(EXB_NOT_IMPLEMENTED, "k-sharded dbfv_mul needs a single ciphertext prime");
+        return rns_mul(c, hp, rlk, ct1, ct2, out, batch, 0, (cudaStream_t)stream);
+    }
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -690,14 +777,34 @@ static int host_pipeline(exb_context *c, uint64_t base, uint32_t d, uint64_t pm,
                          bool taper, Ticket *tk) {
     int rc = mul_precheck(c, rlk);
     if (rc) return rc;
-    if (c->ct_moduli.size() > 1)
-        return fail(EXB_NOT_IMPLEMENTED, "host-buffer entry points need a single ciphertext prime (use the device-resident call)");
     if (base < 2) return fail(EXB_INVALID_PARAM, "base must be >= 2");
     HostPlan hp;
     if ((rc = build_plan(d, base, pm, flags, 0, &hp))) return rc;
+    if (c->rns_enabled && (rc = rns_check_plan(hp))) return rc;
     if (batch == 0) return EXB_OK;
     std::lock_guard<std::mutex> lock(c->host_mu);
     EXB_CUDA(cudaSetDevice(c->device));
+    if (c->rns_enabled) {
+        // multi-prime ciphertext modulus: [batch][d][2][L][n], staged through one slot in bounded chunks
+        Workspace &w = c->hs[0];
+        const size_t stride = (size_t)d * 2 * c->R.L * c->n;
+        size_t chunk = ((size_t)256 << 20) / (stride * 8);
+        if (chunk < 1) chunk = 1;
+        for (size_t off = 0; off < batch; off += chunk) {
+            const size_t cnt = batch - off < chunk ? batch - off : chunk, bytes = cnt * stride * 8;
+            if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
+            if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
+            EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+            EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+            if ((rc = rns_mul_on(c, &w, hp, rlk, w.in1, w.in2, w.out, cnt, 0, w.stream))) return rc;
+            EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
+        }
+        cudaEvent_t e;
+        EXB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        tk->events.push_back(e);
+        EXB_CUDA(cudaEventRecord(e, w.stream));
+        return EXB_OK;
+    }
     const size_t stride = (size_t)d * 2 * c->n;
     // chunk size: enough CTAs to fill the GPU, small enough that H2D / kernels / D2H of consecutive chunks overlap
     size_t chunk = c->tune.host_chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
@@ -897,6 +1004,7 @@ extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const u
     HostPlan hp;
     int rc = build_plan(1, 2, 0, 0, 0, &hp);
     if (rc) return rc;
+    if (c->rns_enabled) return rns_mul(c, hp, nullptr, ct1, ct2, out3, batch, 1, (cudaStream_t)stream);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -927,14 +1035,34 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
     if (!c || !rlk) return fail(EXB_INVALID_PARAM, "null argument");
     if (rlk->ctx != c) return fail(EXB_INVALID_PARAM, "relinearisation key belongs to another context");
     if (ncomp > 3) return fail(EXB_INVALID_PARAM, "relinearization only supports degree-2 ciphertexts");   // :66-70
-    if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "relinearize on the device path needs a single ciphertext prime");
+    if (c->ct_moduli.size() != 1 && !c->rns_enabled) return fail(c->mul_status ? c->mul_status : EXB_NOT_IMPLEMENTED, c->mul_error);
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = c->n;
+    const size_t n = c->n * c->ct_moduli.size();                               // words per component
     if (ncomp < 3) {                                                           // :63-65 already degree 1: unchanged
         if (out != ct) EXB_CUDA(cudaMemcpyAsync(out, ct, batch * ncomp * n * 8, cudaMemcpyDeviceToDevice, st));
         return EXB_OK;
+    }
+    if (c->rns_enabled) {
+        HostPlan hp1;
+        int rc1 = build_plan(1, 2, 0, 0, 0, &hp1);
+        if (rc1) return rc1;
+        std::unique_lock<std::mutex> held1;
+        Workspace *w1 = nullptr;
+        if ((rc1 = acquire(c, st, &held1, &w1))) return rc1;
+        const u32 G1 = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;
+        const size_t per = rns_relin_workspace_words(c->R, 1) * 8;
+        size_t chunk1 = c->tune.device_chunk_bytes / per;
+        if (chunk1 < 1) chunk1 = 1;
+        for (size_t off = 0; off < batch && !rc1; off += chunk1) {
+            const size_t cnt = batch - off < chunk1 ? batch - off : chunk1;
+            if ((rc1 = grow((void **)&w1->ext, &w1->ext_b, per * cnt))) break;
+            launch_rns_relinearize(c->R, c->T, hp1.M, ct + off * 3 * n, rlk->d_mont, G1, w1->ext, out + off * 2 * n, cnt, st);
+            rc1 = check_launch("multi-prime relinearize");
+        }
+        const int rc2 = release(w1, st);
+        return rc1 ? rc1 : rc2;
     }
     if (c->gadget_base < 2 || c->gadget_base > (1ull << 32))
         return fail(EXB_NOT_IMPLEMENTED, "device path supports gadget bases in [2, 2^32]");

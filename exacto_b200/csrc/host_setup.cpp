@@ -174,15 +174,127 @@ static bool schoolbook_middle_term_overflow(u64 p, u64 q, u32 n) {
     return mt > i128_max || ms > i128_max;
 }
 
+
+// ---- multi-prime ciphertext modulus: constants of rns.cuh ---------------------------------------------------
+static std::vector<u32> bn_from(u64 v) { return std::vector<u32>{(u32)v, (u32)(v >> 32)}; }
+static void bn_trim(std::vector<u32> &a) { while (a.size() > 1 && a.back() == 0) a.pop_back(); }
+static std::vector<u32> bn_half(const std::vector<u32> &a) {
+    std::vector<u32> r(a.size());
+    for (size_t i = 0; i < a.size(); i++) r[i] = (a[i] >> 1) | (i + 1 < a.size() ? (a[i + 1] << 31) : 0u);
+    return r;
+}
+static size_t bn_bits(std::vector<u32> a) {
+    bn_trim(a);
+    size_t b = (a.size() - 1) * 32;
+    for (u32 t = a.back(); t; t >>= 1) b++;
+    return b;
+}
+static void bn_store(const std::vector<u32> &a, u32 *dst, int cap) {
+    for (int i = 0; i < cap; i++) dst[i] = (size_t)i < a.size() ? a[i] : 0u;
+}
+
+// Builds HostSetup::R / plans for 2 <= L <= 4 ciphertext primes with Q < 2^127 (the range in which the
+// reference's own relinearize, whose to_coeff_poly multiplies in u128, is defined without overflow).
+static int build_rns(HostSetup *c, std::string *err) {
+    c->rns_enabled = false;
+    c->mul_error.clear();
+    const u32 L = (u32)c->ct_moduli.size(), n = c->n;
+    if (L < 2) return EXB_OK;
+    memset(&c->R, 0, sizeof c->R);
+    memset(&c->T, 0, sizeof c->T);
+    auto refuse = [&](const std::string &why) { c->mul_error = why; return EXB_OK; };
+    if (L > (u32)kRnsMaxL) return refuse("multi-prime ciphertext modulus: the device path supports up to 4 ciphertext primes");
+    for (u32 i = 0; i < L; i++)
+        for (u32 j = i + 1; j < L; j++)
+            if (c->ct_moduli[i] == c->ct_moduli[j]) return refuse("non-coprime ciphertext moduli");
+    std::vector<u32> Q{1};
+    for (u64 m : c->ct_moduli) bn_mul(Q, m);
+    bn_trim(Q);
+    const size_t qbits = bn_bits(Q);
+    if (qbits > 126)
+        return refuse("multi-prime ciphertext modulus: Q must stay below 2^126 (the reference's relinearize reconstructs c2 "
+                      "with u128 products, ring/rns.rs:133-150, which overflow beyond that)");
+    if (c->gadget_base < 2) return refuse("device path supports gadget bases >= 2");
+    if (c->gadget_digits > 128) return refuse("device path supports up to 128 gadget digits");
+    RnsConsts &R = c->R;
+    R.L = L; R.n = n; R.logn = c->logn;
+    R.gadget_digits = c->gadget_digits; R.gadget_base = c->gadget_base; R.plain = c->plain;
+    R.gadget_log2 = c->P.gadget_log2;
+    R.Qlen = (u32)Q.size();
+    bn_store(Q, R.Q, kMwQ);
+    bn_store(bn_half(Q), R.halfQ, kMwQ);
+    u128 bigq = 1;
+    for (u64 m : c->ct_moduli) bigq *= m;
+    R.bigq_lo = (u64)bigq; R.bigq_hi = (u64)(bigq >> 64);
+    if (R.bigq_lo == 0) return refuse("multi-prime ciphertext modulus: Q = 0 mod 2^64 (the reference's gadget_decompose divides by it)");
+    for (u32 l = 0; l < L; l++) {
+        const u64 ql = c->ct_moduli[l];
+        u64 psi = 0;
+        int rc = build_modulus(n, c->logn, ql, &R.q[l], &c->rns_twf_q[l], &c->rns_twi_q[l], &psi, err);
+        if (rc != EXB_OK) return rc;
+        for (u32 k = 0; k < 16 && k < n; k++) { c->T.headf_q[l].t[k] = c->rns_twf_q[l][k]; c->T.headi_q[l].t[k] = c->rns_twi_q[l][k]; }
+        std::vector<u32> qs{1};
+        u64 prod = 1;
+        for (u32 j = 0; j < L; j++)
+            if (j != l) { bn_mul(qs, c->ct_moduli[j]); prod = h_mul(prod, c->ct_moduli[j] % ql, ql); }
+        bn_store(qs, R.Qstar[l], kMwQ);
+        u64 inv = 0;
+        if (!h_inv(prod, ql, &inv)) return refuse("non-coprime ciphertext moduli");
+        R.crt_inv[l] = inv; R.crt_inv_s[l] = shoup_of(inv, ql);
+        R.c32_q[l] = (u64)(((u128)1 << 32) % ql); R.c32_q_s[l] = shoup_of(R.c32_q[l], ql);
+        const u128 qstar = bigq / ql;
+        R.qstar_lo[l] = (u64)qstar; R.qstar_hi[l] = (u64)(qstar >> 64);
+    }
+    // extended basis: 61-bit primes = 1 mod 2n, prod(E) >= 4 n Q^2 > 4 max |t|
+    const size_t need_bits = 2 * qbits + c->logn + 3;
+    std::vector<u32> E{1};
+    c->ext_primes.clear();
+    const u64 step = 2ull * n, top = (u64)1 << 61;
+    for (u64 cand = (top - 1) / step * step + 1; cand > top / 2 && bn_bits(E) <= need_bits; cand -= step) {
+        bool clash = false;
+        for (u64 m : c->ct_moduli) clash |= (m == cand);
+        if (clash || !h_is_prime(cand)) continue;
+        if (c->ext_primes.size() == (size_t)kRnsMaxK) return refuse("multi-prime ciphertext modulus: extended basis too large");
+        c->ext_primes.push_back(cand);
+        bn_mul(E, cand);
+        bn_trim(E);
+    }
+    if (bn_bits(E) <= need_bits) return refuse("multi-prime ciphertext modulus: not enough NTT primes for the extended basis");
+    const u32 K = (u32)c->ext_primes.size();
+    R.K = K;
+    R.Elen = (u32)E.size();
+    if (R.Elen > (u32)kMwE) return refuse("multi-prime ciphertext modulus: extended basis too large");
+    bn_store(E, R.E, kMwE);
+    bn_store(bn_half(E), R.halfE, kMwE);
+    for (u32 k = 0; k < K; k++) {
+        const u64 ek = c->ext_primes[k];
+        u64 psi = 0;
+        int rc = build_modulus(n, c->logn, ek, &R.e[k], &c->rns_twf_e[k], &c->rns_twi_e[k], &psi, err);
+        if (rc != EXB_OK) return rc;
+        for (u32 t = 0; t < 16 && t < n; t++) { c->T.headf_e[k].t[t] = c->rns_twf_e[k][t]; c->T.headi_e[k].t[t] = c->rns_twi_e[k][t]; }
+        R.c32_e[k] = (u64)(((u128)1 << 32) % ek); R.c32_e_s[k] = shoup_of(R.c32_e[k], ek);
+        for (u32 j = 0; j < k; j++) {
+            u64 inv = 0;
+            if (!h_inv(c->ext_primes[j] % ek, ek, &inv)) return refuse("extended basis primes not coprime");
+            R.garner[k][j] = inv; R.garner_s[k][j] = shoup_of(inv, ek);
+        }
+    }
+    c->rns_enabled = true;
+    return EXB_OK;
+}
+
 // The dispatch of bfv_mul_no_relin (bfv/eval.rs:89-108), evaluated once per parameter set.
 static void decide_mul_support(HostSetup *c) {
     const u32 A = (u32)c->aux_moduli.size();
     const u64 q = c->ct_moduli[0];
     c->mul_status = EXB_OK;
     if (c->ct_moduli.size() > 1) {
-        c->mul_status = EXB_NOT_IMPLEMENTED;
-        c->mul_error = "multi-prime ciphertext modulus: the reference's BigInt path (bfv/eval.rs:113-147) is "
-                       "not provided by the device library";
+        // bfv_mul_generic_rns (bfv/eval.rs:113-147): handled by the extended-basis path when build_rns succeeded
+        if (!c->rns_enabled) {
+            c->mul_status = EXB_NOT_IMPLEMENTED;
+            if (c->mul_error.empty())
+                c->mul_error = "multi-prime ciphertext modulus outside the device path's range";
+        }
     } else if (A == 0) {
         c->mul_status = EXB_NOT_IMPLEMENTED;
         c->mul_error = schoolbook_overflow_risk(c->plain, q, c->n)
@@ -453,6 +565,7 @@ int host_setup_build(const exb_bfv_params *p, HostSetup *c, std::string *err, ui
     }
     int rc = fill_scale_consts(c, err);
     if (rc != EXB_OK) return rc;
+    if ((rc = build_rns(c, err)) != EXB_OK) return rc;
     decide_mul_support(c);
     build_small_basis(c, flags);
     return EXB_OK;

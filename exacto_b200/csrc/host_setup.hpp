@@ -11,6 +11,7 @@
 #include "hps32.cuh"
 #include "modarith.cuh"
 #include "ntt_core.cuh"
+#include "rns.cuh"
 
 namespace exb {
 
@@ -76,6 +77,13 @@ struct MulPlan {
     u64 *peer_out[kMaxPeers];
 };
 
+// Device tables of the multi-prime path: plans of the ciphertext primes q_l and the extended primes e_k.
+struct RnsPlans {
+    const Tw *twf_q[kRnsMaxL], *twi_q[kRnsMaxL];
+    const Tw *twf_e[kRnsMaxK], *twi_e[kRnsMaxK];
+    TwHead headf_q[kRnsMaxL], headi_q[kRnsMaxL], headf_e[kRnsMaxK], headi_e[kRnsMaxK];
+};
+
 struct HostSetup {
     u32 n = 0, logn = 0;
     std::vector<u64> ct_moduli, aux_moduli;
@@ -92,6 +100,12 @@ struct HostSetup {
     std::vector<Tw> twf[kMaxBases], twi[kMaxBases];
     std::vector<Tw32> twf32[kMaxSmall], twi32[kMaxSmall];   // internal small basis (if P.sb.enabled)
     std::vector<u64> small_primes;
+    // multi-prime ciphertext modulus (ct_moduli.size() > 1): constants and host copies of the plans
+    bool rns_enabled = false;
+    RnsConsts R;
+    RnsPlans T;                              // table pointers are filled by the owner
+    std::vector<Tw> rns_twf_q[kRnsMaxL], rns_twi_q[kRnsMaxL], rns_twf_e[kRnsMaxK], rns_twi_e[kRnsMaxK];
+    std::vector<u64> ext_primes;
 };
 
 // BfvParamsBuilder::build (params/mod.rs:81-124) + RnsBasis::new (ring/rns.rs:35-63).

@@ -1386,57 +1386,62 @@ static inline u32 block_threads(const DeviceParams &P) {
 
 
 template <bool FWD, int LAZY, int NB>
-static void launch_ntt12_nb(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+static void launch_ntt12_nb(const Modulus &mod, const Tw *tw, const TwHead &head, const u64 *in, u64 *out, size_t count,
+                            cudaStream_t s) {
     const size_t sm = 2 * 4096 * 8;
     const size_t slots = (size_t)num_sms() * 2;               // persistent: 2 CTAs per SM
     const unsigned grid = (unsigned)(count < slots ? count : slots);
-    const Tw *tw = FWD ? P.twf[base] : P.twi[base];
-    const TwHead &head = FWD ? P.headf[base] : P.headi[base];
 #ifdef EXB_LAB
     static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;   // lab build: copy only
     if (dbg == 1) {
-        ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+        ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count);
         return;
     }
 #endif
-    ntt12_persist_kernel<FWD, LAZY, NB><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, P.mod[base], (u32)count);
+    ntt12_persist_kernel<FWD, LAZY, NB><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count);
 }
 template <bool FWD, int LAZY>
-static void launch_ntt12_l(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
+static void launch_ntt12_l(const Modulus &mod, const Tw *tw, const TwHead &head, const u64 *in, u64 *out, size_t count,
+                           cudaStream_t s) {
 #ifdef EXB_LAB
     static const int nb = getenv("EXB_NTT_NB") ? atoi(getenv("EXB_NTT_NB")) : kNB;   // lab build: 16 values per thread
-    if (nb == 4) { launch_ntt12_nb<FWD, LAZY, 4>(P, base, in, out, count, s); return; }
+    if (nb == 4) { launch_ntt12_nb<FWD, LAZY, 4>(mod, tw, head, in, out, count, s); return; }
 #endif
-    launch_ntt12_nb<FWD, LAZY, 3>(P, base, in, out, count, s);
+    launch_ntt12_nb<FWD, LAZY, 3>(mod, tw, head, in, out, count, s);
 }
 template <bool FWD>
-static void launch_ntt12(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
-    const u32 lazy = P.mod[base].lazy;
-    if (lazy == 2) launch_ntt12_l<FWD, 2>(P, base, in, out, count, s);
-    else if (lazy == 1) launch_ntt12_l<FWD, 1>(P, base, in, out, count, s);
-    else launch_ntt12_l<FWD, 0>(P, base, in, out, count, s);
+static void launch_ntt12(const Modulus &mod, const Tw *tw, const TwHead &head, const u64 *in, u64 *out, size_t count,
+                         cudaStream_t s) {
+    if (mod.lazy == 2) launch_ntt12_l<FWD, 2>(mod, tw, head, in, out, count, s);
+    else if (mod.lazy == 1) launch_ntt12_l<FWD, 1>(mod, tw, head, in, out, count, s);
+    else launch_ntt12_l<FWD, 0>(mod, tw, head, in, out, count, s);
+}
+
+void launch_ntt_plan(const Modulus &mod, const Tw *tw, const TwHead &head, u32 logn, bool forward, const u64 *in,
+                     u64 *out, size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    const u32 n = 1u << logn;
+    const size_t sm = (size_t)n * 8;
+    u32 threads = n / 2;
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    if (logn == 12) {
+        if (forward) launch_ntt12<true>(mod, tw, head, in, out, count, s);
+        else launch_ntt12<false>(mod, tw, head, in, out, count, s);
+    } else if (forward) {
+        ntt_fwd_kernel<0><<<(unsigned)count, threads, sm, s>>>(in, out, tw, head, mod, logn);
+    } else {
+        ntt_inv_kernel<0><<<(unsigned)count, threads, sm, s>>>(in, out, tw, head, mod, logn);
+    }
+    g_launch_count++;
 }
 
 void launch_ntt_fwd(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
-    if (count == 0) return;
-    const size_t sm = (size_t)P.n * 8;
-    if (P.logn == 12) {
-        launch_ntt12<true>(P, base, in, out, count, s);
-    } else {
-        ntt_fwd_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twf[base], P.headf[base], P.mod[base], P.logn);
-    }
-    g_launch_count++;
+    launch_ntt_plan(P.mod[base], P.twf[base], P.headf[base], P.logn, true, in, out, count, s);
 }
 
 void launch_ntt_inv(const DeviceParams &P, int base, const u64 *in, u64 *out, size_t count, cudaStream_t s) {
-    if (count == 0) return;
-    const size_t sm = (size_t)P.n * 8;
-    if (P.logn == 12) {
-        launch_ntt12<false>(P, base, in, out, count, s);
-    } else {
-        ntt_inv_kernel<0><<<(unsigned)count, block_threads(P), sm, s>>>(in, out, P.twi[base], P.headi[base], P.mod[base], P.logn);
-    }
-    g_launch_count++;
+    launch_ntt_plan(P.mod[base], P.twi[base], P.headi[base], P.logn, false, in, out, count, s);
 }
 
 void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64 scalar, u64 *out,

@@ -60,6 +60,20 @@ void launch_galois(const DeviceParams &P, const u64 *ct, const u64 *gk_mont, u32
 void launch_decrypt(const DeviceParams &P, const u64 *ct, u32 ncomp, const u64 *sk_ntt, u64 *out, size_t count,
                     cudaStream_t s);
 
+// Batched transform with an explicit plan (any prime below 2^62): the multi-prime path's ct and extended primes.
+void launch_ntt_plan(const Modulus &mod, const Tw *tw, const TwHead &head, u32 logn, bool forward, const u64 *in,
+                     u64 *out, size_t count, cudaStream_t s);
+
+// ---- multi-prime ciphertext modulus (rns_kernels.cu) ----------------------------------------------------
+// ct batches are [pairs][d][2][L][n] (BFV: d = 1), keys [G][2][L][n]; `ws` holds rns_workspace_words u64.
+size_t rns_workspace_words(const RnsConsts &R, const MulPlan &M, size_t pairs);
+size_t rns_relin_workspace_words(const RnsConsts &R, size_t pairs);
+void launch_rns_to_mont(const RnsConsts &R, u64 *key, size_t polys, cudaStream_t s);
+void launch_rns_mul(const RnsConsts &R, const RnsPlans &T, const MulPlan &M, const u64 *ct1, const u64 *ct2,
+                    const u64 *rlk_mont, u32 G, u64 *ws, u64 *out, size_t pairs, int mode, cudaStream_t s);
+void launch_rns_relinearize(const RnsConsts &R, const RnsPlans &T, const MulPlan &M, const u64 *ct3,
+                            const u64 *rlk_mont, u32 G, u64 *ws, u64 *out, size_t pairs, cudaStream_t s);
+
 // Once per device: opt the kernels into their dynamic shared-memory sizes.
 void launch_prepare(int device);
 #endif

@@ -88,7 +88,8 @@ def dbfv_mul_batch(params: DbfvParams, ct1: np.ndarray, ct2: np.ndarray, rlk: Re
     """Batched host-buffer form: ct [B][d][2][n] -> [B][d][2][n] (exb_dbfv_mul_host)."""
     ct1, ct2 = _u64(ct1), _u64(ct2)
     n, d = params.bfv_params.ring_degree, params.num_digits
-    if ct1.shape != ct2.shape or ct1.shape[1:] != (d, 2, n):
+    Lq = params.bfv_params.ct_basis.num_moduli()          # multi-prime limbs are [2][L][n]
+    if ct1.shape != ct2.shape or ct1.shape[1:] != ((d, 2, n) if Lq == 1 else (d, 2, Lq, n)):
         raise InvalidParam("multiplication requires d-limb ciphertexts")
     ctx = params.bfv_params.context(device)
     out = np.empty_like(ct1)

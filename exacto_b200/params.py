@@ -149,10 +149,18 @@ class BfvParams:
             return ctx
 
     def modulus(self, index: int) -> int:
-        """Native modulus index: 0 = q_0, 1..A = aux primes."""
+        """Native modulus index: 0 = q_0, 1..A = aux primes, then the remaining ciphertext primes q_1.."""
         if index == 0:
             return self.ct_basis.moduli[0]
-        return self.aux_basis.moduli[index - 1]
+        num_aux = len(self.aux_basis.moduli) if self.aux_basis is not None else 0
+        if index <= num_aux:
+            return self.aux_basis.moduli[index - 1]
+        return self.ct_basis.moduli[index - num_aux]
+
+    def ct_index(self, l: int) -> int:
+        """Native modulus index of ciphertext prime q_l."""
+        num_aux = len(self.aux_basis.moduli) if self.aux_basis is not None else 0
+        return 0 if l == 0 else num_aux + l
 
 
 _default_device = [None]

@@ -200,24 +200,47 @@ class RnsPoly:
 
     @staticmethod
     def zero(params: BfvParams) -> "RnsPoly":
-        plan = Plan(params, 0)
-        return RnsPoly([NttPoly.zero(params.ring_degree, plan.modulus(), plan)], params.ring_degree)
+        comps = []
+        for l in range(params.ct_basis.num_moduli()):
+            plan = Plan(params, params.ct_index(l))
+            comps.append(NttPoly.zero(params.ring_degree, plan.modulus(), plan))
+        return RnsPoly(comps, params.ring_degree)
 
     @staticmethod
-    def from_coeff_poly(poly: CoeffPoly, params: BfvParams) -> "RnsPoly":     # :84-105 (single-prime basis)
+    def from_coeff_poly(poly: CoeffPoly, params: BfvParams) -> "RnsPoly":     # :84-105
         if len(poly) != params.ring_degree:
             raise DimensionMismatch(params.ring_degree, len(poly))
-        if params.ct_basis.num_moduli() != 1:
-            raise ExactoError(9, "multi-prime RnsPoly conversion is not provided by the device library")
-        plan = Plan(params, 0)
-        q = plan.modulus()
-        reduced = CoeffPoly.from_coeffs(poly.coeffs, q)
-        return RnsPoly([NttPoly.from_coeff_poly(reduced, plan)], params.ring_degree)
+        comps = []
+        for l in range(params.ct_basis.num_moduli()):
+            plan = Plan(params, params.ct_index(l))
+            comps.append(NttPoly.from_coeff_poly(CoeffPoly.from_coeffs(poly.coeffs, plan.modulus()), plan))
+        return RnsPoly(comps, params.ring_degree)
 
-    def to_coeff_poly(self) -> CoeffPoly:                                      # :114-132 (1-prime fast path)
-        if len(self.components) != 1:
-            raise ExactoError(9, "multi-prime CRT reconstruction is not provided by the device library")
-        return self.components[0].to_coeff_poly()
+    def to_coeff_poly(self) -> CoeffPoly:                                      # :114-151
+        coeff = [c.to_coeff_poly() for c in self.components]
+        if len(coeff) == 1:                                                    # :130-132
+            return coeff[0]
+        # u128 CRT of the reference, truncated like `val as u64` / `big_q as u64` (:135-150)
+        moduli = [c.modulus for c in coeff]
+        m128, m64 = (1 << 128) - 1, (1 << 64) - 1
+        big_q = 1
+        for q in moduli:
+            big_q = (big_q * q) & m128
+        inv = []
+        for i, qi in enumerate(moduli):                                        # RnsBasis::new :46-55
+            prod = 1
+            for j, qj in enumerate(moduli):
+                if i != j:
+                    prod = prod * (qj % qi) % qi
+            inv.append(pow(prod, -1, qi))
+        out = np.zeros(self.ring_degree, np.uint64)
+        for j in range(self.ring_degree):
+            val = 0
+            for i, qi in enumerate(moduli):
+                t = int(coeff[i].coeffs[j]) * inv[i] % qi
+                val = ((val + t * (big_q // qi)) & m128) % big_q
+            out[j] = val & m64
+        return CoeffPoly(out, big_q & m64)
 
     def num_components(self) -> int:
         return len(self.components)

@@ -62,6 +62,8 @@ class Emulator:
         L.emu_bfv_mul_no_relin.argtypes = [vp, vp, vp, vp, ctypes.c_size_t]
         L.emu_bfv_relinearize.argtypes = [vp, vp, vp, u32, vp, ctypes.c_size_t, ctypes.c_int]
         L.emu_gadget_decompose.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.emu_rns_info.argtypes = [vp, ctypes.POINTER(u32), ctypes.POINTER(u32), vp]
+        L.emu_rns_mul.argtypes = [vp, u64, u32, u64, vp, vp, vp, u32, vp, ctypes.c_size_t, ctypes.c_int]
         self.L = L
 
     @staticmethod
@@ -139,6 +141,20 @@ class Emulator:
         self.L.emu_bfv_decrypt(h, self._p(ct), ct.shape[-2], self._p(sk_ntt), self._p(out), out.size // ct.shape[-1])
         return out
 
+    def rns_info(self, h):
+        L_, K_ = ctypes.c_uint32(), ctypes.c_uint32()
+        primes = np.zeros(8, np.uint64)
+        rc = self.L.emu_rns_info(h, ctypes.byref(L_), ctypes.byref(K_), self._p(primes))
+        return rc, L_.value, K_.value, [int(v) for v in primes[:K_.value]], self.L.emu_last_error().decode()
+
+    def rns_mul(self, h, base, d, pm, ct1, ct2, rlk, mode, out_shape):
+        """Multi-prime path (rns_kernels.cu): mode 0 dbfv_mul, 1 bfv_mul_no_relin, 2 relinearize(ct1)."""
+        ct1, ct2, rlk = (np.ascontiguousarray(v, np.uint64) for v in (ct1, ct2, rlk))
+        out = np.zeros(out_shape, np.uint64)
+        rc = self.L.emu_rns_mul(h, base, d, pm, self._p(ct1), self._p(ct2), self._p(rlk), rlk.shape[0], self._p(out),
+                                out_shape[0], mode)
+        return rc, out, self.L.emu_last_error().decode()
+
     def dbfv_mul(self, h, base, d, pm, ct1, ct2, rlk, flags=0, limb_mask=0, out=None):
         ct1, ct2, rlk = (np.ascontiguousarray(v, np.uint64) for v in (ct1, ct2, rlk))
         pairs = ct1.size // (d * 2 * ct1.shape[-1])
@@ -146,3 +162,31 @@ class Emulator:
         rc = self.L.emu_dbfv_mul(h, base, d, pm, self._p(ct1), self._p(ct2), self._p(rlk), rlk.shape[0],
                                  self._p(out), pairs, flags, limb_mask)
         return rc, out, self.L.emu_last_error().decode()
+
+
+# ---- multi-prime ciphertext modulus (oracle/rns_ref.py) ----------------------------------------------------
+from oracle import rns_ref as R            # noqa: E402
+
+RNS_CASES = {
+    # the reference's own multi-prime test set (bfv/eval.rs:903-927): Q = 65537 * 1099509805057 < 2^64
+    "ref_n16": (R.RnsParams(16, (65537, 1099509805057), 257, 8), 1, 2, 0),
+    # two 60-bit primes: Q ~ 2^119 > 2^64, so relinearize runs on the reference's truncated (u64) reconstruction
+    "n64_two60": (R.RnsParams(64, (1152921504606830593, 576460752308273153), 65537, 1 << 16), 1, 2, 0),
+    # three 40-bit primes wrapped as dBFV d = 2, b = 16, p = 256
+    "n32_three40_d2": (R.RnsParams(32, (1099509805057, 1099510054913, 1099507695617), 257, 1 << 20), 2, 16, 256),
+}
+
+
+def rns_inputs(P, d, pairs, seed):
+    """Seeded multi-prime inputs: ct [pairs][d][2][L][n] x2 and rlk [G][2][L][n], with edge patterns in pair 0."""
+    rng = np.random.default_rng(seed)
+
+    def rnd(prefix):
+        return np.stack([rng.integers(0, q, prefix + (P.n,), dtype=np.uint64) for q in P.moduli], axis=-2)
+    ct1, ct2, rlk = rnd((pairs, d, 2)), rnd((pairs, d, 2)), rnd((P.G, 2))
+    ct1[0, 0, 0, :, :4] = 0
+    for l, q in enumerate(P.moduli):
+        ct1[0, 0, 1, l, :4] = q - 1
+        ct2[0, 0, 0, l, :4] = q // 2
+        ct2[0, 0, 1, l, :4] = q // 2 + 1
+    return ct1, ct2, rlk

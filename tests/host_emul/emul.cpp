@@ -35,6 +35,7 @@ static inline void __syncthreads() { pthread_barrier_wait(emu_barrier); }
 #define EXB_DYN_SMEM(name) exb::u64 *name = (exb::u64 *)emu_smem_ptr
 
 #include "../../exacto_b200/csrc/kernels.cu"
+#include "../../exacto_b200/csrc/rns_kernels.cu"
 
 using namespace exb;
 
@@ -101,6 +102,10 @@ int emu_create(uint32_t n, const uint64_t *ct_moduli, uint32_t num_ct, const uin
         if (c->hs.has_plan[b]) { c->hs.P.twf[b] = c->hs.twf[b].data(); c->hs.P.twi[b] = c->hs.twi[b].data(); }
     for (u32 i = 0; c->hs.P.sb.enabled && i < c->hs.P.sb.K; i++) {
         c->hs.P.sb.twf[i] = c->hs.twf32[i].data(); c->hs.P.sb.twi[i] = c->hs.twi32[i].data();
+    }
+    if (c->hs.rns_enabled) {
+        for (u32 l = 0; l < c->hs.R.L; l++) { c->hs.T.twf_q[l] = c->hs.rns_twf_q[l].data(); c->hs.T.twi_q[l] = c->hs.rns_twi_q[l].data(); }
+        for (u32 k = 0; k < c->hs.R.K; k++) { c->hs.T.twf_e[k] = c->hs.rns_twf_e[k].data(); c->hs.T.twi_e[k] = c->hs.rns_twi_e[k].data(); }
     }
     *out = c;
     return 0;
@@ -366,6 +371,89 @@ int emu_bfv_decrypt(emu_ctx *c, const uint64_t *ct, uint32_t ncomp, const uint64
     const size_t n = c->hs.n;
     if (P.logn == 12) emu_launch((unsigned)count, kThreads12, n * 8, [&]() { decrypt_kernel<12>(P, ct, ncomp, sk_ntt, out); });
     else emu_launch((unsigned)count, emu_block_threads(P), n * 8, [&]() { decrypt_kernel<0>(P, ct, ncomp, sk_ntt, out); });
+    return 0;
+}
+
+// ---- multi-prime ciphertext modulus: the launch sequence of launch_rns_mul / launch_rns_relinearize -----------
+static void emu_ntt_plan(const Modulus &m, const Tw *tw, const TwHead &head, u32 logn, bool fwd, u64 *buf, size_t count) {
+    const u32 n = 1u << logn;
+    if (logn == 12) {
+        const unsigned grid = count < 3 ? (unsigned)count : 3u;
+        const u32 cnt = (u32)count;
+        if (fwd) emu_launch(grid, 512, 2 * (size_t)n * 8, [&]() { ntt12_persist_kernel<true, 0, 3>(buf, buf, tw, head, m, cnt); });
+        else emu_launch(grid, 512, 2 * (size_t)n * 8, [&]() { ntt12_persist_kernel<false, 0, 3>(buf, buf, tw, head, m, cnt); });
+        return;
+    }
+    unsigned thr = n / 2;
+    if (thr < 32) thr = 32;
+    if (thr > 256) thr = 256;
+    if (fwd) emu_launch((unsigned)count, thr, (size_t)n * 8, [&]() { ntt_fwd_kernel<0>(buf, buf, tw, head, m, logn); });
+    else emu_launch((unsigned)count, thr, (size_t)n * 8, [&]() { ntt_inv_kernel<0>(buf, buf, tw, head, m, logn); });
+}
+
+int emu_rns_info(const emu_ctx *c, uint32_t *L, uint32_t *K, uint64_t *ext_primes) {
+    if (!c->hs.rns_enabled) { g_emu_err = c->hs.mul_error; return c->hs.mul_status ? c->hs.mul_status : EXB_NOT_IMPLEMENTED; }
+    *L = c->hs.R.L; *K = c->hs.R.K;
+    for (size_t i = 0; i < c->hs.ext_primes.size(); i++) ext_primes[i] = c->hs.ext_primes[i];
+    return 0;
+}
+
+// mode 0: dbfv_mul / bfv_mul_and_relin -> out [pairs][d][2][L][n]; mode 1: bfv_mul_no_relin -> [pairs][3][L][n];
+// mode 2: relinearize of ct1 = [pairs][3][L][n] -> [pairs][2][L][n].  rlk [num_keys][2][L][n].
+int emu_rns_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1, const uint64_t *ct2,
+                const uint64_t *rlk, uint32_t num_keys, uint64_t *out, size_t pairs, int mode) {
+    HostSetup &hs = c->hs;
+    if (!hs.rns_enabled) { g_emu_err = hs.mul_error; return hs.mul_status ? hs.mul_status : EXB_NOT_IMPLEMENTED; }
+    HostPlan hp;
+    int rc = host_build_plan(d, base, pm, 0, 0, &hp, &g_emu_err);
+    if (rc) return rc;
+    const RnsConsts R = hs.R;
+    const RnsPlans &T = hs.T;
+    const MulPlan M = hp.M;
+    const size_t n = hs.n;
+    const u32 G = num_keys < hs.gadget_digits ? num_keys : hs.gadget_digits;
+    std::vector<u64> key((size_t)num_keys * 2 * R.L * n + 1);
+    for (size_t i = 0; i + 1 < key.size(); i++) key[i] = rlk[i];
+    u64 *kp = key.data();
+    const size_t kpolys = (size_t)num_keys * 2 * R.L;
+    if (kpolys) emu_launch(2, 64, 0, [&]() { rns_to_mont_kernel(R, kp, kpolys); });
+    if (mode == 2) {
+        RnsShape S{1, 1, 1, pairs};
+        const size_t nd = pairs * R.gadget_digits;
+        std::vector<u64> c2((size_t)R.L * pairs * n + 1), dig((size_t)R.L * nd * n + 1);
+        u64 *c2p = c2.data(), *dp = dig.data();
+        emu_launch(2, 64, 0, [&]() { rns_gather_c2_kernel(R, pairs, ct1, c2p); });
+        for (u32 l = 0; l < R.L; l++) emu_ntt_plan(R.q[l], T.twi_q[l], T.headi_q[l], R.logn, false, c2p + l * pairs * n, pairs);
+        emu_launch(2, 64, 0, [&]() { rns_digits_kernel(R, M, S, c2p, 1u, dp); });
+        for (u32 l = 0; l < R.L; l++) emu_ntt_plan(R.q[l], T.twf_q[l], T.headf_q[l], R.logn, true, dp + l * nd * n, nd);
+        emu_launch(2, 64, 0, [&]() { rns_relin_mac_kernel(R, M, S, nullptr, ct1, dp, kp, G, out); });
+        return 0;
+    }
+    const size_t npoly = pairs * 4 * M.d, nt = pairs * M.num_products * 3;
+    RnsShape S{M.d, M.num_products, M.num_limbs, pairs};
+    const size_t nc = pairs * M.num_limbs * 2, nd = pairs * M.num_limbs * R.gadget_digits;
+    std::vector<u64> coef((size_t)R.L * npoly * n + 1), ext((size_t)R.K * npoly * n + 1), tens((size_t)R.K * nt * n + 1),
+        res((size_t)R.L * nt * n + 1), c01((size_t)R.L * nc * n + 1), dig((size_t)R.L * nd * n + 1);
+    u64 *cp = coef.data(), *ep = ext.data(), *tp = tens.data(), *rp = res.data(), *c01p = c01.data(), *dp = dig.data();
+    emu_launch(2, 64, 0, [&]() { rns_gather_kernel(R, S, ct1, ct2, cp); });
+    for (u32 l = 0; l < R.L; l++) emu_ntt_plan(R.q[l], T.twi_q[l], T.headi_q[l], R.logn, false, cp + l * npoly * n, npoly);
+    emu_launch(2, 64, 0, [&]() { rns_extend_kernel(R, S, cp, ep); });
+    for (u32 k = 0; k < R.K; k++) emu_ntt_plan(R.e[k], T.twf_e[k], T.headf_e[k], R.logn, true, ep + k * npoly * n, npoly);
+    emu_launch(2, 64, 0, [&]() { rns_tensor_kernel(R, M, S, ep, tp); });
+    for (u32 k = 0; k < R.K; k++) emu_ntt_plan(R.e[k], T.twi_e[k], T.headi_e[k], R.logn, false, tp + k * nt * n, nt);
+    emu_launch(2, 64, 0, [&]() { rns_scale_kernel(R, nt, tp, rp); });
+    if (mode == 1) {
+        for (u32 l = 0; l < R.L; l++) emu_ntt_plan(R.q[l], T.twf_q[l], T.headf_q[l], R.logn, true, rp + l * nt * n, nt);
+        emu_launch(2, 64, 0, [&]() { rns_scatter3_kernel(R, pairs, rp, out); });
+        return 0;
+    }
+    emu_launch(2, 64, 0, [&]() { rns_sum01_kernel(R, M, S, rp, c01p); });
+    emu_launch(2, 64, 0, [&]() { rns_digits_kernel(R, M, S, rp, 3u, dp); });
+    for (u32 l = 0; l < R.L; l++) {
+        emu_ntt_plan(R.q[l], T.twf_q[l], T.headf_q[l], R.logn, true, c01p + l * nc * n, nc);
+        emu_ntt_plan(R.q[l], T.twf_q[l], T.headf_q[l], R.logn, true, dp + l * nd * n, nd);
+    }
+    emu_launch(2, 64, 0, [&]() { rns_relin_mac_kernel(R, M, S, c01p, nullptr, dp, kp, G, out); });
     return 0;
 }
 

@@ -371,3 +371,51 @@ def test_kernels_race_free_under_thread_sanitizer():
     assert res.returncode == 0 and "ThreadSanitizer" not in res.stdout + res.stderr, res.stdout + res.stderr
     st = subprocess.run(["/tmp/exb_tsan_kernels", "--selftest"], capture_output=True, text=True)
     assert "ThreadSanitizer: data race" in st.stdout + st.stderr
+
+
+# ---- multi-prime ciphertext modulus: rns_kernels.cu / rns.cuh vs oracle/rns_ref.py --------------------------
+@pytest.mark.parametrize("name", ["ref_n16", "n64_two60", "n32_three40_d2"])
+def test_multi_prime_path_matches_bigint_oracle(emu, name):
+    """bfv_mul_generic_rns (bfv/eval.rs:113-147) and the L > 1 relinearize (bfv/keyswitch.rs:59-101 on the
+    truncating to_coeff_poly of ring/rns.rs:114-151): the product's extended-basis kernels, replayed on the CPU,
+    word for word against the big-integer restatement."""
+    from common import RNS_CASES, R, rns_inputs
+    P, d, base, pm = RNS_CASES[name]
+    rc, h, err = emu.create(P.n, list(P.moduli), [], P.plain_modulus, P.gadget_base, 0)
+    assert rc == 0, err
+    rc, L, K, ext, err = emu.rns_info(h)
+    assert rc == 0 and L == len(P.moduli), err
+    prod = 1
+    for e in ext:
+        assert O.is_prime(e) and e % (2 * P.n) == 1 and e not in P.moduli
+        prod *= e
+    assert prod > 4 * P.n * P.Q * P.Q                           # every tensor coefficient is represented exactly
+    assert emu.info(h)[1] == P.G
+    pairs = 2
+    ct1, ct2, rlk = rns_inputs(P, d, pairs, 5)
+    n = P.n
+    if d == 1:
+        rc, got3, err = emu.rns_mul(h, 2, 1, 0, ct1, ct2, rlk[:0], 1, (pairs, 3, L, n))
+        assert rc == 0, err
+        want3 = np.stack([R.bfv_mul_no_relin(P, a[0], b[0]) for a, b in zip(ct1, ct2)])
+        assert np.array_equal(got3, want3)
+        rc, got2, err = emu.rns_mul(h, 2, 1, 0, want3, want3, rlk, 2, (pairs, 2, L, n))
+        assert rc == 0 and np.array_equal(got2, np.stack([R.relinearize(P, c, rlk) for c in want3]))
+        rc, got2, err = emu.rns_mul(h, 2, 1, 0, want3, want3, rlk[:3], 2, (pairs, 2, L, n))     # fewer keys than digits
+        assert rc == 0 and np.array_equal(got2, np.stack([R.relinearize(P, c, rlk[:3]) for c in want3]))
+    rc, got, err = emu.rns_mul(h, base, d, pm, ct1, ct2, rlk, 0, (pairs, d, 2, L, n))
+    assert rc == 0, err
+    assert np.array_equal(got, np.stack([R.dbfv_mul(P, d, a, b, rlk) for a, b in zip(ct1, ct2)]))
+
+
+def test_multi_prime_dispatch_limits(emu):
+    """What the device path refuses for L > 1, with the reason (the single-prime messages are pinned above)."""
+    q40 = [1099509805057, 1099510054913, 1099507695617]
+    rc, h, err = emu.create(32, [1152921504606830593, 576460752308273153, 1099509805057], [], 257, 1 << 16)
+    assert rc == 0
+    assert emu.rns_info(h)[0] == 9 and "2^126" in emu.rns_info(h)[4]                  # Q ~ 2^159
+    assert emu.info(h)[2] == 9
+    rc, h, err = emu.create(32, q40 + [65537, 786433], [], 257, 1 << 16)            # five primes
+    assert rc == 0 and emu.rns_info(h)[0] == 9 and "4 ciphertext primes" in emu.rns_info(h)[4]
+    rc, h, err = emu.create(32, [q40[0], q40[0]], [], 257, 1 << 16)
+    assert rc == 0 and emu.rns_info(h)[0] == 9 and "coprime" in emu.rns_info(h)[4]

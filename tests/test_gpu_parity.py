@@ -790,6 +790,82 @@ def test_dbfv_mul_scatter_peer_stores(pairs):
     assert rc == 9 and b"small representatives" in L.exb_last_error()
 
 
+def _rns_params(P):
+    return E.BfvParamsBuilder().ring_degree(P.n).plain_modulus(P.plain_modulus).ct_moduli(list(P.moduli)).gadget_base(P.gadget_base).build()
+
+
+@pytest.mark.parametrize("name", ["ref_n16", "n64_two60", "n32_three40_d2"])
+def test_multi_prime_ct_modulus(name):
+    """Multi-prime ciphertext modulus on the GPU: bfv_mul_generic_rns (bfv/eval.rs:113-147) and the
+    L > 1 relinearize, device- and host-buffer entry points, word for word against oracle/rns_ref.py."""
+    from exacto_b200 import batch
+    from common import RNS_CASES, R, rns_inputs
+    P, d, base, pm = RNS_CASES[name]
+    bp = _rns_params(P)
+    assert bp.gadget_digits == P.G
+    pairs, L, n = 3, len(P.moduli), P.n
+    ct1, ct2, rlk_arr = rns_inputs(P, d, pairs, 11)
+    rlk = E.RelinKey(rlk_arr, bp)
+    want = np.stack([R.dbfv_mul(P, d, a, b, rlk_arr) for a, b in zip(ct1, ct2)])
+    if d == 1:
+        a, b = batch.to_device(ct1[:, 0]), batch.to_device(ct2[:, 0])
+        want3 = np.stack([R.bfv_mul_no_relin(P, x[0], y[0]) for x, y in zip(ct1, ct2)])
+        got3 = batch.bfv_mul_no_relin(bp, a, b)
+        assert np.array_equal(batch.to_host(got3), want3)
+        assert np.array_equal(batch.to_host(batch.relinearize(bp, got3, rlk)), want[:, 0])
+        assert np.array_equal(batch.to_host(batch.bfv_mul_and_relin(bp, a, b, rlk)), want[:, 0])
+        assert np.array_equal(E.bfv_mul_and_relin_batch(bp, ct1[:, 0], ct2[:, 0], rlk), want[:, 0])      # host buffers
+        # object API: RnsPoly with one NttPoly per prime
+        o = E.bfv_mul_and_relin(E.BfvCiphertext.from_array(ct1[0, 0], bp), E.BfvCiphertext.from_array(ct2[0, 0], bp), rlk)
+        assert len(o.c) == 2 and len(o.c[0].components) == L and np.array_equal(o.to_array(), want[0, 0])
+        o3 = E.bfv_mul_no_relin(E.BfvCiphertext.from_array(ct1[1, 0], bp), E.BfvCiphertext.from_array(ct2[1, 0], bp))
+        assert np.array_equal(E.relinearize(o3, rlk).to_array(), want[1, 0])
+    dp = E.DbfvParams.new(bp, base, d, pm)
+    got = batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk)
+    assert np.array_equal(batch.to_host(got), want)
+    assert np.array_equal(E.dbfv_mul_batch(dp, ct1, ct2, rlk), want)
+    # ring layer on every ciphertext prime: from_coeff_poly / to_coeff_poly (ring/rns.rs:84-151)
+    rng = np.random.default_rng(3)
+    coeffs = rng.integers(0, min(P.moduli), n, dtype=np.uint64)
+    rp = E.RnsPoly.from_coeff_poly(E.CoeffPoly(coeffs, P.moduli[0]), bp)
+    assert all(np.array_equal(c.evals, O.ntt_fwd(coeffs % np.uint64(q), q)) for c, q in zip(rp.components, P.moduli))
+    back = rp.to_coeff_poly()
+    tc, tm = R.to_coeff_poly_truncated(P, np.stack([c.evals for c in rp.components]))
+    assert back.modulus == tm and [int(x) for x in back.coeffs] == tc
+
+
+def test_multi_prime_reference_kat_and_full_ring_degree():
+    """The reference's own multi-prime test (bfv/eval.rs:903-927: 3*7, 10*20, 0*5 at n = 16, Q = 65537 * 1099509805057)
+    through the GPU, and one product at n = 4096 with two 60-bit ciphertext primes against the big-integer oracle."""
+    from exacto_b200 import batch
+    from common import R
+    P = R.RnsParams(16, (65537, 1099509805057), 257, 8)
+    bp = _rns_params(P)
+    rng = np.random.default_rng(1234)
+    s = R.gen_secret_key(P, rng)
+    rlk_arr = R.gen_relin_key(P, s, rng)
+    rlk = E.RelinKey(rlk_arr, bp)
+    for a, b, want in [(3, 7, 21), (10, 20, 200), (0, 5, 0)]:
+        c1 = R.encrypt_sk(P, [a] + [0] * 15, s, rng)
+        c2 = R.encrypt_sk(P, [b] + [0] * 15, s, rng)
+        prod = E.bfv_mul_and_relin(E.BfvCiphertext.from_array(c1, bp), E.BfvCiphertext.from_array(c2, bp), rlk)
+        assert R.decrypt(P, prod.to_array(), s) == [want] + [0] * 15
+        assert np.array_equal(prod.to_array(), R.bfv_mul_and_relin(P, c1, c2, rlk_arr))
+    P2 = R.RnsParams(4096, (1152921504606830593, 576460752308273153), 65537, 1 << 16)
+    bp2 = _rns_params(P2)
+    c1 = np.stack([np.stack([rng.integers(0, q, 4096, dtype=np.uint64) for q in P2.moduli]) for _ in range(2)])
+    c2 = np.stack([np.stack([rng.integers(0, q, 4096, dtype=np.uint64) for q in P2.moduli]) for _ in range(2)])
+    got3 = batch.to_host(batch.bfv_mul_no_relin(bp2, batch.to_device(c1[None]), batch.to_device(c2[None])))[0]
+    assert np.array_equal(got3, R.bfv_mul_no_relin(P2, c1, c2))
+    # refused sets report why (the single-prime pins are in test_native_error_pins)
+    big = E.BfvParamsBuilder().ring_degree(32).plain_modulus(257).ct_moduli(
+        [1152921504606830593, 576460752308273153, 1099509805057]).build()
+    z = np.zeros((1, 2, 3, 32), np.uint64)
+    with pytest.raises(E.ExactoError) as ei:
+        E.bfv_mul_and_relin_batch(big, z, z, E.RelinKey(np.zeros((big.gadget_digits, 2, 3, 32), np.uint64), big))
+    assert "2^126" in str(ei.value)
+
+
 def test_per_limb_tensor_path_on_gpu():
     """Batches large enough for tensor01_kernel (components 0/1 summed per output limb) vs the oracle, device and
     host entry points, and the same batch through the per-product kernel only (option "tensor_per_product")."""

@@ -330,3 +330,37 @@ def test_dbfv_mul_then_bootstrap_and_chain_oracle():
     mk = lambda m: H.dbfv_encrypt_poly_sk(S, np.array([m % 16] + [0] * 15, np.uint64), s, rng)
     S3, chained = B.dbfv_mul_chain_then_bootstrap([(S, mk(3)), (S, mk(2)), (S, mk(5))], rlk, bk)
     assert S3.bfv.plain_modulus == 257 and H.dbfv_decrypt_poly(S3, chained, boot_sk).shape == (16,)
+
+
+def test_multi_prime_oracle_reference_kat():
+    """oracle/rns_ref.py pinned on the reference's own multi-prime test (bfv/eval.rs:903-927): n = 16,
+    ct_moduli [65537, 1099509805057], p = 257, gadget base 8 -- 3*7, 10*20 and 0*5 decrypt to 21, 200, 0 after
+    bfv_mul_and_relin (and already after bfv_mul_no_relin with the three-component decrypt)."""
+    from oracle import rns_ref as R
+    P = R.RnsParams(16, (65537, 1099509805057), 257, 8)
+    assert P.G == 19                                               # compute_gadget_digits: 8^19 >= Q
+    rng = np.random.default_rng(1234)
+    s = R.gen_secret_key(P, rng)
+    rlk = R.gen_relin_key(P, s, rng)
+    for a, b, want in [(3, 7, 21), (10, 20, 200), (0, 5, 0)]:
+        c1 = R.encrypt_sk(P, [a] + [0] * 15, s, rng)
+        c2 = R.encrypt_sk(P, [b] + [0] * 15, s, rng)
+        assert R.decrypt(P, c1, s)[0] == a
+        assert R.decrypt(P, R.bfv_mul_no_relin(P, c1, c2), s) == [want] + [0] * 15
+        assert R.decrypt(P, R.bfv_mul_and_relin(P, c1, c2, rlk), s) == [want] + [0] * 15
+    # exact negacyclic product: Kronecker substitution == the reference's O(n^2) loop (bfv/eval.rs:792-810)
+    a = [int(x) for x in rng.integers(-10**6, 10**6, 16)]
+    b = [int(x) for x in rng.integers(-10**6, 10**6, 16)]
+    ref = [0] * 16
+    for i in range(16):
+        for j in range(16):
+            if i + j < 16:
+                ref[i + j] += a[i] * b[j]
+            else:
+                ref[i + j - 16] -= a[i] * b[j]
+    assert ref == R.negacyclic_mul(a, b, 16)
+    # scale_tensor_component_bigint rounds half away from zero on the magnitude (bfv/eval.rs:818-831)
+    Q = P.Q
+    assert R.scale_component(P, [Q, -Q, 0, (Q + 1) // 2]) == [257, -257, 0, 129]
+    # gadget KAT of the reference (bfv/keyswitch.rs:112-116) through the i128 restatement
+    assert [d[0] for d in R.gadget_decompose([42], 65537, 16, 2)] == [65531, 3]
