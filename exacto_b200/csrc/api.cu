@@ -959,8 +959,11 @@ extern "C" int exb_bfv_apply_automorphism_host(exb_context *c, const uint64_t *c
 // ---- decrypt (bfv/encrypt.rs:111-178) -------------------------------------------------------------
 static int decrypt_precheck(exb_context *c, uint32_t ncomp) {
     if (!c) return fail(EXB_INVALID_PARAM, "null argument");
-    if (c->ct_moduli.size() != 1) return fail(EXB_NOT_IMPLEMENTED, "decrypt on the device path needs a single ciphertext prime");
     if (ncomp < 1) return fail(EXB_INVALID_PARAM, "ciphertext has no components");
+    if (c->ct_moduli.size() != 1) {
+        if (!c->rns_enabled) return fail(c->mul_status ? c->mul_status : EXB_NOT_IMPLEMENTED, c->mul_error);
+        return EXB_OK;                                    // multi-prime: BigUint CRT of bfv/encrypt.rs:136-170 on the device
+    }
     if (c->plain >= c->ct_moduli[0]) return fail(EXB_NOT_IMPLEMENTED, "decrypt on the device path needs plain_modulus < q");
     return EXB_OK;
 }
@@ -971,6 +974,19 @@ extern "C" int exb_bfv_decrypt(exb_context *c, const uint64_t *ct, uint32_t ncom
     if (rc) return rc;
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
+    if (c->rns_enabled) {
+        cudaStream_t st = (cudaStream_t)stream;
+        std::unique_lock<std::mutex> held;
+        Workspace *w = nullptr;
+        if ((rc = acquire(c, st, &held, &w))) return rc;
+        rc = grow((void **)&w->ext, &w->ext_b, batch * c->R.L * c->n * 8);
+        if (!rc) {
+            launch_rns_decrypt(c->R, c->T, ct, ncomp, sk_ntt, w->ext, out, batch, st);
+            rc = check_launch("multi-prime decrypt");
+        }
+        const int rc2 = release(w, st);
+        return rc ? rc : rc2;
+    }
     launch_decrypt(c->P, ct, ncomp, sk_ntt, out, batch, (cudaStream_t)stream);
     return check_launch("decrypt");
 }
@@ -983,11 +999,16 @@ extern "C" int exb_bfv_decrypt_host(exb_context *c, const uint64_t *ct, uint32_t
     if (batch == 0) return EXB_OK;
     EXB_CUDA(cudaSetDevice(c->device));
     Workspace &w = c->hs[0];
-    const size_t n = c->n, in_bytes = batch * ncomp * n * 8, out_bytes = batch * n * 8;
+    const size_t Lq = c->ct_moduli.size();
+    const size_t n = c->n, in_bytes = batch * ncomp * Lq * n * 8, out_bytes = batch * n * 8, sk_bytes = Lq * n * 8;
     if ((rc = grow((void **)&w.in1, &w.in_b, in_bytes))) return rc;
-    if ((rc = grow_in2_out(w, out_bytes > n * 8 ? out_bytes : n * 8))) return rc;
+    if ((rc = grow_in2_out(w, out_bytes > sk_bytes ? out_bytes : sk_bytes))) return rc;
     EXB_CUDA(cudaMemcpyAsync(w.in1, ct, in_bytes, cudaMemcpyHostToDevice, w.stream));
-    EXB_CUDA(cudaMemcpyAsync(w.in2, sk_ntt, n * 8, cudaMemcpyHostToDevice, w.stream));
+    EXB_CUDA(cudaMemcpyAsync(w.in2, sk_ntt, sk_bytes, cudaMemcpyHostToDevice, w.stream));
+    if (c->rns_enabled) {
+        if ((rc = grow((void **)&w.ext, &w.ext_b, batch * Lq * n * 8))) return rc;
+        launch_rns_decrypt(c->R, c->T, w.in1, ncomp, w.in2, w.ext, w.out, batch, w.stream);
+    } else
     launch_decrypt(c->P, w.in1, ncomp, w.in2, w.out, batch, w.stream);
     if ((rc = check_launch("decrypt"))) return rc;
     EXB_CUDA(cudaMemcpyAsync(out, w.out, out_bytes, cudaMemcpyDeviceToHost, w.stream));

@@ -74,6 +74,9 @@ void launch_rns_mul(const RnsConsts &R, const RnsPlans &T, const MulPlan &M, con
 void launch_rns_relinearize(const RnsConsts &R, const RnsPlans &T, const MulPlan &M, const u64 *ct3,
                             const u64 *rlk_mont, u32 G, u64 *ws, u64 *out, size_t pairs, cudaStream_t s);
 
+void launch_rns_decrypt(const RnsConsts &R, const RnsPlans &T, const u64 *ct, u32 ncomp, const u64 *sk, u64 *ws,
+                        u64 *out, size_t count, cudaStream_t s);
+
 // Once per device: opt the kernels into their dynamic shared-memory sizes.
 void launch_prepare(int device);
 #endif

@@ -244,6 +244,32 @@ EXB_HD void rns_scale_coeff(const u64 *tr, const RnsConsts &R, u64 *out) {
     }
 }
 
+// ---- decrypt for L > 1 (bfv/encrypt.rs:111-178): x = CRT value in [0, Q) of the phase coefficient,
+// m = floor((x p + floor(Q/2)) / Q) mod p.  x[l] = phase residue mod q_l.
+EXB_HD u64 rns_decrypt_coeff(const u64 *x, const RnsConsts &R) {
+    u32 mag[kMwQ];
+    const bool neg = rns_centered(x, R, mag);
+    const int QL = (int)R.Qlen;
+    u32 num[kMwQ + 3];
+    for (int i = 0; i < kMwQ + 3; i++) num[i] = i < QL ? mag[i] : 0u;
+    if (neg) mw_rsub(num, R.Q, QL);                       // centred value c = x - Q  =>  x = Q - |c|
+    mw_mul_add64(num, kMwQ + 3, R.plain, 0);
+    u64 carry = 0;
+    for (int i = 0; i < kMwQ + 3; i++) {
+        const u64 sum = (u64)num[i] + (i < QL ? R.halfQ[i] : 0u) + carry;
+        num[i] = (u32)sum;
+        carry = sum >> 32;
+    }
+    int ulen = kMwQ + 3;
+    while (ulen > QL && num[ulen - 1] == 0) ulen--;
+    u32 quo[kMwQ + 3];
+    for (int i = 0; i < kMwQ + 3; i++) quo[i] = 0;
+    mw_div<kMwQ + 3, kMwQ>(num, ulen, R.Q, QL, quo);
+    unsigned __int128 r = 0;                              // quotient <= p < 2^64 (+1): two limbs and a bit
+    for (int i = ulen - QL; i >= 0; i--) r = ((r << 32) | quo[i]) % R.plain;
+    return (u64)r;
+}
+
 // ---- relinearize for L > 1: RnsPoly::to_coeff_poly (ring/rns.rs:133-150) then gadget_decompose
 // (bfv/keyswitch.rs:11-52) on the truncated (coefficient, modulus) pair, i128 semantics ------------------
 typedef unsigned __int128 exb_u128;

@@ -173,6 +173,34 @@ __global__ void rns_gather_c2_kernel(const __grid_constant__ RnsConsts R, size_t
     }
 }
 
+// decrypt (bfv/encrypt.rs:111-178), step 1: phase[l][b][n] = c0 + c1 s + c2 s^2 + ... mod q_l (NTT domain);
+// ct [count][ncomp][L][n], sk [L][n].
+__global__ void rns_phase_kernel(const __grid_constant__ RnsConsts R, const u64 *__restrict__ ct, u32 ncomp,
+                                 const u64 *__restrict__ sk, u64 *__restrict__ phase, size_t count) {
+    const size_t n = R.n, total = count * R.L * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = idx % n, r = idx / n, b = r % count, l = r / count;
+        const Modulus &m = R.q[l];
+        const u64 s_m = csub(mont_mul_lazy(sk[l * n + j], m.r2_mod, m.m, m.minv_neg), m.m);          // s * 2^64
+        u64 acc = ct[((b * ncomp + 0) * R.L + l) * n + j], spow = s_m;
+        for (u32 i = 1; i < ncomp; i++) {
+            acc = mod_add(acc, csub(mont_mul_lazy(ct[((b * ncomp + i) * R.L + l) * n + j], spow, m.m, m.minv_neg), m.m), m.m);
+            if (i + 1 < ncomp) spow = csub(mont_mul_lazy(spow, s_m, m.m, m.minv_neg), m.m);
+        }
+        phase[idx] = acc;
+    }
+}
+// step 2 (after INTT per prime): out[b][n] = round(p x / Q) mod p with x the CRT value in [0, Q)
+__global__ void rns_decrypt_kernel(const __grid_constant__ RnsConsts R, const u64 *__restrict__ phase,
+                                   u64 *__restrict__ out, size_t count) {
+    const size_t n = R.n, total = count * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        u64 x[kRnsMaxL];
+        for (u32 l = 0; l < R.L; l++) x[l] = phase[l * total + idx];
+        out[idx] = rns_decrypt_coeff(x, R);
+    }
+}
+
 // key [G][2][L][n] -> Montgomery form per prime (in place)
 __global__ void rns_to_mont_kernel(const __grid_constant__ RnsConsts R, u64 *__restrict__ key, size_t polys) {
     const size_t n = R.n, total = polys * n;
@@ -254,6 +282,17 @@ void launch_rns_relinearize(const RnsConsts &R, const RnsPlans &T, const MulPlan
         launch_ntt_plan(R.q[l], T.twf_q[l], T.headf_q[l], R.logn, true, dig + l * nd * n, dig + l * nd * n, nd, s);
     rns_relin_mac_kernel<<<grid_for(pairs * 2 * R.L * n), 256, 0, s>>>(R, M, S, nullptr, ct3, dig, rlk_mont, G, out);
     g_launch_count += 3;
+}
+// decrypt of [count][ncomp][L][n] with sk [L][n] -> [count][n]; ws holds L * count * n words
+void launch_rns_decrypt(const RnsConsts &R, const RnsPlans &T, const u64 *ct, u32 ncomp, const u64 *sk, u64 *ws,
+                        u64 *out, size_t count, cudaStream_t s) {
+    if (!count) return;
+    const size_t n = R.n;
+    rns_phase_kernel<<<grid_for(count * R.L * n), 256, 0, s>>>(R, ct, ncomp, sk, ws, count);
+    for (u32 l = 0; l < R.L; l++)
+        launch_ntt_plan(R.q[l], T.twi_q[l], T.headi_q[l], R.logn, false, ws + l * count * n, ws + l * count * n, count, s);
+    rns_decrypt_kernel<<<grid_for(count * n), 256, 0, s>>>(R, ws, out, count);
+    g_launch_count += 2;
 }
 size_t rns_relin_workspace_words(const RnsConsts &R, size_t pairs) {
     return (size_t)R.L * pairs * R.n * (1 + (size_t)R.gadget_digits);

@@ -44,7 +44,10 @@ class SecretKey:
         return SecretKey(ct.c[0], params)
 
     def ntt_array(self) -> np.ndarray:
-        return self.poly.components[0].evals
+        """[n] for a single ciphertext prime, [L][n] otherwise."""
+        if len(self.poly.components) == 1:
+            return self.poly.components[0].evals
+        return np.stack([c.evals for c in self.poly.components])
 
 
 def encode_scalar(m: int, params: BfvParams) -> CoeffPoly:
@@ -100,11 +103,13 @@ def decrypt(ct: BfvCiphertext, sk: SecretKey) -> CoeffPoly:
 def decrypt_batch(params: BfvParams, ct: np.ndarray, sk: SecretKey, device: Optional[int] = None) -> np.ndarray:
     """Batched host-buffer form: ct [B][k][n] -> plaintext coefficients [B][n] (exb_bfv_decrypt_host)."""
     ct = _u64(ct)
-    if ct.ndim != 3 or ct.shape[2] != params.ring_degree or ct.shape[1] < 1:
+    Lq = params.ct_basis.num_moduli()                    # multi-prime ciphertexts are [batch][components][L][n]
+    tail = (params.ring_degree,) if Lq == 1 else (Lq, params.ring_degree)
+    if ct.ndim != 2 + len(tail) or ct.shape[2:] != tail or ct.shape[1] < 1:
         raise InvalidParam("decrypt expects [batch][components][n]")
     ctx = params.context(device)
-    out = np.empty((ct.shape[0], ct.shape[2]), np.uint64)
-    s = sk.ntt_array()
+    out = np.empty((ct.shape[0], params.ring_degree), np.uint64)
+    s = np.ascontiguousarray(sk.ntt_array())
     _native.check(_native.lib().exb_bfv_decrypt_host(ctx.handle, _ptr(ct), ct.shape[1], _ptr(s), _ptr(out), ct.shape[0]))
     return out
 

@@ -113,7 +113,8 @@ void exb_context_destroy(exb_context *ctx);
 int exb_context_set_option(exb_context *ctx, const char *name, int64_t value);
 /* Effective values after defaults were applied. */
 int exb_context_gadget(const exb_context *ctx, uint64_t *gadget_base, uint32_t *gadget_digits);
-/* psi of modulus `modulus_index` (0 = q, 1.. = aux primes). */
+/* psi of modulus `modulus_index`: 0 = q_0, 1..A = the aux primes, A+1.. = the remaining ciphertext primes q_1..
+ * (the same indices address exb_ntt_* and exb_poly_*). */
 int exb_context_psi(const exb_context *ctx, uint32_t modulus_index, uint64_t *psi);
 /* Number of kernels this library has launched in this process. */
 unsigned long long exb_launch_count(void);
@@ -198,7 +199,14 @@ void exb_relin_key_destroy(exb_relin_key *key);
  *     convolution wraps)        -> EXB_NOT_IMPLEMENTED "...overflows i128 in its middle tensor term..."
  *   no aux basis otherwise: the exact schoolbook result, computed by the HPS pipeline on an internal
  *     auxiliary basis;
- *   more than one ciphertext prime -> EXB_NOT_IMPLEMENTED (the reference's BigInt branch is outside the device path). */
+ *   more than one ciphertext prime (bfv_mul_generic_rns, bfv/eval.rs:113-147, the reference's BigInt branch):
+ *     2..4 primes with Q = prod q_l < 2^126 run on the device -- the integer tensor is computed exactly in an
+ *     internal extended RNS basis and scaled with one multiword division per coefficient, bit-identical to the
+ *     BigInt result; relinearize reproduces RnsPoly::to_coeff_poly's u128 reconstruction INCLUDING its truncation to
+ *     u64 (ring/rns.rs:133-150), so it is word-identical for Q >= 2^64 too.  Ciphertexts are then
+ *     [batch][2][L][n] (dBFV: [batch][d][2][L][n]), keys [G][2][L][n], secret keys [L][n]: one row per prime, in
+ *     ct_moduli order.  Larger Q / more primes -> EXB_NOT_IMPLEMENTED with the reason (beyond 2^127 the reference's
+ *     own u128 products overflow).  Multi-prime dbfv_mul needs p = b^d (all-zero small representatives). */
 int exb_bfv_mul_and_relin(exb_context *ctx, const uint64_t *ct1_dev, const uint64_t *ct2_dev,
                           const exb_relin_key *rlk, uint64_t *out_dev, size_t batch, void *stream);
 int exb_bfv_mul_and_relin_host(exb_context *ctx, const uint64_t *ct1_host, const uint64_t *ct2_host,
@@ -233,8 +241,9 @@ int exb_bfv_apply_automorphism_host(exb_context *ctx, const uint64_t *ct_host, u
 /* ---- decrypt (bfv/encrypt.rs:111-178), batched: phase = c0 + c1 s + c2 s^2 + ..., then
  * m = floor((p * INTT(phase) + floor(q/2)) / q) mod p per coefficient.  ct [batch][num_components][n]
  * (NTT domain), sk_ntt [n] = SecretKey.poly (NTT domain), out [batch][n] coefficients mod p.
- * Needs a single ciphertext prime and p < q (EXB_NOT_IMPLEMENTED otherwise: the reference's
- * BigUint CRT path is outside the device path). */
+ * A single ciphertext prime needs p < q.  Multi-prime sets (see exb_bfv_mul_and_relin) take ct
+ * [batch][num_components][L][n] and sk_ntt [L][n] and run the reference's BigUint CRT scaling (:136-170) with
+ * multiword arithmetic on the device. */
 int exb_bfv_decrypt(exb_context *ctx, const uint64_t *ct_dev, uint32_t num_components, const uint64_t *sk_ntt_dev,
                     uint64_t *out_dev, size_t batch, void *stream);
 int exb_bfv_decrypt_host(exb_context *ctx, const uint64_t *ct_host, uint32_t num_components,

@@ -169,9 +169,9 @@ from oracle import rns_ref as R            # noqa: E402
 
 RNS_CASES = {
     # the reference's own multi-prime test set (bfv/eval.rs:903-927): Q = 65537 * 1099509805057 < 2^64
-    "ref_n16": (R.RnsParams(16, (65537, 1099509805057), 257, 8), 1, 2, 0),
+    "ref_n16": (R.RnsParams(16, (65537, 1099509805057), 257, 8), 1, 2, 2),
     # two 60-bit primes: Q ~ 2^119 > 2^64, so relinearize runs on the reference's truncated (u64) reconstruction
-    "n64_two60": (R.RnsParams(64, (1152921504606830593, 576460752308273153), 65537, 1 << 16), 1, 2, 0),
+    "n64_two60": (R.RnsParams(64, (1152921504606830593, 576460752308273153), 65537, 1 << 16), 1, 2, 2),
     # three 40-bit primes wrapped as dBFV d = 2, b = 16, p = 256
     "n32_three40_d2": (R.RnsParams(32, (1099509805057, 1099510054913, 1099507695617), 257, 1 << 20), 2, 16, 256),
 }

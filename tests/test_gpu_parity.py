@@ -851,12 +851,20 @@ def test_multi_prime_reference_kat_and_full_ring_degree():
         prod = E.bfv_mul_and_relin(E.BfvCiphertext.from_array(c1, bp), E.BfvCiphertext.from_array(c2, bp), rlk)
         assert R.decrypt(P, prod.to_array(), s) == [want] + [0] * 15
         assert np.array_equal(prod.to_array(), R.bfv_mul_and_relin(P, c1, c2, rlk_arr))
+        # decrypt on the device too (bfv/encrypt.rs:111-178 with its BigUint CRT), degree 1 and degree 2
+        sk = E.SecretKey(E.BfvCiphertext.from_array(s[None], bp).c[0], bp)
+        assert [int(x) for x in E.decrypt(prod, sk).coeffs] == [want] + [0] * 15
+        prod3 = E.bfv_mul_no_relin(E.BfvCiphertext.from_array(c1, bp), E.BfvCiphertext.from_array(c2, bp))
+        assert [int(x) for x in E.decrypt(prod3, sk).coeffs] == [want] + [0] * 15
     P2 = R.RnsParams(4096, (1152921504606830593, 576460752308273153), 65537, 1 << 16)
     bp2 = _rns_params(P2)
     c1 = np.stack([np.stack([rng.integers(0, q, 4096, dtype=np.uint64) for q in P2.moduli]) for _ in range(2)])
     c2 = np.stack([np.stack([rng.integers(0, q, 4096, dtype=np.uint64) for q in P2.moduli]) for _ in range(2)])
     got3 = batch.to_host(batch.bfv_mul_no_relin(bp2, batch.to_device(c1[None]), batch.to_device(c2[None])))[0]
     assert np.array_equal(got3, R.bfv_mul_no_relin(P2, c1, c2))
+    s2 = np.stack([rng.integers(0, q, 4096, dtype=np.uint64) for q in P2.moduli])
+    sk2 = E.SecretKey(E.BfvCiphertext.from_array(s2[None], bp2).c[0], bp2)
+    assert [int(x) for x in E.decrypt_batch(bp2, got3[None], sk2)[0]] == R.decrypt(P2, got3, s2)      # random phase: every digit path
     # refused sets report why (the single-prime pins are in test_native_error_pins)
     big = E.BfvParamsBuilder().ring_degree(32).plain_modulus(257).ct_moduli(
         [1152921504606830593, 576460752308273153, 1099509805057]).build()
