@@ -14,6 +14,7 @@
 //   dbfv/    DbfvCiphertext (dbfv/ciphertext.rs:10-22), dbfv_add (dbfv/eval.rs:11-33), dbfv_mul (dbfv/eval.rs:82-149)
 #pragma once
 #include <cstdint>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -330,6 +331,163 @@ inline BfvCiphertext bfv_trace(const BfvCiphertext &ct, const std::vector<size_t
     return result;
 }
 
+
+// ---- plaintext-side operations used by the bootstrap (bfv/encrypt.rs:181-229, bfv/eval.rs:468-486, :613-634,
+// bootstrap/digit_extract.rs:161-197) ---------------------------------------------------------------------
+namespace detail {
+inline std::vector<uint64_t> pointwise(const BfvParams &params, int op, const std::vector<uint64_t> &a,
+                                       const std::vector<uint64_t> &b) {                  // op 0: add, 1: mul
+    exb_context *ctx = params.context();
+    return device_round_trip(ctx, {&a, &b}, a.size(), [&](std::vector<void *> &d) {
+        return op == 0 ? exb_poly_add(ctx, 0, (const uint64_t *)d[0], (const uint64_t *)d[1], (uint64_t *)d[2], a.size(), nullptr)
+                       : exb_poly_mul(ctx, 0, (const uint64_t *)d[0], (const uint64_t *)d[1], (uint64_t *)d[2], a.size(), nullptr);
+    });
+}
+inline NttPoly ntt_of(const std::vector<uint64_t> &coeffs_mod_q, const BfvParams &params) {
+    return NttPoly::from_coeff_poly(CoeffPoly{coeffs_mod_q, params.q()}, params);
+}
+inline BfvCiphertext times_ntt(const BfvCiphertext &ct, const NttPoly &m) {               // every component * m
+    BfvCiphertext out{{}, ct.params};
+    for (const RnsPoly &c : ct.c)
+        out.c.push_back(RnsPoly{{NttPoly{pointwise(*ct.params, 1, c.components.at(0).evals, m.evals), ct.params->q()}}, c.ring_degree});
+    return out;
+}
+}  // namespace detail
+
+inline RnsPoly scale_plaintext(const CoeffPoly &pt, const std::shared_ptr<BfvParams> &params) {   // bfv/encrypt.rs:181-229
+    const uint64_t q = params->q(), delta = q / params->plain_modulus;
+    std::vector<uint64_t> c(pt.coeffs.size());
+    for (size_t i = 0; i < c.size(); i++) c[i] = (uint64_t)((unsigned __int128)(pt.coeffs[i] % q) * delta % q);
+    return RnsPoly{{detail::ntt_of(c, *params)}, params->ring_degree};
+}
+inline BfvCiphertext trivial_encrypt_poly(const CoeffPoly &pt, const std::shared_ptr<BfvParams> &params) {   // digit_extract.rs:180-189
+    const size_t n = params->ring_degree;
+    return BfvCiphertext{{scale_plaintext(pt, params), RnsPoly{{NttPoly{std::vector<uint64_t>(n, 0), params->q()}}, n}}, params};
+}
+inline BfvCiphertext trivial_encrypt(uint64_t m, const std::shared_ptr<BfvParams> &params) {       // digit_extract.rs:161-177
+    CoeffPoly pt{std::vector<uint64_t>(params->ring_degree, 0), params->plain_modulus};
+    pt.coeffs[0] = m % params->plain_modulus;
+    return trivial_encrypt_poly(pt, params);
+}
+inline BfvCiphertext bfv_plain_mul(const BfvCiphertext &ct, const CoeffPoly &pt) {                 // bfv/eval.rs:468-486
+    std::vector<uint64_t> c(pt.coeffs.size());
+    for (size_t i = 0; i < c.size(); i++) c[i] = pt.coeffs[i] % ct.params->q();
+    return detail::times_ntt(ct, detail::ntt_of(c, *ct.params));
+}
+inline BfvCiphertext bfv_scalar_mul(const BfvCiphertext &ct, uint64_t scalar) {                    // digit_extract.rs:192-197
+    CoeffPoly pt{std::vector<uint64_t>(ct.params->ring_degree, 0), ct.params->plain_modulus};
+    pt.coeffs[0] = scalar % ct.params->plain_modulus;
+    return bfv_plain_mul(ct, pt);
+}
+inline BfvCiphertext bfv_monomial_mul(const BfvCiphertext &ct, size_t j) {                         // bfv/eval.rs:613-634
+    const size_t n = ct.params->ring_degree;
+    j %= 2 * n;
+    if (j == 0) return ct;
+    std::vector<uint64_t> c(n, 0);
+    c[j % n] = j < n ? 1 : ct.params->q() - 1;                                                     // X^n = -1
+    return detail::times_ntt(ct, detail::ntt_of(c, *ct.params));
+}
+
+// bootstrap/digit_extract.rs:100-157: Paterson-Stockmeyer, every product a bfv_mul_and_relin on the GPU.
+inline BfvCiphertext eval_poly_homomorphic(const BfvCiphertext &ct_x, const std::vector<uint64_t> &coeffs, const RelinKey &rlk) {
+    const auto &params = ct_x.params;
+    const size_t d = coeffs.empty() ? 0 : coeffs.size() - 1;
+    if (d == 0) return trivial_encrypt(coeffs.empty() ? 0 : coeffs[0], params);
+    size_t k = (size_t)std::ceil(std::sqrt((double)d + 1.0));
+    if (k < 2) k = 2;
+    std::vector<BfvCiphertext> baby{trivial_encrypt(1, params), ct_x};
+    for (size_t i = 2; i <= k; i++) baby.push_back(bfv_mul_and_relin(baby[i / 2], baby[i - i / 2], rlk));
+    const size_t groups_n = (d + k) / k;
+    std::vector<BfvCiphertext> groups;
+    for (size_t i = 0; i < groups_n; i++) {
+        BfvCiphertext g = trivial_encrypt(0, params);
+        for (size_t j = 0; j < k; j++) {
+            const size_t idx = i * k + j;
+            if (idx >= coeffs.size()) break;
+            if (coeffs[idx] == 0) continue;
+            g = bfv_add(g, bfv_scalar_mul(baby[j], coeffs[idx]));
+        }
+        groups.push_back(std::move(g));
+    }
+    BfvCiphertext result = std::move(groups.back());
+    groups.pop_back();
+    while (!groups.empty()) {
+        result = bfv_add(bfv_mul_and_relin(result, baby[k], rlk), groups.back());
+        groups.pop_back();
+    }
+    return result;
+}
+
+// ---- bootstrap/coeffs_to_slots.rs ---------------------------------------------------------------------------------
+using GaloisKeys = std::map<size_t, std::shared_ptr<GaloisKey>>;
+inline std::vector<size_t> required_trace_elements(size_t n) {                                     // :167-181
+    std::vector<size_t> e;
+    if (n <= 32 || (n & (n - 1))) { for (size_t k = 3; k < 2 * n; k += 2) e.push_back(k); return e; }
+    for (size_t step = n; step >= 2; step >>= 1) e.push_back(step + 1);
+    return e;
+}
+inline BfvCiphertext extract_coefficient(const BfvCiphertext &ct, size_t j, const GaloisKeys &gks) {   // :21-95
+    const size_t n = ct.params->ring_degree;
+    const uint64_t t = ct.params->plain_modulus;
+    const BfvCiphertext shifted = j == 0 ? ct : bfv_monomial_mul(ct, 2 * n - j);
+    auto key = [&](size_t k) -> const GaloisKey & {
+        auto it = gks.find(k);
+        if (it == gks.end()) throw ExactoError(ExactoError::InvalidParam, "missing Galois key for element " + std::to_string(k));
+        return *it->second;
+    };
+    BfvCiphertext result = shifted;
+    if (n <= 32 || (n & (n - 1))) {                                                                // naive trace
+        for (size_t k = 3; k < 2 * n; k += 2) result = bfv_add(result, bfv_apply_automorphism(shifted, key(k)));
+    } else {
+        for (size_t k : required_trace_elements(n)) result = bfv_add(result, bfv_apply_automorphism(result, key(k)));
+    }
+    uint64_t n_inv = 0;                                                                            // n^-1 mod t
+    for (uint64_t x = 1; x < t; x++) if ((unsigned __int128)(n % t) * x % t == 1) { n_inv = x; break; }
+    if (!n_inv) throw ExactoError(ExactoError::InvalidParam, "n not invertible mod t");
+    return bfv_scalar_mul(result, n_inv);
+}
+inline std::vector<BfvCiphertext> coeffs_to_slots(const BfvCiphertext &ct, const GaloisKeys &gks) {    // :103-116
+    std::vector<BfvCiphertext> out;
+    for (size_t j = 0; j < ct.params->ring_degree; j++) out.push_back(extract_coefficient(ct, j, gks));
+    return out;
+}
+inline BfvCiphertext slots_to_coeffs(const std::vector<BfvCiphertext> &slots) {                    // :122-142
+    if (slots.empty()) throw ExactoError(ExactoError::InvalidParam, "empty slots");
+    BfvCiphertext result = slots[0];
+    for (size_t j = 1; j < slots.size(); j++) result = bfv_add(result, bfv_monomial_mul(slots[j], j));
+    return result;
+}
+
+// ---- bootstrap/bfv_host.rs ------------------------------------------------------------------------------------------
+struct BootstrapKey {                                // :19-41
+    std::shared_ptr<BfvParams> boot_params;
+    uint64_t q_prime = 0;
+    BfvCiphertext bsk;                               // encryption of s under the boot scheme
+    std::shared_ptr<RelinKey> boot_rlk;
+    std::vector<uint64_t> rounding_poly;             // coefficients mod t_boot
+    GaloisKeys galois_keys;
+};
+
+inline BfvCiphertext bfv_bootstrap(const BfvCiphertext &ct, const BootstrapKey &bsk) {             // :134-209
+    if (ct.c.size() != 2) throw ExactoError(ExactoError::InvalidParam, "bootstrap requires degree-1 ciphertext");
+    const uint64_t q = ct.params->q(), qp = bsk.q_prime, tb = bsk.boot_params->plain_modulus;
+    const size_t n = ct.params->ring_degree;
+    const CoeffPoly c0 = ct.c[0].components.at(0).to_coeff_poly(*ct.params), c1 = ct.c[1].components.at(0).to_coeff_poly(*ct.params);
+    CoeffPoly p0{std::vector<uint64_t>(n), tb}, p1{std::vector<uint64_t>(n), tb};
+    bool trivial = true;
+    for (size_t i = 0; i < n; i++) {                                                               // :150-171
+        p0.coeffs[i] = (uint64_t)(((unsigned __int128)qp * c0.coeffs[i] + q / 2) / q) % qp % tb;
+        p1.coeffs[i] = (uint64_t)(((unsigned __int128)qp * c1.coeffs[i] + q / 2) / q) % qp % tb;
+        trivial = trivial && c1.coeffs[i] == 0;
+    }
+    const BfvCiphertext phase = bfv_add(trivial_encrypt_poly(p0, bsk.boot_params), bfv_plain_mul(bsk.bsk, p1));   // :173-176
+    if (trivial) return eval_poly_homomorphic(phase, bsk.rounding_poly, *bsk.boot_rlk);            // :179-186
+    std::vector<BfvCiphertext> rounded;
+    for (const BfvCiphertext &slot : coeffs_to_slots(phase, bsk.galois_keys))                      // :189-194
+        rounded.push_back(eval_poly_homomorphic(slot, bsk.rounding_poly, *bsk.boot_rlk));
+    return slots_to_coeffs(rounded);                                                               // :197-201
+}
+
 // ---- dbfv/ -----------------------------------------------------------------------------------------------
 struct DbfvCiphertext {                              // dbfv/ciphertext.rs:10-22
     std::vector<BfvCiphertext> limbs;
@@ -389,6 +547,37 @@ inline DbfvCiphertext dbfv_apply_automorphism(const DbfvCiphertext &ct, const Ga
     const size_t n = bfv->ring_degree;
     for (size_t i = 0; i < ct.num_limbs(); i++) res.limbs.push_back(detail::unflatten(out.data() + i * 2 * n, 2, bfv));
     return res;
+}
+
+// bootstrap/bfv_host.rs:212-236: every limb refreshed; dBFV metadata kept, BFV params swapped, mul_depth restarted.
+inline DbfvCiphertext dbfv_bootstrap(const DbfvCiphertext &ct, const BootstrapKey &bsk) {
+    auto refreshed = DbfvParams::create(bsk.boot_params, ct.params->base, ct.params->num_digits, ct.params->plain_modulus);
+    DbfvCiphertext out{{}, ct.degree, 0, refreshed};
+    for (const BfvCiphertext &limb : ct.limbs) out.limbs.push_back(bfv_bootstrap(limb, bsk));
+    return out;
+}
+
+// bootstrap/bfv_host.rs:242-250
+inline DbfvCiphertext dbfv_mul_then_bootstrap(const DbfvCiphertext &ct1, const DbfvCiphertext &ct2, const RelinKey &rlk,
+                                              const BootstrapKey &bsk) {
+    return dbfv_bootstrap(dbfv_mul(ct1, ct2, rlk), bsk);
+}
+
+// bootstrap/bfv_host.rs:258-288: fold with the relinearisation key chosen by parameter equality (:271-284).
+inline DbfvCiphertext dbfv_mul_chain_then_bootstrap(const std::vector<DbfvCiphertext> &cts, const RelinKey &rlk,
+                                                    const BootstrapKey &bsk) {
+    if (cts.empty())
+        throw ExactoError(ExactoError::InvalidParam, "dbfv_mul_chain_then_bootstrap requires at least one ciphertext");
+    auto same = [](const BfvParams &a, const BfvParams &b) {
+        return a.plain_modulus == b.plain_modulus && a.ring_degree == b.ring_degree && a.ct_moduli == b.ct_moduli;
+    };
+    DbfvCiphertext acc = cts[0];
+    for (size_t i = 1; i < cts.size(); i++) {
+        const bool use_boot_rlk = same(*acc.params->bfv_params, *bsk.boot_params);
+        const DbfvCiphertext rhs = same(*acc.params->bfv_params, *cts[i].params->bfv_params) ? cts[i] : dbfv_bootstrap(cts[i], bsk);
+        acc = dbfv_mul_then_bootstrap(acc, rhs, use_boot_rlk ? *bsk.boot_rlk : rlk, bsk);
+    }
+    return acc;
 }
 
 }  // namespace exacto

@@ -634,6 +634,43 @@ def test_dbfv_mul_then_bootstrap_and_chain():
     assert len(E.dbfv_decrypt_poly(chained, boot_sk)) == 16
 
 
+def test_cpp_dbfv_mul_then_bootstrap_and_chain(tmp_path):
+    """north_star's dbfv_mul_then_bootstrap / dbfv_mul_chain_then_bootstrap at the COMPILED boundary
+    (include/exacto_b200.hpp, bootstrap/bfv_host.rs:242-288 with the rlk selection of :271-284): the C++ host mirror
+    drives the GPU through the C ABI on the reference's toy parameter sets; every ciphertext equals the oracle
+    pipeline's word for word."""
+    import subprocess
+    import __graft_entry__ as g
+    from oracle import bootstrap_ref as B
+    from test_oracle import _dbfv_boot_params
+    exe = g.build_cpp_driver(name="bootstrap_driver")
+    S, boot, qp = _dbfv_boot_params()
+    orig = S.bfv
+    rng = np.random.default_rng(777)
+    s = H.gen_secret_key(orig, rng)
+    rlk_arr = H.gen_relin_key(orig, s, rng)
+    bk = B.gen_bootstrap_key(orig, boot, s, qp, orig.plain_modulus, rng)
+    mk = lambda m: H.dbfv_encrypt_poly_sk(S, np.array([m % 16] + [0] * 15, np.uint64), s, rng)
+    cts = [mk(3), mk(2), mk(5)]
+    words = [orig.n, orig.q, orig.plain_modulus, orig.gadget_base, boot.q, boot.plain_modulus, boot.gadget_base,
+             qp, S.base, S.d, S.plain_modulus, len(bk.rounding_poly), len(bk.galois_keys), len(cts)]
+    parts = [np.array(words, np.uint64), np.array(bk.rounding_poly, np.uint64), rlk_arr.ravel(), bk.bsk.ravel(), bk.boot_rlk.ravel()]
+    for k in sorted(bk.galois_keys):
+        parts += [np.array([k], np.uint64), bk.galois_keys[k].ravel()]
+    parts += [c.ravel() for c in cts]
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    np.concatenate(parts).astype(np.uint64).tofile(fin)
+    res = subprocess.run([exe, str(fin), str(fout)], capture_output=True, text=True)
+    assert res.returncode == 0 and "metadata ok" in res.stdout, res.stdout + res.stderr
+    out = np.fromfile(fout, dtype=np.uint64).reshape(3, S.d, 2, orig.n)
+    S2, want = B.dbfv_mul_then_bootstrap(S, cts[0], cts[1], rlk_arr, bk)
+    assert np.array_equal(out[0], want)
+    _, want_chain = B.dbfv_mul_chain_then_bootstrap([(S, a) for a in cts], rlk_arr, bk)
+    assert np.array_equal(out[1], want_chain)
+    _, third = B.dbfv_bootstrap(S, cts[2], bk)
+    assert np.array_equal(out[2], O.dbfv_mul(S2.bfv, S2.base, S2.d, S2.plain_modulus, want, third, bk.boot_rlk))
+
+
 def test_shared_context_from_host_threads_and_streams():
     """The reference's functions are re-entrant (no global state).  One context shared by host threads
     (ctypes drops the GIL) and by device-resident calls on different CUDA streams must still give the oracle's
