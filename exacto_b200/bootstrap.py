@@ -181,7 +181,10 @@ def slots_to_coeffs(slots: Sequence[BfvCiphertext]) -> BfvCiphertext:
 
 # ---- bfv_host.rs ------------------------------------------------------------------------------------------
 def _center_to(coeffs, q_from: int, m_to: int) -> np.ndarray:
-    """c in [0, q_from) read as centred and reduced to [0, m_to) (bfv_host.rs:72-90, :297-311)."""
+    """c in [0, q_from) read as centred and reduced mod m_to (bfv_host.rs:72-90, :297-311).  Like the reference, a
+    negative value that is a multiple of m_to comes out as m_to itself, not 0: create_boot_sk reduces it in
+    RnsPoly::from_coeff_poly (c % q), and the plaintext copy goes through scale_plaintext's `m % q_i`
+    (bfv/encrypt.rs:193) exactly as upstream.  Ternary keys never reach that branch."""
     out = []
     for c in coeffs:
         c = int(c)
@@ -267,11 +270,11 @@ def _bootstrap_batch(orig: BfvParams, cts: np.ndarray, bsk: BootstrapKey) -> np.
     if r_idx:                                                                    # full ring path :188-206
         R = len(r_idx)
         ph = phase[r_idx].contiguous()                                           # [R][2][n]
-        mono_in = np.stack([_monomial(2 * n - j, boot).components[0].evals for j in range(n)])      # X^-j
-        mono_out = np.stack([_monomial(j, boot).components[0].evals for j in range(n)])             # X^j
+        # monomial tables are built once, uploaded once ([n][n]) and broadcast on the device
+        mono_in = batch.to_device(np.stack([_monomial(2 * n - j, boot).components[0].evals for j in range(n)]))    # X^-j
+        mono_out = batch.to_device(np.stack([_monomial(j, boot).components[0].evals for j in range(n)]))           # X^j
         def times(x, mono):                                                      # x [R][n][2][n] * mono[j]
-            m = batch.to_device(np.broadcast_to(mono[None, :, None, :], (R, n, 2, n)).copy())
-            return batch.poly_mul(boot, 0, x, m)
+            return batch.poly_mul(boot, 0, x, mono[None, :, None, :].expand(R, n, 2, n).contiguous())
         shifted = times(ph[:, None].expand(R, n, 2, n).contiguous(), mono_in)
         flat = shifted.reshape(R * n, 2, n)
         gks = bsk.galois_keys

@@ -268,6 +268,7 @@ extern "C" int exb_context_set_option(exb_context *c, const char *name, int64_t 
     else if (k == "host_chunk_products" && value > 0) c->tune.host_chunk_products = (size_t)value;
     else if (k == "tensor_per_product") c->P.tensor_per_product = value ? 1u : 0u;
     else if (k == "relin_narrow") c->P.relin_narrow = value ? 1u : 0u;
+    else if (k == "ntt_cp_async") g_ntt_path.store(value ? 1 : 0);     // process-wide: A/B of the two n = 4096 transform kernels
     else return fail(EXB_INVALID_PARAM, "unknown option or value out of range: " + k);
     return EXB_OK;
 }

@@ -15,6 +15,9 @@
 // basis, 32-bit) modular arithmetic on the integer pipes, staged through shared memory.
 #include "kernels.cuh"
 
+#ifndef EXB_HOST_EMUL
+#include <cuda.h>
+#endif
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -69,8 +72,10 @@ constexpr int kThreads12 = 4096 >> kNB;
 
 // CANON = false leaves the outputs lazily reduced (any u64 below the transform's growth bound): enough for a
 // consumer that feeds them to a Montgomery REDC, which accepts any x < 2^64 against a canonical multiplier.
-template <int NB, int LAZY, bool CANON = true>
-__device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head,
+// `twm` serves the middle passes (table indices 8 .. 511: 8 KiB, staged in shared memory by the TMA kernel),
+// `tw` the pass whose 7 twiddles per thread are all different (indices >= 512, coalesced 16-byte global loads).
+template <int NB, int LAZY, bool CANON = true, class TWT = const Tw *, class TWM = const Tw *>
+__device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
                                            const LazyC &c, const u32 t) {
     u64 v[1 << NB];
     if constexpr (NB == 4) {
@@ -82,9 +87,9 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, c
     } else {
         load_vals<3, 9>(v, sm, t); fwd_pass<12, 9, 3, LAZY>(v, head, t, c); store_vals<3, 9>(v, sm, t);
         __syncthreads();
-        load_vals<3, 6>(v, sm, t); fwd_pass<12, 6, 3, LAZY>(v, tw, t, c); store_vals<3, 6>(v, sm, t);
+        load_vals<3, 6>(v, sm, t); fwd_pass<12, 6, 3, LAZY>(v, twm, t, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
-        load_vals<3, 3>(v, sm, t); fwd_pass<12, 3, 3, LAZY>(v, tw, t, c); store_vals<3, 3>(v, sm, t);
+        load_vals<3, 3>(v, sm, t); fwd_pass<12, 3, 3, LAZY>(v, twm, t, c); store_vals<3, 3>(v, sm, t);
         __syncthreads();
         load_vals<3, 0>(v, sm, t); fwd_pass<12, 0, 3, LAZY>(v, tw, t, c);
     }
@@ -96,8 +101,8 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const Tw *__restrict__ tw, c
 }
 
 // Inputs < 4q (LAZY >= 1) or < 2q (LAZY == 0); outputs canonical.
-template <int NB, int LAZY>
-__device__ __forceinline__ void inv_body12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head,
+template <int NB, int LAZY, class TWT = const Tw *, class TWM = const Tw *>
+__device__ __forceinline__ void inv_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
                                            const Modulus &mod, const LazyC &c, const u32 t) {
     u64 v[1 << NB];
     if constexpr (NB == 4) {
@@ -109,9 +114,9 @@ __device__ __forceinline__ void inv_body12(u64 *sm, const Tw *__restrict__ tw, c
     } else {
         load_vals<3, 0>(v, sm, t); inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 0>(v, sm, t);
         __syncthreads();
-        load_vals<3, 3>(v, sm, t); inv_pass<12, 3, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 3>(v, sm, t);
+        load_vals<3, 3>(v, sm, t); inv_pass<12, 3, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 3>(v, sm, t);
         __syncthreads();
-        load_vals<3, 6>(v, sm, t); inv_pass<12, 6, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 6>(v, sm, t);
+        load_vals<3, 6>(v, sm, t); inv_pass<12, 6, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
         load_vals<3, 9>(v, sm, t); inv_pass<12, 9, 3, true, LAZY>(v, head, t, mod, c); store_vals<3, 9>(v, sm, t);
     }
@@ -121,14 +126,14 @@ template <int LAZY, bool CANON = true>
 __device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
     const LazyC c = make_lazyc(mod);
     __syncthreads();
-    fwd_body12<kNB, LAZY, CANON>(sm, tw, head, c, threadIdx.x);
+    fwd_body12<kNB, LAZY, CANON>(sm, tw, tw, head, c, threadIdx.x);
     __syncthreads();
 }
 template <int LAZY>
 __device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
     const LazyC c = make_lazyc(mod);
     __syncthreads();
-    inv_body12<kNB, LAZY>(sm, tw, head, mod, c, threadIdx.x);
+    inv_body12<kNB, LAZY>(sm, tw, tw, head, mod, c, threadIdx.x);
     __syncthreads();
 }
 
@@ -396,7 +401,14 @@ __device__ __forceinline__ void store_poly(u64 *dst, const u64 *buf) {
 }
 
 // NB = 3: 512 threads x 8 values (<= 64 registers, 2 CTAs = 32 warps per SM);
-// NB = 4: 256 threads x 16 values.  DBG = 1 (lab, env EXB_NTT_DBG): copy only.
+// NB = 4: 256 threads x 16 values.  DBG (lab builds, env EXB_NTT_DBG): 1 = copy only, 2 = transforms without any
+// global traffic, 3 = every twiddle load hits the same 16 table entries.
+#ifdef EXB_LAB
+struct TwMasked {
+    const Tw *p;
+    __device__ __forceinline__ Tw operator[](u32 i) const { return p[i & 15u]; }
+};
+#endif
 template <bool FWD, int LAZY, int NB, int DBG = 0>
 __global__ void __launch_bounds__(4096 >> NB, NB == 3 ? 2 : 2)
 ntt12_persist_kernel(const u64 *in, u64 *out, const Tw *__restrict__ tw, const __grid_constant__ TwHead head,
@@ -409,26 +421,145 @@ ntt12_persist_kernel(const u64 *in, u64 *out, const Tw *__restrict__ tw, const _
     u32 poly = blockIdx.x;
     if (poly >= count) return;
     u32 cur = 0;
-    prefetch_poly<THREADS>(smem, in + (size_t)poly * n);
+    if (DBG != 2) prefetch_poly<THREADS>(smem, in + (size_t)poly * n);
     cp_async_commit();
     for (; poly < count; poly += gridDim.x) {
         u64 *buf = smem + cur * n;
         const u32 next = poly + gridDim.x;
-        if (next < count) prefetch_poly<THREADS>(smem + (cur ^ 1) * n, in + (size_t)next * n);
+        if (DBG != 2 && next < count) prefetch_poly<THREADS>(smem + (cur ^ 1) * n, in + (size_t)next * n);
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
         if (DBG != 1) {
-            if (FWD) fwd_body12<NB, LAZY>(buf, tw, head, c, t);
-            else inv_body12<NB, LAZY>(buf, tw, head, mod, c, t);
+#ifdef EXB_LAB
+            if (DBG == 3) {
+                const TwMasked twm{tw};
+                if (FWD) fwd_body12<NB, LAZY>(buf, twm, twm, head, c, t);
+                else inv_body12<NB, LAZY>(buf, twm, twm, head, mod, c, t);
+            } else
+#endif
+            if (FWD) fwd_body12<NB, LAZY>(buf, tw, tw, head, c, t);
+            else inv_body12<NB, LAZY>(buf, tw, tw, head, mod, c, t);
         }
         __syncthreads();
-        store_poly<THREADS>(out + (size_t)poly * n, buf);
+        if (DBG != 2) store_poly<THREADS>(out + (size_t)poly * n, buf);
         __syncthreads();      // buf is the prefetch target of the next iteration
         cur ^= 1;
     }
     cp_async_wait<0>();
 }
+
+
+#ifndef EXB_HOST_EMUL
+// ---------------------------------------------------------------------------------
+// K1 / K2 with the Tensor Memory Accelerator (n = 4096).  One elected thread moves whole polynomials:
+//   * load : cp.async.bulk.tensor.2d of a [256 rows][128 B] box with SWIZZLE_128B -- the hardware swizzle IS the
+//            16-byte XOR swizzle of the shared-memory image (swz16), so a polynomial arrives transform-ready with
+//            one instruction, completion signalled on an mbarrier (no per-thread copies, no address arithmetic);
+//   * store: cp.async.bulk.tensor.2d shared -> global straight out of the image (bulk async-group);
+//   * twiddles: table entries 0 .. 511 (the middle passes; 8 KiB) are staged into shared memory once per CTA with a
+//            1-D cp.async.bulk; the first pass reads its 7 entries from the constant bank and the last pass keeps its
+//            per-thread coalesced 16-byte loads (every entry is used by exactly one thread there).
+// Three image buffers rotate: poly i is transformed while poly i+1 is landing and poly i-1 is draining, with ONE
+// block barrier per polynomial (the cp.async version needs three plus per-thread LDGSTS / LDS / STG).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, u64 *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr u32 kTmaStages = 3;
+constexpr u32 kTwStaged = 512;                                 // twiddle entries kept in shared memory
+constexpr size_t kTmaSmemBytes = 1024 + kTmaStages * 4096 * 8 + kTwStaged * sizeof(Tw) + 64;
+
+template <bool FWD, int LAZY, bool SMEM_TW = true>
+__global__ void __launch_bounds__(512, 2)
+ntt12_tma_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+                 const Tw *__restrict__ tw, const __grid_constant__ TwHead head, const __grid_constant__ Modulus mod,
+                 u32 count) {
+    extern __shared__ unsigned char raw_smem[];
+    // SWIZZLE_128B keys on address bits 7..9: the images must start on a 1024-byte boundary
+    u64 *bufs = reinterpret_cast<u64 *>((reinterpret_cast<uintptr_t>(raw_smem) + 1023) & ~(uintptr_t)1023);
+    Tw *stw = reinterpret_cast<Tw *>(bufs + kTmaStages * 4096);
+    u64 *full = reinterpret_cast<u64 *>(stw + kTwStaged);      // full[stage], then the twiddle barrier
+    u64 *twbar = full + kTmaStages;
+    const LazyC c = make_lazyc(mod);
+    const u32 t = threadIdx.x;
+    if (blockIdx.x >= count) return;
+    if (t == 0) {
+        for (u32 s = 0; s < kTmaStages; s++) mbar_init(full + s, 1);
+        mbar_init(twbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(twbar, kTwStaged * (u32)sizeof(Tw));
+        bulk_load_1d(stw, tw, kTwStaged * (u32)sizeof(Tw), twbar);
+        for (u32 s = 0; s < 2; s++) {
+            const u32 p = blockIdx.x + s * gridDim.x;
+            if (p < count) {
+                mbar_expect_tx(full + s, 4096 * 8);
+                tma_load_2d(bufs + s * 4096, &tin, 0, (int)(p * 256), full + s);
+            }
+        }
+    }
+    mbar_wait(twbar, 0);
+    u32 it = 0;
+    for (u32 poly = blockIdx.x; poly < count; poly += gridDim.x, it++) {
+        const u32 b = it % kTmaStages;
+        u64 *buf = bufs + b * 4096;
+        mbar_wait(full + b, (it / kTmaStages) & 1u);
+        if (SMEM_TW) {
+            if (FWD) fwd_body12<3, LAZY>(buf, tw, stw, head, c, t);
+            else inv_body12<3, LAZY>(buf, tw, stw, head, mod, c, t);
+        } else {
+            if (FWD) fwd_body12<3, LAZY>(buf, tw, tw, head, c, t);
+            else inv_body12<3, LAZY>(buf, tw, tw, head, mod, c, t);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA store
+        __syncthreads();
+        if (t == 0) {
+            tma_store_2d(&tout, 0, (int)(poly * 256), buf);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            const u32 next = poly + 2 * gridDim.x;
+            if (next < count) {
+                // the buffer poly i+2 lands in was drained by the store of poly i-1: all but the newest group done reading
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const u32 nb = (it + 2) % kTmaStages;
+                mbar_expect_tx(full + nb, 4096 * 8);
+                tma_load_2d(bufs + nb * 4096, &tin, 0, (int)(next * 256), full + nb);
+            }
+        }
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+#endif  // EXB_HOST_EMUL
 
 // ---------------------------------------------------------------------------------
 // K3: element-wise ring ops on canonical residues.
@@ -1392,11 +1523,10 @@ static void launch_ntt12_nb(const Modulus &mod, const Tw *tw, const TwHead &head
     const size_t slots = (size_t)num_sms() * 2;               // persistent: 2 CTAs per SM
     const unsigned grid = (unsigned)(count < slots ? count : slots);
 #ifdef EXB_LAB
-    static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;   // lab build: copy only
-    if (dbg == 1) {
-        ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count);
-        return;
-    }
+    static const int dbg = getenv("EXB_NTT_DBG") ? atoi(getenv("EXB_NTT_DBG")) : 0;   // lab build: see the kernel
+    if (dbg == 1) { ntt12_persist_kernel<FWD, LAZY, NB, 1><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count); return; }
+    if (dbg == 2) { ntt12_persist_kernel<FWD, LAZY, NB, 2><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count); return; }
+    if (dbg == 3) { ntt12_persist_kernel<FWD, LAZY, NB, 3><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count); return; }
 #endif
     ntt12_persist_kernel<FWD, LAZY, NB><<<grid, 4096 >> NB, sm, s>>>(in, out, tw, head, mod, (u32)count);
 }
@@ -1409,9 +1539,63 @@ static void launch_ntt12_l(const Modulus &mod, const Tw *tw, const TwHead &head,
 #endif
     launch_ntt12_nb<FWD, LAZY, 3>(mod, tw, head, in, out, count, s);
 }
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// [count] polynomials of 4096 u64 as a 2-D tensor of 128-byte rows; one box = one polynomial (256 rows), SWIZZLE_128B.
+static bool poly_tensor_map(CUtensorMap *map, const u64 *base, size_t count) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15u) || count * 256 > 0xffffffffull) return false;
+    const cuuint64_t dims[2] = {16, (cuuint64_t)count * 256};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<u64 *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <bool FWD, int LAZY>
+static bool launch_ntt12_tma(const Modulus &mod, const Tw *tw, const TwHead &head, const u64 *in, u64 *out, size_t count,
+                             cudaStream_t s) {
+    CUtensorMap tin, tout;
+    if (!poly_tensor_map(&tin, in, count) || !poly_tensor_map(&tout, out, count)) return false;
+    const size_t slots = (size_t)num_sms() * 2;               // persistent: 2 CTAs per SM
+    const unsigned grid = (unsigned)(count < slots ? count : slots);
+    // measured (tools/lab_ntt.py): the staged table wins everywhere except the csub-free inverse (LAZY 2), whose
+    // middle passes are short enough for the L1-resident table to keep up
+    constexpr bool kStaged = FWD || LAZY != 2;
+#ifdef EXB_LAB
+    static const int gtw = getenv("EXB_TMA_GLOBAL_TW") ? 1 : 0;
+    if (gtw) { ntt12_tma_kernel<FWD, LAZY, false><<<grid, 512, kTmaSmemBytes, s>>>(tin, tout, tw, head, mod, (u32)count); return true; }
+#endif
+    ntt12_tma_kernel<FWD, LAZY, kStaged><<<grid, 512, kTmaSmemBytes, s>>>(tin, tout, tw, head, mod, (u32)count);
+    return true;
+}
+
+std::atomic<int> g_ntt_path{0};                               // 0: TMA kernel, 1: cp.async kernel (exb_set_ntt_path)
+
 template <bool FWD>
 static void launch_ntt12(const Modulus &mod, const Tw *tw, const TwHead &head, const u64 *in, u64 *out, size_t count,
                          cudaStream_t s) {
+    if (g_ntt_path.load(std::memory_order_relaxed) == 0) {
+        bool ok;
+        if (mod.lazy == 2) ok = launch_ntt12_tma<FWD, 2>(mod, tw, head, in, out, count, s);
+        else if (mod.lazy == 1) ok = launch_ntt12_tma<FWD, 1>(mod, tw, head, in, out, count, s);
+        else ok = launch_ntt12_tma<FWD, 0>(mod, tw, head, in, out, count, s);
+        if (ok) return;
+    }
     if (mod.lazy == 2) launch_ntt12_l<FWD, 2>(mod, tw, head, in, out, count, s);
     else if (mod.lazy == 1) launch_ntt12_l<FWD, 1>(mod, tw, head, in, out, count, s);
     else launch_ntt12_l<FWD, 0>(mod, tw, head, in, out, count, s);
@@ -1612,10 +1796,15 @@ void launch_prepare(int device) {
     EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
 #undef EXB_OPT_NTT
 #ifdef EXB_LAB
-#define EXB_OPT_NTT(F, L) opt_in(ntt12_persist_kernel<F, L, 4>, optin); opt_in(ntt12_persist_kernel<F, L, 3, 1>, optin); opt_in(ntt12_persist_kernel<F, L, 4, 1>, optin);
+#define EXB_OPT_NTT(F, L) opt_in(ntt12_persist_kernel<F, L, 4>, optin); opt_in(ntt12_persist_kernel<F, L, 3, 1>, optin); opt_in(ntt12_persist_kernel<F, L, 4, 1>, optin); \
+    opt_in(ntt12_persist_kernel<F, L, 3, 2>, optin); opt_in(ntt12_persist_kernel<F, L, 3, 3>, optin); \
+    opt_in(ntt12_persist_kernel<F, L, 4, 2>, optin); opt_in(ntt12_persist_kernel<F, L, 4, 3>, optin);
     EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
 #undef EXB_OPT_NTT
 #endif
+#define EXB_OPT_NTT(F, L) opt_in(ntt12_tma_kernel<F, L>, optin); opt_in(ntt12_tma_kernel<F, L, false>, optin);
+    EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
+#undef EXB_OPT_NTT
     opt_in(lift32_kernel, optin); opt_in(lift_kernel<12>, optin); opt_in(lift_kernel<0>, optin);
     opt_in(tensor01_kernel, optin);
     opt_in(tensor32_kernel<int16_t>, optin); opt_in(tensor32_kernel<int32_t>, optin);

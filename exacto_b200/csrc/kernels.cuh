@@ -81,6 +81,8 @@ void launch_rns_decrypt(const RnsConsts &R, const RnsPlans &T, const u64 *ct, u3
 void launch_prepare(int device);
 #endif
 
+extern std::atomic<int> g_ntt_path;                      // 0: TMA transform kernel (default), 1: cp.async kernel
+
 int num_sms();                                           // SM count of the current device (148 on B200)
 
 // Count of kernels launched by this library (bench.py's gpu_launches).

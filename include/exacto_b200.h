@@ -109,7 +109,9 @@ void exb_context_destroy(exb_context *ctx);
  *   "device_chunk_bytes"  workspace budget of one chunk of a device-resident call (default 4 GiB)
  *   "host_chunk_products" per-digit products per chunk of the host-buffer pipeline (default 1024)
  *   "tensor_per_product"  1 = never sum components 0/1 per output limb (tensor01_kernel off)
- *   "relin_narrow"        1 = never give each relinearisation transform its own CTA */
+ *   "relin_narrow"        1 = never give each relinearisation transform its own CTA
+ *   "ntt_cp_async"        1 = batched n = 4096 transforms use the cp.async kernel instead of the TMA kernel
+ *                         (process-wide; A/B measurements) */
 int exb_context_set_option(exb_context *ctx, const char *name, int64_t value);
 /* Effective values after defaults were applied. */
 int exb_context_gadget(const exb_context *ctx, uint64_t *gadget_base, uint32_t *gadget_digits);
