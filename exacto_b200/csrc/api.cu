@@ -45,7 +45,7 @@ static int fail(int code, const std::string &msg) {
 // enqueue (two host threads on two streams get two slots and overlap on the host and on the GPU); the
 // host-buffer pipeline owns the `hs` slots, each with its own stream and staging buffers.
 static const int kSlots = 4;
-static const int kHostSlots = 4;
+static const int kHostSlots = 8;                        // allocated; Tuning::host_slots of them rotate
 
 struct Workspace {
     std::mutex mu;                                        // held while a call enqueues work that uses the slot
@@ -72,7 +72,10 @@ struct Ticket {
 
 struct Tuning {                                           // exb_context_set_option
     size_t device_chunk_bytes = (size_t)4 << 30;          // workspace budget of one device-resident chunk
-    size_t host_chunk_products = 1024;                    // products per chunk of the host-buffer pipeline
+    size_t host_chunk_products = 0;                       // products per chunk of the host-buffer pipeline; 0 = auto:
+                                                          // 1024 for a synchronous call (short fill / drain), 3996 when
+                                                          // calls are pipelined (measured optimum, tools/sweep_e2e.py)
+    int host_slots = 4;                                   // pipeline depth (streams / staging sets in rotation)
 };
 
 struct exb_context : HostSetup {
@@ -266,6 +269,12 @@ extern "C" int exb_context_set_option(exb_context *c, const char *name, int64_t 
     const std::string k(name);
     if (k == "device_chunk_bytes" && value > 0) c->tune.device_chunk_bytes = (size_t)value;
     else if (k == "host_chunk_products" && value > 0) c->tune.host_chunk_products = (size_t)value;
+    else if (k == "host_slots" && value >= 2 && value <= kHostSlots) {
+        std::lock_guard<std::mutex> hl(c->host_mu);
+        cudaSetDevice(c->device);
+        for (Workspace &w : c->hs) cudaStreamSynchronize(w.stream);
+        c->tune.host_slots = (int)value;
+    }
     else if (k == "tensor_per_product") c->P.tensor_per_product = value ? 1u : 0u;
     else if (k == "relin_narrow") c->P.relin_narrow = value ? 1u : 0u;
     else if (k == "ntt_cp_async") g_ntt_path.store(value ? 1 : 0);     // process-wide: A/B of the two n = 4096 transform kernels
@@ -808,13 +817,15 @@ static int host_pipeline(exb_context *c, uint64_t base, uint32_t d, uint64_t pm,
     }
     const size_t stride = (size_t)d * 2 * c->n;
     // chunk size: enough CTAs to fill the GPU, small enough that H2D / kernels / D2H of consecutive chunks overlap
-    size_t chunk = c->tune.host_chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
+    const size_t chunk_products = c->tune.host_chunk_products ? c->tune.host_chunk_products : (taper ? 1024 : 3996);
+    size_t chunk = chunk_products / (hp.M.num_products ? hp.M.num_products : 1);
     if (chunk < 1) chunk = 1;
-    if (batch < chunk * (kHostSlots - 1)) chunk = (batch + kHostSlots - 2) / (kHostSlots - 1);
+    const int slots = c->tune.host_slots;
+    if (batch < chunk * (size_t)(slots - 1)) chunk = (batch + slots - 2) / (size_t)(slots - 1);
     bool used[kHostSlots] = {};
     size_t ci = 0;
     for (size_t off = 0; off < batch; ci++) {
-        const int si = (int)(c->host_rr++ % kHostSlots);
+        const int si = (int)(c->host_rr++ % (unsigned)slots);
         Workspace &w = c->hs[si];
         const size_t left = batch - off;
         size_t cnt = chunk;

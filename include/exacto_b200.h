@@ -107,7 +107,9 @@ int exb_context_create_ex(const exb_bfv_params *params, int device, uint32_t fla
 void exb_context_destroy(exb_context *ctx);
 /* Tuning knobs (the defaults are the measured optimum; tests use them to force every code path):
  *   "device_chunk_bytes"  workspace budget of one chunk of a device-resident call (default 4 GiB)
- *   "host_chunk_products" per-digit products per chunk of the host-buffer pipeline (default 1024)
+ *   "host_chunk_products" per-digit products per chunk of the host-buffer pipeline (default: 1024 for the
+ *                         synchronous calls, 3996 for the asynchronous ones)
+ *   "host_slots"          depth of that pipeline: 2..8 staging sets / streams in rotation (default 4)
  *   "tensor_per_product"  1 = never sum components 0/1 per output limb (tensor01_kernel off)
  *   "relin_narrow"        1 = never give each relinearisation transform its own CTA
  *   "ntt_cp_async"        1 = batched n = 4096 transforms use the cp.async kernel instead of the TMA kernel
