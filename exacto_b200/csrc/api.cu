@@ -617,6 +617,13 @@ static size_t device_chunk_pairs(const exb_context *c, const HostPlan &hp, u32 G
     size_t eb, rb, db, xb;
     const size_t per = ws_bytes_per_pair(c, hp, G, &eb, &rb, &db, &xb);
     size_t chunk = c->tune.device_chunk_bytes / (per ? per : 1);
+    // whole waves: the per-limb kernels (tensor01, relin) run num_limbs CTAs per pair on 2 x #SM resident CTAs, so a
+    // chunk that is a multiple of slots / gcd(slots, limbs) pairs leaves no partially filled last wave
+    const size_t slots = (size_t)num_sms() * 2, limbs = hp.M.num_limbs ? hp.M.num_limbs : 1;
+    size_t a = slots, b = limbs;
+    while (b) { const size_t t = a % b; a = b; b = t; }
+    const size_t wave = slots / a;
+    if (chunk > wave) chunk -= chunk % wave;
     return chunk ? chunk : 1;
 }
 
