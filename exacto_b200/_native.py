@@ -39,6 +39,7 @@ SYMBOLS = {
     "exb_context_set_option": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int64]),
     "exb_ntt_format_id": (ctypes.c_int, [c_vp, c_u32, ctypes.POINTER(c_u64)]),
     "exb_host_alloc": (ctypes.c_int, [c_vp, c_sz, ctypes.POINTER(c_vp)]),
+    "exb_host_alloc_ex": (ctypes.c_int, [c_vp, c_sz, c_u32, ctypes.POINTER(c_vp)]),
     "exb_host_free": (ctypes.c_int, [c_vp, c_vp]),
     "exb_host_register": (ctypes.c_int, [c_vp, c_vp, c_sz]),
     "exb_host_unregister": (ctypes.c_int, [c_vp, c_vp]),
@@ -89,6 +90,7 @@ SYMBOLS = {
 
 EXB_DBFV_ALL_PRODUCTS = 1
 EXB_CTX_REFERENCE_AUX_BASIS = 1
+EXB_HOST_WRITE_COMBINED = 1
 
 _lib = None
 

@@ -759,12 +759,15 @@ extern "C" int exb_bfv_mul_and_relin(exb_context *c, const uint64_t *ct1, const 
 // The reference owns plain Vec<u64> (bfv/mod.rs:19-24).  Page-locked memory is what lets the copies of the
 // host-buffer pipeline run asynchronously at PCIe speed: allocate ciphertext storage with exb_host_alloc, or
 // pin an existing allocation in place with exb_host_register.
-extern "C" int exb_host_alloc(exb_context *c, size_t bytes, void **p) {
+extern "C" int exb_host_alloc_ex(exb_context *c, size_t bytes, uint32_t flags, void **p) {
     if (!c || !p) return fail(EXB_INVALID_PARAM, "null argument");
+    if (flags & ~(uint32_t)EXB_HOST_WRITE_COMBINED) return fail(EXB_INVALID_PARAM, "unknown host allocation flag");
     EXB_CUDA(cudaSetDevice(c->device));
-    EXB_CUDA(cudaHostAlloc(p, bytes ? bytes : 8, cudaHostAllocPortable));
+    EXB_CUDA(cudaHostAlloc(p, bytes ? bytes : 8,
+                           cudaHostAllocPortable | ((flags & EXB_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0)));
     return EXB_OK;
 }
+extern "C" int exb_host_alloc(exb_context *c, size_t bytes, void **p) { return exb_host_alloc_ex(c, bytes, 0, p); }
 extern "C" int exb_host_free(exb_context *c, void *p) {
     if (!c) return fail(EXB_INVALID_PARAM, "null context");
     EXB_CUDA(cudaSetDevice(c->device));

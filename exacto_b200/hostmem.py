@@ -20,11 +20,12 @@ from .params import DbfvParams
 class PinnedArray:
     """A page-locked uint64 array (exb_host_alloc); ``.array`` is a numpy view.  Freed on close()/GC."""
 
-    def __init__(self, ctx, shape: Tuple[int, ...]):
+    def __init__(self, ctx, shape: Tuple[int, ...], write_combined: bool = False):
         self._ctx, self._L = ctx, _native.lib()
         nbytes = int(np.prod(shape)) * 8
         p = ctypes.c_void_p()
-        _native.check(self._L.exb_host_alloc(ctx.handle, nbytes, ctypes.byref(p)))
+        flags = _native.EXB_HOST_WRITE_COMBINED if write_combined else 0     # inputs the CPU only writes
+        _native.check(self._L.exb_host_alloc_ex(ctx.handle, nbytes, flags, ctypes.byref(p)))
         self._ptr = p
         buf = (ctypes.c_uint64 * (max(nbytes, 8) // 8)).from_address(p.value)
         self.array = np.frombuffer(buf, dtype=np.uint64, count=int(np.prod(shape))).reshape(shape)

@@ -145,6 +145,10 @@ int exb_synchronize(exb_context *ctx, void *stream);
  * ciphertext storage here (exb_host_alloc / exb_host_free) or pin an existing allocation in place
  * (exb_host_register / exb_host_unregister, e.g. a long-lived Vec<u64>). */
 int exb_host_alloc(exb_context *ctx, size_t bytes, void **host_ptr);
+/* EXB_HOST_WRITE_COMBINED: for buffers the CPU only WRITES (inputs of the *_host calls): uploads skip the cache
+ * snoop, CPU reads from such memory are very slow. */
+enum { EXB_HOST_WRITE_COMBINED = 1u };
+int exb_host_alloc_ex(exb_context *ctx, size_t bytes, uint32_t flags, void **host_ptr);
 int exb_host_free(exb_context *ctx, void *host_ptr);
 int exb_host_register(exb_context *ctx, void *host_ptr, size_t bytes);
 int exb_host_unregister(exb_context *ctx, void *host_ptr);

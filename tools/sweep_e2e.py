@@ -10,9 +10,12 @@ params = E.u64_dbfv(); P = params.bfv_params; q = P.modulus(0)
 ctx = P.context(0)
 pairs = 1480
 shape = (pairs, 8, 2, 4096)
-h1, h2 = hostmem.PinnedArray(ctx, shape), hostmem.PinnedArray(ctx, shape)
+WC = bool(int(os.environ.get("WC", "0")))
+h1, h2 = hostmem.PinnedArray(ctx, shape, WC), hostmem.PinnedArray(ctx, shape, WC)
 rng = np.random.default_rng(1)
-bench.fill_uniform(rng, h1.array, q); bench.fill_uniform(rng, h2.array, q)
+tmp = np.empty(shape, np.uint64)
+bench.fill_uniform(rng, tmp, q); h1.array[:] = tmp
+bench.fill_uniform(rng, tmp, q); h2.array[:] = tmp
 outs = [hostmem.PinnedArray(ctx, shape), hostmem.PinnedArray(ctx, shape)]
 rlk = E.RelinKey(rng.integers(0, q, (8, 2, 4096), dtype=np.uint64), P)
 def run(steps):
@@ -25,7 +28,7 @@ def run(steps):
     pend.wait()
     return pairs * steps / (time.perf_counter() - t0)
 for slots in (4,):
-    for chunk in (2048, 2664, 3996, 5328, 7992):
+    for chunk in (3996,):
         ctx.set_option("host_slots", slots); ctx.set_option("host_chunk_products", chunk)
         run(2)
         print(f"slots={slots} chunk_products={chunk}: {run(8):.0f} dbfv_mul/s", flush=True)
