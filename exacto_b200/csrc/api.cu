@@ -76,6 +76,8 @@ struct Tuning {                                           // exb_context_set_opt
                                                           // 1024 for a synchronous call (short fill / drain), 3996 when
                                                           // calls are pipelined (measured optimum, tools/sweep_e2e.py)
     int host_slots = 4;                                   // pipeline depth (streams / staging sets in rotation)
+    int kshard_kernel_stores = 0;                         // k-shard exchange: 0 = copy engines (peer DMA), 1 = stores from
+                                                          // the relin kernel's epilogue (measured slower: SM-issued NVLink writes)
 };
 
 struct exb_context : HostSetup {
@@ -87,6 +89,8 @@ struct exb_context : HostSetup {
     Workspace hs[kHostSlots];         // host-buffer pipeline
     std::mutex mu;                    // slot selection, profiling record, tickets
     std::mutex host_mu;               // one host-buffer call enqueues at a time (its chunks stay in order)
+    cudaStream_t xs[kMaxPeers] = {};  // k-shard exchange: one copy stream per peer (created on first use)
+    cudaEvent_t xev[kMaxPeers + 1] = {};
     std::vector<StageEvents> events;
     unsigned rr = 0, host_rr = 0;
     uint64_t next_ticket = 1;
@@ -181,6 +185,8 @@ extern "C" void exb_context_destroy(exb_context *c) {
     for (Tw *t : c->d_tables) cudaFree(t);
     for (Workspace &w : c->ws) free_workspace(w);
     for (Workspace &w : c->hs) free_workspace(w);
+    for (cudaStream_t s : c->xs) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : c->xev) if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -277,6 +283,7 @@ extern "C" int exb_context_set_option(exb_context *c, const char *name, int64_t 
     }
     else if (k == "tensor_per_product") c->P.tensor_per_product = value ? 1u : 0u;
     else if (k == "relin_narrow") c->P.relin_narrow = value ? 1u : 0u;
+    else if (k == "kshard_kernel_stores") c->tune.kshard_kernel_stores = value ? 1 : 0;
     else if (k == "ntt_cp_async") g_ntt_path.store(value ? 1 : 0);     // process-wide: A/B of the two n = 4096 transform kernels
     else return fail(EXB_INVALID_PARAM, "unknown option or value out of range: " + k);
     return EXB_OK;
@@ -672,6 +679,36 @@ static int rns_mul(exb_context *c, const HostPlan &hp, const exb_relin_key *rlk,
     return rc ? rc : rc2;
 }
 
+// k-shard exchange on the copy engines: the owned output limbs (runs of consecutive k are one 2-D copy) go from this
+// rank's output into every peer's, one stream per peer so the NVLink DMAs run side by side; `st` continues only
+// after all of them (fork / join with events), so whatever the caller enqueues next -- its barrier -- is ordered.
+static int scatter_limbs(exb_context *c, const HostPlan &hp, const u64 *out, uint64_t *const *peers, uint32_t num_peers,
+                         size_t batch, cudaStream_t st) {
+    const size_t n = c->n, d = hp.M.d, pitch = d * 2 * n * 8;
+    std::lock_guard<std::mutex> g(c->mu);
+    for (uint32_t p = 0; p < num_peers; p++)
+        if (!c->xs[p]) {
+            EXB_CUDA(cudaStreamCreateWithFlags(&c->xs[p], cudaStreamNonBlocking));
+            EXB_CUDA(cudaEventCreateWithFlags(&c->xev[p], cudaEventDisableTiming));
+        }
+    if (!c->xev[kMaxPeers]) EXB_CUDA(cudaEventCreateWithFlags(&c->xev[kMaxPeers], cudaEventDisableTiming));
+    EXB_CUDA(cudaEventRecord(c->xev[kMaxPeers], st));
+    for (uint32_t p = 0; p < num_peers; p++) {
+        EXB_CUDA(cudaStreamWaitEvent(c->xs[p], c->xev[kMaxPeers], 0));
+        for (u32 l = 0; l < hp.M.num_low;) {
+            u32 e = l;
+            while (e + 1 < hp.M.num_low && hp.M.limb_k[e + 1] == hp.M.limb_k[e] + 1) e++;
+            const size_t k0 = hp.M.limb_k[l], run = e - l + 1;
+            EXB_CUDA(cudaMemcpy2DAsync(peers[p] + k0 * 2 * n, pitch, out + k0 * 2 * n, pitch, run * 2 * n * 8, batch,
+                                       cudaMemcpyDefault, c->xs[p]));
+            l = e + 1;
+        }
+        EXB_CUDA(cudaEventRecord(c->xev[p], c->xs[p]));
+        EXB_CUDA(cudaStreamWaitEvent(st, c->xev[p], 0));
+    }
+    return EXB_OK;
+}
+
 static int dbfv_mul_device(exb_context *c, uint64_t base, uint32_t d, uint64_t pm, const uint64_t *ct1,
                            const uint64_t *ct2, const exb_relin_key *rlk, uint64_t *out, uint64_t *const *peers,
                            uint32_t num_peers, size_t batch, uint32_t flags, uint32_t limb_mask, void *stream) {
@@ -694,12 +731,14 @@ static int dbfv_mul_device(exb_context *c, uint64_t base, uint32_t d, uint64_t p
     if ((rc = acquire(c, st, &held, &w))) return rc;
     const size_t stride = (size_t)d * 2 * c->n;
     const size_t chunk = device_chunk_pairs(c, hp, c->gadget_digits);
-    hp.M.num_peers = num_peers;
+    const bool kernel_stores = num_peers && c->tune.kshard_kernel_stores;
+    hp.M.num_peers = kernel_stores ? num_peers : 0;
     for (size_t off = 0; off < batch && !rc; off += chunk) {
         const size_t cnt = batch - off < chunk ? batch - off : chunk;
-        for (uint32_t p = 0; p < num_peers; p++) hp.M.peer_out[p] = peers[p] + off * stride;
+        for (uint32_t p = 0; p < hp.M.num_peers; p++) hp.M.peer_out[p] = peers[p] + off * stride;
         rc = run_pairs(c, *w, hp, rlk, ct1 + off * stride, ct2 + off * stride, out + off * stride, cnt, st);
     }
+    if (!rc && num_peers && !kernel_stores) rc = scatter_limbs(c, hp, out, peers, num_peers, batch, st);
     const int rc2 = release(w, st);
     return rc ? rc : rc2;
 }

@@ -43,7 +43,8 @@ __device__ __forceinline__ u64 ld_stream(const u64 *p) {
 #endif
 }
 
-// Stores into peer GPUs' memory (k-sharded dbfv_mul) are made visible system-wide before the kernel ends.
+// Stores into peer GPUs' memory (k-sharded dbfv_mul, kernel-store transport) are made visible system-wide before
+// the kernel ends.
 __device__ __forceinline__ void peer_fence() {
 #ifndef EXB_HOST_EMUL
     __threadfence_system();

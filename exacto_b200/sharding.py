@@ -82,9 +82,9 @@ class KShard:
     """k-sharded dbfv_mul over the GPUs of one box (one process per GPU, ``torch.distributed`` initialised).
 
     Every rank holds the same pairs and owns the output limbs of ``masks[rank]``.  Each rank's output buffer is a
-    cudaMalloc allocation shared with the other ranks through CUDA IPC; ``exb_dbfv_mul_scatter`` makes the
-    relinearisation kernel store every finished limb into all N output buffers over NVLink peer memory, so the
-    exchange overlaps the compute.  One tiny all-reduce per call orders the ranks; two output buffers alternate so
+    cudaMalloc allocation shared with the other ranks through CUDA IPC; ``exb_dbfv_mul_scatter`` copies every
+    finished limb into all N output buffers over NVLink peer memory (copy engines by default; the relinearisation
+    kernel's epilogue can do the stores itself, measured slower).  One tiny all-reduce per call orders the ranks; two output buffers alternate so
     a rank may still read call i's result while call i+1 is being written.  ``mul`` returns the complete
     [pairs, d, 2, n] tensor (a view of the current buffer, valid until the call after next)."""
 
@@ -120,7 +120,8 @@ class KShard:
             self._peer_arr.append((ctypes.c_void_p * max(len(peers), 1))(*[q.value for q in peers]))
             self._views.append(torch.as_tensor(_DevBuf(p.value, self.shape, self), device=device))
         self._i = 0
-        self.transport = "nvlink peer stores from the relin kernel epilogue (CUDA IPC) + 1 all-reduce barrier"
+        self.transport = ("peer DMA over NVLink (one strided cudaMemcpy2DAsync per peer and run of owned limbs, CUDA IPC "
+                          "mappings, per-peer streams joined to the compute stream) + 1 all-reduce barrier")
         dist.barrier(group=group)
 
     def wire_bytes_per_pair_per_rank(self) -> int:

@@ -112,6 +112,8 @@ void exb_context_destroy(exb_context *ctx);
  *   "host_slots"          depth of that pipeline: 2..8 staging sets / streams in rotation (default 4)
  *   "tensor_per_product"  1 = never sum components 0/1 per output limb (tensor01_kernel off)
  *   "relin_narrow"        1 = never give each relinearisation transform its own CTA
+ *   "kshard_kernel_stores" 1 = exb_dbfv_mul_scatter writes the peers from the relin kernel's epilogue instead of
+ *                         using the copy engines (A/B; measured slower)
  *   "ntt_cp_async"        1 = batched n = 4096 transforms use the cp.async kernel instead of the TMA kernel
  *                         (process-wide; A/B measurements) */
 int exb_context_set_option(exb_context *ctx, const char *name, int64_t value);
@@ -272,11 +274,12 @@ int exb_dbfv_mul_host(exb_context *ctx, uint64_t base, uint32_t num_digits, uint
                       uint64_t *out_host, size_t batch, uint32_t flags);
 /* ---- k-sharded dbfv_mul across the GPUs of one box (one process per GPU).  Every rank holds the same
  * ciphertext pairs and owns the output limbs of its `limb_mask` (products with equal i + j stay on one rank, so
- * the per-k accumulation of dbfv/eval.rs:125-136 is local).  The relinearisation kernel stores each finished
- * limb into this rank's `out_dev` and into `peer_outs_dev[0..num_peers)` -- the other ranks' output buffers,
- * same [batch][d][2][n] layout, mapped over NVLink with exb_ipc_open -- so the path's only exchange step
- * overlaps the compute and moves exactly 512 KiB * (N-1)/N per dbfv_mul into each rank.  The caller
- * synchronises the ranks (any barrier after the stream work) before reading.  Needs p = b^d (all-zero small
+ * the per-k accumulation of dbfv/eval.rs:125-136 is local).  The finished limbs go into this rank's `out_dev` and
+ * into `peer_outs_dev[0..num_peers)` -- the other ranks' output buffers, same [batch][d][2][n] layout, mapped over
+ * NVLink with exb_ipc_open: by default with one strided peer DMA per (peer, run of owned limbs) on per-peer
+ * streams that the call's stream joins, or (option "kshard_kernel_stores") with stores from the relinearisation
+ * kernel's epilogue.  Either way the path's only exchange step moves exactly 512 KiB * (N-1)/N per dbfv_mul into
+ * each rank.  The caller synchronises the ranks (any barrier after the stream work) before reading.  Needs p = b^d (all-zero small
  * representatives, every BASELINE config): EXB_NOT_IMPLEMENTED otherwise. */
 int exb_dbfv_mul_scatter(exb_context *ctx, uint64_t base, uint32_t num_digits, uint64_t dbfv_plain_modulus,
                          const uint64_t *ct1_dev, const uint64_t *ct2_dev, const exb_relin_key *rlk,

@@ -778,11 +778,12 @@ def test_async_host_api_pinned_memory_and_slot_pool():
     assert ctx.ntt_format_id(0) >> 56 == 1
 
 
-@pytest.mark.parametrize("pairs", [2, 30])
-def test_dbfv_mul_scatter_peer_stores(pairs):
-    """exb_dbfv_mul_scatter (k-sharded dbfv_mul): two 'ranks' on one GPU own disjoint output limbs and store their
-    finished limbs into both output buffers from the relin epilogue (narrow and wide relin paths); the union is the
-    oracle's dbfv_mul, and limbs a rank does not own stay untouched in its peers' buffers until their owner writes."""
+@pytest.mark.parametrize("pairs,kernel_stores", [(2, 0), (30, 0), (2, 1), (30, 1)])
+def test_dbfv_mul_scatter_peer_stores(pairs, kernel_stores):
+    """exb_dbfv_mul_scatter (k-sharded dbfv_mul): two 'ranks' on one GPU own disjoint output limbs and deliver their
+    finished limbs into both output buffers -- with the copy engines (default) or from the relin epilogue (narrow and
+    wide relin paths); the union is the oracle's dbfv_mul, and limbs a rank does not own stay untouched in its
+    peers' buffers until their owner writes."""
     import ctypes
     from exacto_b200 import _native, batch
     from exacto_b200.sharding import limb_masks
@@ -802,6 +803,7 @@ def test_dbfv_mul_scatter_peer_stores(pairs):
     masks = limb_masks(S.d, 2)
     outs = [torch.full_like(a, -1), torch.full_like(a, -1)]
     st = torch.cuda.current_stream().cuda_stream
+    ctx.set_option("kshard_kernel_stores", kernel_stores)
     for r in range(2):
         peer = (ctypes.c_void_p * 1)(outs[1 - r].data_ptr())
         _native.check(L.exb_dbfv_mul_scatter(ctx.handle, dp.base, S.d, dp.plain_modulus, a.data_ptr(), b.data_ptr(),
@@ -815,6 +817,7 @@ def test_dbfv_mul_scatter_peer_stores(pairs):
                 else:
                     assert np.all(h0[:, k] == np.uint64(0xFFFFFFFFFFFFFFFF))
     torch.cuda.synchronize()
+    ctx.set_option("kshard_kernel_stores", 0)
     assert np.array_equal(batch.to_host(outs[0])[:3], want) and torch.equal(outs[0], outs[1])
     # p != b^d (non-zero small representatives) is refused: the general reduction needs limbs of other ranks
     C = CASES["n64_a2_rep"]
