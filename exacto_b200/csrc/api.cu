@@ -549,7 +549,7 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
     *ext_b = 2 * d * 2 * (1 + A) * n * 8;
     if (c->P.sb.enabled && c->logn == 12) *ext_b = 2 * d * 2 * (size_t)c->P.sb.K * n * 4;
     *r01_b = (size_t)hp.M.num_products * 2 * n * 8;
-    *dig_b = (size_t)hp.M.num_products * (G ? G : 1) * n * (c->digits32 ? 4 : 2);
+    *dig_b = (size_t)hp.M.num_products * (G ? G : 1) * n * c->digit_bytes();
     *exc_b = (size_t)(hp.M.num_limbs - hp.num_low) * 2 * n * 8;
     return *ext_b + *r01_b + *dig_b + *exc_b;
 }
@@ -578,14 +578,14 @@ static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb
     launch_lift(P, hp.M, ct1, ct2, w.ext, pairs, stream);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[1], stream));
     se.has_c2 = tensor_sums_per_limb(P, hp.M, pairs);
-    launch_tensor(P, hp.M, ct1, ct2, w.ext, w.r01, w.digits, c->digits32, pairs, stream, prof ? se.ev[2] : nullptr);
+    launch_tensor(P, hp.M, ct1, ct2, w.ext, w.r01, w.digits, c->digit_kind(), pairs, stream, prof ? se.ev[2] : nullptr);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[3], stream));
     u64 *wide = nullptr;
     if (relin_goes_wide(P, hp.M, pairs)) {
         if ((rc = grow((void **)&w.wide, &w.wide_b, relin_wide_scratch_bytes(P, hp.M, pairs)))) return rc;
         wide = w.wide;
     }
-    launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out, w.excess, pairs, stream, wide);
+    launch_relin(P, hp.M, w.r01, w.digits, c->digit_kind(), rlk->d_mont, out, w.excess, pairs, stream, wide);
     if (prof) EXB_CUDA(cudaEventRecord(se.ev[4], stream));
     // reduction::reduce for non-zero small representatives (dbfv/reduction.rs:34-52)
     const u32 d = hp.M.d;
@@ -1105,7 +1105,7 @@ extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const u
         if ((rc = grow((void **)&w.ext, &w.ext_b, eb * cnt))) return rc;
         if ((rc = grow((void **)&w.r01, &w.r01_b, 3 * n * 8 * cnt))) return rc;
         launch_lift(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, cnt, st);
-        launch_tensor(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, w.r01, nullptr, c->digits32, cnt, st, nullptr, true);
+        launch_tensor(c->P, hp.M, ct1 + off * 2 * n, ct2 + off * 2 * n, w.ext, w.r01, nullptr, c->digit_kind(), cnt, st, nullptr, true);
         launch_ntt_fwd(c->P, 0, w.r01, out3 + off * 3 * n, 3 * cnt, st);      // hps_scale ends with from_coeff_poly (:412)
     }
     if ((rc = release(&w, st))) return rc;
@@ -1158,7 +1158,7 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
     Workspace *wp = nullptr;
     if ((rc = acquire(c, st, &held, &wp))) return rc;
     Workspace &w = *wp;
-    const size_t dig_b = (size_t)(G ? G : 1) * n * (c->digits32 ? 4 : 2);
+    const size_t dig_b = (size_t)(G ? G : 1) * n * c->digit_bytes();
     const size_t per = n * 8 + 2 * n * 8 + dig_b + (size_t)(G + 1) * 2 * n * 8;
     size_t chunk = ((size_t)4 << 30) / per;
     if (chunk < 1) chunk = 1;
@@ -1171,13 +1171,13 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
         EXB_CUDA(cudaMemcpy2DAsync(w.r01, 2 * n * 8, src, 3 * n * 8, 2 * n * 8, cnt, cudaMemcpyDeviceToDevice, st));
         EXB_CUDA(cudaMemcpy2DAsync(w.ext, n * 8, src + 2 * n, 3 * n * 8, n * 8, cnt, cudaMemcpyDeviceToDevice, st));
         launch_ntt_inv(P, 0, w.ext, w.ext, cnt, st);                           // :76
-        launch_gadget_digits(P, w.ext, w.digits, c->digits32 ? 1 : 0, cnt, st);   // :79
+        launch_gadget_digits(P, w.ext, w.digits, c->digit_kind() == 2 ? 3 : c->digit_kind(), cnt, st);   // :79
         u64 *wide = nullptr;
         if (relin_goes_wide(P, hp.M, cnt)) {
             if ((rc = grow((void **)&w.wide, &w.wide_b, relin_wide_scratch_bytes(P, hp.M, cnt)))) return rc;
             wide = w.wide;
         }
-        launch_relin(P, hp.M, w.r01, w.digits, c->digits32, rlk->d_mont, out + off * 2 * n, nullptr, cnt, st, wide, true);
+        launch_relin(P, hp.M, w.r01, w.digits, c->digit_kind(), rlk->d_mont, out + off * 2 * n, nullptr, cnt, st, wide, true);
     }
     if ((rc = release(&w, st))) return rc;
     return check_launch("relinearize");

@@ -93,6 +93,9 @@ struct HostSetup {
     u64 plain = 0, gadget_base = 0;
     u32 gadget_digits = 0;
     bool digits32 = false;                   // gadget digits need 32-bit storage
+    // storage of the balanced digits in [-B/2, B/2): 2 = int8 (B <= 2^8), 0 = int16 (B <= 2^16), 1 = int32
+    int digit_kind() const { return digits32 ? 1 : (gadget_base <= 256 ? 2 : 0); }
+    size_t digit_bytes() const { return digits32 ? 4 : (gadget_base <= 256 ? 1 : 2); }
     int mul_status = EXB_OK;                 // bfv_mul_no_relin dispatch result for these params
     std::string mul_error;
     DeviceParams P;                          // table pointers are filled by the owner

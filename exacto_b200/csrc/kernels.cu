@@ -758,7 +758,11 @@ __device__ __forceinline__ void sts_u32x8(u32 *sm, u32 e0, const u32 *v) {
 // 8 consecutive gadget digits (int16: one 16-byte piece, int32: two)
 template <typename DigT>
 __device__ __forceinline__ void ldg_dig8(const DigT *p, i64 *acc) {
-    if constexpr (sizeof(DigT) == 2) {
+    if constexpr (sizeof(DigT) == 1) {                     // 8 digits = one 8-byte piece
+        const u64 a = *reinterpret_cast<const u64 *>(p);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += (i64)(int8_t)((a >> (8 * i)) & 0xffu);
+    } else if constexpr (sizeof(DigT) == 2) {
         const Vec16 a = *reinterpret_cast<const Vec16 *>(p);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -773,7 +777,12 @@ __device__ __forceinline__ void ldg_dig8(const DigT *p, i64 *acc) {
 }
 template <typename DigT>
 __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
-    if constexpr (sizeof(DigT) == 2) {
+    if constexpr (sizeof(DigT) == 1) {
+        u64 a = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a |= ((u64)d[i] & 0xffu) << (8 * i);
+        *reinterpret_cast<u64 *>(p) = a;
+    } else if constexpr (sizeof(DigT) == 2) {
         Vec16 a;
 #pragma unroll
         for (int i = 0; i < 4; i++) a.w[i] = ((u32)d[2 * i] & 0xffffu) | ((u32)d[2 * i + 1] << 16);
@@ -1693,9 +1702,10 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
 }
 
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
-                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid, bool raw3) {
+                   void *digits, int digit_kind, size_t pairs, cudaStream_t s, cudaEvent_t mid, bool raw3) {
     if (pairs == 0) { if (mid) cudaEventRecord(mid, s); return; }
-    if (digits32) launch_tensor_t<int32_t>(P, M, ct1, ct2, ext, r01, (int32_t *)digits, pairs, s, mid, raw3);
+    if (digit_kind == 2) launch_tensor_t<int8_t>(P, M, ct1, ct2, ext, r01, (int8_t *)digits, pairs, s, mid, raw3);
+    else if (digit_kind == 1) launch_tensor_t<int32_t>(P, M, ct1, ct2, ext, r01, (int32_t *)digits, pairs, s, mid, raw3);
     else launch_tensor_t<int16_t>(P, M, ct1, ct2, ext, r01, (int16_t *)digits, pairs, s, mid, raw3);
 }
 
@@ -1703,7 +1713,8 @@ void launch_gadget_digits(const DeviceParams &P, const u64 *coeffs, void *out, i
     if (count == 0) return;
     size_t blocks = (count * P.n + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
-    if (out_kind == 0) gadget_digits_kernel<int16_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int16_t *)out, count);
+    if (out_kind == 3) gadget_digits_kernel<int8_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int8_t *)out, count);
+    else if (out_kind == 0) gadget_digits_kernel<int16_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int16_t *)out, count);
     else if (out_kind == 1) gadget_digits_kernel<int32_t, false><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (int32_t *)out, count);
     else gadget_digits_kernel<u64, true><<<(unsigned)blocks, 256, 0, s>>>(P, coeffs, (u64 *)out, count);
     g_launch_count++;
@@ -1735,11 +1746,12 @@ static void launch_relin_t(const DeviceParams &P, const MulPlan &M, const u64 *r
     g_launch_count++;
 }
 
-void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits, bool digits32,
+void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits, int digit_kind,
                   const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs, cudaStream_t s, u64 *wide_scratch,
                   bool r01_ntt) {
     if (pairs == 0) return;
-    if (digits32) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
+    if (digit_kind == 2) launch_relin_t<int8_t>(P, M, r01, (const int8_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
+    else if (digit_kind == 1) launch_relin_t<int32_t>(P, M, r01, (const int32_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
     else launch_relin_t<int16_t>(P, M, r01, (const int16_t *)digits, rlk_mont, out, excess, pairs, s, wide_scratch, r01_ntt);
 }
 
@@ -1808,12 +1820,12 @@ void launch_prepare(int device) {
 #undef EXB_OPT_NTT
     opt_in(lift32_kernel, optin); opt_in(lift_kernel<12>, optin); opt_in(lift_kernel<0>, optin);
     opt_in(tensor01_kernel, optin);
-    opt_in(tensor32_kernel<int16_t>, optin); opt_in(tensor32_kernel<int32_t>, optin);
-    opt_in(tensor_kernel<12, int16_t>, optin); opt_in(tensor_kernel<12, int32_t>, optin);
-    opt_in(tensor_kernel<0, int16_t>, optin); opt_in(tensor_kernel<0, int32_t>, optin);
-    opt_in(relin12_kernel<int16_t>, optin); opt_in(relin12_kernel<int32_t>, optin);
-    opt_in(relin12_wide_kernel<int16_t>, optin); opt_in(relin12_wide_kernel<int32_t>, optin);
-    opt_in(relin_kernel<0, int16_t>, optin); opt_in(relin_kernel<0, int32_t>, optin);
+    opt_in(tensor32_kernel<int16_t>, optin); opt_in(tensor32_kernel<int32_t>, optin); opt_in(tensor32_kernel<int8_t>, optin);
+    opt_in(tensor_kernel<12, int16_t>, optin); opt_in(tensor_kernel<12, int32_t>, optin); opt_in(tensor_kernel<12, int8_t>, optin);
+    opt_in(tensor_kernel<0, int16_t>, optin); opt_in(tensor_kernel<0, int32_t>, optin); opt_in(tensor_kernel<0, int8_t>, optin);
+    opt_in(relin12_kernel<int16_t>, optin); opt_in(relin12_kernel<int32_t>, optin); opt_in(relin12_kernel<int8_t>, optin);
+    opt_in(relin12_wide_kernel<int16_t>, optin); opt_in(relin12_wide_kernel<int32_t>, optin); opt_in(relin12_wide_kernel<int8_t>, optin);
+    opt_in(relin_kernel<0, int16_t>, optin); opt_in(relin_kernel<0, int32_t>, optin); opt_in(relin_kernel<0, int8_t>, optin);
     opt_in(galois_kernel<12>, optin); opt_in(galois_kernel<0>, optin);
     opt_in(decrypt_kernel<12>, optin); opt_in(decrypt_kernel<0>, optin);
     if (device >= 0 && device < 64) done.fetch_or(1ull << device);

@@ -25,7 +25,7 @@ void launch_poly_op(const Modulus &m, PolyOp op, const u64 *a, const u64 *b, u64
 //   ct1, ct2 : [pairs][d][2][n]  NTT domain, canonical mod q
 //   ext      : [pairs][2 sides][d][2][1+A][n] u64, or [pairs][2 sides][d][2][K][n] u32 with the internal basis  (workspace)
 //   r01      : [pairs][products][2][n] u64      (workspace, coefficient domain)
-//   digits   : [pairs][products][G][n] int16|int32 (workspace)
+//   digits   : [pairs][products][G][n] int8|int16|int32 (workspace; digit_kind 2 / 0 / 1: base <= 2^8 / 2^16 / 2^32)
 //   rlk_mont : [G][2][n] relin key in Montgomery form
 //   out      : [pairs][d][2][n];  excess: [pairs][num_limbs - d'][2][n] for k >= d
 void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, u64 *ext,
@@ -33,17 +33,17 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 // `mid` (optional) is recorded after the first of the two tensor kernels (per-limb components 0/1), or after
 // the only one.
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
-                   void *digits, bool digits32, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr,
+                   void *digits, int digit_kind, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr,
                    bool raw3 = false);   // raw3 (bfv_mul_no_relin): r01 = [pairs][products][3][n], all scaled components
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs);   // r01 is [pairs][limbs][2][n] when true
 // `wide_scratch` (relin_wide_scratch_bytes, optional): lets small batches use one CTA per transform.
 bool relin_goes_wide(const DeviceParams &P, const MulPlan &M, size_t pairs);
 size_t relin_wide_scratch_bytes(const DeviceParams &P, const MulPlan &M, size_t pairs);
 void launch_relin(const DeviceParams &P, const MulPlan &M, const u64 *r01, const void *digits,
-                  bool digits32, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
+                  int digit_kind, const u64 *rlk_mont, u64 *out, u64 *excess, size_t pairs,
                   cudaStream_t s, u64 *wide_scratch = nullptr, bool r01_ntt = false);
-// gadget_decompose of coefficient polynomials [count][n] -> [count][G][n]; out_kind 0: int16, 1: int32 signed digits
-// (relin layout), 2: u64 digits mod q (the reference's return value)
+// gadget_decompose of coefficient polynomials [count][n] -> [count][G][n]; out_kind 0: int16, 1: int32, 3: int8 signed
+// digits (relin layout), 2: u64 digits mod q (the reference's return value)
 void launch_gadget_digits(const DeviceParams &P, const u64 *coeffs, void *out, int out_kind, size_t count, cudaStream_t s);
 // out[pairs][d][2][n] limb i += rep * excess limb (signed scalar, reduction.rs:34-52)
 void launch_reduce_mac(const DeviceParams &P, u64 *out_limb, const u64 *excess_limb, u64 abs_scalar_mod_q,

@@ -14,6 +14,7 @@
 
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 // ---- CUDA shim ---------------------------------------------------------------------
@@ -182,10 +183,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
                                : pairs * 2 * d * 2 * (1 + A) * n),
         r01(pairs * M.num_products * 2 * n + 1);
     std::vector<u64> excess(pairs * nx * 2 * n + 1), rlk_mont((size_t)num_keys * 2 * n + 1);
-    std::vector<int32_t> dig32;
-    std::vector<int16_t> dig16;
-    if (hs.digits32) dig32.resize(pairs * M.num_products * (G ? G : 1) * n);
-    else dig16.resize(pairs * M.num_products * (G ? G : 1) * n);
+    std::vector<u64> digbuf((pairs * M.num_products * (G ? G : 1) * n * hs.digit_bytes() + 7) / 8 + 1);
     const Modulus mq = P.mod[0];
     const size_t kw = (size_t)num_keys * 2 * n;
     if (kw) emu_launch(4, 64, 0, [&]() { poly_op_kernel(mq, OP_TO_MONT, rlk, nullptr, 0, rlk_mont.data(), kw); });
@@ -209,40 +207,36 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         std::vector<u64> wide(wide_relin ? relin_wide_scratch_bytes(P, M, pairs) / 8 + 1 : 1);
         u64 *wp = wide.data();
         const unsigned rgrid = (unsigned)(pairs * M.num_limbs);
-        if (hs.digits32) {
-            int32_t *dg = dig32.data();
-            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int32_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
-            if (wide_relin) emu_launch(rgrid * (G + 1), thr, n * 8, [&]() { relin12_wide_kernel<int32_t>(P, M, r01p, dg, rk, wp, c2); });
-            else emu_launch(rgrid, thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, c2); });
-        } else {
-            int16_t *dg = dig16.data();
-            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<int16_t>(P, M, ct1, ct2, exts, r01p, dg, c2); });
-            if (wide_relin) emu_launch(rgrid * (G + 1), thr, n * 8, [&]() { relin12_wide_kernel<int16_t>(P, M, r01p, dg, rk, wp, c2); });
-            else emu_launch(rgrid, thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, c2); });
-        }
+        auto run = [&](auto *dg) {
+            typedef typename std::remove_pointer<decltype(dg)>::type DigT;
+            emu_launch(tgrid, thr, sm32, [&]() { tensor32_kernel<DigT>(P, M, ct1, ct2, exts, r01p, dg, c2); });
+            if (wide_relin) emu_launch(rgrid * (G + 1), thr, n * 8, [&]() { relin12_wide_kernel<DigT>(P, M, r01p, dg, rk, wp, c2); });
+            else emu_launch(rgrid, thr, n * 24, [&]() { relin12_kernel<DigT>(P, M, r01p, dg, rk, out, xp, c2); });
+        };
+        if (hs.digit_kind() == 1) run(reinterpret_cast<int32_t *>(digbuf.data()));
+        else if (hs.digit_kind() == 2) run(reinterpret_cast<int8_t *>(digbuf.data()));
+        else run(reinterpret_cast<int16_t *>(digbuf.data()));
         if (wide_relin) emu_launch(4, 256, 0, [&]() { relin_reduce_kernel(P, M, wp, out, xp, pairs); });
     } else if (P.logn == 12) {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<12>(P, d, M.need_lhs, M.need_rhs, ct1, ct2, extp); });
-        if (hs.digits32) {
-            int32_t *dg = dig32.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, xp, 0u); });
-        } else {
-            int16_t *dg = dig16.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, int16_t>(P, M, ct1, extp, r01p, dg, 0u); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
-        }
+        auto run = [&](auto *dg) {
+            typedef typename std::remove_pointer<decltype(dg)>::type DigT;
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<12, DigT>(P, M, ct1, extp, r01p, dg, 0u); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin12_kernel<DigT>(P, M, r01p, dg, rk, out, xp, 0u); });
+        };
+        if (hs.digit_kind() == 1) run(reinterpret_cast<int32_t *>(digbuf.data()));
+        else if (hs.digit_kind() == 2) run(reinterpret_cast<int8_t *>(digbuf.data()));
+        else run(reinterpret_cast<int16_t *>(digbuf.data()));
     } else {
         emu_launch((unsigned)(pairs * 4 * d), thr, n * 16, [&]() { lift_kernel<0>(P, d, M.need_lhs, M.need_rhs, ct1, ct2, extp); });
-        if (hs.digits32) {
-            int32_t *dg = dig32.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int32_t>(P, M, ct1, extp, r01p, dg, 0u); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, xp, 0u); });
-        } else {
-            int16_t *dg = dig16.data();
-            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, int16_t>(P, M, ct1, extp, r01p, dg, 0u); });
-            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, xp, 0u); });
-        }
+        auto run = [&](auto *dg) {
+            typedef typename std::remove_pointer<decltype(dg)>::type DigT;
+            emu_launch((unsigned)(pairs * M.num_products * 3), thr, n * 8 * (1 + A), [&]() { tensor_kernel<0, DigT>(P, M, ct1, extp, r01p, dg, 0u); });
+            emu_launch((unsigned)(pairs * M.num_limbs), thr, n * 24, [&]() { relin_kernel<0, DigT>(P, M, r01p, dg, rk, out, xp, 0u); });
+        };
+        if (hs.digit_kind() == 1) run(reinterpret_cast<int32_t *>(digbuf.data()));
+        else if (hs.digit_kind() == 2) run(reinterpret_cast<int8_t *>(digbuf.data()));
+        else run(reinterpret_cast<int16_t *>(digbuf.data()));
     }
     const u64 q = hs.ct_moduli[0];
     for (uint32_t j = d; j + 1 < 2 * d; j++) {
@@ -313,25 +307,20 @@ int emu_bfv_relinearize(emu_ctx *c, const uint64_t *ct, const uint64_t *rlk, uin
     const Modulus mq = P.mod[0];
     if (kw) emu_launch(4, 64, 0, [&]() { poly_op_kernel(mq, OP_TO_MONT, rlk, nullptr, 0, rlk_mont.data(), kw); });
     if ((rc = emu_ntt(c, 0, 0, c2.data(), c2.data(), pairs))) return rc;
-    std::vector<int32_t> dig32; std::vector<int16_t> dig16;
+    std::vector<u64> digbuf((pairs * (G ? G : 1) * n * hs.digit_bytes() + 7) / 8 + 1);
     const u64 *c2p = c2.data(), *r01p = r01.data(), *rk = rlk_mont.data();
     u64 *wp = widebuf.data(), *none = nullptr;
     const unsigned thr = emu_block_threads(P);
-    if (hs.digits32) {
-        dig32.resize(pairs * (G ? G : 1) * n);
-        int32_t *dg = dig32.data();
-        emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<int32_t, false>(P, c2p, dg, pairs); });
-        if (P.logn == 12 && wide) emu_launch((unsigned)(pairs * (G + 1)), thr, n * 8, [&]() { relin12_wide_kernel<int32_t>(P, M, r01p, dg, rk, wp, 3u); });
-        else if (P.logn == 12) emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin12_kernel<int32_t>(P, M, r01p, dg, rk, out, none, 3u); });
-        else emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin_kernel<0, int32_t>(P, M, r01p, dg, rk, out, none, 1u); });
-    } else {
-        dig16.resize(pairs * (G ? G : 1) * n);
-        int16_t *dg = dig16.data();
-        emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<int16_t, false>(P, c2p, dg, pairs); });
-        if (P.logn == 12 && wide) emu_launch((unsigned)(pairs * (G + 1)), thr, n * 8, [&]() { relin12_wide_kernel<int16_t>(P, M, r01p, dg, rk, wp, 3u); });
-        else if (P.logn == 12) emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin12_kernel<int16_t>(P, M, r01p, dg, rk, out, none, 3u); });
-        else emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin_kernel<0, int16_t>(P, M, r01p, dg, rk, out, none, 1u); });
-    }
+    auto run = [&](auto *dg) {
+        typedef typename std::remove_pointer<decltype(dg)>::type DigT;
+        emu_launch(4, 64, 0, [&]() { gadget_digits_kernel<DigT, false>(P, c2p, dg, pairs); });
+        if (P.logn == 12 && wide) emu_launch((unsigned)(pairs * (G + 1)), thr, n * 8, [&]() { relin12_wide_kernel<DigT>(P, M, r01p, dg, rk, wp, 3u); });
+        else if (P.logn == 12) emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin12_kernel<DigT>(P, M, r01p, dg, rk, out, none, 3u); });
+        else emu_launch((unsigned)pairs, thr, n * 24, [&]() { relin_kernel<0, DigT>(P, M, r01p, dg, rk, out, none, 1u); });
+    };
+    if (hs.digit_kind() == 1) run(reinterpret_cast<int32_t *>(digbuf.data()));
+    else if (hs.digit_kind() == 2) run(reinterpret_cast<int8_t *>(digbuf.data()));
+    else run(reinterpret_cast<int16_t *>(digbuf.data()));
     if (P.logn == 12 && wide) emu_launch(4, 256, 0, [&]() { relin_reduce_kernel(P, M, wp, out, none, pairs); });
     return 0;
 }

@@ -113,7 +113,7 @@ def test_dispatch_errors(emu):
     assert st[2] == 9 and "schoolbook BFV multiplication can overflow i128" in st[4]
     rc, h, _ = emu.create(16, [65537, 1099509805057], [], 257, 8)
     st = emu.info(h)
-    assert st[1] == 19 and st[2] == 9 and "multi-prime" in st[4]
+    assert st[1] == 19 and st[2] == 0                    # the reference's multi-prime set runs on the device (rns_kernels.cu)
     rc, h, err = emu.create(4096, [0xFFFFFFFFFFE00001], [], 257)
     assert rc == 1 and "cannot create NTT plan" in err
     rc, h, err = emu.create(1000, [65537], [], 257)
