@@ -872,39 +872,49 @@ static int host_pipeline(exb_context *c, uint64_t base, uint32_t d, uint64_t pm,
     const int slots = c->tune.host_slots;
     if (batch < chunk * (size_t)(slots - 1)) chunk = (batch + slots - 2) / (size_t)(slots - 1);
     bool used[kHostSlots] = {};
-    size_t ci = 0;
-    for (size_t off = 0; off < batch; ci++) {
-        const int si = (int)(c->host_rr++ % (unsigned)slots);
-        Workspace &w = c->hs[si];
-        const size_t left = batch - off;
-        size_t cnt = chunk;
-        if (taper) {
-            // a synchronous call exposes the first chunk's H2D and the last chunk's kernels + D2H: taper both
-            // ends (half-size first chunk, remainder split over the last two)
-            if (ci == 0 && batch > 2 * chunk) cnt = (chunk + 1) / 2;
-            else if (left <= chunk) cnt = left;
-            else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
+    auto enqueue = [&]() -> int {
+        size_t ci = 0;
+        for (size_t off = 0; off < batch; ci++) {
+            const int si = (int)(c->host_rr++ % (unsigned)slots);
+            Workspace &w = c->hs[si];
+            const size_t left = batch - off;
+            size_t cnt = chunk;
+            if (taper) {
+                // a synchronous call exposes the first chunk's H2D and the last chunk's kernels + D2H: taper both
+                // ends (half-size first chunk, remainder split over the last two)
+                if (ci == 0 && batch > 2 * chunk) cnt = (chunk + 1) / 2;
+                else if (left <= chunk) cnt = left;
+                else if (left < 2 * chunk) cnt = (left + 1) / 2 + (left + 1) / 8;
+            }
+            if (cnt > left) cnt = left;
+            if (cnt > chunk) cnt = chunk;
+            const size_t bytes = cnt * stride * 8;
+            int r;
+            if ((r = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return r;
+            if ((r = grow_in2_out(w, chunk * stride * 8))) return r;
+            used[si] = true;
+            EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+            EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
+            if ((r = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream, true))) return r;
+            EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
+            off += cnt;
         }
-        if (cnt > left) cnt = left;
-        if (cnt > chunk) cnt = chunk;
-        const size_t bytes = cnt * stride * 8;
-        if ((rc = grow((void **)&w.in1, &w.in_b, chunk * stride * 8))) return rc;
-        if ((rc = grow_in2_out(w, chunk * stride * 8))) return rc;
-        EXB_CUDA(cudaMemcpyAsync(w.in1, ct1 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
-        EXB_CUDA(cudaMemcpyAsync(w.in2, ct2 + off * stride, bytes, cudaMemcpyHostToDevice, w.stream));
-        if ((rc = run_pairs(c, w, hp, rlk, w.in1, w.in2, w.out, cnt, w.stream, true))) return rc;
-        EXB_CUDA(cudaMemcpyAsync(out + off * stride, w.out, bytes, cudaMemcpyDeviceToHost, w.stream));
-        used[si] = true;
-        off += cnt;
+        for (int si = 0; si < kHostSlots; si++) {
+            if (!used[si]) continue;
+            cudaEvent_t e;
+            EXB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            tk->events.push_back(e);
+            EXB_CUDA(cudaEventRecord(e, c->hs[si].stream));
+        }
+        return EXB_OK;
+    };
+    rc = enqueue();
+    if (rc) {   // nothing of a failed call may still be reading the caller's buffers when we return
+        const std::string msg = g_err;
+        for (int si = 0; si < kHostSlots; si++) if (used[si]) cudaStreamSynchronize(c->hs[si].stream);
+        g_err = msg;
     }
-    for (int si = 0; si < kHostSlots; si++) {
-        if (!used[si]) continue;
-        cudaEvent_t e;
-        EXB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        tk->events.push_back(e);
-        EXB_CUDA(cudaEventRecord(e, c->hs[si].stream));
-    }
-    return EXB_OK;
+    return rc;
 }
 
 static int wait_ticket(Ticket &tk) {

@@ -64,6 +64,34 @@ def test_ntt_vs_oracle(n, q):
         assert digest(batch.to_host(batch.ntt_forward(plan.params, 0, batch.to_device(ramp)))) == str(g[key])
 
 
+@pytest.mark.parametrize("count", [1, 3, 297, 899, 2 * 296 * 3 + 5])
+def test_ntt_tma_pipeline_many_polys(count):
+    """The TMA transform kernel's three-image ring (mbarrier phases, store drain before reload) over several
+    iterations per CTA, ragged tails and in place, word for word against the oracle; the cp.async kernel (option
+    "ntt_cp_async") must give the same words."""
+    from exacto_b200 import batch
+    P = E.u64_dbfv().bfv_params
+    rng = np.random.default_rng(count)
+    for idx in (0, 1):                                                   # LAZY 1 (60-bit q) and LAZY 2 (54-bit aux prime)
+        q = P.modulus(idx)
+        x = rng.integers(0, q, (count, 4096), dtype=np.uint64)
+        x[0, :3] = [0, q - 1, 1]
+        want = O.ntt_fwd(x, q, threads=O.max_threads())
+        dx = batch.to_device(x)
+        fy = batch.ntt_forward(P, idx, dx)
+        assert np.array_equal(batch.to_host(fy), want)
+        assert np.array_equal(batch.to_host(batch.ntt_inverse(P, idx, fy)), x)
+        batch.ntt_forward(P, idx, dx, out=dx)                            # in place
+        assert np.array_equal(batch.to_host(dx), want)
+        ctx = P.context()
+        ctx.set_option("ntt_cp_async", 1)
+        try:
+            assert np.array_equal(batch.to_host(batch.ntt_inverse(P, idx, dx)), x)
+            assert np.array_equal(batch.to_host(batch.ntt_forward(P, idx, batch.to_device(x))), want)
+        finally:
+            ctx.set_option("ntt_cp_async", 0)
+
+
 def test_ntt_linearity_full_size():
     """Size-independent property at the bench size: NTT(a + b) = NTT(a) + NTT(b), round trip."""
     from exacto_b200 import batch
