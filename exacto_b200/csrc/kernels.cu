@@ -1217,6 +1217,9 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
         sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
         fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);       // lazy outputs: they only feed the REDCs below
         const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
+        // lazy accumulation for 2^36 <= q < 2^60 (mq.lazy >= 1): the sums stay below 4q + 2^32 (a REDC adds < 2q, then
+        // a 3-instruction high-word conditional subtract of 4q) and are made canonical once, when the limb is written out
+        const bool lazy_acc = mq.lazy != 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             u64 x[4], kk[4], a[4];
@@ -1224,12 +1227,18 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
             ldg_u64x4(k0 + 4 * h, kk);
             lds_u64x4(acc0, e0 + 4 * h, a);
 #pragma unroll
-            for (int j = 0; j < 4; j++) a[j] = mod_add(a[j], csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q), q);
+            for (int j = 0; j < 4; j++) {
+                const u64 t = mont_mul_lazy(x[j], kk[j], q, mq.minv_neg);
+                a[j] = lazy_acc ? csub_hi(a[j] + t, mq.four_m, mq.hi_four_m) : mod_add(a[j], csub(t, q), q);
+            }
             sts_u64x4(acc0, e0 + 4 * h, a);
             ldg_u64x4(k1 + 4 * h, kk);
             lds_u64x4(acc1, e0 + 4 * h, a);
 #pragma unroll
-            for (int j = 0; j < 4; j++) a[j] = mod_add(a[j], csub(mont_mul_lazy(x[j], kk[j], q, mq.minv_neg), q), q);
+            for (int j = 0; j < 4; j++) {
+                const u64 t = mont_mul_lazy(x[j], kk[j], q, mq.minv_neg);
+                a[j] = lazy_acc ? csub_hi(a[j] + t, mq.four_m, mq.hi_four_m) : mod_add(a[j], csub(t, q), q);
+            }
             sts_u64x4(acc1, e0 + 4 * h, a);
         }
     }
@@ -1239,9 +1248,13 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
     const size_t off = ((pair * d + k) * 2) * (size_t)n;
     u64 v[8];
     lds_u64x4(acc0, e0, v); lds_u64x4(acc0, e0 + 4, v + 4);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = mq.lazy != 0 ? reduce4(csub(v[j], mq.four_m), q, mq.two_m) : v[j];   // < 4q + 2^32 -> [0, q)
     stg_u64x4(dst + e0, v); stg_u64x4(dst + e0 + 4, v + 4);
     for (u32 p = 0; p < np; p++) { u64 *pd = M.peer_out[p] + off + e0; stg_u64x4(pd, v); stg_u64x4(pd + 4, v + 4); }
     lds_u64x4(acc1, e0, v); lds_u64x4(acc1, e0 + 4, v + 4);
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = mq.lazy != 0 ? reduce4(csub(v[j], mq.four_m), q, mq.two_m) : v[j];
     stg_u64x4(dst + n + e0, v); stg_u64x4(dst + n + e0 + 4, v + 4);
     for (u32 p = 0; p < np; p++) { u64 *pd = M.peer_out[p] + off + n + e0; stg_u64x4(pd, v); stg_u64x4(pd + 4, v + 4); }
     if (np) peer_fence();
