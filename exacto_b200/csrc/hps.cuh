@@ -100,6 +100,51 @@ EXB_HD i64 gadget_digit_pow2(i64 &remaining, u32 w) {
     remaining = (remaining - rem) >> w;
     return rem;
 }
+// Base 2^8, all digits at once: the balanced-digit carry chain (bfv/keyswitch.rs:33-42) IS the carry chain of one
+// 64-bit addition.  With W = v + 0x8080..80 (mod 2^64), byte g of W is digit_g + 128, so W ^ 0x8080..80 holds the
+// eight digits as int8 (valid while |v| < 2^62, i.e. the remainder after eight digits is zero).
+EXB_HD u64 gadget_digits_base256(i64 v) {
+    const u64 bias = 0x8080808080808080ull;
+    return ((u64)v + bias) ^ bias;
+}
+// __byte_perm (PRMT): byte i of the result is byte ((s >> 4i) & 7) of the 8-byte pool {x, y}.
+EXB_HD u32 byte_perm(u32 x, u32 y, u32 s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, s);
+#else
+    const u64 pool = ((u64)y << 32) | x;
+    u32 r = 0;
+    for (int i = 0; i < 4; i++) r |= (u32)((pool >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+// 4 x 4 byte transpose: out[g] byte j = in[j] byte g.
+EXB_HD void transpose4x4_bytes(const u32 *in, u32 *out) {
+    const u32 t0 = byte_perm(in[0], in[1], 0x5140), t1 = byte_perm(in[0], in[1], 0x7362);
+    const u32 t2 = byte_perm(in[2], in[3], 0x5140), t3 = byte_perm(in[2], in[3], 0x7362);
+    out[0] = byte_perm(t0, t2, 0x5410); out[1] = byte_perm(t0, t2, 0x7632);
+    out[2] = byte_perm(t1, t3, 0x5410); out[3] = byte_perm(t1, t3, 0x7632);
+}
+// Eight coefficients' digit words (byte g of w[j] = digit g of coefficient j) -> eight plane words
+// (byte j of plane[g] = digit g of coefficient j): an 8 x 8 byte transpose as four 4 x 4 ones.
+EXB_HD void digits_to_planes(const u64 *w, u64 *plane) {
+    u32 a[4], b[4], c[4], d[4], ta[4], tb[4], tc[4], td[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; j++) {
+        a[j] = (u32)w[j]; b[j] = (u32)w[4 + j];                 // digits 0..3 of coefficients 0..3 / 4..7
+        c[j] = (u32)(w[j] >> 32); d[j] = (u32)(w[4 + j] >> 32); // digits 4..7
+    }
+    transpose4x4_bytes(a, ta); transpose4x4_bytes(b, tb); transpose4x4_bytes(c, tc); transpose4x4_bytes(d, td);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int g = 0; g < 4; g++) {
+        plane[g] = (u64)ta[g] | ((u64)tb[g] << 32);
+        plane[4 + g] = (u64)tc[g] | ((u64)td[g] << 32);
+    }
+}
 // General base: the reference's truncating % and / on signed values.
 EXB_HD i64 gadget_digit_general(i64 &remaining, i64 base) {
     const i64 half = base / 2;

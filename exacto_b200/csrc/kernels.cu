@@ -795,6 +795,36 @@ __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
     }
 }
 
+// Sum over the products of output limb k of digit plane g, for this thread's 8 coefficients.  int8 planes are summed
+// as packed bytes: biased to unsigned (x ^ 0x80) and accumulated in 16-bit lanes, four coefficients per 64-bit word.
+template <typename DigT>
+__device__ __forceinline__ void digit_sums8(const DigT *__restrict__ digits, const MulPlan &M, size_t pair, u32 NP, u32 G,
+                                            u32 g, u32 n, u32 e0, u32 k, u32 i_lo, u32 i_hi, i64 *ds) {
+    if constexpr (sizeof(DigT) == 1) {
+        const u64 bias = 0x8080808080808080ull, lanes = 0x00FF00FF00FF00FFull;
+        u64 even = 0, odd = 0;
+        for (u32 i = i_lo; i <= i_hi; i++) {
+            const size_t pr = (size_t)M.prod_of[i][k - i];
+            const u64 x = *reinterpret_cast<const u64 *>(digits + ((pair * NP + pr) * G + g) * n + e0) ^ bias;
+            even += x & lanes;
+            odd += (x >> 8) & lanes;
+        }
+        const i64 off = 128 * (i64)(i_hi - i_lo + 1);          // at most 16 products: 16 * 255 fits a 16-bit lane
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ds[2 * j] = (i64)((even >> (16 * j)) & 0xffffu) - off;
+            ds[2 * j + 1] = (i64)((odd >> (16 * j)) & 0xffffu) - off;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) ds[j] = 0;
+        for (u32 i = i_lo; i <= i_hi; i++) {
+            const size_t pr = (size_t)M.prod_of[i][k - i];
+            ldg_dig8<DigT>(digits + ((pair * NP + pr) * G + g) * n + e0, ds);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // K4' / K5': lift and tensor+scale on the internal 27-bit auxiliary basis (n = 4096 only;
 // see ntt32_core.cuh for why this is result-identical).  Layouts:
@@ -923,6 +953,18 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         i64 rem[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) rem[k] = center_i64(av[k], P.sc.q, P.sc.half_q);
+        if (sizeof(DigT) == 1 && P.gadget_log2 == 8 && G <= 8) {
+            // base 256 (the u64 profile): one addition per coefficient yields all eight digits, an 8 x 8 byte
+            // transpose turns them into the eight 8-byte plane words of this thread
+            u64 w[8], plane[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = gadget_digits_base256(rem[k]);
+            digits_to_planes(w, plane);
+#pragma unroll
+            for (u32 g = 0; g < 8; g++)
+                if (g < G) *reinterpret_cast<u64 *>(od + (size_t)g * n + e0) = plane[g];
+            return;
+        }
         for (u32 g = 0; g < G; g++) {
             i64 dg[8];
 #pragma unroll
@@ -1202,11 +1244,8 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
         sts_u64x4(acc, e0, sum); sts_u64x4(acc, e0 + 4, sum + 4);
     }
     for (u32 g = 0; g < G; g++) {
-        i64 ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (u32 i = i_lo; i <= i_hi; i++) {
-            const size_t pr = (size_t)M.prod_of[i][k - i];
-            ldg_dig8<DigT>(digits + ((pair * NP + pr) * G + g) * n + e0, ds);
-        }
+        i64 ds[8];
+        digit_sums8<DigT>(digits, M, pair, NP, G, g, n, e0, k, i_lo, i_hi, ds);
         u64 v[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
@@ -1313,11 +1352,8 @@ relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constan
         return;
     }
     const u32 g = role;
-    i64 ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (u32 i = i_lo; i <= i_hi; i++) {
-        const size_t pr = (size_t)M.prod_of[i][k - i];
-        ldg_dig8<DigT>(digits + ((pair * NP + pr) * G + g) * n + e0, ds);
-    }
+    i64 ds[8];
+    digit_sums8<DigT>(digits, M, pair, NP, G, g, n, e0, k, i_lo, i_hi, ds);
     u64 v[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
