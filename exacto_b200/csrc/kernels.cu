@@ -795,6 +795,15 @@ __device__ __forceinline__ void stg_dig8(DigT *p, const i64 *d) {
     }
 }
 
+// A sum of at most 16 balanced digits (|s| <= 2^35) as a canonical residue.  For q >= 2^36 (`big_q`: the lazy prime
+// classes) that is s or s + q; smaller primes take the general reduction.
+__device__ __forceinline__ u64 signed_sum_to_mod(i64 s, u64 q, bool big_q) {
+    if (big_q) return (u64)(s + ((s >> 63) & (i64)q));
+    const u64 mag = s < 0 ? (u64)(-s) : (u64)s;
+    const u64 r = mag < q ? mag : mag % q;
+    return (s < 0 && r) ? q - r : r;
+}
+
 // Sum over the products of output limb k of digit plane g, for this thread's 8 coefficients.  int8 planes are summed
 // as packed bytes: biased to unsigned (x ^ 0x80) and accumulated in 16-bit lanes, four coefficients per 64-bit word.
 template <typename DigT>
@@ -1248,11 +1257,7 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
         digit_sums8<DigT>(digits, M, pair, NP, G, g, n, e0, k, i_lo, i_hi, ds);
         u64 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const u64 mag = ds[j] < 0 ? (u64)(-ds[j]) : (u64)ds[j];
-            const u64 r = mag < q ? mag : mag % q;
-            v[j] = (ds[j] < 0 && r) ? q - r : r;
-        }
+        for (int j = 0; j < 8; j++) v[j] = signed_sum_to_mod(ds[j], q, mq.lazy != 0);
         sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
         fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);       // lazy outputs: they only feed the REDCs below
         const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
@@ -1356,11 +1361,7 @@ relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constan
     digit_sums8<DigT>(digits, M, pair, NP, G, g, n, e0, k, i_lo, i_hi, ds);
     u64 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const u64 mag = ds[j] < 0 ? (u64)(-ds[j]) : (u64)ds[j];
-        const u64 r = mag < q ? mag : mag % q;
-        v[j] = (ds[j] < 0 && r) ? q - r : r;
-    }
+    for (int j = 0; j < 8; j++) v[j] = signed_sum_to_mod(ds[j], q, mq.lazy != 0);
     sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
     fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);           // lazy outputs: they only feed the REDCs below
     const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
