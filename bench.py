@@ -276,7 +276,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")    # a caller's own NCCL_DEBUG (e.g. INFO for communicator evidence) wins
+        # NCCL_DEBUG is left to the caller (INFO for communicator evidence); unset, NCCL prints nothing to stdout
         dist.init_process_group("nccl", device_id=dev)
     params = E.u64_dbfv()
     P = params.bfv_params

@@ -1006,9 +1006,9 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     const u32 comp = blockIdx.x & 1u;
     const u32 duo = (blockIdx.x >> 1) % ND;
     const size_t pair = (blockIdx.x >> 1) / ND;
-    i64 *racc = reinterpret_cast<i64 *>(smem);                 // sum of signed rounding terms
-    i64 *sacc = reinterpret_cast<i64 *>(smem + n);             // sum of centred a_ij
-    u64 *bq = smem + 2 * (size_t)n;                            // base-q work image, later the K u32 images
+    i64 *sacc = reinterpret_cast<i64 *>(smem);                 // sum of centred a_ij
+    u32 *racc = reinterpret_cast<u32 *>(smem + n);             // sum of signed rounding terms (i32: max_terms * p / 2 < 2^31)
+    u64 *bq = smem + n + n / 2;                                // base-q work image, later the K u32 images
     u32 *bs = reinterpret_cast<u32 *>(bq);
     const Modulus &mb = P.sb.mq_r;                   // q with n^-1 * 2^64 as the inverse transform's scaling
     const ScaleConsts &c = P.sc;
@@ -1047,21 +1047,22 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
             u64 a[4];
-            i64 r[4], sv[4];
+            i64 sv[4];
+            Vec16 r;                       // racc rows are private to the thread: plain 16-byte pieces, no swizzle
             lds_u64x4(bq, eh, a);
             if (i != i_lo) {
-                lds_u64x4(reinterpret_cast<const u64 *>(racc), eh, reinterpret_cast<u64 *>(r));
+                r = *reinterpret_cast<const Vec16 *>(racc + eh);
                 lds_u64x4(reinterpret_cast<const u64 *>(sacc), eh, reinterpret_cast<u64 *>(sv));
             } else {
 #pragma unroll
-                for (int t = 0; t < 4; t++) r[t] = sv[t] = 0;
+                for (int t = 0; t < 4; t++) { r.w[t] = 0; sv[t] = 0; }
             }
 #pragma unroll
             for (int t = 0; t < 4; t++) {
-                r[t] += sc.plain32 ? round_term32_signed(a[t], c) : round_term_signed(a[t], c);
+                r.w[t] += (u32)(sc.plain32 ? round_term32_signed(a[t], c) : round_term_signed(a[t], c));
                 sv[t] += center_i64(a[t], c.q, c.half_q);
             }
-            sts_u64x4(reinterpret_cast<u64 *>(racc), eh, reinterpret_cast<const u64 *>(r));
+            *reinterpret_cast<Vec16 *>(racc + eh) = r;
             sts_u64x4(reinterpret_cast<u64 *>(sacc), eh, reinterpret_cast<const u64 *>(sv));
         }
         __syncthreads();                   // bq is rewritten by the next product / the small-prime images
@@ -1101,15 +1102,15 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     u64 res[8];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        i64 r[4], sv[4];
-        lds_u64x4(reinterpret_cast<const u64 *>(racc), e0 + 4 * h, reinterpret_cast<u64 *>(r));
+        i64 sv[4];
+        const Vec16 r = *reinterpret_cast<const Vec16 *>(racc + e0 + 4 * h);
         lds_u64x4(reinterpret_cast<const u64 *>(sacc), e0 + 4 * h, reinterpret_cast<u64 *>(sv));
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             u32 b[kMaxSmall];
 #pragma unroll
             for (u32 pi = 0; pi < (u32)kMaxSmall; pi++) b[pi] = pi < K ? bv[pi][4 * h + t] : 0u;
-            res[4 * h + t] = hps_scale32_sum(r[t], sv[t], b, c, sc);
+            res[4 * h + t] = hps_scale32_sum((i64)(int32_t)r.w[t], sv[t], b, c, sc);
         }
     }
     stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
@@ -1729,7 +1730,7 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
         const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
         if (!raw3 && tensor_sums_per_limb(P, M, pairs)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
-            const size_t sm01 = 2 * 4096 * 8 + (sm32 > 4096 * 8 + 4096 * 8 ? sm32 - 4096 * 8 : 4096 * 8);
+            const size_t sm01 = smem_tensor01(P.sb.K);
             tensor01_kernel<<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
             if (mid) cudaEventRecord(mid, s);
             tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01,

@@ -201,7 +201,7 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         const u32 c2 = per_limb ? 1u : 0u;
         const unsigned tgrid = (unsigned)(pairs * M.num_products * (per_limb ? 1 : 3));
         if (per_limb) {
-            const size_t sm01 = 2 * n * 8 + (sm32 > n * 16 ? sm32 - n * 8 : n * 8);
+            const size_t sm01 = smem_tensor01(P.sb.K);
             emu_launch((unsigned)(pairs * M.num_duos * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, ct2, exts, r01p); });
         }
         std::vector<u64> wide(wide_relin ? relin_wide_scratch_bytes(P, M, pairs) / 8 + 1 : 1);
