@@ -204,14 +204,15 @@ __device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb) {
     }
     __syncthreads();
 }
-template <int KK>
+// Primes P0 .. P0 + KK - 1 of the basis; image i of the call is prime P0 + i.
+template <int KK, int P0 = 0>
 __device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb) {
     const u32 t = threadIdx.x;
     u32 v[KK][8];
     __syncthreads();
 #define EXB_PASS(S, LAST, TW)                                                                         \
     _Pragma("unroll") for (int i = 0; i < KK; i++) load_vals32<3, S>(v[i], sm + i * 4096, t);          \
-    _Pragma("unroll") for (int i = 0; i < KK; i++) inv_pass32<12, S, 3, LAST>(v[i], sb.TW[i], t, sb.sc.m[i]); \
+    _Pragma("unroll") for (int i = 0; i < KK; i++) inv_pass32<12, S, 3, LAST>(v[i], sb.TW[P0 + i], t, sb.sc.m[P0 + i]); \
     _Pragma("unroll") for (int i = 0; i < KK; i++) store_vals32<3, S>(v[i], sm + i * 4096, t);         \
     __syncthreads();
     EXB_PASS(0, false, twi)
@@ -985,6 +986,52 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     }
 }
 
+// tensor01_kernel, small primes P0 and P0 + 1 (those below K): sum the point-wise products of output limb k over its
+// products, inverse-transform, and leave this thread's 8 coefficients of each in bv[prime].
+template <int P0>
+__device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, const u32 *__restrict__ ext_s, u32 *bs,
+                                                     size_t pair, u32 d, u32 k, u32 i_lo, u32 i_hi, u32 comp, u32 e0,
+                                                     u32 (&bv)[kMaxSmall][8]) {
+    constexpr u32 n = 4096;
+    const u32 K = P.sb.K;
+    const u32 kk = K - P0 >= 2 ? 2u : 1u;
+    __syncthreads();                       // the images' previous contents are dead
+#pragma unroll
+    for (u32 r = 0; r < 2; r++) {
+        if (r < kk) {
+            const u32 pi = P0 + r;
+            const Mod32 &m = P.sb.sc.m[pi];
+            u32 acc[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc[t] = 0;
+            for (u32 i = i_lo; i <= i_hi; i++) {
+                const u32 j = k - i;
+                const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + i) * 2) * (size_t)K + pi) * n, *l1 = l0 + (size_t)K * n;
+                const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + j) * 2) * (size_t)K + pi) * n, *r1 = r0 + (size_t)K * n;
+                u32 a[8], b[8];
+                if (comp == 1) {
+                    u32 cc[8], dd[8];
+                    ldg_u32x8(l0 + e0, a); ldg_u32x8(r1 + e0, b); ldg_u32x8(l1 + e0, cc); ldg_u32x8(r0 + e0, dd);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t] + (u64)cc[t] * dd[t], m.p, m.pinv_neg);
+                } else {
+                    ldg_u32x8(l0 + e0, a); ldg_u32x8(r0 + e0, b);
+#pragma unroll
+                    for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t], m.p, m.pinv_neg);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // <= 16 * 2p < 2^32 -> [0, 2p)
+            sts_u32x8(bs + (size_t)r * n, e0, acc);
+        }
+    }
+    if (kk == 2) inv32_smK<2, P0>(bs, P.sb);
+    else inv32_smK<1, P0>(bs, P.sb);
+#pragma unroll
+    for (u32 r = 0; r < 2; r++)
+        if (r < kk) lds_u32x8(bs + (size_t)r * n, e0, bv[P0 + r]);
+}
+
 // ---------------------------------------------------------------------------------
 // K5'' : components 0 and 1 per OUTPUT LIMB (n = 4096, internal basis).  relinearize only needs
 //   sum_{i+j=k} [ round(p a_ij / q) + p m_ij ]  (mod q),   a_ij = t_ij mod q (centred),  m_ij = (t_ij - a_ij) / q,
@@ -1067,38 +1114,13 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         }
         __syncthreads();                   // bq is rewritten by the next product / the small-prime images
     }
-    for (u32 pi = 0; pi < K; pi++) {       // small primes: point-wise products summed over the limb's products
-        const Mod32 &m = sc.m[pi];
-        u32 acc[8];
-#pragma unroll
-        for (int t = 0; t < 8; t++) acc[t] = 0;
-        for (u32 i = i_lo; i <= i_hi; i++) {
-            const u32 j = k - i;
-            const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + i) * 2) * (size_t)K + pi) * n, *l1 = l0 + (size_t)K * n;
-            const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + j) * 2) * (size_t)K + pi) * n, *r1 = r0 + (size_t)K * n;
-            u32 a[8], b[8];
-            if (comp == 1) {
-                u32 cc[8], dd[8];
-                ldg_u32x8(l0 + e0, a); ldg_u32x8(r1 + e0, b); ldg_u32x8(l1 + e0, cc); ldg_u32x8(r0 + e0, dd);
-#pragma unroll
-                for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t] + (u64)cc[t] * dd[t], m.p, m.pinv_neg);
-            } else {
-                ldg_u32x8(l0 + e0, a); ldg_u32x8(r0 + e0, b);
-#pragma unroll
-                for (int t = 0; t < 8; t++) acc[t] += mont32_redc_lazy((u64)a[t] * b[t], m.p, m.pinv_neg);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // <= 16 * 2p < 2^32 -> [0, 2p)
-        sts_u32x8(bs + (size_t)pi * n, e0, acc);
-    }
-    if (K == 3) inv32_smK<3>(bs, P.sb);
-    else for (u32 pi = 0; pi < K; pi++) inv32_sm(bs + (size_t)pi * n, P.sb.twi[pi], P.sb.headi[pi], sc.m[pi]);
-    u64 *o = r01s + ((pair * NL + limb) * 2 + comp) * (size_t)n;
+    // small primes: point-wise products summed over the limb's products, then one inverse transform per prime.  Two
+    // primes per round share the 32 KB the base-q image occupied (a third image would cost 16 KB of the L1 that
+    // holds the inverse twiddle table of the product loop above).
     u32 bv[kMaxSmall][8];
-#pragma unroll
-    for (u32 pi = 0; pi < (u32)kMaxSmall; pi++)
-        if (pi < K) lds_u32x8(bs + (size_t)pi * n, e0, bv[pi]);
+    tensor01_small_round<0>(P, ext_s, bs, pair, d, k, i_lo, i_hi, comp, e0, bv);
+    if (K > 2) tensor01_small_round<2>(P, ext_s, bs, pair, d, k, i_lo, i_hi, comp, e0, bv);
+    u64 *o = r01s + ((pair * NL + limb) * 2 + comp) * (size_t)n;
     u64 res[8];
 #pragma unroll
     for (int h = 0; h < 2; h++) {

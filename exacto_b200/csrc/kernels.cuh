@@ -11,9 +11,9 @@
 
 namespace exb {
 
-// dynamic shared memory of tensor01_kernel (n = 4096): i64 and i32 per-limb accumulators + the base-q image, which the
-// up to four u32 small-prime images reuse
-inline size_t smem_tensor01(u32 K) { return 4096 * 8 + 4096 * 4 + (K > 2 ? (size_t)K * 4096 * 4 : 4096 * 8); }
+// dynamic shared memory of tensor01_kernel (n = 4096): i64 and i32 per-limb accumulators + the base-q image, which two
+// u32 small-prime images at a time reuse
+inline size_t smem_tensor01(u32) { return 4096 * 8 + 4096 * 4 + 4096 * 8; }
 
 enum PolyOp { OP_ADD = 0, OP_SUB = 1, OP_NEG = 2, OP_MUL = 3, OP_SCALAR_MUL = 4, OP_TO_MONT = 5 };
 
