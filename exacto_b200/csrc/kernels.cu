@@ -75,6 +75,30 @@ constexpr int kThreads12 = 4096 >> kNB;
 // consumer that feeds them to a Montgomery REDC, which accepts any x < 2^64 against a canonical multiplier.
 // `twm` serves the middle passes (table indices 8 .. 511: 8 KiB, staged in shared memory by the TMA kernel),
 // `tw` the pass whose 7 twiddles per thread are all different (indices >= 512, coalesced 16-byte global loads).
+#if defined(EXB_LAB) && defined(EXB_SHFL_STAGE) && !defined(EXB_HOST_EMUL)
+// Lab (EXB_LAB_FLAGS=-DEXB_SHFL_STAGE sh tools/lab_build.sh; profiles/r02_shuffle_stage_ab.json): the S = 3 <-> S = 0
+// regrouping is an 8 x 8 transpose inside groups of 8 consecutive lanes; done with warp shuffles (three xor stages,
+// four 64-bit exchanges each) instead of a shared-memory round trip + block barrier.  Measured slower; not shipped.
+__device__ __forceinline__ void transpose8_shfl(u64 (&v)[8]) {
+    const u32 lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            if (a & s) continue;
+            const u64 send = up ? v[a] : v[a + s];
+            const u64 recv = __shfl_xor_sync(0xffffffffu, send, s);
+            if (up) v[a] = recv; else v[a + s] = recv;
+        }
+    }
+}
+#define EXB_REGROUP_F(v, sm, t) transpose8_shfl(v)
+#define EXB_REGROUP_I(v, sm, t) transpose8_shfl(v)
+#else
+#define EXB_REGROUP_F(v, sm, t) store_vals<3, 3>(v, sm, t); __syncthreads(); load_vals<3, 0>(v, sm, t)
+#define EXB_REGROUP_I(v, sm, t) store_vals<3, 0>(v, sm, t); __syncthreads(); load_vals<3, 3>(v, sm, t)
+#endif
 template <int NB, int LAZY, bool CANON = true, class TWT = const Tw *, class TWM = const Tw *>
 __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
                                            const LazyC &c, const u32 t) {
@@ -90,9 +114,9 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm,
         __syncthreads();
         load_vals<3, 6>(v, sm, t); fwd_pass<12, 6, 3, LAZY>(v, twm, t, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
-        load_vals<3, 3>(v, sm, t); fwd_pass<12, 3, 3, LAZY>(v, twm, t, c); store_vals<3, 3>(v, sm, t);
-        __syncthreads();
-        load_vals<3, 0>(v, sm, t); fwd_pass<12, 0, 3, LAZY>(v, tw, t, c);
+        load_vals<3, 3>(v, sm, t); fwd_pass<12, 3, 3, LAZY>(v, twm, t, c);
+        EXB_REGROUP_F(v, sm, t);
+        fwd_pass<12, 0, 3, LAZY>(v, tw, t, c);
     }
     if constexpr (CANON) {
 #pragma unroll
@@ -113,9 +137,9 @@ __device__ __forceinline__ void inv_body12(u64 *sm, const TWT tw, const TWM twm,
         __syncthreads();
         load_vals<4, 8>(v, sm, t); inv_pass<12, 8, 4, true, LAZY>(v, head, t, mod, c); store_vals<4, 8>(v, sm, t);
     } else {
-        load_vals<3, 0>(v, sm, t); inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c); store_vals<3, 0>(v, sm, t);
-        __syncthreads();
-        load_vals<3, 3>(v, sm, t); inv_pass<12, 3, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 3>(v, sm, t);
+        load_vals<3, 0>(v, sm, t); inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c);
+        EXB_REGROUP_I(v, sm, t);
+        inv_pass<12, 3, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 3>(v, sm, t);
         __syncthreads();
         load_vals<3, 6>(v, sm, t); inv_pass<12, 6, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
