@@ -671,6 +671,27 @@ def bench_widened(torch, batch, P, peak, args):
         ms = statistics.median(times)
         res[name] = {"per_s": count / (ms * 1e-3), "ms": ms, "algorithmic_bytes_each": nbytes,
                      "hbm_frac": count * nbytes / (ms * 1e-3) / 1e9 / peak}
+    # multi-prime ciphertext modulus (bfv/eval.rs:113-147, the reference's BigInt branch): two 60-bit primes at n = 4096
+    mp = E.BfvParamsBuilder().ring_degree(N).plain_modulus(65537).ct_moduli(
+        [1152921504606830593, 576460752308273153]).gadget_base(1 << 16).build()
+    pairs = 64
+    moduli = [mp.modulus(i) for i in range(2)]
+    rnd = lambda prefix: np.stack([rng.integers(0, m, prefix + (N,), dtype=np.uint64) for m in moduli], axis=-2)
+    a, b = batch.to_device(rnd((pairs, 2))), batch.to_device(rnd((pairs, 2)))
+    rlk = E.RelinKey(rnd((mp.gadget_digits, 2)), mp)
+    for _ in range(2):
+        batch.bfv_mul_and_relin(mp, a, b, rlk)
+    times = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); batch.bfv_mul_and_relin(mp, a, b, rlk); e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    res["multi_prime_bfv_mul_and_relin"] = {
+        "per_s": pairs / (ms * 1e-3), "ms": ms, "pairs": pairs, "ct_primes": 2, "log2_Q": 119, "n": N,
+        "note": "bit-identical to the reference's BigInt branch (O(n^2) schoolbook there); correctness-first kernels "
+                "around the tuned transforms, parity in tests/test_gpu_parity.py"}
     return res
 
 
