@@ -348,6 +348,30 @@ def test_per_limb_tensor_path_sixteen_digits(emu):
     assert rc == 0 and np.array_equal(got[0], want), err
 
 
+@pytest.mark.parametrize("plain,per_limb", [((1 << 28) - 57, 1), ((1 << 29) + 11, 0)])
+def test_per_limb_rounding_sums_fit_i32(emu, plain, per_limb):
+    """tensor01_kernel keeps the per-limb sums of rounding terms in an i32 image: the host may only choose it while
+    (products per limb) * (p/2 + 2) < 2^31.  p just below 2^28 with 8 products per limb and every residue at q/2 puts
+    the sum at 2^30; p above 2^29 must fall back to the per-product kernel.  Both stay word-exact."""
+    P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=plain,
+                       gadget_base=256)
+    h = emu.from_oracle(P)
+    d, b = 8, 256
+    assert emu.tensor_per_limb(h, b, d, 0) == per_limb
+    q, n = P.q, P.n
+    rng = np.random.default_rng(plain & 0xffff)
+    rlk = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    one = np.zeros(n, np.uint64); one[0] = 1
+    half = O.ntt_fwd(np.full(n, q // 2, np.uint64), q)
+    # (q/2) * 1 = q/2 per product and coefficient in component 0: every rounding term is round(p/2) with one sign
+    a = np.stack([np.stack([half, half])] * d)
+    bb = np.stack([np.stack([O.ntt_fwd(one, q), O.ntt_fwd(one, q)])] * d)
+    bb[1::3] = rng.integers(0, q, (len(bb[1::3]), 2, n), dtype=np.uint64)
+    want = O.dbfv_mul(P, b, d, 0, a, bb, rlk, threads=8)
+    rc, got, err = emu.dbfv_mul(h, b, d, 0, a[None], bb[None], rlk)
+    assert rc == 0 and np.array_equal(got[0], want), err
+
+
 def test_schoolbook_middle_term_band_refused(emu):
     """The band the reference's overflow guard misses (bfv/eval.rs:457-464 bounds n (q/2)^2 p, the middle tensor
     term reaches twice that): refused, while the literal oracle wraps and the big-int definition does not."""

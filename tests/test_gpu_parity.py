@@ -969,6 +969,33 @@ def test_per_limb_tensor_path_on_gpu():
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("plain", [(1 << 28) - 57, (1 << 29) + 11, (1 << 33) + 7])
+def test_per_limb_rounding_sums_large_plain_modulus(plain):
+    """tensor01_kernel's i32 sums of rounding terms: p just below 2^28 with 8 products per limb puts them at 2^30
+    (per-limb kernel), p above 2^29 / above 2^32 must take the per-product kernel; all word-exact at a batch size
+    that selects the per-limb kernel when it is legal."""
+    from exacto_b200 import batch
+    P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=plain,
+                       gadget_base=256)
+    d, b = 8, 256
+    dp = to_dbfv_params(P, b, d, 0)
+    q, n = P.q, P.n
+    rng = np.random.default_rng(plain & 0xffff)
+    rlk_arr = rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64)
+    rlk = E.RelinKey(rlk_arr, dp.bfv_params)
+    one = np.zeros(n, np.uint64); one[0] = 1
+    half = O.ntt_fwd(np.full(n, q // 2, np.uint64), q)
+    a = np.stack([np.stack([half, half])] * d)
+    bb = np.stack([np.stack([O.ntt_fwd(one, q), O.ntt_fwd(one, q)])] * d)
+    bb[1::3] = rng.integers(0, q, (len(bb[1::3]), 2, n), dtype=np.uint64)
+    a2 = rng.integers(0, q, (d, 2, n), dtype=np.uint64)
+    want = np.stack([O.dbfv_mul(P, b, d, 0, x, bb, rlk_arr, threads=O.max_threads()) for x in (a, a2)])
+    ct1 = np.tile(np.stack([a, a2]), (13, 1, 1, 1))                      # 26 pairs: per-limb kernel when legal
+    ct2 = np.tile(bb[None], (26, 1, 1, 1))
+    got = batch.to_host(batch.dbfv_mul(dp, batch.to_device(ct1), batch.to_device(ct2), rlk))
+    assert np.array_equal(got[:2], want) and np.array_equal(got[-2:], want)
+
+
 @pytest.mark.parametrize("preset", ["compact", "u64", "cfg3", "toy16_noaux", "n64_base10"])
 def test_mul_no_relin_relinearize_gadget_decompose(preset):
     """The halves of bfv_mul_and_relin as the reference exposes them (bfv/eval.rs:89-108, bfv/keyswitch.rs:11-101):
