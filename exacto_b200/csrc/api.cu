@@ -555,8 +555,18 @@ static size_t ws_bytes_per_pair(const exb_context *c, const HostPlan &hp, u32 G,
 }
 
 // Run the pipeline for `pairs` pairs whose inputs/outputs are on the device.  The caller holds the slot.
+// The n = 4096 kernels move a thread's 8 words with 256-bit accesses: device buffers handed to the multiplication
+// entry points must be 32-byte aligned (cudaMalloc / exb_device_alloc / torch allocations are; rows are 32 KiB).
+static bool misaligned32(const void *a, const void *b = nullptr, const void *c = nullptr) {
+    return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 31u) != 0;
+}
+static const char *const kAlignMsg = "device buffers must be 32-byte aligned";
+
 static int run_pairs(exb_context *c, Workspace &w, const HostPlan &hp, const exb_relin_key *rlk, const u64 *ct1,
                      const u64 *ct2, u64 *out, size_t pairs, cudaStream_t stream, bool pipelined = false) {
+    if (misaligned32(ct1, ct2, out)) return fail(EXB_INVALID_PARAM, kAlignMsg);
+    for (uint32_t p = 0; p < hp.M.num_peers; p++)
+        if (misaligned32(hp.M.peer_out[p])) return fail(EXB_INVALID_PARAM, kAlignMsg);
     DeviceParams P = c->P;
     P.pipelined = pipelined ? 1u : 0u;
     const u32 G = rlk->num_keys < c->gadget_digits ? rlk->num_keys : c->gadget_digits;   // keyswitch.rs:86-89
@@ -1098,6 +1108,7 @@ extern "C" int exb_bfv_mul_no_relin(exb_context *c, const uint64_t *ct1, const u
     if (rc) return rc;
     if (c->rns_enabled) return rns_mul(c, hp, nullptr, ct1, ct2, out3, batch, 1, (cudaStream_t)stream);
     if (batch == 0) return EXB_OK;
+    if (misaligned32(ct1, ct2, out3)) return fail(EXB_INVALID_PARAM, kAlignMsg);
     EXB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     std::unique_lock<std::mutex> held;
@@ -1158,6 +1169,7 @@ extern "C" int exb_bfv_relinearize(exb_context *c, const uint64_t *ct, uint32_t 
     }
     if (c->gadget_base < 2 || c->gadget_base > (1ull << 32))
         return fail(EXB_NOT_IMPLEMENTED, "device path supports gadget bases in [2, 2^32]");
+    if (misaligned32(ct, out)) return fail(EXB_INVALID_PARAM, kAlignMsg);
     HostPlan hp;
     int rc = build_plan(1, 2, 0, 0, 0, &hp);
     if (rc) return rc;

@@ -735,25 +735,38 @@ tensor_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ Mu
 // ---------------------------------------------------------------------------------
 struct alignas(16) Vec16 { u32 w[4]; };
 
-__device__ __forceinline__ void ldg_u64x4(const u64 *p, u64 *v) {   // 4 consecutive u64, 16-byte aligned
-    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(p)[0], b = reinterpret_cast<const ulonglong2 *>(p)[1];
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+// One 256-bit access per thread (sm_100: LDG.E.256 / STG.E.256): a thread's 32-byte piece is exactly one DRAM/L2
+// sector, so operand rows -- read once per CTA -- need no L1 allocation and leave L1 to the twiddle tables.
+#define EXB_LD256 "ld.global.nc.L1::no_allocate"
+__device__ __forceinline__ void ldg_u64x4(const u64 *p, u64 *v) {   // 4 consecutive u64, 32-byte aligned
+#ifndef EXB_HOST_EMUL
+    asm volatile(EXB_LD256 ".v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+#else
+    for (int i = 0; i < 4; i++) v[i] = p[i];
+#endif
 }
 __device__ __forceinline__ void stg_u64x4(u64 *p, const u64 *v) {
-    ulonglong2 a, b;
-    a.x = v[0]; a.y = v[1]; b.x = v[2]; b.y = v[3];
-    reinterpret_cast<ulonglong2 *>(p)[0] = a; reinterpret_cast<ulonglong2 *>(p)[1] = b;
+#ifndef EXB_HOST_EMUL
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+#else
+    for (int i = 0; i < 4; i++) p[i] = v[i];
+#endif
 }
-__device__ __forceinline__ void ldg_u32x8(const u32 *p, u32 *v) {   // 8 consecutive u32, 16-byte aligned
-    const Vec16 a = reinterpret_cast<const Vec16 *>(p)[0], b = reinterpret_cast<const Vec16 *>(p)[1];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { v[i] = a.w[i]; v[4 + i] = b.w[i]; }
+__device__ __forceinline__ void ldg_u32x8(const u32 *p, u32 *v) {   // 8 consecutive u32, 32-byte aligned
+#ifndef EXB_HOST_EMUL
+    asm volatile(EXB_LD256 ".v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+#else
+    for (int i = 0; i < 8; i++) v[i] = p[i];
+#endif
 }
 __device__ __forceinline__ void stg_u32x8(u32 *p, const u32 *v) {
-    Vec16 a, b;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { a.w[i] = v[i]; b.w[i] = v[4 + i]; }
-    reinterpret_cast<Vec16 *>(p)[0] = a; reinterpret_cast<Vec16 *>(p)[1] = b;
+#ifndef EXB_HOST_EMUL
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+#else
+    for (int i = 0; i < 8; i++) p[i] = v[i];
+#endif
 }
 // swizzled u64 image: elements e0 .. e0+3 (e0 % 4 == 0) are two 16-byte chunks
 __device__ __forceinline__ void lds_u64x4(const u64 *sm, u32 e0, u64 *v) {
@@ -839,7 +852,7 @@ __device__ __forceinline__ void digit_sums8(const DigT *__restrict__ digits, con
         u64 even = 0, odd = 0;
         for (u32 i = i_lo; i <= i_hi; i++) {
             const size_t pr = (size_t)M.prod_of[i][k - i];
-            const u64 x = *reinterpret_cast<const u64 *>(digits + ((pair * NP + pr) * G + g) * n + e0) ^ bias;
+                        const u64 x = ld_stream(reinterpret_cast<const u64 *>(digits + ((pair * NP + pr) * G + g) * n + e0)) ^ bias;
             even += x & lanes;
             odd += (x >> 8) & lanes;
         }

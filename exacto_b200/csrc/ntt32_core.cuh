@@ -86,15 +86,44 @@ EXB_HD void gs32(u32 &x, u32 &y, const Tw32 t, const Mod32 &m, u32 bias) {
     y = shoup32_lazy(D, t.w, t.s, m.p);
 }
 
+// CNT consecutive twiddles from entry `first`; like load_tws (ntt_core.cuh): a thread's own entries of a global
+// table (S == 0) come as one vector load that bypasses L1.
+template <int CNT, bool OWN, class TW>
+EXB_HD void load_tws32(const TW &tw, u32 first, Tw32 (&w)[CNT]) {
+#pragma unroll
+    for (int g = 0; g < CNT; g++) w[g] = tw[first + g];
+}
+#if defined(__CUDA_ARCH__)
+template <int CNT, bool OWN>
+EXB_HD void load_tws32(const Tw32 *const &tw, u32 first, Tw32 (&w)[CNT]) {
+    static_assert(CNT == 1 || CNT == 2 || CNT == 4, "one vector load");
+    const Tw32 *p = tw + first;
+    if constexpr (!OWN) {
+#pragma unroll
+        for (int g = 0; g < CNT; g++) w[g] = p[g];
+    } else if constexpr (CNT == 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[0].w), "=r"(w[0].s) : "l"(p));
+    } else if constexpr (CNT == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0].w), "=r"(w[0].s), "=r"(w[1].w), "=r"(w[1].s) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(w[0].w), "=r"(w[0].s), "=r"(w[1].w), "=r"(w[1].s), "=r"(w[2].w), "=r"(w[2].s), "=r"(w[3].w),
+                       "=r"(w[3].s) : "l"(p));
+    }
+}
+#endif
+
 template <int LOGN, int S, int NB, int J, class TW>
 EXB_HD void fwd_stage32(u32 (&v)[1 << NB], const TW &tw, u32 pre, const Mod32 &m) {
     constexpr int P = LOGN - NB - S;
     constexpr int half = (1 << NB) >> (J + 1);
+    Tw32 w[1 << J];
+    load_tws32<(1 << J), S == 0>(tw, (1u << (P + J)) + (pre << J), w);
 #pragma unroll
     for (int g = 0; g < (1 << J); g++) {
-        const Tw32 w = tw[(1u << (P + J)) + (pre << J) + g];
 #pragma unroll
-        for (int u = 0; u < half; u++) ct32(v[g * 2 * half + u], v[g * 2 * half + u + half], w, m);
+        for (int u = 0; u < half; u++) ct32(v[g * 2 * half + u], v[g * 2 * half + u + half], w[g], m);
     }
 }
 // Values grow by < 6p over the pass (no reduction inside).
@@ -112,11 +141,13 @@ EXB_HD void inv_stage32(u32 (&v)[1 << NB], const TW &tw, u32 pre, const Mod32 &m
     constexpr int P = LOGN - NB - S;
     constexpr int half = 1 << J;
     const u32 bias = m.four_p << J;
+    constexpr int CNT = (1 << NB) >> (J + 1);
+    Tw32 w[CNT];
+    load_tws32<CNT, S == 0>(tw, (1u << (P + NB - 1 - J)) + (pre << (NB - 1 - J)), w);
 #pragma unroll
-    for (int g = 0; g < ((1 << NB) >> (J + 1)); g++) {
-        const Tw32 w = tw[(1u << (P + NB - 1 - J)) + (pre << (NB - 1 - J)) + g];
+    for (int g = 0; g < CNT; g++) {
 #pragma unroll
-        for (int u = 0; u < half; u++) gs32(v[g * 2 * half + u], v[g * 2 * half + u + half], w, m, bias);
+        for (int u = 0; u < half; u++) gs32(v[g * 2 * half + u], v[g * 2 * half + u + half], w[g], m, bias);
     }
 }
 // Inputs < 4p.  !LAST: outputs < 4p.  LAST: the final stage folds n^-1, outputs canonical.

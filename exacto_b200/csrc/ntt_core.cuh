@@ -111,17 +111,46 @@ struct TwHead {
     EXB_HD const Tw &operator[](u32 i) const { return t[i]; }
 };
 
+// CNT consecutive twiddles starting at entry `first` (CNT-aligned).  Generic tables (the uniform head, shared-memory
+// copies) and the passes whose entries are shared by groups of threads: plain indexing.  A global table in the pass
+// where every thread has its own entries (OWN: S == 0) is read with one 128-bit or one / two 256-bit loads that do not
+// allocate in L1: that part of a table (57 KB) is larger than the L1 the fused kernels leave beside their shared
+// memory (228 KB - 2 x 80..96 KB), so caching it only evicts the small shared entries of the other passes; measured
+// against keeping any share of it cacheable.
+template <int CNT, bool OWN, class TW>
+EXB_HD void load_tws(const TW &tw, u32 first, Tw (&w)[CNT]) {
+#pragma unroll
+    for (int g = 0; g < CNT; g++) w[g] = tw[first + g];
+}
+#if defined(__CUDA_ARCH__)
+template <int CNT, bool OWN>
+EXB_HD void load_tws(const Tw *const &tw, u32 first, Tw (&w)[CNT]) {
+    if constexpr (!OWN) {
+#pragma unroll
+        for (int g = 0; g < CNT; g++) w[g] = tw[first + g];
+    } else if constexpr (CNT == 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(w[0].w), "=l"(w[0].s) : "l"(tw + first));
+    } else {
+#pragma unroll
+        for (int g = 0; g < CNT; g += 2)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];"
+                         : "=l"(w[g].w), "=l"(w[g].s), "=l"(w[g + 1].w), "=l"(w[g + 1].s) : "l"(tw + first + g));
+    }
+}
+#endif
+
 // One butterfly stage J (0..NB-1) of a forward pass over local bits [S, S+NB): global stage
 // P + J with P = LOGN-NB-S.  Compile-time J keeps v[] in registers.
 template <int LOGN, int S, int NB, int J, int LAZY, class TW>
 EXB_HD void fwd_stage(u64 (&v)[1 << NB], const TW &tw, u32 pre, const LazyC &c) {
     constexpr int P = LOGN - NB - S;
     constexpr int half = (1 << NB) >> (J + 1);
+    Tw w[1 << J];
+    load_tws<(1 << J), S == 0>(tw, (1u << (P + J)) + (pre << J), w);
 #pragma unroll
     for (int g = 0; g < (1 << J); g++) {
-        const Tw w = tw[(1u << (P + J)) + (pre << J) + g];
 #pragma unroll
-        for (int u = 0; u < half; u++) ct_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w, c);
+        for (int u = 0; u < half; u++) ct_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w[g], c);
     }
 }
 
@@ -150,12 +179,14 @@ EXB_HD void inv_stage(u64 (&v)[1 << NB], const TW &tw, u32 pre, const LazyC &c) 
     constexpr int GSI = S + J;
     constexpr int r = GSI <= kRecentre ? GSI : GSI - kRecentre - 1;
     const u64 bias = LAZY == 2 ? (c.four_q << r) : (c.four_q << 1);
+    constexpr int CNT = (1 << NB) >> (J + 1);
+    Tw w[CNT];
+    load_tws<CNT, S == 0>(tw, (1u << (P + NB - 1 - J)) + (pre << (NB - 1 - J)), w);
 #pragma unroll
-    for (int g = 0; g < ((1 << NB) >> (J + 1)); g++) {
-        const Tw w = tw[(1u << (P + NB - 1 - J)) + (pre << (NB - 1 - J)) + g];
+    for (int g = 0; g < CNT; g++) {
 #pragma unroll
         for (int u = 0; u < half; u++) {
-            gs_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w, c, bias);
+            gs_bfly_l<LAZY>(v[g * 2 * half + u], v[g * 2 * half + u + half], w[g], c, bias);
             if (LAZY == 2 && GSI == kRecentre)
                 v[g * 2 * half + u] = reduce_to_2m(v[g * 2 * half + u], c.neg_q, c.rhi, c.rsh);
         }

@@ -12,6 +12,10 @@
  *   - Plain pointers and sizes only.  `*_dev` pointers are CUDA device pointers
  *     on the context's device, `*_host` pointers are host memory (pinned host
  *     memory makes the copies asynchronous).
+ *     Device buffers passed to the multiplication / relinearisation entry points
+ *     must be 32-byte aligned (the kernels use 256-bit accesses; cudaMalloc,
+ *     exb_device_alloc and framework allocators are): EXB_INVALID_PARAM otherwise.
+ *     Host buffers have no alignment requirement beyond that of uint64_t.
  *   - Polynomials are n 64-bit words of canonical residues in [0, modulus).
  *     Ciphertext polynomials are in the NTT (evaluation) domain like the
  *     reference's NttPoly (ring/ntt.rs:11-15).  The evaluation order is this

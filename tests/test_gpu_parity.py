@@ -257,6 +257,27 @@ def test_commutativity_full_size():
 
 
 # ---- error pins through the native context (dbfv/eval.rs:385-453) ---------------------------------------------
+def test_misaligned_device_buffers_are_refused():
+    """The n = 4096 kernels use 256-bit accesses: a device pointer that is not 32-byte aligned is an
+    EXB_INVALID_PARAM, not a fault; a 32-byte-aligned view (any whole row offset) works."""
+    import torch
+    from exacto_b200 import batch
+    dp = E.u64_dbfv()
+    P = dp.bfv_params
+    q, n, d = P.modulus(0), 4096, 8
+    rng = np.random.default_rng(5)
+    rlk = E.RelinKey(rng.integers(0, q, (P.gadget_digits, 2, n), dtype=np.uint64), P)
+    flat = batch.to_device(rng.integers(0, q, 2 * d * 2 * n + 4, dtype=np.uint64))
+    good = flat[: d * 2 * n].view(1, d, 2, n)
+    odd = flat[1: 1 + d * 2 * n].view(1, d, 2, n)                 # 8 bytes past a 32-byte boundary
+    shifted = flat[4: 4 + d * 2 * n].view(1, d, 2, n)             # 32 bytes past: fine
+    with pytest.raises(E.ExactoError, match="32-byte aligned"):
+        batch.dbfv_mul(dp, odd, good, rlk)
+    a = batch.dbfv_mul(dp, shifted, good, rlk)
+    b = batch.dbfv_mul(dp, shifted.clone(), good, rlk)
+    assert torch.equal(a, b)
+
+
 def test_native_error_pins():
     n = 4096
     z = np.zeros((1, 2, n), np.uint64)
