@@ -701,8 +701,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="exacto_b200", choices=["exacto_b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=20 * 148,
-                    help="ciphertext pairs per GPU per step (20 x 148: a 20-step timed region lasts > 1 s)")
+    ap.add_argument("--pairs", type=int, default=24 * 148,
+                    help="ciphertext pairs per GPU per step (24 x 148: a 20-step timed region lasts > 1 s)")
     ap.add_argument("--ntt-count", type=int, default=16384)
     ap.add_argument("--ntt-reps", type=int, default=10)
     ap.add_argument("--cpu-trials", type=int, default=20)
