@@ -464,17 +464,18 @@ static void build_small_basis(HostSetup *c, uint32_t flags) {
     s.plain32 = (p < ((u64)1 << 32) && c->P.sc.plain_s < ((u64)1 << 32)) ? 1u : 0u;
     // tensor01_kernel sums the products of one output limb before the small-prime inverse transforms:
     // cnt terms are exact while cnt*|m|max still leaves the alpha margin (2^5), the sum of cnt centred residues
-    // (|.| <= cnt*q/2) fits an i64, and the summed rounding terms (each <= p/2 + 1) stay below q and below 2^31 in
-    // magnitude (tensor01_kernel keeps them in an i32 image).
-    u32 mt = 0;
+    // (|.| <= cnt*q/2) fits an i64, and the summed rounding terms (each <= p/2 + 1) stay below q in magnitude;
+    // max_terms_r32: ... and below 2^31 (tensor01_kernel then keeps them in an i32 image).
+    u32 mt = 0, mt32 = 0;
     for (u32 cnt = 1; cnt <= 16; cnt++) {
         if (prod < (mmax * cnt) << 5) break;
         if ((u128)cnt * q >= ((u128)1 << 64)) break;
         if ((u128)cnt * (p / 2 + 2) >= q) break;
-        if ((u128)cnt * (p / 2 + 2) >= ((u128)1 << 31)) break;
         mt = cnt;
+        if ((u128)cnt * (p / 2 + 2) < ((u128)1 << 31)) mt32 = cnt;
     }
     sb.max_terms = mt;
+    sb.max_terms_r32 = mt32;
     sb.mq_r = c->P.mod[0];
     {
         const u64 r64 = (u64)((((u128)1) << 64) % q);

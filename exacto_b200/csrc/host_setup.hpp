@@ -26,7 +26,8 @@ constexpr int kMaxPeers = 7;                   // other GPUs of one 8-GPU box (k
 // primes inside the lift / tensor kernels when that is provably result-identical.
 struct SmallBasis {
     u32 enabled, K;
-    u32 max_terms, pad_;          // most products a limb may sum in tensor01_kernel (0: per-product kernel only)
+    u32 max_terms;                // most products a limb may sum in tensor01_kernel (0: per-product kernel only)
+    u32 max_terms_r32;            // ... with the rounding-term sums still fitting an i32
     const Tw32 *twf[kMaxSmall];
     const Tw32 *twi[kMaxSmall];
     TwHead32 headf[kMaxSmall], headi[kMaxSmall];

@@ -1080,6 +1080,9 @@ __device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, cons
 // digits are a non-linear function of each product.
 // One CTA per (pair, two computed limbs, component in {0, 1}); output r01s [pair][limb][2][n], coefficient domain.
 // ---------------------------------------------------------------------------------
+// R64: the per-limb sums of rounding terms are kept as i64 (any plaintext modulus) instead of i32 (products per limb
+// * (p/2 + 2) < 2^31: SmallBasis::max_terms_r32, every BASELINE config) -- 16 KB more shared memory per CTA.
+template <bool R64>
 __global__ void __launch_bounds__(kThreads12, 2)
 tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ MulPlan M,
                 const u64 *__restrict__ ct1, const u64 *__restrict__ ct2, const u32 *__restrict__ ext_s,
@@ -1091,8 +1094,8 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     const u32 duo = (blockIdx.x >> 1) % ND;
     const size_t pair = (blockIdx.x >> 1) / ND;
     i64 *sacc = reinterpret_cast<i64 *>(smem);                 // sum of centred a_ij
-    u32 *racc = reinterpret_cast<u32 *>(smem + n);             // sum of signed rounding terms (i32: max_terms * p / 2 < 2^31)
-    u64 *bq = smem + n + n / 2;                                // base-q work image, later the K u32 images
+    u32 *racc = reinterpret_cast<u32 *>(smem + n);             // sum of signed rounding terms: i32, or i64 rows (R64)
+    u64 *bq = smem + n + (R64 ? n : n / 2);                    // base-q work image, later two u32 images per round
     u32 *bs = reinterpret_cast<u32 *>(bq);
     const Modulus &mb = P.sb.mq_r;                   // q with n^-1 * 2^64 as the inverse transform's scaling
     const ScaleConsts &c = P.sc;
@@ -1132,21 +1135,37 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             const u32 eh = e0 + 4 * h;
             u64 a[4];
             i64 sv[4];
-            Vec16 r;                       // racc rows are private to the thread: plain 16-byte pieces, no swizzle
             lds_u64x4(bq, eh, a);
-            if (i != i_lo) {
-                r = *reinterpret_cast<const Vec16 *>(racc + eh);
-                lds_u64x4(reinterpret_cast<const u64 *>(sacc), eh, reinterpret_cast<u64 *>(sv));
+            if (i != i_lo) lds_u64x4(reinterpret_cast<const u64 *>(sacc), eh, reinterpret_cast<u64 *>(sv));
+            else {
+#pragma unroll
+                for (int t = 0; t < 4; t++) sv[t] = 0;
+            }
+            // racc rows are private to the thread: plain 16-byte pieces, no swizzle
+            if constexpr (R64) {
+                u64 *rr = reinterpret_cast<u64 *>(racc) + eh;
+                ulonglong2 r0, r1;
+                r0.x = r0.y = r1.x = r1.y = 0;
+                if (i != i_lo) { r0 = reinterpret_cast<const ulonglong2 *>(rr)[0]; r1 = reinterpret_cast<const ulonglong2 *>(rr)[1]; }
+                r0.x += (u64)(sc.plain32 ? round_term32_signed(a[0], c) : round_term_signed(a[0], c));
+                r0.y += (u64)(sc.plain32 ? round_term32_signed(a[1], c) : round_term_signed(a[1], c));
+                r1.x += (u64)(sc.plain32 ? round_term32_signed(a[2], c) : round_term_signed(a[2], c));
+                r1.y += (u64)(sc.plain32 ? round_term32_signed(a[3], c) : round_term_signed(a[3], c));
+                reinterpret_cast<ulonglong2 *>(rr)[0] = r0; reinterpret_cast<ulonglong2 *>(rr)[1] = r1;
             } else {
+                Vec16 r;
+                if (i != i_lo) r = *reinterpret_cast<const Vec16 *>(racc + eh);
+                else {
 #pragma unroll
-                for (int t = 0; t < 4; t++) { r.w[t] = 0; sv[t] = 0; }
+                    for (int t = 0; t < 4; t++) r.w[t] = 0;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    r.w[t] += (u32)(sc.plain32 ? round_term32_signed(a[t], c) : round_term_signed(a[t], c));
+                *reinterpret_cast<Vec16 *>(racc + eh) = r;
             }
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                r.w[t] += (u32)(sc.plain32 ? round_term32_signed(a[t], c) : round_term_signed(a[t], c));
-                sv[t] += center_i64(a[t], c.q, c.half_q);
-            }
-            *reinterpret_cast<Vec16 *>(racc + eh) = r;
+            for (int t = 0; t < 4; t++) sv[t] += center_i64(a[t], c.q, c.half_q);
             sts_u64x4(reinterpret_cast<u64 *>(sacc), eh, reinterpret_cast<const u64 *>(sv));
         }
         __syncthreads();                   // bq is rewritten by the next product / the small-prime images
@@ -1161,15 +1180,23 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     u64 res[8];
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        i64 sv[4];
-        const Vec16 r = *reinterpret_cast<const Vec16 *>(racc + e0 + 4 * h);
+        i64 sv[4], rs[4];
+        if constexpr (R64) {
+            const u64 *rr = reinterpret_cast<const u64 *>(racc) + e0 + 4 * h;
+            const ulonglong2 r0 = reinterpret_cast<const ulonglong2 *>(rr)[0], r1 = reinterpret_cast<const ulonglong2 *>(rr)[1];
+            rs[0] = (i64)r0.x; rs[1] = (i64)r0.y; rs[2] = (i64)r1.x; rs[3] = (i64)r1.y;
+        } else {
+            const Vec16 r = *reinterpret_cast<const Vec16 *>(racc + e0 + 4 * h);
+#pragma unroll
+            for (int t = 0; t < 4; t++) rs[t] = (i64)(int32_t)r.w[t];
+        }
         lds_u64x4(reinterpret_cast<const u64 *>(sacc), e0 + 4 * h, reinterpret_cast<u64 *>(sv));
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             u32 b[kMaxSmall];
 #pragma unroll
             for (u32 pi = 0; pi < (u32)kMaxSmall; pi++) b[pi] = pi < K ? bv[pi][4 * h + t] : 0u;
-            res[4 * h + t] = hps_scale32_sum((i64)(int32_t)r.w[t], sv[t], b, c, sc);
+            res[4 * h + t] = hps_scale32_sum(rs[t], sv[t], b, c, sc);
         }
     }
     stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
@@ -1595,18 +1622,24 @@ int num_sms() {
 int num_sms() { return 148; }
 #endif
 
-// Components 0/1 can be produced per output limb (tensor01_kernel) when the internal basis is on and
-// every limb sums at most SmallBasis::max_terms products.
-bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs) {
-    if (!P.sb.enabled || P.logn != 12) return false;
-    if (P.tensor_per_product) return false;                 // exb_context_set_option: the per-product kernel only
+static u32 most_products_per_limb(const MulPlan &M) {
     u32 worst = 0;
     for (u32 l = 0; l < M.num_limbs; l++) {
         const u32 k = M.limb_k[l];
         const u32 cnt = (k < M.d ? k : M.d - 1) - (k >= M.d ? k - M.d + 1 : 0) + 1;
         worst = cnt > worst ? cnt : worst;
     }
-    if (worst > P.sb.max_terms) return false;
+    return worst;
+}
+bool tensor01_needs_r64(const DeviceParams &P, const MulPlan &M) { return most_products_per_limb(M) > P.sb.max_terms_r32; }
+
+// Components 0/1 can be produced per output limb (tensor01_kernel) when the internal basis is on and
+// every limb sums at most SmallBasis::max_terms products.
+bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs) {
+    if (!P.sb.enabled || P.logn != 12) return false;
+    if (P.tensor_per_product) return false;                 // exb_context_set_option: the per-product kernel only
+    const u32 worst = most_products_per_limb(M);
+    if (worst > P.sb.max_terms) return false;               // launch_tensor picks the i32 / i64 rounding-sum variant
     // It pays when limbs sum several products (fewer small-prime inverse transforms) and the per-limb CTAs
     // (1..d products each) still fill the GPU; small batches keep the finer-grained per-product kernel.
     // measured crossover when the kernel has the GPU to itself: 24-28 pairs at d = 8 (~200 CTAs); chunks of the
@@ -1789,8 +1822,10 @@ static void launch_tensor_t(const DeviceParams &P, const MulPlan &M, const u64 *
         const u32 *ext_s = ext_small_part(const_cast<u64 *>(ext));
         if (!raw3 && tensor_sums_per_limb(P, M, pairs)) {
             // components 0/1 per output limb (one small-prime inverse transform per limb), component 2 per product
-            const size_t sm01 = smem_tensor01(P.sb.K);
-            tensor01_kernel<<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
+            const bool r64 = tensor01_needs_r64(P, M);
+            const size_t sm01 = smem_tensor01(r64);
+            if (r64) tensor01_kernel<true><<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
+            else tensor01_kernel<false><<<(unsigned)(pairs * M.num_duos * 2), kThreads12, sm01, s>>>(P, M, ct1, ct2, ext_s, r01);
             if (mid) cudaEventRecord(mid, s);
             tensor32_kernel<DigT><<<(unsigned)(pairs * M.num_products), kThreads12, sm32, s>>>(P, M, ct1, ct2, ext_s, r01,
                                                                                              digits, 1u);
@@ -1929,7 +1964,7 @@ void launch_prepare(int device) {
     EXB_OPT_NTT(true, 0) EXB_OPT_NTT(true, 1) EXB_OPT_NTT(true, 2) EXB_OPT_NTT(false, 0) EXB_OPT_NTT(false, 1) EXB_OPT_NTT(false, 2)
 #undef EXB_OPT_NTT
     opt_in(lift32_kernel, optin); opt_in(lift_kernel<12>, optin); opt_in(lift_kernel<0>, optin);
-    opt_in(tensor01_kernel, optin);
+    opt_in(tensor01_kernel<false>, optin); opt_in(tensor01_kernel<true>, optin);
     opt_in(tensor32_kernel<int16_t>, optin); opt_in(tensor32_kernel<int32_t>, optin); opt_in(tensor32_kernel<int8_t>, optin);
     opt_in(tensor_kernel<12, int16_t>, optin); opt_in(tensor_kernel<12, int32_t>, optin); opt_in(tensor_kernel<12, int8_t>, optin);
     opt_in(tensor_kernel<0, int16_t>, optin); opt_in(tensor_kernel<0, int32_t>, optin); opt_in(tensor_kernel<0, int8_t>, optin);

@@ -11,9 +11,9 @@
 
 namespace exb {
 
-// dynamic shared memory of tensor01_kernel (n = 4096): i64 and i32 per-limb accumulators + the base-q image, which two
-// u32 small-prime images at a time reuse
-inline size_t smem_tensor01(u32) { return 4096 * 8 + 4096 * 4 + 4096 * 8; }
+// dynamic shared memory of tensor01_kernel (n = 4096): i64 and i32 (r64: i64) per-limb accumulators + the base-q image,
+// which two u32 small-prime images at a time reuse
+inline size_t smem_tensor01(bool r64) { return 4096 * 8 + (r64 ? 4096 * 8 : 4096 * 4) + 4096 * 8; }
 
 enum PolyOp { OP_ADD = 0, OP_SUB = 1, OP_NEG = 2, OP_MUL = 3, OP_SCALAR_MUL = 4, OP_TO_MONT = 5 };
 
@@ -39,6 +39,7 @@ void launch_lift(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const 
 void launch_tensor(const DeviceParams &P, const MulPlan &M, const u64 *ct1, const u64 *ct2, const u64 *ext, u64 *r01,
                    void *digits, int digit_kind, size_t pairs, cudaStream_t s, cudaEvent_t mid = nullptr,
                    bool raw3 = false);   // raw3 (bfv_mul_no_relin): r01 = [pairs][products][3][n], all scaled components
+bool tensor01_needs_r64(const DeviceParams &P, const MulPlan &M);   // i64 instead of i32 rounding sums
 bool tensor_sums_per_limb(const DeviceParams &P, const MulPlan &M, size_t pairs);   // r01 is [pairs][limbs][2][n] when true
 // `wide_scratch` (relin_wide_scratch_bytes, optional): lets small batches use one CTA per transform.
 bool relin_goes_wide(const DeviceParams &P, const MulPlan &M, size_t pairs);

@@ -201,8 +201,10 @@ int emu_dbfv_mul(emu_ctx *c, uint64_t base, uint32_t d, uint64_t pm, const uint6
         const u32 c2 = per_limb ? 1u : 0u;
         const unsigned tgrid = (unsigned)(pairs * M.num_products * (per_limb ? 1 : 3));
         if (per_limb) {
-            const size_t sm01 = smem_tensor01(P.sb.K);
-            emu_launch((unsigned)(pairs * M.num_duos * 2), thr, sm01, [&]() { tensor01_kernel(P, M, ct1, ct2, exts, r01p); });
+            const bool r64 = tensor01_needs_r64(P, M);
+            const size_t sm01 = smem_tensor01(r64);
+            if (r64) emu_launch((unsigned)(pairs * M.num_duos * 2), thr, sm01, [&]() { tensor01_kernel<true>(P, M, ct1, ct2, exts, r01p); });
+            else emu_launch((unsigned)(pairs * M.num_duos * 2), thr, sm01, [&]() { tensor01_kernel<false>(P, M, ct1, ct2, exts, r01p); });
         }
         std::vector<u64> wide(wide_relin ? relin_wide_scratch_bytes(P, M, pairs) / 8 + 1 : 1);
         u64 *wp = wide.data();

@@ -348,11 +348,12 @@ def test_per_limb_tensor_path_sixteen_digits(emu):
     assert rc == 0 and np.array_equal(got[0], want), err
 
 
-@pytest.mark.parametrize("plain,per_limb", [((1 << 28) - 57, 1), ((1 << 29) + 11, 0)])
-def test_per_limb_rounding_sums_fit_i32(emu, plain, per_limb):
-    """tensor01_kernel keeps the per-limb sums of rounding terms in an i32 image: the host may only choose it while
-    (products per limb) * (p/2 + 2) < 2^31.  p just below 2^28 with 8 products per limb and every residue at q/2 puts
-    the sum at 2^30; p above 2^29 must fall back to the per-product kernel.  Both stay word-exact."""
+@pytest.mark.parametrize("plain,per_limb", [((1 << 28) - 57, 1), ((1 << 29) + 11, 1), ((1 << 33) + 7, 1)])
+def test_per_limb_rounding_sums_i32_and_i64(emu, plain, per_limb):
+    """tensor01_kernel keeps the per-limb sums of rounding terms in an i32 image while (products per limb) * (p/2 + 2)
+    < 2^31 and in an i64 image otherwise (tensor01_kernel<true>).  p just below 2^28 with 8 products per limb and every
+    residue at q/2 puts the i32 sum at 2^30; p above 2^29 and above 2^32 (64-bit rounding terms) take the wide variant.
+    All word-exact."""
     P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=plain,
                        gadget_base=256)
     h = emu.from_oracle(P)

@@ -992,9 +992,9 @@ def test_per_limb_tensor_path_on_gpu():
 
 @pytest.mark.parametrize("plain", [(1 << 28) - 57, (1 << 29) + 11, (1 << 33) + 7])
 def test_per_limb_rounding_sums_large_plain_modulus(plain):
-    """tensor01_kernel's i32 sums of rounding terms: p just below 2^28 with 8 products per limb puts them at 2^30
-    (per-limb kernel), p above 2^29 / above 2^32 must take the per-product kernel; all word-exact at a batch size
-    that selects the per-limb kernel when it is legal."""
+    """tensor01_kernel's sums of rounding terms: p just below 2^28 with 8 products per limb puts the i32 sums at 2^30,
+    p above 2^29 / above 2^32 takes the i64 variant (tensor01_kernel<true>); all word-exact at a batch size that selects
+    the per-limb kernel."""
     from exacto_b200 import batch
     P = O.OracleParams(n=4096, q=1152921504606830593, aux=(18014398509998081, 36028797018972161), plain_modulus=plain,
                        gadget_base=256)
