@@ -99,9 +99,11 @@ __device__ __forceinline__ void transpose8_shfl(u64 (&v)[8]) {
 #define EXB_REGROUP_F(v, sm, t) store_vals<3, 3>(v, sm, t); __syncthreads(); load_vals<3, 0>(v, sm, t)
 #define EXB_REGROUP_I(v, sm, t) store_vals<3, 0>(v, sm, t); __syncthreads(); load_vals<3, 3>(v, sm, t)
 #endif
+// `keep` (NB = 3): leave the outputs -- elements 8t .. 8t+7, the last pass's own layout -- in the caller's registers
+// instead of storing them to the image: callers that go on element-wise skip a shared-memory round trip and a barrier.
 template <int NB, int LAZY, bool CANON = true, class TWT = const Tw *, class TWM = const Tw *>
 __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
-                                           const LazyC &c, const u32 t) {
+                                           const LazyC &c, const u32 t, u64 *keep = nullptr) {
     u64 v[1 << NB];
     if constexpr (NB == 4) {
         load_vals<4, 8>(v, sm, t); fwd_pass<12, 8, 4, LAZY>(v, head, t, c); store_vals<4, 8>(v, sm, t);
@@ -122,13 +124,21 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm,
 #pragma unroll
         for (int k = 0; k < (1 << NB); k++) v[k] = fwd_final<LAZY>(v[k], c);
     }
-    store_vals<NB, 0>(v, sm, t);
+    if (keep) {
+#pragma unroll
+        for (int k = 0; k < (1 << NB); k++) keep[k] = v[k];
+    } else {
+        store_vals<NB, 0>(v, sm, t);
+    }
 }
 
 // Inputs < 4q (LAZY >= 1) or < 2q (LAZY == 0); outputs canonical.
+// `feed` (NB = 3): the inputs -- elements 8t .. 8t+7, the first pass's own layout -- come from the caller's registers
+// instead of the image (callers that just computed them element-wise skip a shared-memory round trip and a barrier).
 template <int NB, int LAZY, class TWT = const Tw *, class TWM = const Tw *>
 __device__ __forceinline__ void inv_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
-                                           const Modulus &mod, const LazyC &c, const u32 t) {
+                                           const Modulus &mod, const LazyC &c, const u32 t, const u64 *feed = nullptr,
+                                           u64 *keep = nullptr) {
     u64 v[1 << NB];
     if constexpr (NB == 4) {
         load_vals<4, 0>(v, sm, t); inv_pass<12, 0, 4, false, LAZY>(v, tw, t, mod, c); store_vals<4, 0>(v, sm, t);
@@ -137,29 +147,45 @@ __device__ __forceinline__ void inv_body12(u64 *sm, const TWT tw, const TWM twm,
         __syncthreads();
         load_vals<4, 8>(v, sm, t); inv_pass<12, 8, 4, true, LAZY>(v, head, t, mod, c); store_vals<4, 8>(v, sm, t);
     } else {
-        load_vals<3, 0>(v, sm, t); inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c);
+        if (feed) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = feed[k];
+        } else {
+            load_vals<3, 0>(v, sm, t);
+        }
+        inv_pass<12, 0, 3, false, LAZY>(v, tw, t, mod, c);
         EXB_REGROUP_I(v, sm, t);
         inv_pass<12, 3, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 3>(v, sm, t);
         __syncthreads();
         load_vals<3, 6>(v, sm, t); inv_pass<12, 6, 3, false, LAZY>(v, twm, t, mod, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
-        load_vals<3, 9>(v, sm, t); inv_pass<12, 9, 3, true, LAZY>(v, head, t, mod, c); store_vals<3, 9>(v, sm, t);
+        load_vals<3, 9>(v, sm, t); inv_pass<12, 9, 3, true, LAZY>(v, head, t, mod, c);
+        if (keep) {                        // outputs stay in registers: elements t + 512 k (the last pass's layout)
+#pragma unroll
+            for (int k = 0; k < 8; k++) keep[k] = v[k];
+        } else {
+            store_vals<3, 9>(v, sm, t);
+        }
     }
 }
 
 template <int LAZY, bool CANON = true>
-__device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
+__device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
+                                         u64 *keep = nullptr) {
     const LazyC c = make_lazyc(mod);
     __syncthreads();
-    fwd_body12<kNB, LAZY, CANON>(sm, tw, tw, head, c, threadIdx.x);
-    __syncthreads();
+    fwd_body12<kNB, LAZY, CANON>(sm, tw, tw, head, c, threadIdx.x, keep);
+    if (!keep) __syncthreads();            // kept outputs: the last pass read only this thread's own elements
 }
+// With `feed` there is no leading barrier: the first access to the image is this thread's store of its own elements,
+// and every earlier use of the image must have ended with a barrier after its last strided access (the transforms do).
 template <int LAZY>
-__device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod) {
+__device__ __forceinline__ void inv_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
+                                         const u64 *feed = nullptr, u64 *keep = nullptr) {
     const LazyC c = make_lazyc(mod);
-    __syncthreads();
-    inv_body12<kNB, LAZY>(sm, tw, tw, head, mod, c, threadIdx.x);
-    __syncthreads();
+    if (!feed) __syncthreads();
+    inv_body12<kNB, LAZY>(sm, tw, tw, head, mod, c, threadIdx.x, feed, keep);
+    __syncthreads();                       // (kept outputs too: the last pass read other threads' elements)
 }
 
 // 32-bit transforms of the internal auxiliary basis (n = 4096, 512 threads x 8 values).
@@ -198,15 +224,27 @@ __device__ __forceinline__ void inv32_sm(u32 *sm, const Tw32 *__restrict__ tw, c
 // KK small primes at once: the KK independent 8-value butterfly networks of a thread are
 // interleaved by the compiler (3x the ILP per barrier of one transform at a time).  Image i
 // lives at sm + i * 4096.
+// `io` (optional): inputs come from and outputs go to the caller's registers -- in: elements t + 512 k (first pass
+// layout), out: elements 8t + k (last pass layout) -- instead of the images' first load / last store.
 template <int KK>
-__device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb) {
+__device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb, u32 (*io)[8] = nullptr) {
     const u32 t = threadIdx.x;
     u32 v[KK][8];
-    __syncthreads();
+    if (!io) __syncthreads();
 #define EXB_PASS(S, TW)                                                                               \
     _Pragma("unroll") for (int i = 0; i < KK; i++) load_vals32<3, S>(v[i], sm + i * 4096, t);          \
     _Pragma("unroll") for (int i = 0; i < KK; i++) fwd_pass32<12, S, 3>(v[i], sb.TW[i], t, sb.sc.m[i]);
-    EXB_PASS(9, headf)
+    if (io) {
+#pragma unroll
+        for (int i = 0; i < KK; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[i][k] = io[i][k];
+        }
+#pragma unroll
+        for (int i = 0; i < KK; i++) fwd_pass32<12, 9, 3>(v[i], sb.headf[i], t, sb.sc.m[i]);
+    } else {
+        EXB_PASS(9, headf)
+    }
 #pragma unroll
     for (int i = 0; i < KK; i++) store_vals32<3, 9>(v[i], sm + i * 4096, t);
     __syncthreads();
@@ -224,22 +262,42 @@ __device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb) {
     for (int i = 0; i < KK; i++) {
 #pragma unroll
         for (int k = 0; k < 8; k++) v[i][k] = fold32(v[i][k], sb.sc.m[i]);
-        store_vals32<3, 0>(v[i], sm + i * 4096, t);
+        if (io) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) io[i][k] = v[i][k];
+        } else {
+            store_vals32<3, 0>(v[i], sm + i * 4096, t);
+        }
     }
-    __syncthreads();
+    if (!io) __syncthreads();
 }
 // Primes P0 .. P0 + KK - 1 of the basis; image i of the call is prime P0 + i.
+// `feed` (optional): the inputs -- elements 8t .. 8t+7, the first pass's layout -- come from the caller's registers;
+// the caller guarantees that nobody still reads the images (no leading barrier here).
 template <int KK, int P0 = 0>
-__device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb) {
+__device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb, const u32 (*feed)[8] = nullptr) {
     const u32 t = threadIdx.x;
     u32 v[KK][8];
-    __syncthreads();
+    if (!feed) __syncthreads();
 #define EXB_PASS(S, LAST, TW)                                                                         \
     _Pragma("unroll") for (int i = 0; i < KK; i++) load_vals32<3, S>(v[i], sm + i * 4096, t);          \
     _Pragma("unroll") for (int i = 0; i < KK; i++) inv_pass32<12, S, 3, LAST>(v[i], sb.TW[P0 + i], t, sb.sc.m[P0 + i]); \
     _Pragma("unroll") for (int i = 0; i < KK; i++) store_vals32<3, S>(v[i], sm + i * 4096, t);         \
     __syncthreads();
-    EXB_PASS(0, false, twi)
+    if (feed) {
+#pragma unroll
+        for (int i = 0; i < KK; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[i][k] = feed[i][k];
+        }
+#pragma unroll
+        for (int i = 0; i < KK; i++) inv_pass32<12, 0, 3, false>(v[i], sb.twi[P0 + i], t, sb.sc.m[P0 + i]);
+#pragma unroll
+        for (int i = 0; i < KK; i++) store_vals32<3, 0>(v[i], sm + i * 4096, t);
+        __syncthreads();
+    } else {
+        EXB_PASS(0, false, twi)
+    }
     EXB_PASS(3, false, twi)
     EXB_PASS(6, false, twi)
     EXB_PASS(9, true, headi)
@@ -248,12 +306,13 @@ __device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb) {
 
 template <int LOGN, bool CANON = true>
 __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
-                                       u32 logn) {
+                                       u32 logn, u64 *keep = nullptr) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        if (mod.lazy == 2) fwd_sm12<2, CANON>(sm, tw, head, mod);
-        else if (mod.lazy == 1) fwd_sm12<1, CANON>(sm, tw, head, mod);
-        else fwd_sm12<0, CANON>(sm, tw, head, mod);
+        static_assert(kNB == 3, "kept outputs assume 8 values per thread");
+        if (mod.lazy == 2) fwd_sm12<2, CANON>(sm, tw, head, mod, keep);
+        else if (mod.lazy == 1) fwd_sm12<1, CANON>(sm, tw, head, mod, keep);
+        else fwd_sm12<0, CANON>(sm, tw, head, mod, keep);
     } else {
         // generic path: two butterfly stages per shared-memory round trip (radix 4 on four register values),
         // one radix-2 stage first when logn is odd
@@ -293,12 +352,12 @@ __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const
 // Inputs in [0, 2q).
 template <int LOGN>
 __device__ __forceinline__ void inv_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
-                                       u32 logn) {
+                                       u32 logn, const u64 *feed = nullptr, u64 *keep = nullptr) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
-        if (mod.lazy == 2) inv_sm12<2>(sm, tw, head, mod);
-        else if (mod.lazy == 1) inv_sm12<1>(sm, tw, head, mod);
-        else inv_sm12<0>(sm, tw, head, mod);
+        if (mod.lazy == 2) inv_sm12<2>(sm, tw, head, mod, feed, keep);
+        else if (mod.lazy == 1) inv_sm12<1>(sm, tw, head, mod, feed, keep);
+        else inv_sm12<0>(sm, tw, head, mod, feed, keep);
     } else {
         // generic path: two stages per shared-memory round trip; one radix-2 stage first when logn is odd;
         // the very last stage folds n^-1 (plan.normalize, ring/ntt.rs:62)
@@ -899,6 +958,22 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, u32 need_lhs, u32 n
     const u32 e0 = 8 * threadIdx.x;
     u64 x[8];
     ldg_u64x4(src + e0, x); ldg_u64x4(src + e0 + 4, x + 4);
+    if (K == 3) {
+        // registers all the way: the input row feeds the inverse transform, whose outputs (canonical coefficients
+        // t + 512 k, its last pass's layout) are extended to the three small primes in place and feed the forward
+        // transforms' first pass; their last pass leaves elements 8t .. 8t+7, which go straight to global memory
+        inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12, x, x);
+        u32 y[3][8];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) y[i][k] = ext32_centered_lazy(x[k], mq.m, P.sc.half_q, P.sb.sc.m[i]);
+        }
+        fwd32_smK<3>(work, P.sb, y);
+#pragma unroll
+        for (int i = 0; i < 3; i++) stg_u32x8(ds + (size_t)i * n + e0, y[i]);
+        return;
+    }
     sts_u64x4(coef, e0, x); sts_u64x4(coef, e0 + 4, x + 4);
     inv_sm<12>(coef, P.twi[0], P.headi[0], mq, 12);
     lds_u64x4(coef, e0, x); lds_u64x4(coef, e0 + 4, x + 4);      // canonical coefficients stay in registers
@@ -908,8 +983,7 @@ lift32_kernel(const __grid_constant__ DeviceParams P, u32 d, u32 need_lhs, u32 n
         for (int k = 0; k < 8; k++) y[k] = ext32_centered_lazy(x[k], mq.m, P.sc.half_q, P.sb.sc.m[i]);
         sts_u32x8(work + (size_t)i * n, e0, y);
     }
-    if (K == 3) fwd32_smK<3>(work, P.sb);
-    else for (u32 i = 0; i < K; i++) fwd32_sm(work + (size_t)i * n, P.sb.twf[i], P.sb.headf[i], P.sb.sc.m[i]);
+    for (u32 i = 0; i < K; i++) fwd32_sm(work + (size_t)i * n, P.sb.twf[i], P.sb.headf[i], P.sb.sc.m[i]);
     for (u32 i = 0; i < K; i++) {
         u32 y[8];
         lds_u32x8(work + (size_t)i * n, e0, y);
@@ -941,25 +1015,28 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         const Modulus &mb = P.sb.mq_r;               // q with n^-1 * 2^64 as the inverse transform's scaling
         const u64 *l0 = ct1 + ((pair * d + li) * 2) * (size_t)n, *l1 = l0 + n;
         const u64 *r0 = ct2 + ((pair * d + lj) * 2) * (size_t)n, *r1 = r0 + n;
+        u64 v[8];                          // the products feed the inverse transform from registers
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
-            u64 a[4], b[4], v[4];
+            u64 a[4], b[4];
             if (comp == 1) {
                 u64 c[4], dd[4];
                 ldg_u64x4(l0 + eh, a); ldg_u64x4(r1 + eh, b); ldg_u64x4(l1 + eh, c); ldg_u64x4(r0 + eh, dd);
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = mont_mul2_lazy(a[k], b[k], c[k], dd[k], mb.m, mb.minv_neg);
+                for (int k = 0; k < 4; k++) v[4 * h + k] = mont_mul2_lazy(a[k], b[k], c[k], dd[k], mb.m, mb.minv_neg);
             } else {
                 ldg_u64x4((comp == 0 ? l0 : l1) + eh, a); ldg_u64x4((comp == 0 ? r0 : r1) + eh, b);
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = mont_mul_lazy(a[k], b[k], mb.m, mb.minv_neg);
+                for (int k = 0; k < 4; k++) v[4 * h + k] = mont_mul_lazy(a[k], b[k], mb.m, mb.minv_neg);
             }
-            sts_u64x4(bq, eh, v);
         }
-        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
+        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12, v);
     }
-    for (u32 i = 0; i < K; i++) {   // small primes: 32-bit Montgomery point-wise, then the K INTTs together
+    u32 pw[3][8];                   // K == 3: the point-wise products feed the inverse transforms from registers
+#pragma unroll
+    for (u32 i = 0; i < (u32)kMaxSmall; i++) {   // small primes: 32-bit Montgomery point-wise, then the K INTTs together
+        if (i >= K) break;
         const Mod32 &m = P.sb.sc.m[i];
         const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + li) * 2) * (size_t)K + i) * n, *l1 = l0 + (size_t)K * n;
         const u32 *r0 = ext_s + ((((pair * 2 + 1) * d + lj) * 2) * (size_t)K + i) * n, *r1 = r0 + (size_t)K * n;
@@ -974,9 +1051,14 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 8; k++) v[k] = mont32_redc_lazy((u64)a[k] * b[k], m.p, m.pinv_neg);
         }
-        sts_u32x8(bs + (size_t)i * n, e0, v);
+        if (K == 3) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) pw[i < 3 ? i : 0][k] = v[k];
+        } else {
+            sts_u32x8(bs + (size_t)i * n, e0, v);
+        }
     }
-    if (K == 3) inv32_smK<3>(bs, P.sb);
+    if (K == 3) inv32_smK<3>(bs, P.sb, pw);          // bs is untouched so far: no barrier needed before its first store
     else for (u32 i = 0; i < K; i++) inv32_sm(bs + (size_t)i * n, P.sb.twi[i], P.sb.headi[i], P.sb.sc.m[i]);
     const u32 G = P.gadget_digits;
     u64 av[8];
@@ -1032,15 +1114,15 @@ __device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, cons
     constexpr u32 n = 4096;
     const u32 K = P.sb.K;
     const u32 kk = K - P0 >= 2 ? 2u : 1u;
-    __syncthreads();                       // the images' previous contents are dead
+    u32 accs[2][8];                        // the sums feed the inverse transforms from registers
 #pragma unroll
     for (u32 r = 0; r < 2; r++) {
+        u32 (&acc)[8] = accs[r];
+#pragma unroll
+        for (int t = 0; t < 8; t++) acc[t] = 0;
         if (r < kk) {
             const u32 pi = P0 + r;
             const Mod32 &m = P.sb.sc.m[pi];
-            u32 acc[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) acc[t] = 0;
             for (u32 i = i_lo; i <= i_hi; i++) {
                 const u32 j = k - i;
                 const u32 *l0 = ext_s + ((((pair * 2 + 0) * d + i) * 2) * (size_t)K + pi) * n, *l1 = l0 + (size_t)K * n;
@@ -1059,11 +1141,11 @@ __device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, cons
             }
 #pragma unroll
             for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // <= 16 * 2p < 2^32 -> [0, 2p)
-            sts_u32x8(bs + (size_t)r * n, e0, acc);
         }
     }
-    if (kk == 2) inv32_smK<2, P0>(bs, P.sb);
-    else inv32_smK<1, P0>(bs, P.sb);
+    __syncthreads();                       // the images' previous contents (the base-q image, the round before) are dead
+    if (kk == 2) inv32_smK<2, P0>(bs, P.sb, accs);
+    else inv32_smK<1, P0>(bs, P.sb, accs);
 #pragma unroll
     for (u32 r = 0; r < 2; r++)
         if (r < kk) lds_u32x8(bs + (size_t)r * n, e0, bv[P0 + r]);
@@ -1113,23 +1195,23 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
         const u32 j = k - i;
         const u64 *l0 = ct1 + ((pair * d + i) * 2) * (size_t)n, *l1 = l0 + n;
         const u64 *r0 = ct2 + ((pair * d + j) * 2) * (size_t)n, *r1 = r0 + n;
+        u64 v[8];                          // the products feed the inverse transform from registers
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
-            u64 a[4], b[4], v[4];
+            u64 a[4], b[4];
             if (comp == 1) {
                 u64 cc[4], dd[4];
                 ldg_u64x4(l0 + eh, a); ldg_u64x4(r1 + eh, b); ldg_u64x4(l1 + eh, cc); ldg_u64x4(r0 + eh, dd);
 #pragma unroll
-                for (int t = 0; t < 4; t++) v[t] = mont_mul2_lazy(a[t], b[t], cc[t], dd[t], mb.m, mb.minv_neg);
+                for (int t = 0; t < 4; t++) v[4 * h + t] = mont_mul2_lazy(a[t], b[t], cc[t], dd[t], mb.m, mb.minv_neg);
             } else {
                 ldg_u64x4(l0 + eh, a); ldg_u64x4(r0 + eh, b);
 #pragma unroll
-                for (int t = 0; t < 4; t++) v[t] = mont_mul_lazy(a[t], b[t], mb.m, mb.minv_neg);
+                for (int t = 0; t < 4; t++) v[4 * h + t] = mont_mul_lazy(a[t], b[t], mb.m, mb.minv_neg);
             }
-            sts_u64x4(bq, eh, v);
         }
-        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12);
+        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12, v);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
@@ -1334,8 +1416,7 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
         u64 *acc = comp ? acc1 : acc0;
         if (!(r01_summed & 2u)) {          // bit 1: r0 / r1 are already in the NTT domain (standalone relinearize)
             sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
-            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
-            lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum);          // outputs stay in registers
         }
         sts_u64x4(acc, e0, sum); sts_u64x4(acc, e0 + 4, sum + 4);
     }
@@ -1346,15 +1427,15 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = signed_sum_to_mod(ds[j], q, mq.lazy != 0);
         sts_u64x4(work, e0, v); sts_u64x4(work, e0 + 4, v + 4);
-        fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12);       // lazy outputs: they only feed the REDCs below
+        fwd_sm<12, false>(work, P.twf[0], P.headf[0], mq, 12, v);    // lazy outputs, kept in registers: they only feed the REDCs below
         const u64 *k0 = rlk_mont + ((size_t)g * 2) * n + e0, *k1 = k0 + n;
         // lazy accumulation for 2^36 <= q < 2^60 (mq.lazy >= 1): the sums stay below 4q + 2^32 (a REDC adds < 2q, then
         // a 3-instruction high-word conditional subtract of 4q) and are made canonical once, when the limb is written out
         const bool lazy_acc = mq.lazy != 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            u64 x[4], kk[4], a[4];
-            lds_u64x4(work, e0 + 4 * h, x);
+            u64 kk[4], a[4];
+            const u64 *x = v + 4 * h;
             ldg_u64x4(k0 + 4 * h, kk);
             lds_u64x4(acc0, e0 + 4 * h, a);
 #pragma unroll
