@@ -275,7 +275,8 @@ __device__ __forceinline__ void fwd32_smK(u32 *sm, const SmallBasis &sb, u32 (*i
 // `feed` (optional): the inputs -- elements 8t .. 8t+7, the first pass's layout -- come from the caller's registers;
 // the caller guarantees that nobody still reads the images (no leading barrier here).
 template <int KK, int P0 = 0>
-__device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb, const u32 (*feed)[8] = nullptr) {
+__device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb, const u32 (*feed)[8] = nullptr,
+                                          u32 (*keep)[8] = nullptr) {
     const u32 t = threadIdx.x;
     u32 v[KK][8];
     if (!feed) __syncthreads();
@@ -300,7 +301,20 @@ __device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb, const u
     }
     EXB_PASS(3, false, twi)
     EXB_PASS(6, false, twi)
-    EXB_PASS(9, true, headi)
+    if (keep) {                            // outputs stay in registers: elements t + 512 k (the last pass's layout)
+#pragma unroll
+        for (int i = 0; i < KK; i++) load_vals32<3, 9>(v[i], sm + i * 4096, t);
+#pragma unroll
+        for (int i = 0; i < KK; i++) inv_pass32<12, 9, 3, true>(v[i], sb.headi[P0 + i], t, sb.sc.m[P0 + i]);
+#pragma unroll
+        for (int i = 0; i < KK; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) keep[i][k] = v[i][k];
+        }
+        __syncthreads();                   // the images may be rewritten once every thread has read its inputs
+    } else {
+        EXB_PASS(9, true, headi)
+    }
 #undef EXB_PASS
 }
 
@@ -1106,7 +1120,8 @@ tensor32_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
 }
 
 // tensor01_kernel, small primes P0 and P0 + 1 (those below K): sum the point-wise products of output limb k over its
-// products, inverse-transform, and leave this thread's 8 coefficients of each in bv[prime].
+// products, inverse-transform, and leave this thread's 8 coefficients of each -- elements t + 512 k, the transforms'
+// last-pass layout -- in bv[prime].  Every earlier use of the images ended with a barrier after its last read.
 template <int P0>
 __device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, const u32 *__restrict__ ext_s, u32 *bs,
                                                      size_t pair, u32 d, u32 k, u32 i_lo, u32 i_hi, u32 comp, u32 e0,
@@ -1143,12 +1158,8 @@ __device__ __forceinline__ void tensor01_small_round(const DeviceParams &P, cons
             for (int t = 0; t < 8; t++) acc[t] = fold32(acc[t], m);          // <= 16 * 2p < 2^32 -> [0, 2p)
         }
     }
-    __syncthreads();                       // the images' previous contents (the base-q image, the round before) are dead
-    if (kk == 2) inv32_smK<2, P0>(bs, P.sb, accs);
-    else inv32_smK<1, P0>(bs, P.sb, accs);
-#pragma unroll
-    for (u32 r = 0; r < 2; r++)
-        if (r < kk) lds_u32x8(bs + (size_t)r * n, e0, bv[P0 + r]);
+    if (kk == 2) inv32_smK<2, P0>(bs, P.sb, accs, &bv[P0]);
+    else inv32_smK<1, P0>(bs, P.sb, accs, &bv[P0]);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1189,7 +1200,10 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
     if (limb == 0xFFu) break;
     const u32 k = M.limb_k[limb];
     const u32 i_lo = k >= d ? k - d + 1 : 0, i_hi = k < d ? k : d - 1;
-    __syncthreads();                       // the previous limb's images are dead
+    // Registers carry the data between the element-wise phases and the transforms: the point-wise products feed the
+    // inverse transform (8 consecutive elements per thread), its outputs stay in registers in the last pass's layout
+    // (elements t + 512 k), and the per-limb accumulators, the small-prime results and the final combine all use that
+    // layout -- slot s of a thread's private accumulator rows belongs to element t + 512 s.
 
     for (u32 i = i_lo; i <= i_hi; i++) {   // base q: Montgomery point-wise + INTT per product
         const u32 j = k - i;
@@ -1211,13 +1225,12 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
                 for (int t = 0; t < 4; t++) v[4 * h + t] = mont_mul_lazy(a[t], b[t], mb.m, mb.minv_neg);
             }
         }
-        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12, v);
+        inv_sm<12>(bq, P.twi[0], P.headi[0], mb, 12, v, v);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const u32 eh = e0 + 4 * h;
-            u64 a[4];
+            const u64 *a = v + 4 * h;
             i64 sv[4];
-            lds_u64x4(bq, eh, a);
             if (i != i_lo) lds_u64x4(reinterpret_cast<const u64 *>(sacc), eh, reinterpret_cast<u64 *>(sv));
             else {
 #pragma unroll
@@ -1250,7 +1263,6 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             for (int t = 0; t < 4; t++) sv[t] += center_i64(a[t], c.q, c.half_q);
             sts_u64x4(reinterpret_cast<u64 *>(sacc), eh, reinterpret_cast<const u64 *>(sv));
         }
-        __syncthreads();                   // bq is rewritten by the next product / the small-prime images
     }
     // small primes: point-wise products summed over the limb's products, then one inverse transform per prime.  Two
     // primes per round share the 32 KB the base-q image occupied (a third image would cost 16 KB of the L1 that
@@ -1281,7 +1293,8 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             res[4 * h + t] = hps_scale32_sum(rs[t], sv[t], b, c, sc);
         }
     }
-    stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
+#pragma unroll
+    for (int s8 = 0; s8 < 8; s8++) o[threadIdx.x + 512u * s8] = res[s8];      // a warp writes 256 contiguous bytes per slot
   }
 }
 
