@@ -78,7 +78,9 @@ def static_profile(kernel_prefix):
         except Exception:
             continue
         for k in doc.get("kernels", []):
-            if k.get("Kernel Name", "").startswith(kernel_prefix):
+            name = k.get("Kernel Name", "")
+            name = name[5:] if name.startswith("void ") else name          # templates print as "void name<..>(...)"
+            if name.startswith(kernel_prefix):
                 best = (path, doc, k)
     if best is None:
         return None
@@ -89,11 +91,18 @@ def static_profile(kernel_prefix):
             return float(str(k[key]).split()[0])
         except Exception:
             return None
+    def duration_ms():
+        v, txt = num("gpu__time_duration.sum"), str(k.get("gpu__time_duration.sum", ""))
+        if v is None:
+            return None
+        unit = txt.split()[1] if len(txt.split()) > 1 else "ms"
+        scale = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}
+        return v * scale.get(unit, 1.0)
     rd, wr = num("dram__bytes_read.sum"), num("dram__bytes_write.sum")
     unit = 1e6 if "Mbyte" in str(k.get("dram__bytes_read.sum", "")) else (1e9 if "Gbyte" in str(k.get("dram__bytes_read.sum", "")) else 1.0)
     pairs = doc.get("pairs_per_launch", 148)
     return {"source": "static: " + os.path.relpath(path, ROOT), "pairs_per_launch": pairs,
-            "duration_ms": num("gpu__time_duration.sum"),
+            "duration_ms": duration_ms(),
             "dram_bytes_per_pair": (rd + wr) * unit / pairs if rd is not None and wr is not None else None,
             "fmaheavy_busy_frac": (num("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed") or 0) / 100.0,
             "issue_active_frac": (num("smsp__issue_active.avg.pct_of_peak_sustained_active") or 0) / 100.0}
