@@ -103,7 +103,7 @@ __device__ __forceinline__ void transpose8_shfl(u64 (&v)[8]) {
 // instead of storing them to the image: callers that go on element-wise skip a shared-memory round trip and a barrier.
 template <int NB, int LAZY, bool CANON = true, class TWT = const Tw *, class TWM = const Tw *>
 __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm, const TwHead &head,
-                                           const LazyC &c, const u32 t, u64 *keep = nullptr) {
+                                           const LazyC &c, const u32 t, u64 *keep = nullptr, const u64 *feed = nullptr) {
     u64 v[1 << NB];
     if constexpr (NB == 4) {
         load_vals<4, 8>(v, sm, t); fwd_pass<12, 8, 4, LAZY>(v, head, t, c); store_vals<4, 8>(v, sm, t);
@@ -112,7 +112,13 @@ __device__ __forceinline__ void fwd_body12(u64 *sm, const TWT tw, const TWM twm,
         __syncthreads();
         load_vals<4, 0>(v, sm, t); fwd_pass<12, 0, 4, LAZY>(v, tw, t, c);
     } else {
-        load_vals<3, 9>(v, sm, t); fwd_pass<12, 9, 3, LAZY>(v, head, t, c); store_vals<3, 9>(v, sm, t);
+        if (feed) {                        // inputs from the caller's registers: elements t + 512 k (first pass layout)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = feed[k];
+        } else {
+            load_vals<3, 9>(v, sm, t);
+        }
+        fwd_pass<12, 9, 3, LAZY>(v, head, t, c); store_vals<3, 9>(v, sm, t);
         __syncthreads();
         load_vals<3, 6>(v, sm, t); fwd_pass<12, 6, 3, LAZY>(v, twm, t, c); store_vals<3, 6>(v, sm, t);
         __syncthreads();
@@ -171,10 +177,10 @@ __device__ __forceinline__ void inv_body12(u64 *sm, const TWT tw, const TWM twm,
 
 template <int LAZY, bool CANON = true>
 __device__ __forceinline__ void fwd_sm12(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
-                                         u64 *keep = nullptr) {
+                                         u64 *keep = nullptr, const u64 *feed = nullptr) {
     const LazyC c = make_lazyc(mod);
-    __syncthreads();
-    fwd_body12<kNB, LAZY, CANON>(sm, tw, tw, head, c, threadIdx.x, keep);
+    __syncthreads();                       // (fed from registers too: an earlier transform may have ended without a barrier)
+    fwd_body12<kNB, LAZY, CANON>(sm, tw, tw, head, c, threadIdx.x, keep, feed);
     if (!keep) __syncthreads();            // kept outputs: the last pass read only this thread's own elements
 }
 // With `feed` there is no leading barrier: the first access to the image is this thread's store of its own elements,
@@ -320,13 +326,13 @@ __device__ __forceinline__ void inv32_smK(u32 *sm, const SmallBasis &sb, const u
 
 template <int LOGN, bool CANON = true>
 __device__ __forceinline__ void fwd_sm(u64 *sm, const Tw *__restrict__ tw, const TwHead &head, const Modulus &mod,
-                                       u32 logn, u64 *keep = nullptr) {
+                                       u32 logn, u64 *keep = nullptr, const u64 *feed = nullptr) {
     const u64 q = mod.m, q2 = mod.two_m;
     if constexpr (LOGN == 12) {
         static_assert(kNB == 3, "kept outputs assume 8 values per thread");
-        if (mod.lazy == 2) fwd_sm12<2, CANON>(sm, tw, head, mod, keep);
-        else if (mod.lazy == 1) fwd_sm12<1, CANON>(sm, tw, head, mod, keep);
-        else fwd_sm12<0, CANON>(sm, tw, head, mod, keep);
+        if (mod.lazy == 2) fwd_sm12<2, CANON>(sm, tw, head, mod, keep, feed);
+        else if (mod.lazy == 1) fwd_sm12<1, CANON>(sm, tw, head, mod, keep, feed);
+        else fwd_sm12<0, CANON>(sm, tw, head, mod, keep, feed);
     } else {
         // generic path: two butterfly stages per shared-memory round trip (radix 4 on four register values),
         // one radix-2 stage first when logn is odd
@@ -1293,8 +1299,9 @@ tensor01_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ 
             res[4 * h + t] = hps_scale32_sum(rs[t], sv[t], b, c, sc);
         }
     }
-#pragma unroll
-    for (int s8 = 0; s8 < 8; s8++) o[threadIdx.x + 512u * s8] = res[s8];      // a warp writes 256 contiguous bytes per slot
+    // r01s rows are stored in the transforms' strided layout: word 8t + s holds element t + 512 s, so the relinearisation
+    // kernels feed their forward transform's first pass from one 64-byte piece per thread
+    stg_u64x4(o + e0, res); stg_u64x4(o + e0 + 4, res + 4);
   }
 }
 
@@ -1428,8 +1435,12 @@ relin12_kernel(const __grid_constant__ DeviceParams P, const __grid_constant__ M
         }
         u64 *acc = comp ? acc1 : acc0;
         if (!(r01_summed & 2u)) {          // bit 1: r0 / r1 are already in the NTT domain (standalone relinearize)
-            sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
-            fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum);          // outputs stay in registers
+            if (r01_summed & 1u) {         // tensor01_kernel's rows: already in the first pass's register layout
+                fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum, sum);
+            } else {
+                sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+                fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum);      // outputs stay in registers
+            }
         }
         sts_u64x4(acc, e0, sum); sts_u64x4(acc, e0 + 4, sum + 4);
     }
@@ -1528,9 +1539,12 @@ relin12_wide_kernel(const __grid_constant__ DeviceParams P, const __grid_constan
                 }
             }
             if (!(r01_summed & 2u)) {
-                sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
-                fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12);
-                lds_u64x4(work, e0, sum); lds_u64x4(work, e0 + 4, sum + 4);
+                if (r01_summed & 1u) {     // tensor01_kernel's rows: already in the first pass's register layout
+                    fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum, sum);
+                } else {
+                    sts_u64x4(work, e0, sum); sts_u64x4(work, e0 + 4, sum + 4);
+                    fwd_sm<12>(work, P.twf[0], P.headf[0], mq, 12, sum);
+                }
             }
             stg_u64x4(dst + comp * n + e0, sum); stg_u64x4(dst + comp * n + e0 + 4, sum + 4);
             __syncthreads();
